@@ -1,0 +1,225 @@
+"""ctypes binding of the C ABI in include/adsurf_b200.h (libadsurf_b200.so).
+
+Plain pointers and sizes only cross this boundary; torch is used for device memory and the
+current CUDA stream.  There is no CPU fallback: if the shared library is missing or the tensors
+are not CUDA tensors these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libadsurf_b200.so")
+
+OP_POINTS_FWD, OP_POINTS_BWD, OP_POINTS_JAC, OP_GRID_FWD, OP_GRID_BWD, OP_DMF_STEP = range(6)
+COMPRESS_NONE, COMPRESS_EXP, COMPRESS_LOG, COMPRESS_EXP_NONORM, COMPRESS_NORM = range(5)
+
+EXPORTS = (
+    "adsurf_version",
+    "adsurf_error_string",
+    "adsurf_workspace_bytes",
+    "adsurf_det_points_fwd",
+    "adsurf_det_points_bwd",
+    "adsurf_det_points_jac",
+    "adsurf_det_grid_fwd",
+    "adsurf_det_grid_bwd",
+    "adsurf_dmf_step",
+    "adsurf_fp64_peak_probe",
+)
+
+_lib = None
+launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+class AdsurfError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libadsurf_b200.so (built by __graft_entry__.build()); raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AdsurfError(
+                f"{LIB_PATH} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()'); "
+                "adsurf_b200 has no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+        L.adsurf_version.restype = ctypes.c_char_p
+        L.adsurf_error_string.restype = ctypes.c_char_p
+        L.adsurf_error_string.argtypes = [ci]
+        L.adsurf_workspace_bytes.restype = sz
+        L.adsurf_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
+        L.adsurf_det_points_fwd.argtypes = [vp] * 6 + [ci] * 3 + [vp, vp]
+        L.adsurf_det_points_bwd.argtypes = [vp] * 7 + [ci] * 3 + [vp] * 6 + [vp, sz, vp]
+        L.adsurf_det_points_jac.argtypes = [vp] * 6 + [ci] * 3 + [vp] * 6 + [vp]
+        L.adsurf_det_grid_fwd.argtypes = [vp] * 6 + [ci] * 4 + [vp] * 4 + [vp, sz, vp]
+        L.adsurf_det_grid_bwd.argtypes = [vp] * 7 + [ci] * 4 + [vp] * 5 + [vp, sz, vp]
+        L.adsurf_dmf_step.argtypes = [vp] * 7 + [ci] * 6 + [vp] * 7 + [vp, sz, vp]
+        L.adsurf_fp64_peak_probe.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]
+        for name in EXPORTS:
+            if name.startswith("adsurf_det") or name in ("adsurf_dmf_step", "adsurf_fp64_peak_probe"):
+                getattr(L, name).restype = ci
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise AdsurfError(f"adsurf_b200 C ABI error {rc}: {lib().adsurf_error_string(rc).decode()}")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(ref):
+    return ctypes.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream)
+
+
+def _req(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise AdsurfError("adsurf_b200 kernels need CUDA tensors (no CPU fallback)")
+        if t.dtype != torch.float64 or not t.is_contiguous():
+            raise AdsurfError("adsurf_b200 kernels need contiguous float64 tensors")
+
+
+def _workspace(op, S, L, n, K, ref):
+    nbytes = lib().adsurf_workspace_bytes(op, S, L, n, K)
+    ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=ref.device)
+    return ws, nbytes
+
+
+def version():
+    return lib().adsurf_version().decode()
+
+
+def points_fwd(d, a, b, rho, t, c):
+    """F[S,N]; all inputs contiguous float64 CUDA, model arrays [S,L], t,c [S,N]."""
+    global launch_count
+    _req(d, a, b, rho, t, c)
+    S, L = d.shape
+    N = c.shape[1]
+    F = torch.empty((S, N), dtype=torch.float64, device=d.device)
+    with torch.cuda.device(d.device):
+        _check(lib().adsurf_det_points_fwd(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), _ptr(c), S, L, N, _ptr(F),
+                                           _stream(d)))
+    launch_count += 1
+    return F
+
+
+def points_bwd(d, a, b, rho, t, c, gF, want_F=False):
+    """(F or None, gd, ga, gb, grho [S,L], gc [S,N])"""
+    global launch_count
+    _req(d, a, b, rho, t, c, gF)
+    S, L = d.shape
+    N = c.shape[1]
+    dev = d.device
+    F = torch.empty((S, N), dtype=torch.float64, device=dev) if want_F else None
+    gd, ga, gb, gr = (torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4))
+    gc = torch.empty((S, N), dtype=torch.float64, device=dev)
+    ws, nbytes = _workspace(OP_POINTS_BWD, S, L, N, 0, d)
+    with torch.cuda.device(dev):
+        _check(lib().adsurf_det_points_bwd(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), _ptr(c), _ptr(gF), S, L, N,
+                                           _ptr(F), _ptr(gd), _ptr(ga), _ptr(gb), _ptr(gr), _ptr(gc), _ptr(ws), nbytes,
+                                           _stream(d)))
+    launch_count += 2
+    return F, gd, ga, gb, gr, gc
+
+
+def points_jac(d, a, b, rho, t, c):
+    """(F [S,N], Jd, Ja, Jb, Jrho [S,N,L], Jc [S,N])"""
+    global launch_count
+    _req(d, a, b, rho, t, c)
+    S, L = d.shape
+    N = c.shape[1]
+    dev = d.device
+    F = torch.empty((S, N), dtype=torch.float64, device=dev)
+    J = [torch.empty((S, N, L), dtype=torch.float64, device=dev) for _ in range(4)]
+    Jc = torch.empty((S, N), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().adsurf_det_points_jac(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), _ptr(c), S, L, N, _ptr(F),
+                                           _ptr(J[0]), _ptr(J[1]), _ptr(J[2]), _ptr(J[3]), _ptr(Jc), _stream(d)))
+    launch_count += 1
+    return F, J[0], J[1], J[2], J[3], Jc
+
+
+def grid_fwd(d, a, b, rho, t, c, want_det=True, want_minmax=False, want_signbits=False):
+    """(det [S,K,NF] | None, cmax, cmin [S,NF] | None, signbits uint32 [S,K,ceil(NF/32)] | None)"""
+    global launch_count
+    _req(d, a, b, rho, t, c)
+    S, L = d.shape
+    NF, K = t.shape[1], c.shape[1]
+    dev = d.device
+    det = torch.empty((S, K, NF), dtype=torch.float64, device=dev) if want_det else None
+    cmax = torch.empty((S, NF), dtype=torch.float64, device=dev) if want_minmax else None
+    cmin = torch.empty((S, NF), dtype=torch.float64, device=dev) if want_minmax else None
+    bits = torch.empty((S, K, (NF + 31) // 32), dtype=torch.int32, device=dev) if want_signbits else None
+    ws, nbytes = _workspace(OP_GRID_FWD, S, L, NF, K, d)
+    with torch.cuda.device(dev):
+        _check(lib().adsurf_det_grid_fwd(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), _ptr(c), S, L, NF, K, _ptr(det),
+                                         _ptr(cmax), _ptr(cmin), _ptr(bits), _ptr(ws), nbytes, _stream(d)))
+    launch_count += 2 if want_minmax else 1
+    return det, cmax, cmin, bits
+
+
+def grid_bwd(d, a, b, rho, t, c, gdet=None, want_det=False, out=None, ws=None):
+    """(det | None, gd, ga, gb, grho [S,L]); gdet None means all-ones upstream gradient.
+
+    `out` (tuple of 4 [S,L] tensors) and `ws` (uint8 tensor) let a caller reuse buffers."""
+    global launch_count
+    _req(d, a, b, rho, t, c, gdet)
+    S, L = d.shape
+    NF, K = t.shape[1], c.shape[1]
+    dev = d.device
+    det = torch.empty((S, K, NF), dtype=torch.float64, device=dev) if want_det else None
+    if out is None:
+        out = tuple(torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4))
+    nbytes = lib().adsurf_workspace_bytes(OP_GRID_BWD, S, L, NF, K)
+    if ws is None:
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().adsurf_det_grid_bwd(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), _ptr(c), _ptr(gdet), S, L, NF,
+                                         K, _ptr(det), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
+                                         _ptr(ws), ws.numel(), _stream(d)))
+    launch_count += 2
+    return (det,) + tuple(out)
+
+
+def dmf_step(d, a, b, rho, t, c, C, compress, with_grad=True, want_F=False, want_norm=False):
+    """(loss [S], F | None, norm | None, gd, ga, gb, grho | None x4)"""
+    global launch_count
+    _req(d, a, b, rho, t, c, C)
+    S, L = d.shape
+    N = c.shape[1]
+    K = C.shape[1] if C is not None else 0
+    dev = d.device
+    normalised = compress in (COMPRESS_EXP, COMPRESS_LOG, COMPRESS_NORM)
+    loss = torch.empty((S,), dtype=torch.float64, device=dev)
+    F = torch.empty((S, N), dtype=torch.float64, device=dev) if want_F else None
+    norm = torch.empty((S, N), dtype=torch.float64, device=dev) if (want_norm and normalised) else None
+    grads = tuple(torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4)) if with_grad else (None,) * 4
+    ws, nbytes = _workspace(OP_DMF_STEP, S, L, N, K if normalised else 0, d)
+    with torch.cuda.device(dev):
+        _check(lib().adsurf_dmf_step(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), _ptr(c), _ptr(C), S, L, N, K,
+                                     int(compress), int(bool(with_grad)), _ptr(loss), _ptr(F), _ptr(norm),
+                                     _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]), _ptr(grads[3]), _ptr(ws), nbytes,
+                                     _stream(d)))
+    launch_count += (1 if normalised else 0) + 2 + (1 if with_grad else 0)
+    return (loss, F, norm) + grads
+
+
+def fp64_peak_probe(iters=2048, repeats=5, device=None):
+    """(TFLOP/s, ms) of a register-resident DFMA loop on the current device."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    tf, ms = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    with torch.cuda.device(dev):
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _check(lib().adsurf_fp64_peak_probe(int(iters), int(repeats), ctypes.byref(tf), ctypes.byref(ms), st))
+    return tf.value, ms.value

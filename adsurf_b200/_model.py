@@ -1,0 +1,406 @@
+"""DMF loss modules and inversion drivers — host-side mirror of the reference's ADsurf/_model.py.
+
+Same class names, constructor arguments and result dictionaries as the reference
+(`iter_cal_grad` _model.py:236, `multi_cal_grad` :349, `iter_inversion` :12, `multi_inversion` :480)
+so the callers in `_ADsurf.inversion(...)` switch by import.  What differs is underneath:
+
+  * the pointwise determinant, the dense-grid normalisation (max - min over the trial
+    velocities), the compression and the per-model misfit reduction — and their gradient — are one
+    fused kernel sequence (`ops.dmf_data_misfit` -> C ABI `adsurf_dmf_step`) instead of ~3.4e4 ATen
+    calls per step; the Brocher Vp/rho chain rule and the Tikhonov terms stay in torch autograd on
+    tiny [S,L] tensors;
+  * arithmetic is float64 (the reference casts everything to float32, _utils.py:493-500);
+  * the per-iteration clipping of Vs and of the layer depths runs on the device with vectorised
+    torch ops (the reference round-trips through numpy and Python loops, _model.py:126-147,603-621).
+
+Ordering inside one iteration is the reference's: loss -> backward -> clip parameters -> record
+iterate -> optimizer.step() -> scheduler.step() (_model.py:118-162, :589-636).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from ._utils import gen_model, gen_model1, ifunc_list, list2numpy, numpy2tensor
+
+try:  # progress bars are optional
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(x, **kw):
+        return x
+
+
+def _dev(device):
+    if isinstance(device, torch.device):
+        dev = device
+    else:
+        dev = torch.device(str(device).lower())
+    if dev.type != "cuda":
+        # the reference's device="cpu" run: tensors live on the CPU, arithmetic still runs on the GPU
+        return torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def brocher_vp(b):
+    return 0.9409 + 2.0947 * b - 0.8206 * b**2 + 0.2683 * b**3 - 0.0251 * b**4
+
+
+def brocher_rho(a):
+    return 1.6612 * a - 0.4721 * a**2 + 0.0671 * a**3 - 0.0043 * a**4 + 0.000106 * a**5
+
+
+def _second_difference(n, device):
+    """Tikhonov operator of _model.py:292-294 / :407-409: tridiag(-1, 2, -1) with corner entries 1."""
+    L0 = 2.0 * torch.eye(n, dtype=torch.float64, device=device)
+    if n > 1:
+        i = torch.arange(n - 1, device=device)
+        L0[i, i + 1] = -1.0
+        L0[i + 1, i] = -1.0
+    L0[0, 0] = 1.0
+    L0[n - 1, n - 1] = 1.0
+    return L0
+
+
+def _compress_mode(compress, normalized, compress_method):
+    """Map the reference's three switches (_model.py:450-462) to the kernel's compression id."""
+    if not compress:
+        return "none"
+    if not normalized:
+        return "exp_nonorm"
+    if compress_method == "log":
+        return "log"
+    if compress_method == "exp":
+        return "exp"
+    return "norm"  # normalised but no recognised compression: F/n is used as is
+
+
+class _cal_grad_base(torch.nn.Module):
+    def _velocities(self):
+        """Vp and density from Vs inside the graph (_model.py:306-319 / :431-446)."""
+        b = self.b
+        if self.initial_method == "Brocher":
+            a = brocher_vp(b)
+            rho = brocher_rho(a)
+        elif self.initial_method == "Constant":
+            a = b * self.vp_vs_ratio
+            rho = self.rho
+        elif self.initial_method == "USArray":
+            # the reference's AK135 substitution for Vs > 4.6 writes into temporaries (no effect);
+            # what survives is: Brocher where Vs <= 4.6, the initial Vp / rho elsewhere
+            low = b <= 4.6
+            a = torch.where(low, brocher_vp(b), self.a)
+            rho = torch.where(low, brocher_rho(a), self.rho)
+        else:
+            a, rho = self.a, self.rho
+        return a, rho
+
+
+class multi_cal_grad(_cal_grad_base):
+    """Batched DMF: loss[S] for S models at once (reference _model.py:349-478)."""
+
+    def __init__(self, d, a, b, rho, Clist, damp_vertical, damp_horizontal, compress, normalized, compress_method,
+                 inversion_method, initial_method, vp_vs_ratio, AK135_data=[], device="cpu"):
+        super().__init__()
+        self.device = _dev(device)
+        t64 = lambda x: numpy2tensor(x).to(self.device)
+        self.d = t64(d)
+        self.a = t64(a)
+        self.rho = t64(rho)
+        self.b = torch.nn.Parameter(t64(b).clone())
+        if inversion_method.lower() == "vs-and-thick":
+            self.d = torch.nn.Parameter(self.d.clone())
+        self.Clist = t64(Clist).contiguous()
+        self.ifunc = ifunc_list["dunkin"]["rayleigh"]
+        self.llw = 0 if float(self.b[0][0]) <= 0.0 else -1
+        if self.llw == 0:
+            raise NotImplementedError("adsurf_b200: water layer (Vs[0] <= 0) is not supported (broken in the reference too)")
+        self.damp_vertical = damp_vertical
+        self.damp_horizontal = damp_horizontal
+        self.L_vertical = _second_difference(self.b.shape[1], self.device)
+        self.L_horizontal = _second_difference(self.b.shape[0], self.device)
+        self.normalized = normalized
+        self.compress = compress
+        self.compress_method = compress_method
+        self.initial_method = initial_method
+        self.vp_vs_ratio = vp_vs_ratio
+        self.AK135_data = numpy2tensor(list2numpy(AK135_data)).to(self.device)
+
+    def forward(self, vlist, tlist):
+        a, rho = self._velocities()
+        mode = _compress_mode(self.compress, self.normalized, self.compress_method)
+        F_all = ops.dmf_data_misfit(vlist, tlist, self.Clist, self.d, a, self.b, rho, compress=mode,
+                                    device=self.device)
+        out = F_all
+        nL = self.b.shape[1]
+        if self.damp_vertical > 0:
+            mv = self.damp_vertical * torch.matmul(self.b, self.L_vertical.T) / nL
+            out = out + torch.sum(torch.abs(mv), dim=1)
+        if self.damp_horizontal > 0:
+            mh = self.damp_horizontal * torch.matmul(self.L_horizontal, self.b) / nL
+            out = out + torch.sum(torch.abs(mh), dim=1)
+        return out
+
+
+class iter_cal_grad(_cal_grad_base):
+    """Single-model DMF: scalar loss (reference _model.py:236-344)."""
+
+    def __init__(self, d, a, b, rho, Clist, damp, compress, normalized, compress_method, inversion_method,
+                 initial_method, vp_vs_ratio, AK135_data=[], device="cpu"):
+        super().__init__()
+        self.device = _dev(device)
+        t64 = lambda x: numpy2tensor(x).to(self.device)
+        self.d = t64(d).reshape(-1)
+        self.a = t64(a).reshape(-1)
+        self.rho = t64(rho).reshape(-1)
+        self.b = torch.nn.Parameter(t64(b).reshape(-1).clone())
+        if inversion_method.lower() == "vs-and-thick":
+            self.d = torch.nn.Parameter(self.d.clone())
+        self.Clist = t64(Clist).reshape(1, -1).contiguous()
+        self.ifunc = ifunc_list["dunkin"]["rayleigh"]
+        self.llw = 0 if float(self.b[0]) <= 0.0 else -1
+        if self.llw == 0:
+            raise NotImplementedError("adsurf_b200: water layer (Vs[0] <= 0) is not supported (broken in the reference too)")
+        self.damp = damp
+        self.L = _second_difference(self.b.shape[0], self.device)
+        self.normalized = normalized
+        self.compress = compress
+        self.compress_method = compress_method
+        self.initial_method = initial_method
+        self.vp_vs_ratio = vp_vs_ratio
+        self.AK135_data = numpy2tensor(list2numpy(AK135_data)).to(self.device)
+
+    def forward(self, vlist, tlist):
+        a, rho = self._velocities()
+        mode = _compress_mode(self.compress, self.normalized, self.compress_method)
+        vlist = numpy2tensor(vlist).to(self.device).reshape(1, -1)
+        tlist = numpy2tensor(tlist).to(self.device).reshape(1, -1)
+        F_all = ops.dmf_data_misfit(vlist, tlist, self.Clist, self.d.reshape(1, -1), a.reshape(1, -1),
+                                    self.b.reshape(1, -1), rho.reshape(1, -1), compress=mode, device=self.device)[0]
+        if self.damp > 0:
+            m_norm = self.damp * torch.matmul(self.L, self.b) / self.b.shape[0]
+            return F_all + torch.sum(torch.abs(m_norm))
+        return F_all
+
+
+def _clip_depths(thick, layer_mindepth, layer_maxdepth, layering_method):
+    """Depth/thickness projection of _model.py:133-147 (single) and :603-620 (batched), on device.
+
+    thick, layer_mindepth, layer_maxdepth: [..., L].  Returns the projected thickness."""
+    depth = torch.cumsum(thick, dim=-1)
+    if layering_method == "LR":
+        depth = torch.minimum(torch.maximum(depth, layer_mindepth), layer_maxdepth)
+    elif layering_method == "LN":
+        cols = []
+        for ind in range(depth.shape[-1]):
+            lo = layer_mindepth[..., ind] if ind == 0 else cols[-1] + layer_mindepth[..., ind]
+            # torch.clip / np.clip semantics: max wins when min > max
+            cols.append(torch.minimum(torch.maximum(depth[..., ind], lo), layer_maxdepth[..., ind]))
+        depth = torch.stack(cols, dim=-1)
+    zero = torch.zeros_like(depth[..., :1])
+    new_thick = torch.diff(torch.cat((zero, depth), dim=-1), dim=-1)
+    floor = layer_mindepth[..., :1] if layer_mindepth.dim() == 1 else layer_mindepth[:1, :1]
+    return torch.maximum(new_thick, floor.expand_as(new_thick))
+
+
+class iter_inversion:
+    """Single-model inversion loop (reference _model.py:12-234)."""
+
+    def __init__(self, model_param, inv_param, init_model, pvs_obs, vsrange_sign="mul", vsrange=[0.1, 2],
+                 AK135_data=[], device="cuda"):
+        self.init_model = init_model
+        self.model_param = model_param
+        self.inv_param = inv_param
+        self.pvs_obs = pvs_obs
+        self.vsrange_sign = vsrange_sign
+        self.vsrange = vsrange
+        self.AK135_data = AK135_data
+        self.device = _dev(device)
+        self.inv_model = {"vs": [], "vp": [], "rho": [], "thick": []}
+        self.inv_process = {"iter_vs": [], "iter_thick": [], "loss": []}
+        self._run()
+
+    def _run(self):
+        im = self.init_model.init_model
+        dev = self.device
+        t64 = lambda x: numpy2tensor(list2numpy(x)).to(dev)
+        b, a, rho, d = t64(im["vs"]), t64(im["vp"]), t64(im["rho"]), t64(im["thick"])
+        layer_mindepth, layer_maxdepth = t64(im["layer_mindepth"]), t64(im["layer_maxdepth"])
+        obs = list2numpy(self.pvs_obs)
+        tlist, vlist = t64(obs[:, 0].reshape(-1)), t64(obs[:, 1].reshape(-1))
+        ip, mp = self.inv_param, self.model_param
+        Clist = t64(list2numpy(mp.clist).reshape(1, -1))
+        inversion_method = ip.inversion_method
+        calculator = iter_cal_grad(d, a, b, rho, Clist, ip.damp_vertical, ip.compress, ip.normalized,
+                                   ip.compress_method, inversion_method, mp.initialize_method, mp.vp_vs_ratio,
+                                   self.AK135_data, device=dev)
+        if ip.optimizer != "Adam":
+            raise NameError("The input optimizer {} can not find in Pytorch".format(ip.optimizer))
+        optimizer = torch.optim.Adam(calculator.parameters(), lr=ip.lr)
+        scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=ip.step_size, gamma=ip.gamma)
+        iteration = ip.iteration
+        iter_vs = torch.zeros((iteration, b.shape[0]), dtype=torch.float64, device=dev)
+        iter_thick = torch.zeros((iteration, d.shape[0]), dtype=torch.float64, device=dev)
+        loss_list = torch.full((iteration,), 10.0, dtype=torch.float64, device=dev)
+        if self.vsrange_sign == "mul":
+            lower_b, upper_b = self.vsrange[0] * b, self.vsrange[1] * b
+        else:
+            lower_b, upper_b = b + self.vsrange[0], b + self.vsrange[1]
+        patience, eps, trigger_times = 50, 1e-4, 0
+        vs_and_thick = inversion_method.lower() == "vs-and-thick"
+        last = iteration
+        prev = None
+        for j in tqdm(range(iteration), disable=not getattr(ip, "progress", False)):
+            loss = calculator(vlist, tlist)
+            optimizer.zero_grad()
+            loss.backward()
+            with torch.no_grad():
+                pb = calculator.b
+                pb.data = torch.minimum(torch.maximum(pb.data, lower_b), upper_b)
+                if vs_and_thick:
+                    pb.data[-1] = torch.maximum(pb.data[-1], pb.data[-2])  # half-space >= layer above (:129)
+                    iter_vs[j] = pb.data
+                    pd = calculator.d
+                    pd.data = _clip_depths(pd.data, layer_mindepth, layer_maxdepth, mp.layering_method)
+                    iter_thick[j] = pd.data
+                else:
+                    iter_vs[j] = pb.data
+            optimizer.step()
+            scheduler.step()
+            cur = float(loss.detach())  # the reference syncs every iteration for its progress bar (:164)
+            loss_list[j] = cur
+            if j > 0:
+                if cur > 0.6:
+                    trigger_times = 0
+                if (cur > prev) or (abs(cur - prev) / abs(prev) < eps):
+                    trigger_times += 1
+                    if trigger_times >= patience:
+                        print("Early Stopping in Iteration:{}".format(j))
+                        break
+                else:
+                    trigger_times = 0
+            if cur != cur:  # NaN: drop this iterate and stop (:180-186)
+                last = j
+                print("Early Stopping in Iteration:{}".format(j))
+                break
+            prev = cur
+        loss_np = loss_list[:last].cpu().numpy()
+        iter_vs = iter_vs[:last].cpu().numpy()
+        iter_thick = iter_thick[:last].cpu().numpy()
+        best = int(np.argmin(loss_np))
+        inv_thick = iter_thick[best] if vs_and_thick else list2numpy(im["thick"])
+        inv_vs = iter_vs[best]
+        inv_vp, inv_vs, inv_rho = _final_model(mp, inv_thick, inv_vs, self.AK135_data)
+        self.inv_model = {"thick": np.asarray(inv_thick).tolist(), "vp": inv_vp.tolist(), "vs": inv_vs.tolist(),
+                          "rho": inv_rho.tolist()}
+        self.inv_process = {"iter_vs": iter_vs.tolist(), "iter_thick": iter_thick.tolist(), "loss": loss_np.tolist()}
+
+
+def _final_model(model_param, thick, vs, AK135_data):
+    method = model_param.initialize_method
+    if method == "Brocher":
+        _, vp, vs, rho = gen_model(thick=thick, vs=vs, area=True)
+    elif method == "Constant":
+        _, vp, vs, rho = gen_model1(thick=thick, vs=vs, vp_vs_ratio=model_param.vp_vs_ratio, rho=model_param.rho,
+                                    area=True)
+    elif method == "USArray":
+        _, vp, vs, rho = gen_model(thick=thick, vs=vs, area=True)
+        ak = np.asarray(AK135_data)
+        for j in np.nonzero(vs > 4.6)[0]:
+            vp_j, rho_j = vp[j], rho[j]
+            vp[j] = ak[np.argmin(np.abs(ak[:, 2] - vp_j))][2]
+            rho[j] = ak[np.argmin(np.abs(ak[:, 1] - rho_j))][1]
+    else:
+        raise NameError("The initialize method can only select from [Brocher,Constant]")
+    return vp, vs, rho
+
+
+class multi_inversion:
+    """Ensemble inversion loop: all models advance together (reference _model.py:480-701).
+
+    With torch.distributed initialised (one process per GPU) the model axis is sharded across the
+    ranks; the per-model losses and iterates are all-gathered at the end (and neighbouring rows
+    of Vs every iteration when damp_horizontal > 0) — see adsurf_b200/_dist.py."""
+
+    def __init__(self, model_param, inv_param, init_model, pvs_obs, vsrange_sign="mul", vsrange=[0.1, 2],
+                 AK135_data=[], device="cuda"):
+        self.init_model = init_model
+        self.model_param = model_param
+        self.inv_param = inv_param
+        self.pvs_obs = pvs_obs
+        self.vsrange_sign = vsrange_sign
+        self.vsrange = vsrange
+        self.AK135_data = AK135_data
+        self.device = _dev(device)
+        self.inv_model = {"vs": [], "vp": [], "rho": [], "thick": []}
+        self.inv_process = {"iter_vs": [], "iter_thick": [], "loss": []}
+        self._run()
+
+    def _run(self):
+        im = self.init_model.init_model
+        dev = self.device
+        t64 = lambda x: numpy2tensor(list2numpy(x)).to(dev)
+        init_vs = list2numpy(im["vs"])
+        b, a, rho, d = t64(init_vs), t64(im["vp"]), t64(im["rho"]), t64(im["thick"])
+        S, L = b.shape
+        obs = list2numpy(self.pvs_obs)
+        tlist, vlist = t64(obs[:, :, 0]).contiguous(), t64(obs[:, :, 1]).contiguous()
+        ip, mp = self.inv_param, self.model_param
+        clist = t64(mp.clist).reshape(1, -1)
+        Clist = clist.expand(S, -1).contiguous()
+        inversion_method = ip.inversion_method
+        layering_method = mp.layering_method
+        layer_mindepth = torch.ones_like(b) * t64(im["layer_mindepth"])
+        layer_maxdepth = torch.ones_like(b) * t64(im["layer_maxdepth"])
+        calculator = multi_cal_grad(d, a, b, rho, Clist, ip.damp_vertical, ip.damp_horizontal, ip.compress,
+                                    ip.normalized, ip.compress_method, inversion_method, mp.initialize_method,
+                                    mp.vp_vs_ratio, self.AK135_data, device=dev)
+        if ip.optimizer != "Adam":
+            raise NameError("The input optimizer {} can not find in Pytorch".format(ip.optimizer))
+        optimizer = torch.optim.Adam(calculator.parameters(), lr=ip.lr)
+        scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=ip.step_size, gamma=ip.gamma)
+        iteration = ip.iteration
+        iter_vs = torch.zeros((iteration, S, L), dtype=torch.float64, device=dev)
+        iter_thick = torch.zeros((iteration, S, L), dtype=torch.float64, device=dev)
+        loss_list = torch.full((iteration, S), 10.0, dtype=torch.float64, device=dev)
+        if self.vsrange_sign == "mul":
+            lower_b, upper_b = self.vsrange[0] * b, self.vsrange[1] * b
+        else:  # the reference offsets the FIRST model's Vs for every model (_model.py:577-578)
+            lower_b = b[0] * torch.ones_like(b) + self.vsrange[0]
+            upper_b = b[0] * torch.ones_like(b) + self.vsrange[1]
+        vs_and_thick = inversion_method.lower() == "vs-and-thick"
+        b0 = b.clone()
+        ones = torch.ones(S, dtype=torch.float64, device=dev)
+        for j in tqdm(range(iteration), disable=not getattr(ip, "progress", False)):
+            loss = calculator(vlist, tlist)
+            optimizer.zero_grad()
+            loss.backward(ones)
+            with torch.no_grad():
+                pb = calculator.b
+                if not vs_and_thick:  # NaN repair exists only on this branch in the reference (:624-626)
+                    pb.data = torch.where(torch.isnan(pb.data), b0, pb.data)
+                pb.data = torch.minimum(torch.maximum(pb.data, lower_b), upper_b)
+                pb.data[:, -1] = torch.maximum(pb.data[:, -1], pb.data[:, -2])
+                iter_vs[j] = pb.data
+                if vs_and_thick:
+                    pd = calculator.d
+                    pd.data = _clip_depths(pd.data, layer_mindepth, layer_maxdepth, layering_method)
+                    iter_thick[j] = pd.data
+            optimizer.step()
+            scheduler.step()
+            loss_list[j] = loss.detach()
+        loss_list = torch.where(torch.isnan(loss_list), torch.full_like(loss_list, 10.0), loss_list)
+        loss_np = loss_list.cpu().numpy()
+        iter_vs = iter_vs.cpu().numpy()
+        iter_thick = iter_thick.cpu().numpy()
+        best_num = np.argmin(loss_np, axis=0)
+        inv_thick = np.array(list2numpy(im["thick"]), dtype=np.float64, copy=True)
+        if vs_and_thick:
+            for i in range(S):
+                inv_thick[i] = iter_thick[best_num[i], i, :]
+        inv_vs, inv_vp, inv_rho = (np.zeros_like(inv_thick) for _ in range(3))
+        for i in range(S):
+            inv_vp[i], inv_vs[i], inv_rho[i] = _final_model(mp, inv_thick[i], iter_vs[best_num[i], i], self.AK135_data)
+        self.inv_model = {"thick": inv_thick.tolist(), "vp": inv_vp.tolist(), "vs": inv_vs.tolist(),
+                          "rho": inv_rho.tolist()}
+        self.inv_process = {"iter_vs": iter_vs.tolist(), "iter_thick": iter_thick.tolist(), "loss": loss_np.tolist()}

@@ -1,0 +1,707 @@
+// adsurf_kernels.cu — hand-written sm_100a FP64 kernels for the Rayleigh secular function
+// (Dunkin compound-matrix recursion) and its reverse-mode gradient, plus the C ABI
+// declared in include/adsurf_b200.h.
+//
+// What it computes is specified in SURVEY.md Appendix A, which restates
+// /root/reference/ADsurf/_cps/_surf96_vectorAll_gpu.py:52-100 (Dunkin matrix), :102-192
+// (exponent-scaled eigenfunction terms) and :303-399 (layer recursion, no normalisation).
+// How it computes it is new:
+//   * one thread per (model, period, trial velocity) sample, lanes of a warp run over PERIODS
+//     at a fixed trial velocity so that (a) det[s,k,f] is written coalesced and (b) the three-way
+//     branch "c <,==,> layer velocity" is warp-uniform (it does not depend on the period);
+//   * per-model layer constants (1/alpha, 1/beta, 2 beta^2, rho, 1/rho, d) staged once per block
+//     in shared memory; the 5-component compound state lives in registers; the 5x5 matrix is
+//     never formed;
+//   * the adjoint is a hand-derived reverse sweep: pass 1 (bottom-up) keeps the row vectors
+//     E_{m+1} of each layer in shared memory (40 B per thread per layer), pass 2 (top-down)
+//     carries the column vector s_m = CA_{m-1}...CA_0 e_0, recomputes the layer terms and
+//     contracts dDelta = E_{m+1} . dCA_m . s_m analytically into (d, alpha, beta, rho, c);
+//   * per-model gradient sums: warp shuffle -> per-warp shared accumulators -> one partial per
+//     block -> deterministic second-stage reduce (no atomics);
+//   * the dense pass fuses max/min over the trial velocities (what the DMF needs) and an optional
+//     sign bitmap, so det never has to be materialised.
+// No tensor cores (not a contraction), no library calls on the path.
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "adsurf_b200.h"
+#include "adsurf_math.cuh"
+
+namespace {
+
+using namespace adsurf;
+
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// gradient sinks for sample_adjoint
+struct ReduceSink {  // warp-reduce each layer's 4 gradients into per-warp shared accumulators [4][L]
+  double* acc;
+  int L, lane;
+  bool active;
+  __device__ __forceinline__ void operator()(int m, double gd, double ga, double gb, double gr) const {
+    if (!active) { gd = 0.0; ga = 0.0; gb = 0.0; gr = 0.0; }
+    gd = warp_sum(gd); ga = warp_sum(ga); gb = warp_sum(gb); gr = warp_sum(gr);
+    if (lane == 0) {
+      acc[0 * L + m] += gd;
+      acc[1 * L + m] += ga;
+      acc[2 * L + m] += gb;
+      acc[3 * L + m] += gr;
+    }
+  }
+};
+
+struct JacSink {  // write this sample's Jacobian rows
+  double *jd, *ja, *jb, *jr;
+  bool active;
+  __device__ __forceinline__ void operator()(int m, double gd, double ga, double gb, double gr) const {
+    if (!active) return;
+    if (jd) jd[m] = gd;
+    if (ja) ja[m] = ga;
+    if (jb) jb[m] = gb;
+    if (jr) jr[m] = gr;
+  }
+};
+
+// stage the per-model layer constants
+__device__ __forceinline__ void stage_params(double* __restrict__ par, const double* __restrict__ d,
+                                             const double* __restrict__ alpha, const double* __restrict__ beta,
+                                             const double* __restrict__ rho, int s, int L) {
+  for (int m = threadIdx.x; m < L; m += blockDim.x) {
+    stage_one(par, L, m, d[(size_t)s * L + m], alpha[(size_t)s * L + m], beta[(size_t)s * L + m],
+              rho[(size_t)s * L + m]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernels
+// ------------------------------------------------------------------------------------------
+struct GridPlan {
+  int nft;     // period tiles of 32 per model
+  int nchunk;  // trial-velocity chunks per model
+  int chunk;   // trial velocities per chunk
+  int units;   // nft * nchunk warp work units per model
+  int wpb;     // warps per block
+  int bpm;     // blocks per model
+};
+
+// Dense grid, forward only: det / fused max,min over k / sign bitmap.
+__global__ void __launch_bounds__(256) k_grid_fwd(const double* __restrict__ d, const double* __restrict__ alpha,
+                                                  const double* __restrict__ beta, const double* __restrict__ rho,
+                                                  const double* __restrict__ t, const double* __restrict__ c, int L,
+                                                  int NF, int K, GridPlan gp, double* __restrict__ det,
+                                                  double* __restrict__ pmax, double* __restrict__ pmin,
+                                                  uint32_t* __restrict__ signbits) {
+  extern __shared__ double smem[];
+  double* par = smem;
+  const int s = blockIdx.x / gp.bpm;
+  const int blk = blockIdx.x - s * gp.bpm;
+  stage_params(par, d, alpha, beta, rho, s, L);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blk * gp.wpb + warp;
+  if (unit >= gp.units) return;
+  const int ft = unit % gp.nft, ch = unit / gp.nft;
+  const int f = ft * kWarp + lane;
+  const bool active = f < NF;
+  const int fc = active ? f : NF - 1;
+  const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
+  const int k0 = ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
+  double vmax = -INFINITY, vmin = INFINITY;
+  bool anynan = false;
+  const int nw = (NF + 31) / 32;
+  for (int k = k0; k < k1; ++k) {
+    const double ic = 1.0 / c[(size_t)s * K + k];
+    const Sample z = make_sample(omega0, ic);
+    const double v = sample_forward(par, L, z);
+    if (det && active) det[((size_t)s * K + k) * NF + f] = v;
+    vmax = fmax(vmax, v);
+    vmin = fmin(vmin, v);
+    anynan |= (v != v);
+    if (signbits) {
+      const uint32_t bits = __ballot_sync(0xffffffffu, active && (v < 0.0));
+      if (lane == 0) signbits[((size_t)s * K + k) * nw + ft] = bits;
+    }
+  }
+  if (pmax && active) {
+    // torch.max/min propagate NaN; fmax/fmin do not
+    if (anynan) { vmax = NAN; vmin = NAN; }
+    pmax[((size_t)s * gp.nchunk + ch) * NF + f] = vmax;
+    pmin[((size_t)s * gp.nchunk + ch) * NF + f] = vmin;
+  }
+}
+
+__global__ void k_minmax_reduce(const double* __restrict__ pmax, const double* __restrict__ pmin, int NF, int nchunk,
+                                double* __restrict__ cmax, double* __restrict__ cmin, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t s = i / NF, f = i % NF;
+  double vmax = -INFINITY, vmin = INFINITY;
+  bool anynan = false;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const double a = pmax[(s * nchunk + ch) * NF + f], b = pmin[(s * nchunk + ch) * NF + f];
+    anynan |= (a != a) | (b != b);
+    vmax = fmax(vmax, a);
+    vmin = fmin(vmin, b);
+  }
+  if (anynan) { vmax = NAN; vmin = NAN; }
+  if (cmax) cmax[i] = vmax;
+  if (cmin) cmin[i] = vmin;
+}
+
+// Dense grid, fused forward + adjoint with per-model gradient reduction.
+__global__ void __launch_bounds__(128) k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha,
+                                                  const double* __restrict__ beta, const double* __restrict__ rho,
+                                                  const double* __restrict__ t, const double* __restrict__ c,
+                                                  const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp,
+                                                  double* __restrict__ det, double* __restrict__ part) {
+  extern __shared__ double smem[];
+  double* par = smem;                                        // [6][L]
+  double* accs = par + par_doubles(L);                         // [wpb][4][L]
+  double* ests = accs + (size_t)gp.wpb * 4 * L;              // [wpb][L-1][5][32]
+  const int s = blockIdx.x / gp.bpm;
+  const int blk = blockIdx.x - s * gp.bpm;
+  stage_params(par, d, alpha, beta, rho, s, L);
+  for (int i = threadIdx.x; i < gp.wpb * 4 * L; i += blockDim.x) accs[i] = 0.0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blk * gp.wpb + warp;
+  if (unit < gp.units) {
+    double* acc = accs + (size_t)warp * 4 * L;
+    double* est = ests + (size_t)warp * (L - 1) * 5 * kWarp + lane;
+    const int ft = unit % gp.nft, ch = unit / gp.nft;
+    const int f = ft * kWarp + lane;
+    const bool active = f < NF;
+    const int fc = active ? f : NF - 1;
+    const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
+    const int k0 = ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
+    for (int k = k0; k < k1; ++k) {
+      const double ic = 1.0 / c[(size_t)s * K + k];
+      const Sample z = make_sample(omega0, ic);
+      const size_t idx = ((size_t)s * K + k) * NF + fc;
+      const double seed = gdet ? gdet[idx] : 1.0;
+      const double v = sample_forward_store<kWarp>(par, L, z, est);
+      if (det && active) det[idx] = v;
+      ReduceSink sink{acc, L, lane, active};
+      sample_adjoint<kWarp>(par, L, z, seed, est, sink);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
+    double v = 0.0;
+    for (int w = 0; w < gp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
+    part[((size_t)s * gp.bpm + blk) * 4 * L + i] = v;
+  }
+}
+
+// second stage: sum block partials [S][bpm][4][L] -> gd, ga, gb, grho [S,L]
+__global__ void k_grad_reduce(const double* __restrict__ part, int L, int bpm, double* __restrict__ gd,
+                              double* __restrict__ ga, double* __restrict__ gb, double* __restrict__ grho) {
+  const int s = blockIdx.x;
+  for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
+    double v = 0.0;
+    for (int b = 0; b < bpm; ++b) v += part[((size_t)s * bpm + b) * 4 * L + i];
+    const int which = i / L, m = i - which * L;
+    double* out = which == 0 ? gd : (which == 1 ? ga : (which == 2 ? gb : grho));
+    if (out) out[(size_t)s * L + m] = v;
+  }
+}
+
+struct PointsPlan {
+  int units;  // ceil(N/32) warp units per model
+  int wpb;
+  int bpm;
+};
+
+// Pointwise forward at the observed picks.
+__global__ void __launch_bounds__(128) k_points_fwd(const double* __restrict__ d, const double* __restrict__ alpha,
+                                                    const double* __restrict__ beta, const double* __restrict__ rho,
+                                                    const double* __restrict__ t, const double* __restrict__ c, int L,
+                                                    int N, PointsPlan pp, double* __restrict__ F) {
+  extern __shared__ double smem[];
+  double* par = smem;
+  const int s = blockIdx.x / pp.bpm;
+  const int blk = blockIdx.x - s * pp.bpm;
+  stage_params(par, d, alpha, beta, rho, s, L);
+  __syncthreads();
+  const int i = blk * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double omega0 = omega_of_period(t[(size_t)s * N + i]);
+  const Sample z = make_sample(omega0, 1.0 / c[(size_t)s * N + i]);
+  F[(size_t)s * N + i] = sample_forward(par, L, z);
+}
+
+// DMF compression: returns |G| and d|G|/dF (reference _model.py:455-464)
+__device__ __forceinline__ void dmf_compress(int mode, double F, double n, double invN, double& absG, double& seed) {
+  if (mode == ADSURF_COMPRESS_NONE) {
+    absG = fabs(F);
+    seed = (F > 0.0 ? 1.0 : (F < 0.0 ? -1.0 : (F == 0.0 ? 0.0 : NAN))) * invN;
+    return;
+  }
+  const bool norm = (mode == ADSURF_COMPRESS_EXP) || (mode == ADSURF_COMPRESS_LOG) || (mode == ADSURF_COMPRESS_NORM);
+  const double in = norm ? 1.0 / n : 1.0;
+  const double u = F * in;
+  const double au = fabs(u);
+  const double sg = (u > 0.0 ? 1.0 : (u < 0.0 ? -1.0 : (u == 0.0 ? 0.0 : NAN)));
+  if (mode == ADSURF_COMPRESS_NORM) {
+    absG = au;
+    seed = sg * in * invN;
+  } else if (mode == ADSURF_COMPRESS_LOG) {
+    absG = log(au + 1.0);
+    seed = sg / (au + 1.0) * in * invN;
+  } else {
+    const double pw = pow(0.1, au);
+    absG = 1.0 - pw;  // |0.1^|u| - 1|
+    // G = pw - 1 <= 0; d|G|/du = -dG/du = ln(10) pw sign(u); torch's abs'(0) = 0 when G == 0 (u == 0)
+    seed = kLn10 * pw * sg * in * invN;
+  }
+}
+
+// Pointwise forward + adjoint.  kind 0: upstream gF given; kind 1: Jacobian rows; kind 2: fused DMF
+// (normalisation read from the dense pass partials, loss partial written per block).
+template <int kKind>
+__global__ void __launch_bounds__(128) k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha,
+                                                    const double* __restrict__ beta, const double* __restrict__ rho,
+                                                    const double* __restrict__ t, const double* __restrict__ c,
+                                                    const double* __restrict__ gF, int L, int N, PointsPlan pp,
+                                                    double* __restrict__ F, double* __restrict__ gc,
+                                                    double* __restrict__ part,
+                                                    // Jacobian outputs
+                                                    double* __restrict__ Jd, double* __restrict__ Ja,
+                                                    double* __restrict__ Jb, double* __restrict__ Jrho,
+                                                    // DMF
+                                                    const double* __restrict__ pmax, const double* __restrict__ pmin,
+                                                    int nchunk, int compress, int with_grad, double* __restrict__ norm,
+                                                    double* __restrict__ loss_part) {
+  extern __shared__ double smem[];
+  double* par = smem;
+  double* accs = par + par_doubles(L);             // [wpb][4][L]
+  double* lossw = accs + (size_t)pp.wpb * 4 * L;  // [wpb]
+  double* ests = lossw + pp.wpb;                 // [wpb][L-1][5][32]
+  const int s = blockIdx.x / pp.bpm;
+  const int blk = blockIdx.x - s * pp.bpm;
+  stage_params(par, d, alpha, beta, rho, s, L);
+  for (int i = threadIdx.x; i < pp.wpb * 4 * L + pp.wpb; i += blockDim.x) accs[i] = 0.0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blk * pp.wpb + warp;
+  if (unit < pp.units) {
+    double* acc = accs + (size_t)warp * 4 * L;
+    double* est = ests + (size_t)warp * (L - 1) * 5 * kWarp + lane;
+    const int i = unit * kWarp + lane;
+    const bool active = i < N;
+    const size_t idx = (size_t)s * N + (active ? i : N - 1);
+    const double cc = c[idx];
+    const double ic = 1.0 / cc;
+    const Sample z = make_sample(omega_of_period(t[idx]), ic);
+    const double v = sample_forward_store<kWarp>(par, L, z, est);
+    if (F && active) F[idx] = v;
+    double seed = 1.0;
+    if (kKind == 0) seed = gF[idx];
+    if (kKind == 2) {
+      double n = 1.0;
+      if (compress == ADSURF_COMPRESS_EXP || compress == ADSURF_COMPRESS_LOG || compress == ADSURF_COMPRESS_NORM) {
+        double vmax = -INFINITY, vmin = INFINITY;
+        bool anynan = false;
+        const int ii = active ? i : N - 1;
+        for (int ch = 0; ch < nchunk; ++ch) {
+          const double a = pmax[((size_t)s * nchunk + ch) * N + ii], b = pmin[((size_t)s * nchunk + ch) * N + ii];
+          anynan |= (a != a) | (b != b);
+          vmax = fmax(vmax, a);
+          vmin = fmin(vmin, b);
+        }
+        n = anynan ? NAN : (vmax - vmin);
+        if (norm && active) norm[idx] = n;
+      }
+      double absG;
+      dmf_compress(compress, v, n, 1.0 / (double)N, absG, seed);
+      double lsum = warp_sum(active ? absG : 0.0);
+      if (lane == 0) lossw[warp] = lsum;
+    }
+    if (kKind != 2 || with_grad) {
+      double gk;
+      if (kKind == 1) {
+        JacSink sink{Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
+                     Jrho ? Jrho + idx * L : nullptr, active};
+        gk = sample_adjoint<kWarp>(par, L, z, seed, est, sink);
+      } else {
+        ReduceSink sink{acc, L, lane, active};
+        gk = sample_adjoint<kWarp>(par, L, z, seed, est, sink);
+      }
+      if (gc && active) gc[idx] = -z.k * ic * gk;  // k = omega0 / c
+    }
+  }
+  __syncthreads();
+  if (kKind != 1) {
+    for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
+      double v = 0.0;
+      for (int w = 0; w < pp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
+      part[((size_t)s * pp.bpm + blk) * 4 * L + i] = v;
+    }
+    if (kKind == 2 && threadIdx.x == 0) {
+      double v = 0.0;
+      for (int w = 0; w < pp.wpb; ++w) v += lossw[w];
+      loss_part[(size_t)s * pp.bpm + blk] = v;
+    }
+  }
+}
+
+__global__ void k_loss_reduce(const double* __restrict__ loss_part, int bpm, int N, double* __restrict__ loss, int S) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double v = 0.0;
+  for (int b = 0; b < bpm; ++b) v += loss_part[(size_t)s * bpm + b];
+  loss[s] = v / (double)N;
+}
+
+// FP64 peak probe: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) k_dfma_probe(int iters, double* __restrict__ out, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0,
+         x6 = x0 + 6.0, x7 = x0 + 7.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 12345.678) out[0] = r;  // never true; keeps the chains alive
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-side planning
+// ------------------------------------------------------------------------------------------
+constexpr int kNumSM = 148;
+constexpr size_t kSmemBudget = 100 * 1024;   // per block, so that two blocks fit an SM
+constexpr size_t kSmemMax = 227 * 1024;
+
+inline size_t est_bytes_per_warp(int L) { return (size_t)(L > 1 ? L - 1 : 0) * 5 * kWarp * sizeof(double); }
+
+// warps per block for the adjoint kernels; 0 if even one warp does not fit
+inline int adj_wpb(int L) {
+  const size_t fixed = (size_t)par_doubles(L) * sizeof(double) + 64;
+  const size_t per_warp = est_bytes_per_warp(L) + (size_t)4 * L * sizeof(double) + sizeof(double);
+  for (int w = 4; w >= 1; w >>= 1) {
+    const size_t need = fixed + (size_t)w * per_warp;
+    if (need <= (w > 1 ? kSmemBudget : kSmemMax)) return w;
+  }
+  return 0;
+}
+
+inline size_t adj_smem(int L, int wpb) {
+  return (size_t)par_doubles(L) * sizeof(double) + (size_t)wpb * ((size_t)4 * L * sizeof(double) + sizeof(double)) +
+         (size_t)wpb * est_bytes_per_warp(L);
+}
+
+inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
+  GridPlan gp;
+  gp.nft = (NF + kWarp - 1) / kWarp;
+  gp.wpb = adjoint ? adj_wpb(L) : 8;
+  const long long target = (long long)kNumSM * 8 * 24;  // ~24 waves of 8 warps per SM
+  long long nchunk = (target + (long long)S * gp.nft - 1) / ((long long)S * gp.nft);
+  const int maxchunks = K >= 16 ? K / 8 : 1;
+  if (nchunk > maxchunks) nchunk = maxchunks;
+  if (nchunk < 1) nchunk = 1;
+  gp.chunk = (K + (int)nchunk - 1) / (int)nchunk;
+  gp.nchunk = (K + gp.chunk - 1) / gp.chunk;
+  gp.units = gp.nft * gp.nchunk;
+  gp.bpm = gp.wpb > 0 ? (gp.units + gp.wpb - 1) / gp.wpb : 0;
+  return gp;
+}
+
+inline PointsPlan plan_points(int L, int N) {
+  PointsPlan pp;
+  pp.units = (N + kWarp - 1) / kWarp;
+  pp.wpb = adj_wpb(L);
+  if (pp.wpb > pp.units) {
+    int w = 1;
+    while (w < pp.units) w <<= 1;
+    pp.wpb = w < pp.wpb ? w : pp.wpb;
+  }
+  pp.bpm = pp.wpb > 0 ? (pp.units + pp.wpb - 1) / pp.wpb : 0;
+  return pp;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+inline int check_launch() {
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? ADSURF_OK : ADSURF_E_CUDA;
+}
+
+template <typename Kern>
+inline int set_smem(Kern kern, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return ADSURF_E_CUDA;
+    }
+  }
+  return ADSURF_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* adsurf_version(void) { return "adsurf_b200 0.1 (sm_100a, fp64)"; }
+
+const char* adsurf_error_string(int code) {
+  switch (code) {
+    case ADSURF_OK: return "ok";
+    case ADSURF_E_NULL: return "required pointer is NULL";
+    case ADSURF_E_SHAPE: return "bad shape (non-positive or unsupported dimension)";
+    case ADSURF_E_LAYERS: return "too many layers for the shared-memory adjoint state";
+    case ADSURF_E_WORKSPACE: return "workspace missing or too small";
+    case ADSURF_E_CUDA: return "CUDA runtime error";
+    case ADSURF_E_ARG: return "bad argument";
+    default: return "unknown error";
+  }
+}
+
+size_t adsurf_workspace_bytes(int op, int S, int L, int n, int K) {
+  if (S <= 0 || L <= 0 || n <= 0) return 0;
+  switch (op) {
+    case ADSURF_OP_POINTS_FWD:
+    case ADSURF_OP_POINTS_JAC:
+      return 0;
+    case ADSURF_OP_POINTS_BWD: {
+      const PointsPlan pp = plan_points(L, n);
+      return align256((size_t)S * pp.bpm * 4 * L * sizeof(double));
+    }
+    case ADSURF_OP_GRID_FWD: {
+      if (K <= 0) return 0;
+      const GridPlan gp = plan_grid(S, L, n, K, false);
+      return 2 * align256((size_t)S * gp.nchunk * n * sizeof(double));
+    }
+    case ADSURF_OP_GRID_BWD: {
+      if (K <= 0) return 0;
+      const GridPlan gp = plan_grid(S, L, n, K, true);
+      return align256((size_t)S * gp.bpm * 4 * L * sizeof(double));
+    }
+    case ADSURF_OP_DMF_STEP: {
+      const PointsPlan pp = plan_points(L, n);
+      size_t b = align256((size_t)S * pp.bpm * 4 * L * sizeof(double)) + align256((size_t)S * pp.bpm * sizeof(double));
+      if (K > 0) {
+        const GridPlan gp = plan_grid(S, L, n, K, false);
+        b += 2 * align256((size_t)S * gp.nchunk * n * sizeof(double));
+      }
+      return b;
+    }
+    default:
+      return 0;
+  }
+}
+
+int adsurf_det_points_fwd(const double* d, const double* alpha, const double* beta, const double* rho,
+                          const double* t, const double* c, int S, int L, int N, double* F, void* stream) {
+  if (!d || !alpha || !beta || !rho || !t || !c || !F) return ADSURF_E_NULL;
+  if (S <= 0 || L <= 0 || N <= 0 || L > ADSURF_MAX_LAYERS) return ADSURF_E_SHAPE;
+  PointsPlan pp;
+  pp.units = (N + kWarp - 1) / kWarp;
+  pp.wpb = 4;
+  pp.bpm = (N + 127) / 128;
+  const size_t smem = (size_t)par_doubles(L) * sizeof(double);
+  if (set_smem(k_points_fwd, smem)) return ADSURF_E_CUDA;
+  k_points_fwd<<<(unsigned)((size_t)S * pp.bpm), 128, smem, (cudaStream_t)stream>>>(d, alpha, beta, rho, t, c, L, N,
+                                                                                      pp, F);
+  return check_launch();
+}
+
+static int points_adjoint_common(int kind, const double* d, const double* alpha, const double* beta,
+                                 const double* rho, const double* t, const double* c, const double* gF, int S, int L,
+                                 int N, double* F, double* gd, double* ga, double* gb, double* grho, double* gc,
+                                 double* Jd, double* Ja, double* Jb, double* Jrho, void* ws, size_t ws_bytes,
+                                 cudaStream_t st) {
+  if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
+  if (S <= 0 || L <= 0 || N <= 0) return ADSURF_E_SHAPE;
+  if (L - 1 > ADSURF_MAX_ADJ_LAYERS) return ADSURF_E_LAYERS;
+  const PointsPlan pp = plan_points(L, N);
+  if (pp.wpb <= 0) return ADSURF_E_LAYERS;
+  const size_t smem = adj_smem(L, pp.wpb);
+  double* part = nullptr;
+  if (kind == 0) {
+    const size_t need = align256((size_t)S * pp.bpm * 4 * L * sizeof(double));
+    if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
+    part = (double*)ws;
+  }
+  const unsigned grid = (unsigned)((size_t)S * pp.bpm);
+  const unsigned threads = pp.wpb * kWarp;
+  if (kind == 0) {
+    if (set_smem(k_points_bwd<0>, smem)) return ADSURF_E_CUDA;
+    k_points_bwd<0><<<grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, F, gc, part, nullptr,
+                                                 nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, nullptr,
+                                                 nullptr);
+    if (check_launch()) return ADSURF_E_CUDA;
+    k_grad_reduce<<<S, 128, 0, st>>>(part, L, pp.bpm, gd, ga, gb, grho);
+  } else {
+    if (set_smem(k_points_bwd<1>, smem)) return ADSURF_E_CUDA;
+    k_points_bwd<1><<<grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, nullptr, L, N, pp, F, gc, nullptr, Jd, Ja,
+                                                 Jb, Jrho, nullptr, nullptr, 0, 0, 1, nullptr, nullptr);
+  }
+  return check_launch();
+}
+
+int adsurf_det_points_bwd(const double* d, const double* alpha, const double* beta, const double* rho,
+                          const double* t, const double* c, const double* gF, int S, int L, int N, double* F,
+                          double* gd, double* galpha, double* gbeta, double* grho, double* gc, void* ws,
+                          size_t ws_bytes, void* stream) {
+  if (!gF) return ADSURF_E_NULL;
+  return points_adjoint_common(0, d, alpha, beta, rho, t, c, gF, S, L, N, F, gd, galpha, gbeta, grho, gc, nullptr,
+                               nullptr, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int adsurf_det_points_jac(const double* d, const double* alpha, const double* beta, const double* rho,
+                          const double* t, const double* c, int S, int L, int N, double* F, double* Jd,
+                          double* Jalpha, double* Jbeta, double* Jrho, double* Jc, void* stream) {
+  return points_adjoint_common(1, d, alpha, beta, rho, t, c, nullptr, S, L, N, F, nullptr, nullptr, nullptr, nullptr,
+                               Jc, Jd, Jalpha, Jbeta, Jrho, nullptr, 0, (cudaStream_t)stream);
+}
+
+static int grid_fwd_launch(const double* d, const double* alpha, const double* beta, const double* rho,
+                           const double* t, const double* c, int S, int L, int NF, int K, double* det, double* pmax,
+                           double* pmin, uint32_t* signbits, const GridPlan& gp, cudaStream_t st) {
+  const size_t smem = (size_t)par_doubles(L) * sizeof(double);
+  if (set_smem(k_grid_fwd, smem)) return ADSURF_E_CUDA;
+  k_grid_fwd<<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K, gp,
+                                                                            det, pmax, pmin, signbits);
+  return check_launch();
+}
+
+int adsurf_det_grid_fwd(const double* d, const double* alpha, const double* beta, const double* rho,
+                        const double* t, const double* c, int S, int L, int NF, int K, double* det, double* cmax,
+                        double* cmin, uint32_t* signbits, void* ws, size_t ws_bytes, void* stream) {
+  if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
+  if (S <= 0 || L <= 0 || NF <= 0 || K <= 0 || L > ADSURF_MAX_LAYERS) return ADSURF_E_SHAPE;
+  if ((size_t)S * (size_t)((NF + 31) / 32) * 4 > 0x7fffffffull) return ADSURF_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridPlan gp = plan_grid(S, L, NF, K, false);
+  double *pmax = nullptr, *pmin = nullptr;
+  if (cmax || cmin) {
+    const size_t one = align256((size_t)S * gp.nchunk * NF * sizeof(double));
+    if (!ws || ws_bytes < 2 * one) return ADSURF_E_WORKSPACE;
+    pmax = (double*)ws;
+    pmin = (double*)((char*)ws + one);
+  }
+  const int rc = grid_fwd_launch(d, alpha, beta, rho, t, c, S, L, NF, K, det, pmax, pmin, signbits, gp, st);
+  if (rc) return rc;
+  if (pmax) {
+    const size_t total = (size_t)S * NF;
+    k_minmax_reduce<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pmax, pmin, NF, gp.nchunk, cmax, cmin, total);
+    return check_launch();
+  }
+  return ADSURF_OK;
+}
+
+int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta, const double* rho,
+                        const double* t, const double* c, const double* gdet, int S, int L, int NF, int K,
+                        double* det, double* gd, double* galpha, double* gbeta, double* grho, void* ws,
+                        size_t ws_bytes, void* stream) {
+  if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
+  if (S <= 0 || L <= 0 || NF <= 0 || K <= 0) return ADSURF_E_SHAPE;
+  if (L - 1 > ADSURF_MAX_ADJ_LAYERS) return ADSURF_E_LAYERS;
+  const GridPlan gp = plan_grid(S, L, NF, K, true);
+  if (gp.wpb <= 0) return ADSURF_E_LAYERS;
+  const size_t need = align256((size_t)S * gp.bpm * 4 * L * sizeof(double));
+  if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = adj_smem(L, gp.wpb);
+  if (set_smem(k_grid_bwd, smem)) return ADSURF_E_CUDA;
+  k_grid_bwd<<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, gdet, L, NF, K,
+                                                                            gp, det, (double*)ws);
+  if (check_launch()) return ADSURF_E_CUDA;
+  k_grad_reduce<<<S, 128, 0, st>>>((const double*)ws, L, gp.bpm, gd, galpha, gbeta, grho);
+  return check_launch();
+}
+
+int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
+                    const double* c, const double* C, int S, int L, int N, int K, int compress, int with_grad,
+                    double* loss, double* F, double* norm, double* gd, double* galpha, double* gbeta, double* grho,
+                    void* ws, size_t ws_bytes, void* stream) {
+  if (!d || !alpha || !beta || !rho || !t || !c || !loss) return ADSURF_E_NULL;
+  if (compress < ADSURF_COMPRESS_NONE || compress > ADSURF_COMPRESS_NORM) return ADSURF_E_ARG;
+  const bool normalised =
+      (compress == ADSURF_COMPRESS_EXP || compress == ADSURF_COMPRESS_LOG || compress == ADSURF_COMPRESS_NORM);
+  if (normalised && !C) return ADSURF_E_NULL;
+  if (S <= 0 || L <= 0 || N <= 0 || (normalised && K <= 0)) return ADSURF_E_SHAPE;
+  if (L - 1 > ADSURF_MAX_ADJ_LAYERS) return ADSURF_E_LAYERS;
+  const PointsPlan pp = plan_points(L, N);
+  if (pp.wpb <= 0) return ADSURF_E_LAYERS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t need = adsurf_workspace_bytes(ADSURF_OP_DMF_STEP, S, L, N, normalised ? K : 0);
+  if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
+  char* w = (char*)ws;
+  double* part = (double*)w;
+  w += align256((size_t)S * pp.bpm * 4 * L * sizeof(double));
+  double* loss_part = (double*)w;
+  w += align256((size_t)S * pp.bpm * sizeof(double));
+  double *pmax = nullptr, *pmin = nullptr;
+  int nchunk = 0;
+  if (normalised) {
+    // dense pass: max/min over the trial velocities at every observed period (constant for autograd)
+    const GridPlan gp = plan_grid(S, L, N, K, false);
+    const size_t one = align256((size_t)S * gp.nchunk * N * sizeof(double));
+    pmax = (double*)w;
+    pmin = (double*)(w + one);
+    nchunk = gp.nchunk;
+    const int rc = grid_fwd_launch(d, alpha, beta, rho, t, C, S, L, N, K, nullptr, pmax, pmin, nullptr, gp, st);
+    if (rc) return rc;
+  }
+  const size_t smem = adj_smem(L, pp.wpb);
+  if (set_smem(k_points_bwd<2>, smem)) return ADSURF_E_CUDA;
+  k_points_bwd<2><<<(unsigned)((size_t)S * pp.bpm), pp.wpb * kWarp, smem, st>>>(
+      d, alpha, beta, rho, t, c, nullptr, L, N, pp, F, nullptr, part, nullptr, nullptr, nullptr, nullptr, pmax, pmin,
+      nchunk, compress, with_grad, norm, loss_part);
+  if (check_launch()) return ADSURF_E_CUDA;
+  k_loss_reduce<<<(S + 127) / 128, 128, 0, st>>>(loss_part, pp.bpm, N, loss, S);
+  if (check_launch()) return ADSURF_E_CUDA;
+  if (with_grad) {
+    k_grad_reduce<<<S, 128, 0, st>>>(part, L, pp.bpm, gd, galpha, gbeta, grho);
+    return check_launch();
+  }
+  return ADSURF_OK;
+}
+
+int adsurf_fp64_peak_probe(int iters, int repeats, double* tflops, double* ms, void* stream) {
+  if (!tflops) return ADSURF_E_NULL;
+  if (iters <= 0 || repeats <= 0) return ADSURF_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* out = nullptr;
+  if (cudaMalloc(&out, sizeof(double)) != cudaSuccess) return ADSURF_E_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = kNumSM * 8, threads = 256;
+  k_dfma_probe<<<blocks, threads, 0, st>>>(iters, out, 0.999999, 1e-9);  // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < repeats; ++r) {
+    cudaEventRecord(e0, st);
+    k_dfma_probe<<<blocks, threads, 0, st>>>(iters, out, 0.999999, 1e-9);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    if (t < best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess) return ADSURF_E_CUDA;
+  const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops = flops / ((double)best * 1e-3) / 1e12;
+  if (ms) *ms = best;
+  return ADSURF_OK;
+}
+
+}  // extern "C"

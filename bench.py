@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — DMF determinant samples/s, forward + backward, BASELINE.json config 5.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; torchrun launches N ranks for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one fused forward+adjoint sweep of the Rayleigh secular function over the dense grid
+(4096 Monte-Carlo models x 128 periods x 1024 trial velocities, 20 layers = 536 870 912 samples)
+PER GPU (weak scaling: every rank sweeps its own 4096-model ensemble, seed = rank; no data-path
+collective — the path has no exchange step).  Prints ONE JSON line (rank 0).
+
+  value     samples/s over all ranks, inputs resident in HBM, CUDA events on the launching stream.
+  e2e       the same sweep through the C-ABI call with the inputs in pinned HOST memory: every step
+            copies the models / periods / velocities host->device and reads the per-model
+            gradients back device->host inside the timed region.
+  roofline  FP64-pipe roofline of the fused forward+adjoint kernel: achieved = samples/s x
+            3*(168*(L-1)+31) algorithmic FLOP per sample / kernel time measured live
+            with CUDA events; peak = a register-resident DFMA loop measured in this same process
+            (MEASURED_PEAKS.json has no FP64 entry), nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+            = 37.2 TFLOP/s reported beside it.
+  cpu_baseline  the float64 oracle port of the reference's torch path (oracle/dltar_oracle.py)
+            timed on this box's host cores on a bounded chunk of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+L_LAYERS, NF, K_TRIAL, S_MODELS = 20, 128, 1024, 4096
+METRIC = "DMF det samples/s fwd+bwd (model x freq x c)"
+UNIT = "samples/s"
+
+
+def flop_per_sample(L):
+    """algorithmic FLOP per sample, forward + adjoint: 3 x (168 (L-1) + 31)"""
+    return 3 * (168 * (L - 1) + 31)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU oracle leg
+def oracle_fwd_bwd(d, a, b, rho, t, c):
+    """one forward + backward (gdet = 1) of the oracle on a chunk; returns samples processed"""
+    from oracle import dltar_oracle as O
+    td, ta, tb, tr = (torch.tensor(x, requires_grad=True) for x in (d, a, b, rho))
+    det = O.det_grid(torch.tensor(c), torch.tensor(t), td, ta, tb, tr)
+    det.backward(torch.ones_like(det))
+    return det.numel()
+
+
+def cpu_chunk(models=4, kc=128, seed=0):
+    from adsurf_b200.workload import config5_ensemble, config5_periods, config5_velocities
+    d, a, b, rho = config5_ensemble(max(models, 2), L_LAYERS, seed)
+    d, a, b, rho = (x[:models].copy() for x in (d, a, b, rho))
+    t = np.tile(config5_periods(NF), (models, 1))
+    c = np.tile(config5_velocities(K_TRIAL)[:: K_TRIAL // kc][:kc], (models, 1))
+    return d, a, b, rho, t, c
+
+
+def time_cpu(budget_s=15.0, models=4, kc=128):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    args = cpu_chunk(models, kc)
+    oracle_fwd_bwd(*args)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    samples = 0
+    while True:
+        samples += oracle_fwd_bwd(*args)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 50:
+            break
+    return {"value": samples / el, "unit": UNIT, "cores": cores, "threads": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} x fwd+bwd of oracle/dltar_oracle.py (float64 torch-CPU port of the reference's "
+                      f"dltar_matrix) on {models} models x {NF} f x {kc} c x {L_LAYERS} layers of config 5, {el:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the oracle port on the host cores; each step = one bounded chunk."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    models, kc = 4, 128
+    chunk = cpu_chunk(models, kc)
+    for _ in range(args.warmup):
+        oracle_fwd_bwd(*chunk)
+    t0 = time.perf_counter()
+    samples = 0
+    for _ in range(args.steps):
+        samples += oracle_fwd_bwd(*chunk)
+    el = time.perf_counter() - t0
+    value = samples / el
+    sample = (f"each step = fwd+bwd of the float64 oracle port (torch CPU, {torch.get_num_threads()} threads) on "
+              f"{models} models x {NF} f x {kc} c x {L_LAYERS} layers of config 5")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config5: 20-layer FRIUL7W Monte-Carlo ensemble, 128 f x 1024 c dense sweep fwd+bwd "
+                               "(bounded chunk per step)", "layers": L_LAYERS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------- GPU leg
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--models", type=int, default=S_MODELS, help="models per GPU (config 5: 4096)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: adsurf_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from adsurf_b200 import _capi
+    from adsurf_b200.workload import config5
+    _capi.lib()
+
+    S, L = args.models, L_LAYERS
+    host = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in config5(S, NF, K_TRIAL, L, seed=rank)]
+    d, a, b, rho, t, c = (x.to(dev) for x in host)
+    n_samples = S * NF * K_TRIAL
+    det = torch.empty((S, K_TRIAL, NF), dtype=torch.float64, device=dev)   # 4.3 GB per GPU: inputs+outputs >> L2
+    grads = tuple(torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4))
+    ws = torch.empty(max(_capi.lib().adsurf_workspace_bytes(_capi.OP_GRID_BWD, S, L, NF, K_TRIAL), 8),
+                     dtype=torch.uint8, device=dev)
+    lib = _capi.lib()
+    import ctypes
+    P = lambda x: ctypes.c_void_p(x.data_ptr())
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    def step(dd, aa, bb, rr, tt, cc):
+        rc = lib.adsurf_det_grid_bwd(P(dd), P(aa), P(bb), P(rr), P(tt), P(cc), None, S, L, NF, K_TRIAL, P(det),
+                                     P(grads[0]), P(grads[1]), P(grads[2]), P(grads[3]), P(ws), ws.numel(), sp)
+        if rc != 0:
+            raise RuntimeError(f"adsurf_det_grid_bwd failed: {rc}")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        tt_ = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        return float(tt_[0])
+
+    # FP64 peak on this GPU, this process (burst; the sweep itself runs for seconds -> also see clocks)
+    peak_tf, _ = _capi.fp64_peak_probe(iters=4096, repeats=5, device=dev)
+
+    # ---------------- device-resident leg
+    for _ in range(args.warmup):
+        step(d, a, b, rho, t, c)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(d, a, b, rho, t, c)
+    e1.record(stream)
+    barrier()
+    w1 = time.time()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    value = world * n_samples * args.steps / (ms * 1e-3)
+    kernel_ms = ms / args.steps  # the adjoint kernel is >99.9% of the step (second-stage reduce ~ microseconds)
+
+    # sustained FP64 peak right after the sweep (clocks settled under load)
+    peak_tf_after, _ = _capi.fp64_peak_probe(iters=4096, repeats=3, device=dev)
+
+    # ---------------- end-to-end leg: host buffers -> C ABI -> host results
+    hgr = [torch.empty((S, L), dtype=torch.float64).pin_memory() for _ in range(4)]
+    dbuf = [torch.empty_like(x, device=dev) for x in host]
+
+    def e2e_step():
+        for src, dst in zip(host, dbuf):
+            dst.copy_(src, non_blocking=True)
+        step(*dbuf)
+        for src, dst in zip(grads, hgr):
+            dst.copy_(src, non_blocking=True)
+        stream.synchronize()  # the caller reads the gradients on the host
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * n_samples * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(x.numel() * 8 for x in host)
+    d2h = sum(x.numel() * 8 for x in hgr)
+
+    if rank == 0:
+        achieved_tf = (n_samples / (kernel_ms * 1e-3)) * flop_per_sample(L) / 1e12
+        nominal = 148 * 64 * 2 * 1.965e9 / 1e12
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config5: 4096 models x 128 f x 1024 c per GPU, 20-layer FRIUL7W Monte-Carlo ensemble "
+                                   "(reference generator, seed=rank), fused fwd+adjoint, gdet=1, det written",
+                       "models_per_gpu": S, "layers": L, "periods": NF, "trial_velocities": K_TRIAL,
+                       "samples_per_step_per_gpu": n_samples,
+                       "l2": "outputs 4.3 GB/step per GPU (> 126 MB L2); compute-bound, no reuse across steps"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "call": "adsurf_det_grid_bwd (C ABI) with pinned host inputs copied H2D and gradients read D2H every step"},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "peak_source": "measured in-process: register-resident DFMA loop (adsurf_fp64_peak_probe), burst",
+                         "peak_after_sweep": peak_tf_after, "peak_nominal": nominal,
+                         "frac_of_nominal": achieved_tf / nominal,
+                         "flop_per_sample": flop_per_sample(L), "kernel": "k_grid_bwd", "kernel_ms": kernel_ms,
+                         "hbm_bytes_per_sample_algorithmic": 8,
+                         "note": "FP64-pipe bound (~600 FLOP/B); HBM and tensor rooflines do not bind this path"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = time_cpu()
+        elif not args.no_cpu_baseline:
+            out["cpu_baseline"] = time_cpu(budget_s=8.0)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+/*
+ * adsurf_b200.h — C ABI of the B200-native Rayleigh secular-function ("determinant") path.
+ *
+ * Drop-in boundary for the hot path of liufeng2317/ADsurf.  The reference has no
+ * FFI: its boundary is a set of Python module functions.  Each entry point below names the
+ * reference function (file:line under /root/reference/ADsurf) whose arithmetic it replaces; the
+ * Python shims in adsurf_b200/_cps/ keep the reference signatures and call these through ctypes
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer to float64, row-major, contiguous, caller-owned;
+ *   - S = models, L = layers (last = half-space), N = observed picks, NF = periods, K = trial
+ *     phase velocities;  model arrays d, alpha, beta, rho are [S,L];
+ *   - no water layer (reference llw = -1) and Rayleigh/Dunkin (reference ifunc = 2) only — the
+ *     only combination the reference's torch path can execute;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync;
+ *   - `ws` is scratch of at least adsurf_workspace_bytes(...) bytes (may be NULL when that is 0);
+ *   - outputs are overwritten, never accumulated; no global state, re-entrant;
+ *   - return value: ADSURF_OK (0) or a negative ADSURF_E_* code; never throws, NaN/Inf inputs
+ *     propagate to the outputs (the reference's host loop repairs them, _model.py:624-626).
+ */
+#ifndef ADSURF_B200_H
+#define ADSURF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADSURF_OK 0
+#define ADSURF_E_NULL -1     /* required pointer is NULL */
+#define ADSURF_E_SHAPE -2    /* non-positive or unsupported dimension */
+#define ADSURF_E_LAYERS -3   /* L too large for the shared-memory adjoint state (L-1 > ADSURF_MAX_ADJ_LAYERS) */
+#define ADSURF_E_WORKSPACE -4 /* ws too small / NULL */
+#define ADSURF_E_CUDA -5     /* CUDA runtime error (launch failure, bad device pointer...) */
+#define ADSURF_E_ARG -6      /* bad enum / flag */
+
+#define ADSURF_MAX_LAYERS 4096   /* forward kernels: model parameters must fit shared memory */
+#define ADSURF_MAX_ADJ_LAYERS 170 /* adjoint kernels: 40 B of state per (thread, layer), one warp per block minimum */
+
+/* operation ids for adsurf_workspace_bytes */
+enum adsurf_op {
+  ADSURF_OP_POINTS_FWD = 0,
+  ADSURF_OP_POINTS_BWD = 1,
+  ADSURF_OP_POINTS_JAC = 2,
+  ADSURF_OP_GRID_FWD = 3,
+  ADSURF_OP_GRID_BWD = 4,
+  ADSURF_OP_DMF_STEP = 5
+};
+
+/* DMF compression (reference _model.py:450-462) */
+enum adsurf_compress {
+  ADSURF_COMPRESS_NONE = 0,       /* compress=False: G = F (no normalisation) */
+  ADSURF_COMPRESS_EXP = 1,        /* G = 0.1^|F/n| - 1,  n = max_k det - min_k det */
+  ADSURF_COMPRESS_LOG = 2,        /* G = log(|F/n| + 1) */
+  ADSURF_COMPRESS_EXP_NONORM = 3, /* compress=True, normalized=False: G = 0.1^|F| - 1 */
+  ADSURF_COMPRESS_NORM = 4        /* G = F/n only (Monte-Carlo pre-screen, _MonteCarlo.py:188-189) */
+};
+
+const char* adsurf_version(void);
+const char* adsurf_error_string(int code);
+
+/* Scratch bytes needed by an operation.  n = N (points ops) or NF (grid ops); K ignored by points ops
+ * except DMF_STEP. */
+size_t adsurf_workspace_bytes(int op, int S, int L, int n, int K);
+
+/* F[s,i] = Delta_R(model s; t[s,i], c[s,i]).
+ * Replaces dltar_vector / dltar4_vector: _cps/_surf96_vectorAll_gpu.py:194,303-399 (batched),
+ * _cps/_surf96_vector_gpu.py:194,303-399 and _cps/_surf96_vector.py (S = 1). */
+int adsurf_det_points_fwd(const double* d, const double* alpha, const double* beta, const double* rho,
+                          const double* t, const double* c, int S, int L, int N,
+                          double* F, void* stream);
+
+/* Reverse mode of the above: given gF[S,N] returns gd, galpha, gbeta, grho [S,L] (reduced over the
+ * picks of each model) and gc[S,N] (may be NULL).  Also returns F when F != NULL.
+ * Replaces torch.autograd over dltar4_vector (caller: loss.backward(), _model.py:592). */
+int adsurf_det_points_bwd(const double* d, const double* alpha, const double* beta, const double* rho,
+                          const double* t, const double* c, const double* gF, int S, int L, int N,
+                          double* F, double* gd, double* galpha, double* gbeta, double* grho, double* gc,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* Per-sample Jacobian rows: Jd, Jalpha, Jbeta, Jrho [S,N,L], Jc [S,N] (= dF/dc), F [S,N] (any may be
+ * NULL).  Replaces autograd.grad(F, x, grad_outputs=eye, is_grads_batched=True) of the sensitivity
+ * notebook (examples/02_2 cell 12). */
+int adsurf_det_points_jac(const double* d, const double* alpha, const double* beta, const double* rho,
+                          const double* t, const double* c, int S, int L, int N,
+                          double* F, double* Jd, double* Jalpha, double* Jbeta, double* Jrho, double* Jc,
+                          void* stream);
+
+/* det[s,k,f] = Delta_R(model s; t[s,f], c[s,k])  (c is dim 1, f fastest — the reference layout).
+ * det, cmax/cmin [S,NF] (max/min over k, fused) and signbits may each be NULL.
+ * signbits: uint32 [S, K, ceil(NF/32)], bit (f%32) of word [s,k,f/32] set when det < 0.
+ * Replaces dltar_matrix / dltar4_matrix: _cps/_surf96_matrixAll_gpu.py:183,242-353 (batched),
+ * _cps/_surf96_matrix_gpu.py:186,245-342 and _cps/_surf96_matrix.py (S = 1, output [K,NF]),
+ * plus torch.max/min over dim 1 at _model.py:455. */
+int adsurf_det_grid_fwd(const double* d, const double* alpha, const double* beta, const double* rho,
+                        const double* t, const double* c, int S, int L, int NF, int K,
+                        double* det, double* cmax, double* cmin, uint32_t* signbits,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* Fused forward + adjoint on the dense grid: gd, galpha, gbeta, grho [S,L] = sum over (k,f) of
+ * gdet[s,k,f] * dDelta/dparam.  gdet == NULL means gdet = 1 everywhere.  det (may be NULL) receives
+ * the forward values.  Replaces dltar4_matrix(...).backward(gdet). */
+int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta, const double* rho,
+                        const double* t, const double* c, const double* gdet, int S, int L, int NF, int K,
+                        double* det, double* gd, double* galpha, double* gbeta, double* grho,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* One fused Determinant-Misfit-Function evaluation with gradient (a1+a4+a6 of SURVEY.md §8a):
+ *   n[s,i]  = max_k Delta(s; t[s,i], C[s,k]) - min_k ...         (dense pass, constant for autograd)
+ *   G[s,i]  = compress(Delta(s; t[s,i], c[s,i]) / n[s,i])
+ *   loss[s] = (1/N) sum_i |G[s,i]|                                (data term only)
+ * and d loss[s] / d(d, alpha, beta, rho)[s,:] for backward seed 1 per model (_model.py:592).
+ * F (may be NULL) receives the raw pointwise determinants, norm (may be NULL) n[s,i].
+ * with_grad = 0 skips the adjoint (Monte-Carlo pre-screen, _MonteCarlo.py:184-190).
+ * Replaces multi_cal_grad.forward + backward (_model.py:448-464,592), iter_cal_grad (:320-337). */
+int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, const double* rho,
+                    const double* t, const double* c, const double* C, int S, int L, int N, int K,
+                    int compress, int with_grad,
+                    double* loss, double* F, double* norm,
+                    double* gd, double* galpha, double* gbeta, double* grho,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* Register-resident DFMA microbenchmark: runs `iters` dependent-chain iterations on every SM and
+ * returns the achieved FP64 rate in TFLOP/s (2 flops per DFMA) in *tflops.  Synchronises the stream.
+ * Used by bench.py for the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
+int adsurf_fp64_peak_probe(int iters, int repeats, double* tflops, double* ms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADSURF_B200_H */

@@ -1,0 +1,71 @@
+// Host-side check of the kernel arithmetic (TEST ONLY — never part of the product library).
+// Compiles adsurf_b200/csrc/adsurf_math.cuh, the exact per-sample code the CUDA kernels run,
+// for the CPU so tests/test_host_math.py can verify the hand-derived adjoint against the oracle
+// without a GPU.  Built on the fly by the test with g++.
+#include <vector>
+
+#include "adsurf_math.cuh"
+
+using namespace adsurf;
+
+namespace {
+struct HostSink {
+  double *gd, *ga, *gb, *gr;  // accumulate [L]
+  double *jd, *ja, *jb, *jr;  // per-sample rows [L] or null
+  void operator()(int m, double d, double a, double b, double r) const {
+    gd[m] += d; ga[m] += a; gb[m] += b; gr[m] += r;
+    if (jd) { jd[m] = d; ja[m] = a; jb[m] = b; jr[m] = r; }
+  }
+};
+}  // namespace
+
+extern "C" {
+
+// F[S,N], gradients reduced per model with seeds gF (null = 1), gc[S,N], optional Jacobians [S,N,L]
+int host_points(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
+                const double* c, const double* gF, int S, int L, int N, double* F, double* gd, double* ga, double* gb,
+                double* grho, double* gc, double* Jd, double* Ja, double* Jb, double* Jrho) {
+  std::vector<double> par(par_doubles(L)), est(5 * (L > 1 ? L - 1 : 1));
+  for (int s = 0; s < S; ++s) {
+    for (int m = 0; m < L; ++m)
+      stage_one(par.data(), L, m, d[s * L + m], alpha[s * L + m], beta[s * L + m], rho[s * L + m]);
+    for (int m = 0; m < L; ++m) gd[s * L + m] = ga[s * L + m] = gb[s * L + m] = grho[s * L + m] = 0.0;
+    for (int i = 0; i < N; ++i) {
+      const size_t idx = (size_t)s * N + i;
+      const double ic = 1.0 / c[idx];
+      const Sample z = make_sample(omega_of_period(t[idx]), ic);
+      const double v = sample_forward_store<1>(par.data(), L, z, est.data());
+      const double v2 = sample_forward(par.data(), L, z);
+      if (v != v2 && !(v != v && v2 != v2)) return -1;
+      F[idx] = v;
+      HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L,
+                    Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
+                    Jrho ? Jrho + idx * L : nullptr};
+      const double gk = sample_adjoint<1>(par.data(), L, z, gF ? gF[idx] : 1.0, est.data(), sink);
+      if (gc) gc[idx] = -z.k * ic * gk;
+    }
+  }
+  return 0;
+}
+
+// det[S,K,NF] and gradients reduced per model with seeds gdet (null = 1)
+int host_grid(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
+              const double* c, const double* gdet, int S, int L, int NF, int K, double* det, double* gd, double* ga,
+              double* gb, double* grho) {
+  std::vector<double> par(par_doubles(L)), est(5 * (L > 1 ? L - 1 : 1));
+  for (int s = 0; s < S; ++s) {
+    for (int m = 0; m < L; ++m)
+      stage_one(par.data(), L, m, d[s * L + m], alpha[s * L + m], beta[s * L + m], rho[s * L + m]);
+    for (int m = 0; m < L; ++m) gd[s * L + m] = ga[s * L + m] = gb[s * L + m] = grho[s * L + m] = 0.0;
+    for (int k = 0; k < K; ++k)
+      for (int f = 0; f < NF; ++f) {
+        const size_t idx = ((size_t)s * K + k) * NF + f;
+        const Sample z = make_sample(omega_of_period(t[s * NF + f]), 1.0 / c[s * K + k]);
+        det[idx] = sample_forward_store<1>(par.data(), L, z, est.data());
+        HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L, nullptr, nullptr, nullptr, nullptr};
+        sample_adjoint<1>(par.data(), L, z, gdet ? gdet[idx] : 1.0, est.data(), sink);
+      }
+  }
+  return 0;
+}
+}

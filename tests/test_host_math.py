@@ -1,0 +1,100 @@
+"""CPU check of the kernel arithmetic: adsurf_b200/csrc/adsurf_math.cuh compiled for the host.
+
+The CUDA kernels and this test share one header, so the hand-derived adjoint (layer_adjoint,
+half_adjoint, eig_adjoint) is verified against the reference-generated golden vectors here, without
+a GPU.  The compiled helper is test infrastructure (tests/host_math/), not part of the product.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.helpers import COINCIDENT_RTOL, RTOL, assert_det_close, assert_grad_close, coincident_rows, load
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def hm(tmp_path_factory):
+    out = tmp_path_factory.mktemp("host_math") / "libhost_math.so"
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+           "-I", os.path.join(ROOT, "adsurf_b200", "csrc"), os.path.join(HERE, "host_math", "host_math.cpp"),
+           "-o", str(out)]
+    subprocess.run(cmd, check=True)
+    return ctypes.CDLL(str(out))
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def C(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def run_points(hm, g, jac=False, seed_key="gF"):
+    d, a, b, rho, t, c = (C(g[k]) for k in ("d", "a", "b", "rho", "t", "c"))
+    S, L = d.shape
+    N = c.shape[1]
+    gF = C(g[seed_key]) if seed_key else None
+    F = np.empty((S, N)); gc = np.empty((S, N))
+    gd, ga, gb, gr = (np.empty((S, L)) for _ in range(4))
+    J = [np.empty((S, N, L)) for _ in range(4)] if jac else [None] * 4
+    rc = hm.host_points(P(d), P(a), P(b), P(rho), P(t), P(c), P(gF), S, L, N, P(F), P(gd), P(ga), P(gb), P(gr), P(gc),
+                        *(P(j) for j in J))
+    assert rc == 0
+    return F, gd, ga, gb, gr, gc, J
+
+
+@pytest.mark.parametrize("name", ["points_m6", "points_m3", "points_m20", "points_m30"])
+def test_points_forward_adjoint_jacobian(hm, name):
+    g = load(name)
+    F, gd, ga, gb, gr, gc, J = run_points(hm, g, jac=True)
+    assert_det_close(F, g["F"], axis=-1, what="F")
+    for new, key in ((gd, "gd"), (ga, "ga"), (gb, "gb"), (gr, "grho"), (gc, "gc")):
+        assert_grad_close(new, g[key], what=key)
+    # Jacobian rows with unit seeds: re-run with seed 1
+    F, gd, ga, gb, gr, gc, J = run_points(hm, g, jac=True, seed_key=None)
+    for j, key in zip(J, ("Jd", "Ja", "Jb", "Jrho")):
+        assert_grad_close(j[0], g[key], what=key)
+    assert_grad_close(gc[0], np.diag(g["Jc"]), what="Jc")
+
+
+@pytest.mark.parametrize("name", ["grid_m20", "grid_m6", "grid_m3"])
+def test_grid_forward_adjoint(hm, name):
+    g = load(name)
+    d, a, b, rho, t, c, gdet = (C(g[k]) for k in ("d", "a", "b", "rho", "tlist", "vlist", "gdet"))
+    S, L = d.shape
+    K, NF = c.shape[1], t.shape[1]
+    det = np.empty((S, K, NF))
+    outs = [np.empty((S, L)) for _ in range(4)]
+    assert hm.host_grid(P(d), P(a), P(b), P(rho), P(t), P(c), P(gdet), S, L, NF, K, P(det), *(P(o) for o in outs)) == 0
+    assert_det_close(det, g["det"], axis=1)
+    assert np.array_equal(np.sign(det), np.sign(g["det"]))
+    for new, key in zip(outs, ("gd", "ga", "gb", "grho")):
+        assert_grad_close(new, g[key], what=key)
+    assert hm.host_grid(P(d), P(a), P(b), P(rho), P(t), P(c), None, S, L, NF, K, P(det), *(P(o) for o in outs)) == 0
+    for new, key in zip(outs, ("gd_ones", "ga_ones", "gb_ones", "grho_ones")):
+        assert_grad_close(new, g[key], what=key)
+
+
+@pytest.mark.parametrize("name", ["grid_single_m6", "grid_single_m3", "grid_single_m20"])
+def test_grid_single_sign_pattern(hm, name):
+    """includes trial velocities that coincide with layer velocities (c == beta_m) in the forward"""
+    g = load(name)
+    d, a, b, rho = (C(g[k][None]) for k in ("d", "a", "b", "rho"))
+    t, c = C(g["tlist"][None]), C(g["vlist"][None])
+    K, NF, L = c.shape[1], t.shape[1], d.shape[1]
+    det = np.empty((1, K, NF))
+    outs = [np.empty((1, L)) for _ in range(4)]
+    assert hm.host_grid(P(d), P(a), P(b), P(rho), P(t), P(c), None, 1, L, NF, K, P(det), *(P(o) for o in outs)) == 0
+    co = coincident_rows(g["vlist"], g["a"], g["b"])
+    assert co.any()
+    scale = np.max(np.abs(g["det64"]), axis=0, keepdims=True)
+    err = np.abs(det[0] - g["det64"]) / scale
+    assert err[~co].max() <= RTOL
+    assert err[co].max() <= COINCIDENT_RTOL
+    assert np.array_equal(np.sign(det[0]), np.sign(g["det64"]))
