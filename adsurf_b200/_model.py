@@ -112,7 +112,7 @@ class multi_cal_grad(_cal_grad_base):
             self.d = torch.nn.Parameter(self.d.clone())
         self.Clist = t64(Clist).contiguous()
         self.ifunc = ifunc_list["dunkin"]["rayleigh"]
-        self.llw = 0 if float(self.b[0][0]) <= 0.0 else -1
+        self.llw = 0 if float(self.b.detach()[0][0]) <= 0.0 else -1
         if self.llw == 0:
             raise NotImplementedError("adsurf_b200: water layer (Vs[0] <= 0) is not supported (broken in the reference too)")
         self.damp_vertical = damp_vertical
@@ -158,7 +158,7 @@ class iter_cal_grad(_cal_grad_base):
             self.d = torch.nn.Parameter(self.d.clone())
         self.Clist = t64(Clist).reshape(1, -1).contiguous()
         self.ifunc = ifunc_list["dunkin"]["rayleigh"]
-        self.llw = 0 if float(self.b[0]) <= 0.0 else -1
+        self.llw = 0 if float(self.b.detach()[0]) <= 0.0 else -1
         if self.llw == 0:
             raise NotImplementedError("adsurf_b200: water layer (Vs[0] <= 0) is not supported (broken in the reference too)")
         self.damp = damp

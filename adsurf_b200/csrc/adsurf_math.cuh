@@ -34,15 +34,29 @@ ADSURF_HD double rsqrt_hd(double u) {
 // ------------------------------------------------------------------------------------------
 // Per-layer quantities
 // ------------------------------------------------------------------------------------------
+// Structure used below (derived from the entries of Dunkin's matrix, reference :66-99).  With
+//   a  = (gg*rho, gk, 1/rho),  b  = (q1*rho, g1, k2/rho)       acting on components (0,2,4)
+//   a' = (1/rho, t*gk, gg*rho), b' = (k2/rho, t*g1, q1*rho)     (gk = gammk, g1 = gam-1, gg = gam*gk,
+//                                                                q1 = g1^2, t = -2 k2, A = a0 - cp*cq)
+// the compound matrix is
+//   CA[024,024] = a0 I - a' (x) (A b + xz a) - b' (x) (A a + wy b)
+//   CA[024,1] = cpy b' - cqx a',  CA[024,3] = cpz a' - cqw b',
+//   CA[1,024] = cpz a  - cqw b,   CA[3,024] = cpy b  - cqx a,
+//   CA[1,1] = CA[3,3] = cp cq,    CA[1,3] = -w z,   CA[3,1] = -x y
+// i.e. two rank-one couplings around the Kronecker product of the P block [cp w; x cp] and the S block
+// [cq y; z cq].  Row and column products therefore cost ~33 FMAs without ever forming the 13 entries
+// or the 9 eigenfunction products, and the adjoint contracts against the same few scalars.
 struct Eig {
   double r, ir;    // sqrt((k+kx)|k-kx|) and its reciprocal
   double cs, sn;   // cos p / (1+e^-2p)/2   and   sin p / (1-e^-2p)/2
   double w, x;     // sn / r   and   -+ r sn
   double ex, fac;  // exponent carried out of the term (p when evanescent) and e^{-2p}
+  double eh;       // e^{-p} when evanescent (0 once p >= 60: a0 vanishes), 1 otherwise
   int br;          // 0: oscillatory (k<kx), 1: evanescent (k>kx), 2: k==kx, 3: unordered (NaN)
 };
 
-// var_vector, reference :109-136 (P) / :140-167 (S)
+// var_vector, reference :109-136 (P) / :140-167 (S).  e^{-2p} is formed as (e^{-p})^2 and
+// a0 = e^{-(pex+sex)} as e^{-pex} e^{-sex} (thresholds p < 16, pex+sex < 60 kept).
 ADSURF_HD Eig eig_terms(double k, double kx, double dm) {
   Eig e;
   const double u = (k + kx) * fabs(k - kx);
@@ -50,7 +64,7 @@ ADSURF_HD Eig eig_terms(double k, double kx, double dm) {
   e.r = u * e.ir;
   if (!(u > 0.0)) e.r = sqrt(u);  // u == 0 -> 0, NaN -> NaN
   const double p = e.r * dm;
-  e.cs = 0.0; e.sn = 0.0; e.w = 0.0; e.x = 0.0; e.ex = 0.0; e.fac = 0.0; e.br = 3;
+  e.cs = 0.0; e.sn = 0.0; e.w = 0.0; e.x = 0.0; e.ex = 0.0; e.fac = 0.0; e.eh = 1.0; e.br = 3;
   if (k < kx) {
     e.br = 0;
     sincos(p, &e.sn, &e.cs);
@@ -59,7 +73,8 @@ ADSURF_HD Eig eig_terms(double k, double kx, double dm) {
   } else if (k > kx) {
     e.br = 1;
     e.ex = p;
-    e.fac = (p < 16.0) ? exp(-2.0 * p) : 0.0;
+    e.eh = (p < 60.0) ? exp(-p) : 0.0;
+    e.fac = (p < 16.0) ? e.eh * e.eh : 0.0;
     e.cs = (1.0 + e.fac) * 0.5;
     e.sn = (1.0 - e.fac) * 0.5;
     e.w = e.sn * e.ir;
@@ -74,76 +89,65 @@ ADSURF_HD Eig eig_terms(double k, double kx, double dm) {
 
 struct Layer {
   // inputs
-  double ka, kb, gammk, rho, ir, dm;
-  // derived scalars
-  double gam, gamm1, twgm1, gmgmk, gmgm1, gm1sq, t;
+  double ka, kb, gk, rho, ir, dm;
+  // coefficient scalars
+  double gam, g1, gg, q1, ar, br, kr, tg, t1;
   Eig P, S;
-  double a0, a0pq, cpcq, cpy, cpz, cqw, cqx, xy, xz, wy, wz;
-  // the 13 independent Dunkin entries (+ c22); c11 = cpcq
-  double c00, c01, c02, c03, c04, c10, c12, c13, c30, c31, c32, c40, c42, c22;
+  double a0;
 };
 
-// dnka_vector (reference :52-100) on top of var_vector (:170-182)
-ADSURF_HD void layer_terms(Layer& y, double k, double k2) {
+// t2 = -2 k2 (hoisted per sample)
+ADSURF_HD void layer_terms(Layer& y, double k, double k2, double t2) {
   y.P = eig_terms(k, y.ka, y.dm);
   y.S = eig_terms(k, y.kb, y.dm);
-  const double exa = y.P.ex + y.S.ex;
-  y.a0 = (exa < 60.0) ? exp(-exa) : 0.0;
-  y.cpcq = y.P.cs * y.S.cs;
-  y.cpy = y.P.cs * y.S.w;
-  y.cpz = y.P.cs * y.S.x;
-  y.cqw = y.S.cs * y.P.w;
-  y.cqx = y.S.cs * y.P.x;
-  y.xy = y.P.x * y.S.w;
-  y.xz = y.P.x * y.S.x;
-  y.wy = y.P.w * y.S.w;
-  y.wz = y.P.w * y.S.x;
-
-  y.gam = y.gammk * k2;
-  y.gamm1 = y.gam - 1.0;
-  y.twgm1 = y.gam + y.gamm1;
-  y.gmgmk = y.gam * y.gammk;
-  y.gmgm1 = y.gam * y.gamm1;
-  y.gm1sq = y.gamm1 * y.gamm1;
-  y.a0pq = y.a0 - y.cpcq;
-  y.t = -2.0 * k2;
-  const double rho = y.rho, ir = y.ir, rho2 = rho * rho, ir2 = ir * ir;
-
-  y.c00 = y.cpcq - 2.0 * y.gmgm1 * y.a0pq - y.gmgmk * y.xz - k2 * y.gm1sq * y.wy;
-  y.c01 = (k2 * y.cpy - y.cqx) * ir;
-  y.c02 = -(y.twgm1 * y.a0pq + y.gammk * y.xz + k2 * y.gamm1 * y.wy) * ir;
-  y.c03 = (y.cpz - k2 * y.cqw) * ir;
-  y.c04 = -(2.0 * k2 * y.a0pq + y.xz + k2 * k2 * y.wy) * ir2;
-  y.c10 = (y.gmgmk * y.cpz - y.gm1sq * y.cqw) * rho;
-  y.c12 = y.gammk * y.cpz - y.gamm1 * y.cqw;
-  y.c13 = -y.wz;
-  y.c30 = (y.gm1sq * y.cpy - y.gmgmk * y.cqx) * rho;
-  y.c31 = -y.xy;
-  y.c32 = y.gamm1 * y.cpy - y.gammk * y.cqx;
-  y.c40 = -(2.0 * y.gmgmk * y.gm1sq * y.a0pq + y.gmgmk * y.gmgmk * y.xz + y.gm1sq * y.gm1sq * y.wy) * rho2;
-  y.c42 = -(y.gammk * y.gamm1 * y.twgm1 * y.a0pq + y.gam * y.gammk * y.gammk * y.xz + y.gamm1 * y.gm1sq * y.wy) * rho;
-  y.c22 = y.a0 + 2.0 * (y.cpcq - y.c00);
+  y.a0 = (y.P.ex + y.S.ex < 60.0) ? y.P.eh * y.S.eh : 0.0;
+  y.gam = y.gk * k2;
+  y.g1 = y.gam - 1.0;
+  y.gg = y.gam * y.gk;
+  y.q1 = y.g1 * y.g1;
+  y.ar = y.gg * y.rho;
+  y.br = y.q1 * y.rho;
+  y.kr = k2 * y.ir;
+  y.tg = t2 * y.gk;
+  y.t1 = t2 * y.g1;
 }
 
 // E <- E . CA   (row vector times Dunkin matrix, reference :376-383)
 ADSURF_HD void row_apply(double (&e)[5], const Layer& y) {
   const double e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3], e4 = e[4];
-  const double te2 = y.t * e2;
-  e[0] = e0 * y.c00 + e1 * y.c10 + te2 * y.c42 + e3 * y.c30 + e4 * y.c40;
-  e[1] = e0 * y.c01 + e1 * y.cpcq + te2 * y.c32 + e3 * y.c31 + e4 * y.c30;
-  e[2] = e0 * y.c02 + e1 * y.c12 + e2 * y.c22 + e3 * y.c32 + e4 * y.c42;
-  e[3] = e0 * y.c03 + e1 * y.c13 + te2 * y.c12 + e3 * y.cpcq + e4 * y.c10;
-  e[4] = e0 * y.c04 + e1 * y.c03 + te2 * y.c02 + e3 * y.c01 + e4 * y.c00;
+  const double cp = y.P.cs, w = y.P.w, x = y.P.x, cq = y.S.cs, yy = y.S.w, z = y.S.x;
+  const double sa = e0 * y.ir + e2 * y.tg + e4 * y.ar;
+  const double sb = e0 * y.kr + e2 * y.t1 + e4 * y.br;
+  const double h1 = sb * yy + e1 * cq;
+  const double h2 = sa * cq + e3 * yy;
+  const double h3 = sa * z + e3 * cq;
+  const double h4 = sb * cq + e1 * z;
+  const double Ca = cp * h4 - x * h3 - sb * y.a0;
+  const double Cb = cp * h2 - w * h1 - sa * y.a0;
+  e[1] = cp * h1 - x * h2;
+  e[3] = cp * h3 - w * h4;
+  e[0] = y.a0 * e0 + y.ar * Ca + y.br * Cb;
+  e[2] = y.a0 * e2 + y.gk * Ca + y.g1 * Cb;
+  e[4] = y.a0 * e4 + y.ir * Ca + y.kr * Cb;
 }
 
 // s <- CA . s   (column vector of the layers above)
 ADSURF_HD void col_apply(double (&s)[5], const Layer& y) {
   const double s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3], s4 = s[4];
-  s[0] = y.c00 * s0 + y.c01 * s1 + y.c02 * s2 + y.c03 * s3 + y.c04 * s4;
-  s[1] = y.c10 * s0 + y.cpcq * s1 + y.c12 * s2 + y.c13 * s3 + y.c03 * s4;
-  s[2] = y.t * (y.c42 * s0 + y.c32 * s1 + y.c12 * s3 + y.c02 * s4) + y.c22 * s2;
-  s[3] = y.c30 * s0 + y.c31 * s1 + y.c32 * s2 + y.cpcq * s3 + y.c01 * s4;
-  s[4] = y.c40 * s0 + y.c30 * s1 + y.c42 * s2 + y.c10 * s3 + y.c00 * s4;
+  const double cp = y.P.cs, w = y.P.w, x = y.P.x, cq = y.S.cs, yy = y.S.w, z = y.S.x;
+  const double ta = y.ar * s0 + y.gk * s2 + y.ir * s4;
+  const double tb = y.br * s0 + y.g1 * s2 + y.kr * s4;
+  const double m1 = z * ta + cq * s1;
+  const double m2 = cq * tb + z * s3;
+  const double m3 = yy * tb + cq * s3;
+  const double m4 = cq * ta + yy * s1;
+  const double Da = cp * m2 - x * m1 - y.a0 * tb;
+  const double Db = cp * m4 - w * m3 - y.a0 * ta;
+  s[1] = cp * m1 - w * m2;
+  s[3] = cp * m3 - x * m4;
+  s[0] = y.a0 * s0 + y.ir * Da + y.kr * Db;
+  s[2] = y.a0 * s2 + y.tg * Da + y.t1 * Db;
+  s[4] = y.a0 * s4 + y.ar * Da + y.br * Db;
 }
 
 struct LayerGrad {
@@ -178,81 +182,63 @@ ADSURF_HD void eig_adjoint(const Eig& e, double k, double kx, double dm, double 
 }
 
 // Reverse sweep through one layer: given row vector e (= E_{m+1}) and column s (= s_m, already
-// scaled by the upstream seed) returns dDelta/d(layer inputs).
+// scaled by the upstream seed) returns dDelta/d(layer inputs), Delta = e . CA . s.
 ADSURF_HD LayerGrad layer_adjoint(const Layer& y, const double (&e)[5], const double (&s)[5],
-                                                   double k, double k2) {
+                                                   double k, double k2, double t2) {
   const double e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3], e4 = e[4];
   const double s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3], s4 = s[4];
-  const double e2s2 = e2 * s2;
-  const double ts = y.t * e2;
-  const double b00 = e0 * s0 + e4 * s4 - 2.0 * e2s2;
-  const double b01 = e0 * s1 + e3 * s4;
-  const double b02 = e0 * s2 + ts * s4;
-  const double b03 = e0 * s3 + e1 * s4;
-  const double b04 = e0 * s4;
-  const double b10 = e1 * s0 + e4 * s3;
-  const double b11 = e1 * s1 + e3 * s3;
-  const double b12 = e1 * s2 + ts * s3;
-  const double b13 = e1 * s3;
-  const double b30 = e3 * s0 + e4 * s1;
-  const double b31 = e3 * s1;
-  const double b32 = e3 * s2 + ts * s1;
-  const double b40 = e4 * s0;
-  const double b42 = e4 * s2 + ts * s0;
-  const double bt = e2 * (y.c42 * s0 + y.c32 * s1 + y.c12 * s3 + y.c02 * s4);
-
-  const double rho = y.rho, ir = y.ir;
-  const double B01 = ir * b01, B02 = ir * b02, B03 = ir * b03, B04 = ir * ir * b04;
-  const double B10 = rho * b10, B30 = rho * b30, B40 = rho * rho * b40, B42 = rho * b42;
-  const double gam = y.gam, gk = y.gammk, g1 = y.gamm1, tw = y.twgm1, gg = y.gmgmk, q1 = y.gm1sq;
-  const double A = y.a0pq;
-
-  // adjoints of the eigenfunction products
-  const double bA = -2.0 * y.gmgm1 * b00 - tw * B02 - 2.0 * k2 * B04 - 2.0 * gg * q1 * B40 - gk * g1 * tw * B42;
-  const double bxz = -gg * b00 - gk * B02 - B04 - gg * gg * B40 - gam * gk * gk * B42;
-  const double bwy = -k2 * q1 * b00 - k2 * g1 * B02 - k2 * k2 * B04 - q1 * q1 * B40 - g1 * q1 * B42;
-  const double bcpy = k2 * B01 + q1 * B30 + g1 * b32;
-  const double bcqx = -B01 - gg * B30 - gk * b32;
-  const double bcpz = B03 + gg * B10 + gk * b12;
-  const double bcqw = -k2 * B03 - q1 * B10 - g1 * b12;
-  const double bwz = -b13;
-  const double bxy = -b31;
-  const double bcpcq = b00 + b11 + 2.0 * e2s2 - bA;
-  const double ba0 = bA + e2s2;
-
-  // adjoints of the coefficient scalars
-  const double bg1 = -2.0 * A * b00;
-  const double bgg = -y.xz * b00 + y.cpz * B10 - y.cqx * B30 - 2.0 * (q1 * A + gg * y.xz) * B40;
-  const double bq1 = -k2 * y.wy * b00 - y.cqw * B10 + y.cpy * B30 - 2.0 * (gg * A + q1 * y.wy) * B40;
-  const double btw = -A * B02;
-  const double bgm1 = -k2 * y.wy * B02 - y.cqw * b12 + y.cpy * b32;
-  double bgk = -y.xz * B02 + y.cpz * b12 - y.cqx * b32 - (g1 * tw * A + 2.0 * gam * gk * y.xz) * B42;
-  const double bgam = -(gk * (4.0 * gam - 3.0) * A + gk * gk * y.xz + 3.0 * q1 * y.wy) * B42 + tw * bg1 + gk * bgg +
-                      2.0 * g1 * bq1 + 2.0 * btw + bgm1;
-  bgk += gam * bgg + k2 * bgam;
-  const double bk2 = -q1 * y.wy * b00 + y.cpy * B01 - g1 * y.wy * B02 - y.cqw * B03 - 2.0 * (A + k2 * y.wy) * B04 -
-                     2.0 * bt + gk * bgam;
-  const double brho = (-(y.c01 * b01 + y.c02 * b02 + y.c03 * b03) - 2.0 * y.c04 * b04 + y.c10 * b10 + y.c30 * b30 +
-                       2.0 * y.c40 * b40 + y.c42 * b42) * ir;
-
-  // products -> eigenfunction terms
-  const Eig& P = y.P;
-  const Eig& S = y.S;
-  const double bcosp = S.cs * bcpcq + S.w * bcpy + S.x * bcpz;
-  const double bcosq = P.cs * bcpcq + P.w * bcqw + P.x * bcqx;
-  const double bw = S.cs * bcqw + S.w * bwy + S.x * bwz;
-  const double bx = S.cs * bcqx + S.w * bxy + S.x * bxz;
-  const double by = P.cs * bcpy + P.x * bxy + P.w * bwy;
-  const double bz = P.cs * bcpz + P.x * bxz + P.w * bwz;
-  const double bex = -y.a0 * ba0;
+  const double cp = y.P.cs, w = y.P.w, x = y.P.x, cq = y.S.cs, yy = y.S.w, z = y.S.x;
+  const double a0 = y.a0;
+  // the four contractions with the coefficient vectors
+  const double sa = e0 * y.ir + e2 * y.tg + e4 * y.ar;
+  const double sb = e0 * y.kr + e2 * y.t1 + e4 * y.br;
+  const double ta = y.ar * s0 + y.gk * s2 + y.ir * s4;
+  const double tb = y.br * s0 + y.g1 * s2 + y.kr * s4;
+  // S-side combinations of the row vector, P-side combinations of the column vector
+  const double h1 = sb * yy + e1 * cq;
+  const double h2 = sa * cq + e3 * yy;
+  const double h3 = sa * z + e3 * cq;
+  const double h4 = sb * cq + e1 * z;
+  const double g1_ = cp * s1 - w * tb;
+  const double g2_ = cp * tb - x * s1;
+  const double g3_ = cp * s3 - x * ta;
+  const double g4_ = cp * ta - w * s3;
+  // adjoints of the eigenfunction terms
+  const double ba0 = e0 * s0 + e2 * s2 + e4 * s4 - sb * ta - sa * tb;
+  const double bcp = h4 * ta + h2 * tb + h1 * s1 + h3 * s3;
+  const double bx = -(h3 * ta + h2 * s1);
+  const double bw = -(h1 * tb + h4 * s3);
+  const double by = sb * g1_ + e3 * g2_;
+  const double bz = sa * g3_ + e1 * g4_;
+  const double bcq = e1 * g1_ + sa * g2_ + e3 * g3_ + sb * g4_;
+  // adjoints of the contractions
+  const double Dsa = cq * g2_ + z * g3_ - a0 * tb;
+  const double Dsb = yy * g1_ + cq * g4_ - a0 * ta;
+  const double Ca = cp * h4 - x * h3 - sb * a0;
+  const double Cb = cp * h2 - w * h1 - sa * a0;
+  // coefficient scalars
+  const double b_ir = Dsa * e0 + Ca * s4;
+  const double b_tg = Dsa * e2;
+  const double b_ar = Dsa * e4 + Ca * s0;
+  const double b_kr = Dsb * e0 + Cb * s4;
+  const double b_t1 = Dsb * e2;
+  const double b_br = Dsb * e4 + Cb * s0;
+  const double b_gg = y.rho * b_ar;
+  const double b_q1 = y.rho * b_br;
+  const double b_g1 = Cb * s2 + t2 * b_t1 + 2.0 * y.g1 * b_q1;
+  const double b_gam = b_g1 + y.gk * b_gg;
+  const double b_gk = Ca * s2 + t2 * b_tg + y.gam * b_gg + k2 * b_gam;
+  const double b_k2 = y.ir * b_kr + y.gk * b_gam - 2.0 * (y.gk * b_tg + y.g1 * b_t1);
+  const double b_rho = y.gg * b_ar + y.q1 * b_br - y.ir * y.ir * (b_ir + k2 * b_kr);
+  const double bex = -a0 * ba0;
 
   LayerGrad g;
   g.d = 0.0; g.ka = 0.0; g.kb = 0.0;
-  g.k = 2.0 * k * bk2;
-  g.gammk = bgk;
-  g.rho = brho;
-  eig_adjoint(P, k, y.ka, y.dm, bcosp, bw, bx, bex, g.d, g.k, g.ka);
-  eig_adjoint(S, k, y.kb, y.dm, bcosq, by, bz, bex, g.d, g.k, g.kb);
+  g.k = 2.0 * k * b_k2;
+  g.gammk = b_gk;
+  g.rho = b_rho;
+  eig_adjoint(y.P, k, y.ka, y.dm, bcp, bw, bx, bex, g.d, g.k, g.ka);
+  eig_adjoint(y.S, k, y.kb, y.dm, bcq, by, bz, bex, g.d, g.k, g.kb);
   return g;
 }
 
@@ -322,7 +308,7 @@ ADSURF_HD LayerGrad half_adjoint(const Half& h, const double (&e)[5], const doub
 // Sample-level drivers
 // ------------------------------------------------------------------------------------------
 struct Sample {
-  double k, k2, omega, iw2;  // wavenumber, its square, clamped angular frequency, 1/omega^2
+  double k, k2, omega, iw2, t2;  // wavenumber, its square, clamped angular frequency, 1/omega^2, -2 k^2
 };
 
 // omega = twopi / t as torch evaluates `python_float / tensor` (Tensor.__rtruediv__ ==
@@ -338,13 +324,14 @@ ADSURF_HD Sample make_sample(double omega0, double ic) {
   z.k2 = z.k * z.k;
   const double iw = 1.0 / z.omega;
   z.iw2 = iw * iw;
+  z.t2 = -2.0 * z.k2;
   return z;
 }
 
 ADSURF_HD void load_layer(Layer& y, const double* __restrict__ par, int L, int m, const Sample& z) {
   y.ka = z.omega * par[P_IA * L + m];
   y.kb = z.omega * par[P_IB * L + m];
-  y.gammk = par[P_TB2 * L + m] * z.iw2;
+  y.gk = par[P_TB2 * L + m] * z.iw2;
   y.rho = par[P_RHO * L + m];
   y.ir = par[P_IR * L + m];
   y.dm = par[P_D * L + m];
@@ -372,7 +359,7 @@ ADSURF_HD double sample_forward(const double* __restrict__ par, int L, const Sam
   Layer y;
   for (int m = L - 2; m >= 0; --m) {
     load_layer(y, par, L, m, z);
-    layer_terms(y, z.k, z.k2);
+    layer_terms(y, z.k, z.k2, z.t2);
     row_apply(e, y);
   }
   return e[0];
@@ -393,7 +380,7 @@ ADSURF_HD double sample_forward_store(const double* __restrict__ par, int L, con
 #pragma unroll
     for (int i = 0; i < 5; ++i) est[(m * 5 + i) * kStride] = e[i];
     load_layer(y, par, L, m, z);
-    layer_terms(y, z.k, z.k2);
+    layer_terms(y, z.k, z.k2, z.t2);
     row_apply(e, y);
   }
   return e[0];
@@ -412,13 +399,13 @@ ADSURF_HD double sample_adjoint(const double* __restrict__ par, int L, const Sam
 #pragma unroll
     for (int i = 0; i < 5; ++i) e[i] = est[(m * 5 + i) * kStride];
     load_layer(y, par, L, m, z);
-    layer_terms(y, z.k, z.k2);
-    const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2);
+    layer_terms(y, z.k, z.k2, z.t2);
+    const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2, z.t2);
     col_apply(s, y);
     gk += g.k;
     const double ia = par[P_IA * L + m], ib = par[P_IB * L + m];
     // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2
-    sink(m, g.d, -y.ka * ia * g.ka, -y.kb * ib * g.kb + 2.0 * y.gammk * ib * g.gammk, g.rho);
+    sink(m, g.d, -y.ka * ia * g.ka, -y.kb * ib * g.kb + 2.0 * y.gk * ib * g.gammk, g.rho);
   }
   // half-space: dDelta/dE_hs = s_{L-1}
   Half h;

@@ -10,8 +10,9 @@
 These replace `dltar_vector` / `dltar_matrix` of the reference (_cps/*.py) and the autograd tape
 they build (≈10^3 ATen ops per layer): forward saves only the inputs, backward launches the
 hand-written adjoint kernel, which recomputes the layer terms (SURVEY.md §8b "Autograd contract").
-`autograd.grad(..., is_grads_batched=True)` (sensitivity notebook 02_2 cell 12) is served by a
-vmap rule that contracts the batched upstream gradient with the per-sample Jacobian kernel.
+`autograd.grad(..., is_grads_batched=True)` (sensitivity notebook 02_2 cell 12) is served by the
+per-sample Jacobian kernel: backward detects a batched upstream gradient and contracts it with the
+Jacobian rows instead of launching the reducing adjoint.
 
 Everything here needs CUDA; there is no CPU fallback.
 """
@@ -36,30 +37,14 @@ def _c64(x):
     return x.contiguous()
 
 
-class _PointsBwd(torch.autograd.Function):
-    """The adjoint kernel as a (non-differentiable) op, with a vmap rule for batched gF."""
-
-    @staticmethod
-    def forward(gF, c, t, d, a, b, rho):
-        _, gd, ga, gb, gr, gc = _capi.points_bwd(d, a, b, rho, t, c, _c64(gF))
-        return gc, gd, ga, gb, gr
-
-    @staticmethod
-    def setup_context(ctx, inputs, output):
-        pass
-
-    @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError("adsurf_b200: second derivatives of the secular function are not implemented")
-
-    @staticmethod
-    def vmap(info, in_dims, gF, c, t, d, a, b, rho):
-        if any(dim is not None for dim in in_dims[1:]):
-            raise NotImplementedError("adsurf_b200: only the upstream gradient may be batched")
-        gF = _c64(gF.movedim(in_dims[0], 0))  # [B,S,N]
-        _, Jd, Ja, Jb, Jr, Jc = _capi.points_jac(d, a, b, rho, t, c)
-        outs = (gF * Jc,) + tuple(torch.einsum("bsn,snl->bsl", gF, J) for J in (Jd, Ja, Jb, Jr))
-        return outs, (0, 0, 0, 0, 0)
+def _is_batched(t):
+    """True for the BatchedTensors autograd hands to backward under is_grads_batched=True / vmap
+    (they have no storage, so they cannot be passed to a kernel)."""
+    try:
+        t.data_ptr()
+        return False
+    except RuntimeError:
+        return True
 
 
 class _DetPoints(torch.autograd.Function):
@@ -74,7 +59,13 @@ class _DetPoints(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gF):
         c, t, d, a, b, rho = ctx.saved_tensors
-        gc, gd, ga, gb, gr = _PointsBwd.apply(gF, c, t, d, a, b, rho)
+        if _is_batched(gF):
+            # autograd.grad(..., is_grads_batched=True): one Jacobian-kernel launch, then contract the
+            # (batched) upstream gradient with torch ops, which carry batching rules
+            _, Jd, Ja, Jb, Jr, Jc = _capi.points_jac(d, a, b, rho, t, c)
+            gd, ga, gb, gr = ((gF.unsqueeze(-1) * J).sum(dim=-2) for J in (Jd, Ja, Jb, Jr))
+            return gF * Jc, None, gd, ga, gb, gr
+        _, gd, ga, gb, gr, gc = _capi.points_bwd(d, a, b, rho, t, c, _c64(gF))
         return gc, None, gd, ga, gb, gr
 
 
@@ -90,6 +81,8 @@ class _DetGrid(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gdet):
         c, t, d, a, b, rho = ctx.saved_tensors
+        if _is_batched(gdet):
+            raise NotImplementedError("adsurf_b200: batched upstream gradients are supported by det_points only")
         _, gd, ga, gb, gr = _capi.grid_bwd(d, a, b, rho, t, c, _c64(gdet))
         return None, None, gd, ga, gb, gr
 

@@ -13,6 +13,9 @@ from tests.helpers import (COINCIDENT_RTOL, RTOL, assert_det_close, assert_grad_
 
 pytestmark = pytest.mark.gpu
 
+# two kernels compiled from the same source may contract FMAs differently: same value to rounding
+SAME = 1e-12
+
 
 @pytest.fixture(scope="module")
 def ab():
@@ -41,11 +44,11 @@ def test_points_golden(ab, name):
     F = _capi.points_fwd(d, a, b, rho, t, c)
     assert_det_close(N(F), g["F"], axis=-1, what="F")
     F2, gd, ga, gb, gr, gc = _capi.points_bwd(d, a, b, rho, t, c, gF, want_F=True)
-    assert torch.equal(F, F2)
+    assert_det_close(N(F2), N(F), axis=-1, rtol=SAME, what="F (adjoint kernel)")
     for new, key in ((gd, "gd"), (ga, "ga"), (gb, "gb"), (gr, "grho"), (gc, "gc")):
         assert_grad_close(N(new), g[key], what=key)
     F3, Jd, Ja, Jb, Jr, Jc = _capi.points_jac(d, a, b, rho, t, c)
-    assert torch.equal(F, F3)
+    assert_det_close(N(F3), N(F), axis=-1, rtol=SAME, what="F (jacobian kernel)")
     for J, key in ((Jd, "Jd"), (Ja, "Ja"), (Jb, "Jb"), (Jr, "Jrho")):
         assert_grad_close(N(J[0]), g[key], what=key)
     assert_grad_close(N(Jc[0]), np.diag(g["Jc"]), what="Jc")
@@ -75,7 +78,7 @@ def test_points_autograd_and_batched_grads(ab, name):
     assert_grad_close(np.diag(N(Jc)), np.diag(g["Jc"]), what="Jc")
     # the result lands on the CPU when the caller asks for device="cpu" (computed on the GPU anyway)
     Fc = shim1.dltar_vector(g["c"][0], g["t"][0], g["d"][0], g["a"][0], g["b"][0], g["rho"][0], 2, -1)
-    assert not Fc.is_cuda and torch.equal(Fc, F1.detach().cpu())
+    assert not Fc.is_cuda and torch.equal(Fc, F1.detach().cpu())  # same kernel, same inputs: deterministic
 
 
 def test_sensitivity_kernel(ab):
@@ -101,7 +104,7 @@ def test_grid_golden(ab, name):
     unpacked = ((words[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(neg.shape[0], neg.shape[1], -1)[..., :NF]
     assert np.array_equal(unpacked.astype(bool), neg)
     det2, gd, ga, gb, gr = _capi.grid_bwd(d, a, b, rho, t, c, gdet, want_det=True)
-    assert torch.equal(det, det2)
+    assert_det_close(N(det2), N(det), axis=1, rtol=SAME, what="det (adjoint kernel)")
     for new, key in zip((gd, ga, gb, gr), ("gd", "ga", "gb", "grho")):
         assert_grad_close(N(new), g[key], what=key)
     _, gd, ga, gb, gr = _capi.grid_bwd(d, a, b, rho, t, c, None)
@@ -256,7 +259,7 @@ def test_properties_at_scale(ab):
     tt = t[s].unsqueeze(1).expand(-1, K, -1).reshape(4, -1).contiguous()
     F, gd, ga, gb, gr, _ = _capi.points_bwd(d[s].contiguous(), a[s].contiguous(), b[s].contiguous(),
                                             rho[s].contiguous(), tt, cc, torch.ones_like(cc), want_F=True)
-    assert torch.equal(F.reshape(4, K, NF), det[s])
+    assert_det_close(N(F.reshape(4, K, NF)), N(det[s]), axis=1, rtol=SAME)
     for x, y in zip((gd, ga, gb, gr), g1):
         assert_grad_close(N(x), N(y[s]), rtol=1e-11)
 
