@@ -28,6 +28,7 @@ EXPORTS = (
     "adsurf_det_grid_bwd",
     "adsurf_dmf_step",
     "adsurf_fp64_peak_probe",
+    "adsurf_math_probe",
 )
 
 _lib = None
@@ -60,6 +61,8 @@ def lib():
         L.adsurf_det_grid_bwd.argtypes = [vp] * 7 + [ci] * 4 + [vp] * 5 + [vp, sz, vp]
         L.adsurf_dmf_step.argtypes = [vp] * 7 + [ci] * 6 + [vp] * 7 + [vp, sz, vp]
         L.adsurf_fp64_peak_probe.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]
+        L.adsurf_math_probe.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+        L.adsurf_math_probe.restype = ci
         for name in EXPORTS:
             if name.startswith("adsurf_det") or name in ("adsurf_dmf_step", "adsurf_fp64_peak_probe"):
                 getattr(L, name).restype = ci
@@ -223,3 +226,12 @@ def fp64_peak_probe(iters=2048, repeats=5, device=None):
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _check(lib().adsurf_fp64_peak_probe(int(iters), int(repeats), ctypes.byref(tf), ctypes.byref(ms), st))
     return tf.value, ms.value
+
+
+def math_probe(x):
+    """(1/sqrt(x), exp(-x), sin(x), cos(x)) through the kernels' inline device functions."""
+    _req(x)
+    outs = [torch.empty_like(x) for _ in range(4)]
+    with torch.cuda.device(x.device):
+        _check(lib().adsurf_math_probe(_ptr(x), x.numel(), *(_ptr(o) for o in outs), _stream(x)))
+    return tuple(outs)

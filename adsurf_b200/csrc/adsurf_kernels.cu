@@ -26,6 +26,8 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "adsurf_b200.h"
 #include "adsurf_math.cuh"
@@ -42,19 +44,29 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // gradient sinks for sample_adjoint
-struct ReduceSink {  // warp-reduce each layer's 4 gradients into per-warp shared accumulators [4][L]
+// Warp-reduce the 4 gradients of a layer with a transposed butterfly: after the xor-16 and xor-8
+// exchanges each lane carries one of the four values (which one = lane bits 4,3), three more
+// exchanges finish the sums; lanes 0, 8, 16, 24 then add theirs into the per-warp shared
+// accumulators [4][L].  12 SHFL + 6 DADD instead of 40 SHFL + 20 DADD for four plain butterflies.
+struct ReduceSink {
   double* acc;
   int L, lane;
   bool active;
   __device__ __forceinline__ void operator()(int m, double gd, double ga, double gb, double gr) const {
     if (!active) { gd = 0.0; ga = 0.0; gb = 0.0; gr = 0.0; }
-    gd = warp_sum(gd); ga = warp_sum(ga); gb = warp_sum(gb); gr = warp_sum(gr);
-    if (lane == 0) {
-      acc[0 * L + m] += gd;
-      acc[1 * L + m] += ga;
-      acc[2 * L + m] += gb;
-      acc[3 * L + m] += gr;
-    }
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    // xor 16: lower half keeps (gd, ga), upper half keeps (gb, gr)
+    const double k0 = hi16 ? gb : gd, k1 = hi16 ? gr : ga;
+    const double x0 = hi16 ? gd : gb, x1 = hi16 ? ga : gr;
+    const double a0 = k0 + __shfl_xor_sync(0xffffffffu, x0, 16);
+    const double a1 = k1 + __shfl_xor_sync(0xffffffffu, x1, 16);
+    // xor 8: bit 3 clear keeps the first of the pair, set keeps the second
+    const double kk = hi8 ? a1 : a0, xx = hi8 ? a0 : a1;
+    double v = kk + __shfl_xor_sync(0xffffffffu, xx, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if ((lane & 7) == 0) acc[(lane >> 3) * L + m] += v;  // lane>>3: 0 gd, 1 ga, 2 gb, 3 grho
   }
 };
 
@@ -156,48 +168,75 @@ __global__ void k_minmax_reduce(const double* __restrict__ pmax, const double* _
   if (cmin) cmin[i] = vmin;
 }
 
-// Dense grid, fused forward + adjoint with per-model gradient reduction.
-__global__ void __launch_bounds__(128) k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha,
-                                                  const double* __restrict__ beta, const double* __restrict__ rho,
-                                                  const double* __restrict__ t, const double* __restrict__ c,
-                                                  const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp,
-                                                  double* __restrict__ det, double* __restrict__ part) {
+// E-store in global memory (L2-resident working set): cache-global loads/stores, lane-interleaved
+struct GlobalStore {
+  double* p;
+  __device__ __forceinline__ double ld(int i) const { return __ldcg(p + i * kWarp); }
+  __device__ __forceinline__ void st(int i, double v) const { __stcg(p + i * kWarp, v); }
+};
+
+// Dense grid, fused forward + adjoint with per-model gradient reduction.  Persistent: each block
+// walks the virtual blocks vb = blockIdx.x, blockIdx.x + gridDim.x, ... (vb -> model, chunk of units).
+// kGlobal = false: the per-layer row vectors E_{m+1} live in shared memory (40 B per thread per
+//   layer, which caps residency at 8 warps per SM for 20 layers);
+// kGlobal = true: they live in a per-resident-warp slab of global memory that stays in L2
+//   (148 SMs x 12..16 warps x 24 KB = 43..58 MB of the 126 MB L2), so residency is bounded by
+//   registers only and the FP64 pipe sees 3-4 warps per scheduler instead of 2.
+template <bool kGlobal, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks)
+k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const double* __restrict__ beta,
+           const double* __restrict__ rho, const double* __restrict__ t, const double* __restrict__ c,
+           const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp, int total_vblocks,
+           double* __restrict__ det, double* __restrict__ part, double* __restrict__ estore) {
   extern __shared__ double smem[];
-  double* par = smem;                                        // [6][L]
-  double* accs = par + par_doubles(L);                         // [wpb][4][L]
-  double* ests = accs + (size_t)gp.wpb * 4 * L;              // [wpb][L-1][5][32]
-  const int s = blockIdx.x / gp.bpm;
-  const int blk = blockIdx.x - s * gp.bpm;
-  stage_params(par, d, alpha, beta, rho, s, L);
-  for (int i = threadIdx.x; i < gp.wpb * 4 * L; i += blockDim.x) accs[i] = 0.0;
-  __syncthreads();
+  double* par = smem;                               // staged layer constants
+  double* accs = par + par_doubles(L);              // [wpb][4][L]
+  double* ests = accs + (size_t)gp.wpb * 4 * L;     // [wpb][L-1][kSlot][32] (shared-memory variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blk * gp.wpb + warp;
-  if (unit < gp.units) {
-    double* acc = accs + (size_t)warp * 4 * L;
-    double* est = ests + (size_t)warp * (L - 1) * 5 * kWarp + lane;
-    const int ft = unit % gp.nft, ch = unit / gp.nft;
-    const int f = ft * kWarp + lane;
-    const bool active = f < NF;
-    const int fc = active ? f : NF - 1;
-    const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
-    const int k0 = ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
-    for (int k = k0; k < k1; ++k) {
-      const double ic = 1.0 / c[(size_t)s * K + k];
-      const Sample z = make_sample(omega0, ic);
-      const size_t idx = ((size_t)s * K + k) * NF + fc;
-      const double seed = gdet ? gdet[idx] : 1.0;
-      const double v = sample_forward_store<kWarp>(par, L, z, est);
-      if (det && active) det[idx] = v;
-      ReduceSink sink{acc, L, lane, active};
-      sample_adjoint<kWarp>(par, L, z, seed, est, sink);
+  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
+  double* acc = accs + (size_t)warp * 4 * L;
+  double* estp = kGlobal ? estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + lane
+                         : ests + (size_t)warp * slab + lane;
+  for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
+    const int s = vb / gp.bpm;
+    const int blk = vb - s * gp.bpm;
+    __syncthreads();  // previous virtual block has flushed its accumulators
+    stage_params(par, d, alpha, beta, rho, s, L);
+    for (int i = threadIdx.x; i < gp.wpb * 4 * L; i += blockDim.x) accs[i] = 0.0;
+    __syncthreads();
+    const int unit = blk * gp.wpb + warp;
+    if (unit < gp.units) {
+      const int ft = unit % gp.nft, ch = unit / gp.nft;
+      const int f = ft * kWarp + lane;
+      const bool active = f < NF;
+      const int fc = active ? f : NF - 1;
+      const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
+      const int k0 = ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
+      for (int k = k0; k < k1; ++k) {
+        const double ic = 1.0 / c[(size_t)s * K + k];
+        const Sample z = make_sample(omega0, ic);
+        const size_t idx = ((size_t)s * K + k) * NF + fc;
+        const double seed = gdet ? gdet[idx] : 1.0;
+        ReduceSink sink{acc, L, lane, active};
+        double v;
+        if (kGlobal) {
+          const GlobalStore st{estp};
+          v = sample_forward_store(par, L, z, st);
+          sample_adjoint(par, L, z, seed, st, sink);
+        } else {
+          const PlainStore<kWarp> st{estp};
+          v = sample_forward_store(par, L, z, st);
+          sample_adjoint(par, L, z, seed, st, sink);
+        }
+        if (det && active) __stcs(det + idx, v);  // streaming store: keep the E-store lines in L2
+      }
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
-    double v = 0.0;
-    for (int w = 0; w < gp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
-    part[((size_t)s * gp.bpm + blk) * 4 * L + i] = v;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
+      double v = 0.0;
+      for (int w = 0; w < gp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
+      part[((size_t)s * gp.bpm + blk) * 4 * L + i] = v;
+    }
   }
 }
 
@@ -294,14 +333,15 @@ __global__ void __launch_bounds__(128) k_points_bwd(const double* __restrict__ d
   const int unit = blk * pp.wpb + warp;
   if (unit < pp.units) {
     double* acc = accs + (size_t)warp * 4 * L;
-    double* est = ests + (size_t)warp * (L - 1) * 5 * kWarp + lane;
+    double* est = ests + (size_t)warp * (L - 1) * kSlot * kWarp + lane;
     const int i = unit * kWarp + lane;
     const bool active = i < N;
     const size_t idx = (size_t)s * N + (active ? i : N - 1);
     const double cc = c[idx];
     const double ic = 1.0 / cc;
     const Sample z = make_sample(omega_of_period(t[idx]), ic);
-    const double v = sample_forward_store<kWarp>(par, L, z, est);
+    const PlainStore<kWarp> store{est};
+    const double v = sample_forward_store(par, L, z, store);
     if (F && active) F[idx] = v;
     double seed = 1.0;
     if (kKind == 0) seed = gF[idx];
@@ -330,10 +370,10 @@ __global__ void __launch_bounds__(128) k_points_bwd(const double* __restrict__ d
       if (kKind == 1) {
         JacSink sink{Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
                      Jrho ? Jrho + idx * L : nullptr, active};
-        gk = sample_adjoint<kWarp>(par, L, z, seed, est, sink);
+        gk = sample_adjoint(par, L, z, seed, store, sink);
       } else {
         ReduceSink sink{acc, L, lane, active};
-        gk = sample_adjoint<kWarp>(par, L, z, seed, est, sink);
+        gk = sample_adjoint(par, L, z, seed, store, sink);
       }
       if (gc && active) gc[idx] = -z.k * ic * gk;  // k = omega0 / c
     }
@@ -376,6 +416,15 @@ __global__ void __launch_bounds__(256) k_dfma_probe(int iters, double* __restric
   if (r == 12345.678) out[0] = r;  // never true; keeps the chains alive
 }
 
+__global__ void k_math_probe(const double* __restrict__ x, int n, double* __restrict__ rs, double* __restrict__ ex,
+                             double* __restrict__ sn, double* __restrict__ cs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rs[i] = rsqrt_hd(x[i]);
+  ex[i] = exp_neg(x[i]);
+  sincos_fast(x[i], sn + i, cs + i);
+}
+
 // ------------------------------------------------------------------------------------------
 // Host-side planning
 // ------------------------------------------------------------------------------------------
@@ -383,7 +432,7 @@ constexpr int kNumSM = 148;
 constexpr size_t kSmemBudget = 100 * 1024;   // per block, so that two blocks fit an SM
 constexpr size_t kSmemMax = 227 * 1024;
 
-inline size_t est_bytes_per_warp(int L) { return (size_t)(L > 1 ? L - 1 : 0) * 5 * kWarp * sizeof(double); }
+inline size_t est_bytes_per_warp(int L) { return (size_t)(L > 1 ? L - 1 : 0) * kSlot * kWarp * sizeof(double); }
 
 // warps per block for the adjoint kernels; 0 if even one warp does not fit
 inline int adj_wpb(int L) {
@@ -401,10 +450,31 @@ inline size_t adj_smem(int L, int wpb) {
          (size_t)wpb * est_bytes_per_warp(L);
 }
 
+// Where the dense adjoint keeps its per-layer row vectors: 0 = shared memory (2 blocks of 4 warps per
+// SM at 20 layers), 1 / 2 = L2-resident global slab with 3 / 4 blocks of 4 warps per SM.
+// Overridable for experiments with ADSURF_GRID_BWD=smem|g3|g4 (read once).
+enum { kBwdSmem = 0, kBwdG3 = 1, kBwdG4 = 2 };
+inline int bwd_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ADSURF_GRID_BWD");
+    mode = kBwdG3;
+    if (e && !strcmp(e, "g3")) mode = kBwdG3;
+    if (e && !strcmp(e, "g4")) mode = kBwdG4;
+    if (e && !strcmp(e, "smem")) mode = kBwdSmem;
+  }
+  return mode;
+}
+constexpr int kMaxResidentBlocks = 160 * 4;  // upper bound on co-resident adjoint blocks (global E-store slabs)
+
+inline size_t bwd_estore_bytes(int L) {
+  return bwd_mode() == kBwdSmem ? 0 : (size_t)kMaxResidentBlocks * 4 * est_bytes_per_warp(L);
+}
+
 inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
   GridPlan gp;
   gp.nft = (NF + kWarp - 1) / kWarp;
-  gp.wpb = adjoint ? adj_wpb(L) : 8;
+  gp.wpb = adjoint ? (bwd_mode() == kBwdSmem ? adj_wpb(L) : 4) : 8;
   const long long target = (long long)kNumSM * 8 * 24;  // ~24 waves of 8 warps per SM
   long long nchunk = (target + (long long)S * gp.nft - 1) / ((long long)S * gp.nft);
   const int maxchunks = K >= 16 ? K / 8 : 1;
@@ -488,7 +558,7 @@ size_t adsurf_workspace_bytes(int op, int S, int L, int n, int K) {
     case ADSURF_OP_GRID_BWD: {
       if (K <= 0) return 0;
       const GridPlan gp = plan_grid(S, L, n, K, true);
-      return align256((size_t)S * gp.bpm * 4 * L * sizeof(double));
+      return align256((size_t)S * gp.bpm * 4 * L * sizeof(double)) + align256(bwd_estore_bytes(L));
     }
     case ADSURF_OP_DMF_STEP: {
       const PointsPlan pp = plan_points(L, n);
@@ -613,13 +683,37 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   if (L - 1 > ADSURF_MAX_ADJ_LAYERS) return ADSURF_E_LAYERS;
   const GridPlan gp = plan_grid(S, L, NF, K, true);
   if (gp.wpb <= 0) return ADSURF_E_LAYERS;
-  const size_t need = align256((size_t)S * gp.bpm * 4 * L * sizeof(double));
+  const size_t part_bytes = align256((size_t)S * gp.bpm * 4 * L * sizeof(double));
+  const size_t need = part_bytes + align256(bwd_estore_bytes(L));
   if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = adj_smem(L, gp.wpb);
-  if (set_smem(k_grid_bwd, smem)) return ADSURF_E_CUDA;
-  k_grid_bwd<<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, gdet, L, NF, K,
-                                                                            gp, det, (double*)ws);
+  const int mode = bwd_mode();
+  const size_t smem = mode == kBwdSmem ? adj_smem(L, gp.wpb)
+                                       : (size_t)par_doubles(L) * sizeof(double) + (size_t)gp.wpb * 4 * L * sizeof(double);
+  double* estore = mode == kBwdSmem ? nullptr : (double*)((char*)ws + part_bytes);
+  const long long total_vb = (long long)S * gp.bpm;
+  if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;
+  int dev = 0, nsm = kNumSM, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int threads = gp.wpb * kWarp;
+#define ADSURF_LAUNCH_BWD(KERN)                                                                                  \
+  do {                                                                                                           \
+    if (set_smem(KERN, smem)) return ADSURF_E_CUDA;                                                              \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, threads, smem) != cudaSuccess || occ < 1) {    \
+      cudaGetLastError();                                                                                        \
+      return ADSURF_E_CUDA;                                                                                      \
+    }                                                                                                            \
+    long long grid = (long long)occ * nsm;                                                                       \
+    if (grid > kMaxResidentBlocks) grid = kMaxResidentBlocks;                                                    \
+    if (grid > total_vb) grid = total_vb;                                                                        \
+    KERN<<<(unsigned)grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gdet, L, NF, K, gp, (int)total_vb,    \
+                                                det, (double*)ws, estore);                                       \
+  } while (0)
+  if (mode == kBwdG3) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 3>));
+  else if (mode == kBwdG4) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 4>));
+  else ADSURF_LAUNCH_BWD((k_grid_bwd<false, 1>));
+#undef ADSURF_LAUNCH_BWD
   if (check_launch()) return ADSURF_E_CUDA;
   k_grad_reduce<<<S, 128, 0, st>>>((const double*)ws, L, gp.bpm, gd, galpha, gbeta, grho);
   return check_launch();
@@ -671,6 +765,14 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
     return check_launch();
   }
   return ADSURF_OK;
+}
+
+int adsurf_math_probe(const double* x, int n, double* out_rsqrt, double* out_expneg, double* out_sin,
+                      double* out_cos, void* stream) {
+  if (!x || !out_rsqrt || !out_expneg || !out_sin || !out_cos) return ADSURF_E_NULL;
+  if (n <= 0) return ADSURF_E_SHAPE;
+  k_math_probe<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, n, out_rsqrt, out_expneg, out_sin, out_cos);
+  return check_launch();
 }
 
 int adsurf_fp64_peak_probe(int iters, int repeats, double* tflops, double* ms, void* stream) {

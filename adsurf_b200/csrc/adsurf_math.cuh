@@ -8,6 +8,7 @@
 // :52-100 (Dunkin matrix), :102-192 (eigenfunction terms), :303-399 (recursion).
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define ADSURF_HD __host__ __device__ __forceinline__
@@ -23,12 +24,123 @@ constexpr int kWarp = 32;
 constexpr int kNumPar = 6;  // staged per-layer constants
 enum { P_IA = 0, P_IB = 1, P_TB2 = 2, P_RHO = 3, P_IR = 4, P_D = 5 };
 
+// ---- inline elementary functions -------------------------------------------------------------
+// Straight-line (call-free, branch-free on the common path) so that the P and S terms of a layer
+// are scheduled together: the library versions cost about as many FP64 instructions but sit behind
+// calls, slow-path branches and ~3x as many integer/uniform instructions, which compete with the
+// half-rate FP64 pipe for issue slots.
+ADSURF_HD long long dbl_bits(double v) {
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(v);
+#else
+  long long b; memcpy(&b, &v, sizeof(b)); return b;
+#endif
+}
+ADSURF_HD double bits_dbl(long long b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(b);
+#else
+  double v; memcpy(&v, &b, sizeof(v)); return v;
+#endif
+}
+
+// 1/sqrt(u), u > 0 normal.  Device: 23-bit hardware seed (MUFU.RSQ64H) + one cubic Newton step
+// (relative error ~ seed^3): about 1 ulp.  u == 0 / NaN callers test u themselves.
 ADSURF_HD double rsqrt_hd(double u) {
 #if defined(__CUDA_ARCH__)
-  return rsqrt(u);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
+  const double t = u * y;
+  const double e = fma(-t, y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 #else
   return 1.0 / sqrt(u);
 #endif
+}
+
+constexpr double kShifter = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest integer into the low mantissa bits
+
+// Polynomial coefficients live in constant memory on the device so that DFMA reads them as
+// c[bank][offset] operands instead of materialising each 64-bit literal with two UMOVs.
+#define ADSURF_EXP_COEFS                                                                              \
+  { 1.1470745597729725e-11, 2.08767569878681e-09, 2.755731922398589e-07, 2.48015873015873e-05,          \
+    0.001388888888888889, 0.041666666666666664, 0.5, /* even: 1/14! ... 1/2! */                         \
+    1.6059043836821613e-10, 2.505210838544172e-08, 2.7557319223985893e-06, 0.0001984126984126984,      \
+    0.008333333333333333, 0.16666666666666666 /* odd: 1/13! ... 1/3! */ }
+#define ADSURF_SIN_COEFS                                                                              \
+  { 1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,               \
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01 }
+#define ADSURF_COS_COEFS                                                                              \
+  { -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,              \
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02 }
+#define ADSURF_RED_CONSTS                                                                             \
+  { 1.4426950408889634, -0.6931471805599453, -2.3190468138462996e-17, /* log2 e, -ln2 hi, -ln2 lo */    \
+    0.6366197723675814, -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33 /* 2/pi, -pi/2 x3 */ }
+static const double kExpCH[13] = ADSURF_EXP_COEFS;
+static const double kSinCH[6] = ADSURF_SIN_COEFS;
+static const double kCosCH[6] = ADSURF_COS_COEFS;
+static const double kRedCH[7] = ADSURF_RED_CONSTS;
+#if defined(__CUDACC__)
+__constant__ double kExpCD[13] = ADSURF_EXP_COEFS;
+__constant__ double kSinCD[6] = ADSURF_SIN_COEFS;
+__constant__ double kCosCD[6] = ADSURF_COS_COEFS;
+__constant__ double kRedCD[7] = ADSURF_RED_CONSTS;
+#endif
+#if defined(__CUDA_ARCH__)
+#define ADSURF_K(tab, i) tab##D[i]
+#else
+#define ADSURF_K(tab, i) tab##H[i]
+#endif
+
+// exp(-p) for 0 <= p (< ~700): n = rint(-p log2 e), r = -p - n ln2 (two-term), Taylor polynomial in
+// even/odd halves (|r| <= ln2/2, truncation 4e-18), scaled by 2^n through the exponent field.
+ADSURF_HD double exp_neg(double p) {
+  const double x = -fmin(p, 700.0);
+  const double t = fma(x, ADSURF_K(kRedC, 0), kShifter);
+  const double fn = t - kShifter;
+  double r = fma(fn, ADSURF_K(kRedC, 1), x);
+  r = fma(fn, ADSURF_K(kRedC, 2), r);
+  const double r2 = r * r;
+  double ev = ADSURF_K(kExpC, 0);
+#pragma unroll
+  for (int i = 1; i < 7; ++i) ev = fma(ev, r2, ADSURF_K(kExpC, i));
+  double od = ADSURF_K(kExpC, 7);
+#pragma unroll
+  for (int i = 8; i < 13; ++i) od = fma(od, r2, ADSURF_K(kExpC, i));
+  // exp(r) = 1 + r + r2*(ev + r*od)
+  const double q = fma(r, od, ev);
+  const double er = fma(r2, q, r) + 1.0;
+  const long long n = (long long)(int)dbl_bits(t);    // low 32 bits hold the (two's complement) integer
+  return bits_dbl(dbl_bits(er) + (n << 52));
+}
+
+// sin and cos of q for |q| < 1e5: Cody-Waite reduction by pi/2 in three FMA steps, then the fdlibm
+// kernel polynomials on |r| <= pi/4 (coefficients of __kernel_sin/__kernel_cos, (C) 1993 Sun
+// Microsystems, freely usable with this notice; < 1 ulp).  Larger arguments take the library path.
+ADSURF_HD void sincos_fast(double q, double* sn, double* cs) {
+  if (!(fabs(q) < 1.0e5)) {
+    sincos(q, sn, cs);
+    return;
+  }
+  const double t = fma(q, ADSURF_K(kRedC, 3), kShifter);
+  const double fn = t - kShifter;
+  double r = fma(fn, ADSURF_K(kRedC, 4), q);
+  r = fma(fn, ADSURF_K(kRedC, 5), r);
+  r = fma(fn, ADSURF_K(kRedC, 6), r);
+  const double z = r * r;
+  double ps = ADSURF_K(kSinC, 0);
+#pragma unroll
+  for (int i = 1; i < 6; ++i) ps = fma(ps, z, ADSURF_K(kSinC, i));
+  const double s = fma(r * z, ps, r);
+  double pc = ADSURF_K(kCosC, 0);
+#pragma unroll
+  for (int i = 1; i < 6; ++i) pc = fma(pc, z, ADSURF_K(kCosC, i));
+  const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int n = (int)dbl_bits(t);
+  const double a = (n & 1) ? c : s;
+  const double b = (n & 1) ? s : c;
+  *sn = (n & 2) ? -a : a;
+  *cs = ((n + 1) & 2) ? -b : b;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -47,44 +159,59 @@ ADSURF_HD double rsqrt_hd(double u) {
 // [cq y; z cq].  Row and column products therefore cost ~33 FMAs without ever forming the 13 entries
 // or the 9 eigenfunction products, and the adjoint contracts against the same few scalars.
 struct Eig {
-  double r, ir;    // sqrt((k+kx)|k-kx|) and its reciprocal
-  double cs, sn;   // cos p / (1+e^-2p)/2   and   sin p / (1-e^-2p)/2
-  double w, x;     // sn / r   and   -+ r sn
-  double ex, fac;  // exponent carried out of the term (p when evanescent) and e^{-2p}
-  double eh;       // e^{-p} when evanescent (0 once p >= 60: a0 vanishes), 1 otherwise
-  int br;          // 0: oscillatory (k<kx), 1: evanescent (k>kx), 2: k==kx, 3: unordered (NaN)
+  double r, ir;     // sqrt((k+kx)|k-kx|) and its reciprocal
+  double p;         // r * d
+  double cs, sn;    // cos p / (1+e^-2p)/2   and   sin p / (1-e^-2p)/2
+  double w, x;      // sn / r   and   -+ r sn
+  double dcs, dsn;  // d cs / dp, d sn / dp
+  double ex, eh;    // exponent carried out of the term (p when evanescent); e^{-p} (1 when oscillatory)
+  double c0, c1;    // the transcendental results kept for the adjoint sweep: (sin, cos) or (e^{-p}, -)
+  bool lt, pos;     // oscillatory branch (k < kx);  u > 0 (false: k == kx or unordered)
 };
 
-// var_vector, reference :109-136 (P) / :140-167 (S).  e^{-2p} is formed as (e^{-p})^2 and
-// a0 = e^{-(pex+sex)} as e^{-pex} e^{-sex} (thresholds p < 16, pex+sex < 60 kept).
-ADSURF_HD Eig eig_terms(double k, double kx, double dm) {
-  Eig e;
+// var_vector, reference :109-136 (P) / :140-167 (S), split in three steps so that the adjoint sweep can
+// re-use the transcendental values of the forward sweep instead of re-evaluating them:
+//   eig_setup  — r, 1/r, p and the branch   (cheap; done in both sweeps)
+//   eig_trans  — sin/cos or e^{-p}          (expensive; forward sweep only, results stored)
+//   eig_finish — everything derived from them.
+// e^{-2p} is formed as (e^{-p})^2 and a0 = e^{-(pex+sex)} as e^{-pex} e^{-sex} (thresholds kept).
+ADSURF_HD void eig_setup(Eig& e, double k, double kx, double dm) {
   const double u = (k + kx) * fabs(k - kx);
+  e.pos = u > 0.0;
+  e.lt = k < kx;
   e.ir = rsqrt_hd(u);
-  e.r = u * e.ir;
-  if (!(u > 0.0)) e.r = sqrt(u);  // u == 0 -> 0, NaN -> NaN
-  const double p = e.r * dm;
-  e.cs = 0.0; e.sn = 0.0; e.w = 0.0; e.x = 0.0; e.ex = 0.0; e.fac = 0.0; e.eh = 1.0; e.br = 3;
-  if (k < kx) {
-    e.br = 0;
-    sincos(p, &e.sn, &e.cs);
-    e.w = e.sn * e.ir;
-    e.x = -e.r * e.sn;
-  } else if (k > kx) {
-    e.br = 1;
-    e.ex = p;
-    e.eh = (p < 60.0) ? exp(-p) : 0.0;
-    e.fac = (p < 16.0) ? e.eh * e.eh : 0.0;
-    e.cs = (1.0 + e.fac) * 0.5;
-    e.sn = (1.0 - e.fac) * 0.5;
-    e.w = e.sn * e.ir;
-    e.x = e.r * e.sn;
-  } else if (k == kx) {
-    e.br = 2;
-    e.cs = 1.0;
-    e.w = dm;
+  e.r = e.pos ? u * e.ir : u;  // u == 0 -> 0, NaN -> NaN
+  e.p = e.r * dm;
+}
+
+ADSURF_HD void eig_trans(Eig& e) {
+  if (e.lt) {  // warp-uniform in the dense kernels (depends on c and the layer, not on the period)
+    sincos_fast(e.p, &e.c0, &e.c1);
+  } else {
+    e.c0 = exp_neg(e.p);
+    e.c1 = 0.0;
   }
-  return e;
+}
+
+ADSURF_HD void eig_finish(Eig& e, double dm) {
+  if (e.lt) {
+    e.sn = e.c0;
+    e.cs = e.c1;
+    e.dcs = -e.c0;
+    e.dsn = e.c1;
+    e.ex = 0.0;
+    e.eh = 1.0;
+  } else {
+    const double fac = (e.p < 16.0) ? e.c0 * e.c0 : 0.0;
+    e.cs = 0.5 + 0.5 * fac;
+    e.sn = 0.5 - 0.5 * fac;
+    e.dcs = -fac;
+    e.dsn = fac;
+    e.ex = e.p;  // p = 0 when k == kx
+    e.eh = (e.p < 60.0) ? e.c0 : 0.0;
+  }
+  e.w = e.pos ? e.sn * e.ir : dm;  // k == kx: w = d (reference :135)
+  e.x = (e.lt ? -e.r : e.r) * e.sn;
 }
 
 struct Layer {
@@ -96,10 +223,24 @@ struct Layer {
   double a0;
 };
 
-// t2 = -2 k2 (hoisted per sample)
+// forward sweep: evaluate the transcendentals
+ADSURF_HD void layer_eig_forward(Layer& y, double k) {
+  eig_setup(y.P, k, y.ka, y.dm);
+  eig_setup(y.S, k, y.kb, y.dm);
+  eig_trans(y.P);
+  eig_trans(y.S);
+}
+
+// adjoint sweep: restore them from the store (c0, c1 already set by the caller)
+ADSURF_HD void layer_eig_restore(Layer& y, double k) {
+  eig_setup(y.P, k, y.ka, y.dm);
+  eig_setup(y.S, k, y.kb, y.dm);
+}
+
+// t2 = -2 k2 (hoisted per sample); needs P, S set up (layer_eig_forward / layer_eig_restore)
 ADSURF_HD void layer_terms(Layer& y, double k, double k2, double t2) {
-  y.P = eig_terms(k, y.ka, y.dm);
-  y.S = eig_terms(k, y.kb, y.dm);
+  eig_finish(y.P, y.dm);
+  eig_finish(y.S, y.dm);
   y.a0 = (y.P.ex + y.S.ex < 60.0) ? y.P.eh * y.S.eh : 0.0;
   y.gam = y.gk * k2;
   y.g1 = y.gam - 1.0;
@@ -154,31 +295,19 @@ struct LayerGrad {
   double d, ka, kb, gammk, rho, k;  // dDelta/d(each input of the layer), k includes the k2 path
 };
 
-// adjoint of one eigenfunction block: (bcs, bw, bx, bex) -> (bd, bk, bkx)
-ADSURF_HD void eig_adjoint(const Eig& e, double k, double kx, double dm, double bcs, double bw,
-                                            double bx, double bex, double& bd, double& bk, double& bkx) {
-  double bp = 0.0, br = 0.0, sgn = 0.0;
-  if (e.br == 0) {
-    const double bsn = bw * e.ir - e.r * bx;
-    bp = -e.sn * bcs + e.cs * bsn;
-    br = -e.w * e.ir * bw - e.sn * bx;
-    sgn = -1.0;
-  } else if (e.br == 1) {
-    const double bsn = bw * e.ir + e.r * bx;
-    const double bfac = 0.5 * (bcs - bsn);
-    bp = -2.0 * e.fac * bfac + bex;
-    br = -e.w * e.ir * bw + e.sn * bx;
-    sgn = 1.0;
-  } else if (e.br == 2) {
-    bd += bw;  // w = d; the (measure-zero) dependence through r is dropped (finite one-sided value)
-  }
-  if (e.br < 2) {
-    br += dm * bp;
-    bd += e.r * bp;
-    const double h = sgn * br * e.ir;  // d r / d u * 2 = 1/r
-    bk += k * h;
-    bkx -= kx * h;
-  }
+// adjoint of one eigenfunction block: (bcs, bw, bx, bex) -> (bd, bk, bkx).  Both branches share
+// one formula through dcs = d cs/dp, dsn = d sn/dp and the sign of (k - kx).
+ADSURF_HD void eig_adjoint(const Eig& e, double k, double kx, double dm, double bcs, double bw, double bx,
+                           double bex, double& bd, double& bk, double& bkx) {
+  const double sg = e.lt ? -1.0 : 1.0;
+  const double bsn = bw * e.ir + sg * e.r * bx;
+  const double bp = e.dcs * bcs + e.dsn * bsn + (e.lt ? 0.0 : bex);
+  const double br = sg * e.sn * bx - e.w * e.ir * bw + dm * bp;
+  const double h = sg * br * e.ir;  // d u / d k = 2 sg k, d r / d u = 1 / (2 r)
+  // k == kx: w = d and the (measure-zero) dependence through r is dropped (finite one-sided value)
+  bd += e.pos ? e.r * bp : bw;
+  bk += e.pos ? k * h : 0.0;
+  bkx -= e.pos ? kx * h : 0.0;
 }
 
 // Reverse sweep through one layer: given row vector e (= E_{m+1}) and column s (= s_m, already
@@ -359,27 +488,43 @@ ADSURF_HD double sample_forward(const double* __restrict__ par, int L, const Sam
   Layer y;
   for (int m = L - 2; m >= 0; --m) {
     load_layer(y, par, L, m, z);
+    layer_eig_forward(y, z.k);
     layer_terms(y, z.k, z.k2, z.t2);
     row_apply(e, y);
   }
   return e[0];
 }
 
-// forward keeping E_{m+1} of every layer: slot m holds the row vector that multiplies CA_m.
-// `est` points at this thread's lane; element (m, comp) is est[(m*5+comp)*kStride]
-// (kStride = 32 in shared memory: lane-interleaved, conflict-free).
+// Storage policy for what the forward sweep keeps for the adjoint sweep, kSlot = 9 doubles per layer:
+// the row vector E_{m+1} (5) and the transcendental results of the P and S terms (2 + 2).  Element
+// (m, j) of this thread lives at p[(m*kSlot+j)*kStride] (kStride = 32: lane-interleaved, i.e.
+// conflict-free in shared memory and coalesced in global memory; kStride = 1 on the host).
+constexpr int kSlot = 9;
+
 template <int kStride>
-ADSURF_HD double sample_forward_store(const double* __restrict__ par, int L, const Sample& z,
-                                      double* __restrict__ est) {
+struct PlainStore {
+  double* p;
+  ADSURF_HD double ld(int i) const { return p[i * kStride]; }
+  ADSURF_HD void st(int i, double v) const { p[i * kStride] = v; }
+};
+
+// forward keeping E_{m+1} of every layer: slot m holds the row vector that multiplies CA_m.
+template <typename Store>
+ADSURF_HD double sample_forward_store(const double* __restrict__ par, int L, const Sample& z, const Store& est) {
   double e[5];
   Half h;
   load_half(h, par, L, z);
   half_space(h, z.k, z.k2, e);
   Layer y;
   for (int m = L - 2; m >= 0; --m) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i) est[(m * 5 + i) * kStride] = e[i];
     load_layer(y, par, L, m, z);
+    layer_eig_forward(y, z.k);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) est.st(m * kSlot + i, e[i]);
+    est.st(m * kSlot + 5, y.P.c0);
+    est.st(m * kSlot + 6, y.P.c1);
+    est.st(m * kSlot + 7, y.S.c0);
+    est.st(m * kSlot + 8, y.S.c1);
     layer_terms(y, z.k, z.k2, z.t2);
     row_apply(e, y);
   }
@@ -388,17 +533,28 @@ ADSURF_HD double sample_forward_store(const double* __restrict__ par, int L, con
 
 // Top-down adjoint sweep.  s_0 = seed * e_0; for every layer m (and finally the half-space, m = L-1)
 // hands (m, dDelta/dd_m, /dalpha_m, /dbeta_m, /drho_m) * seed to `sink`.  Returns dDelta/dk * seed.
-template <int kStride, typename Sink>
-ADSURF_HD double sample_adjoint(const double* __restrict__ par, int L, const Sample& z, double seed,
-                                const double* __restrict__ est, Sink& sink) {
+// The row vector of the next layer is fetched one iteration ahead (software prefetch).
+template <typename Store, typename Sink>
+ADSURF_HD double sample_adjoint(const double* __restrict__ par, int L, const Sample& z, double seed, const Store& est,
+                                Sink& sink) {
   double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
-  double e[5];
+  double e[5], en[kSlot];
   double gk = 0.0;
   Layer y;
+  if (L > 1) {
+#pragma unroll
+    for (int i = 0; i < kSlot; ++i) en[i] = est.ld(i);
+  }
   for (int m = 0; m <= L - 2; ++m) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) e[i] = est[(m * 5 + i) * kStride];
+    for (int i = 0; i < 5; ++i) e[i] = en[i];
+    y.P.c0 = en[5]; y.P.c1 = en[6]; y.S.c0 = en[7]; y.S.c1 = en[8];
+    if (m + 1 <= L - 2) {
+#pragma unroll
+      for (int i = 0; i < kSlot; ++i) en[i] = est.ld((m + 1) * kSlot + i);
+    }
     load_layer(y, par, L, m, z);
+    layer_eig_restore(y, z.k);
     layer_terms(y, z.k, z.k2, z.t2);
     const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2, z.t2);
     col_apply(s, y);

@@ -38,7 +38,7 @@ extern "C" {
 #define ADSURF_E_ARG -6      /* bad enum / flag */
 
 #define ADSURF_MAX_LAYERS 4096   /* forward kernels: model parameters must fit shared memory */
-#define ADSURF_MAX_ADJ_LAYERS 170 /* adjoint kernels: 40 B of state per (thread, layer), one warp per block minimum */
+#define ADSURF_MAX_ADJ_LAYERS 96 /* adjoint kernels: 72 B of state per (thread, layer), one warp per block minimum */
 
 /* operation ids for adsurf_workspace_bytes */
 enum adsurf_op {
@@ -127,6 +127,12 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
  * returns the achieved FP64 rate in TFLOP/s (2 flops per DFMA) in *tflops.  Synchronises the stream.
  * Used by bench.py for the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
 int adsurf_fp64_peak_probe(int iters, int repeats, double* tflops, double* ms, void* stream);
+
+/* Validation hook: evaluates the kernels' inline elementary functions on the device,
+ * out_rsqrt[i] = 1/sqrt(x[i]), out_expneg[i] = exp(-x[i]), out_sin/out_cos[i] = sin/cos(x[i]).
+ * Used by the GPU tests to bound their error against libm (no reference counterpart). */
+int adsurf_math_probe(const double* x, int n, double* out_rsqrt, double* out_expneg, double* out_sin,
+                      double* out_cos, void* stream);
 
 #ifdef __cplusplus
 }

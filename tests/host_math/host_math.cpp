@@ -21,11 +21,20 @@ struct HostSink {
 
 extern "C" {
 
+// elementary functions of the kernel header, for accuracy tests against libm
+void host_elementary(const double* x, int n, double* rs, double* ex, double* sn, double* cs) {
+  for (int i = 0; i < n; ++i) {
+    rs[i] = rsqrt_hd(x[i]);
+    ex[i] = exp_neg(x[i]);
+    sincos_fast(x[i], sn + i, cs + i);
+  }
+}
+
 // F[S,N], gradients reduced per model with seeds gF (null = 1), gc[S,N], optional Jacobians [S,N,L]
 int host_points(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
                 const double* c, const double* gF, int S, int L, int N, double* F, double* gd, double* ga, double* gb,
                 double* grho, double* gc, double* Jd, double* Ja, double* Jb, double* Jrho) {
-  std::vector<double> par(par_doubles(L)), est(5 * (L > 1 ? L - 1 : 1));
+  std::vector<double> par(par_doubles(L)), est(kSlot * (L > 1 ? L - 1 : 1));
   for (int s = 0; s < S; ++s) {
     for (int m = 0; m < L; ++m)
       stage_one(par.data(), L, m, d[s * L + m], alpha[s * L + m], beta[s * L + m], rho[s * L + m]);
@@ -34,14 +43,14 @@ int host_points(const double* d, const double* alpha, const double* beta, const 
       const size_t idx = (size_t)s * N + i;
       const double ic = 1.0 / c[idx];
       const Sample z = make_sample(omega_of_period(t[idx]), ic);
-      const double v = sample_forward_store<1>(par.data(), L, z, est.data());
+      const double v = sample_forward_store(par.data(), L, z, PlainStore<1>{est.data()});
       const double v2 = sample_forward(par.data(), L, z);
       if (v != v2 && !(v != v && v2 != v2)) return -1;
       F[idx] = v;
       HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L,
                     Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
                     Jrho ? Jrho + idx * L : nullptr};
-      const double gk = sample_adjoint<1>(par.data(), L, z, gF ? gF[idx] : 1.0, est.data(), sink);
+      const double gk = sample_adjoint(par.data(), L, z, gF ? gF[idx] : 1.0, PlainStore<1>{est.data()}, sink);
       if (gc) gc[idx] = -z.k * ic * gk;
     }
   }
@@ -52,7 +61,7 @@ int host_points(const double* d, const double* alpha, const double* beta, const 
 int host_grid(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
               const double* c, const double* gdet, int S, int L, int NF, int K, double* det, double* gd, double* ga,
               double* gb, double* grho) {
-  std::vector<double> par(par_doubles(L)), est(5 * (L > 1 ? L - 1 : 1));
+  std::vector<double> par(par_doubles(L)), est(kSlot * (L > 1 ? L - 1 : 1));
   for (int s = 0; s < S; ++s) {
     for (int m = 0; m < L; ++m)
       stage_one(par.data(), L, m, d[s * L + m], alpha[s * L + m], beta[s * L + m], rho[s * L + m]);
@@ -61,9 +70,9 @@ int host_grid(const double* d, const double* alpha, const double* beta, const do
       for (int f = 0; f < NF; ++f) {
         const size_t idx = ((size_t)s * K + k) * NF + f;
         const Sample z = make_sample(omega_of_period(t[s * NF + f]), 1.0 / c[s * K + k]);
-        det[idx] = sample_forward_store<1>(par.data(), L, z, est.data());
+        det[idx] = sample_forward_store(par.data(), L, z, PlainStore<1>{est.data()});
         HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L, nullptr, nullptr, nullptr, nullptr};
-        sample_adjoint<1>(par.data(), L, z, gdet ? gdet[idx] : 1.0, est.data(), sink);
+        sample_adjoint(par.data(), L, z, gdet ? gdet[idx] : 1.0, PlainStore<1>{est.data()}, sink);
       }
   }
   return 0;

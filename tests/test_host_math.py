@@ -98,3 +98,25 @@ def test_grid_single_sign_pattern(hm, name):
     assert err[~co].max() <= RTOL
     assert err[co].max() <= COINCIDENT_RTOL
     assert np.array_equal(np.sign(det[0]), np.sign(g["det64"]))
+
+
+def _ulps(new, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    return np.abs(new - ref) / np.spacing(np.abs(ref))
+
+
+def test_inline_elementary_functions_accuracy(hm):
+    """exp_neg / sincos_fast of adsurf_math.cuh against numpy's libm: a few ulp at most."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(0, 60, 20000), rng.uniform(0, 700, 5000), np.exp(rng.uniform(-30, 11.4, 20000)),
+                        np.array([0.0, 1e-300, 16.0, 59.999, 60.0, 99999.9, 1.0e5, 3.0e7])])
+    n = len(x)
+    rs, ex, sn, cs = (np.empty(n) for _ in range(4))
+    hm.host_elementary(P(C(x)), n, P(rs), P(ex), P(sn), P(cs))
+    pos = x > 0
+    assert _ulps(rs[pos], 1 / np.sqrt(x[pos])).max() <= 2
+    m = x <= 700
+    assert _ulps(ex[m], np.exp(-x[m])).max() <= 2
+    # sin/cos: error measured against the larger of the two (the reduction error is absolute)
+    err = np.maximum(np.abs(sn - np.sin(x)), np.abs(cs - np.cos(x))) / np.spacing(1.0)
+    assert err.max() <= 2
