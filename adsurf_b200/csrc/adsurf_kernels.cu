@@ -51,9 +51,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 struct ReduceSink {
   double* acc;
   int L, lane;
-  bool active;
   __device__ __forceinline__ void operator()(int m, double gd, double ga, double gb, double gr) const {
-    if (!active) { gd = 0.0; ga = 0.0; gb = 0.0; gr = 0.0; }
     const bool hi16 = lane & 16, hi8 = lane & 8;
     // xor 16: lower half keeps (gd, ga), upper half keeps (gb, gr)
     const double k0 = hi16 ? gb : gd, k1 = hi16 ? gr : ga;
@@ -171,8 +169,10 @@ __global__ void k_minmax_reduce(const double* __restrict__ pmax, const double* _
 // E-store in global memory (L2-resident working set): cache-global loads/stores, lane-interleaved
 struct GlobalStore {
   double* p;
-  __device__ __forceinline__ double ld(int i) const { return __ldcg(p + i * kWarp); }
-  __device__ __forceinline__ void st(int i, double v) const { __stcg(p + i * kWarp, v); }
+  typedef double* Slot;
+  __device__ __forceinline__ Slot slot(int m) const { return p + (size_t)m * (kSlot * kWarp); }
+  __device__ __forceinline__ static double ld(Slot q, int j) { return __ldcg(q + j * kWarp); }
+  __device__ __forceinline__ static void st(Slot q, int j, double v) { __stcg(q + j * kWarp, v); }
 };
 
 // Dense grid, fused forward + adjoint with per-model gradient reduction.  Persistent: each block
@@ -182,8 +182,8 @@ struct GlobalStore {
 // kGlobal = true: they live in a per-resident-warp slab of global memory that stays in L2
 //   (148 SMs x 12..16 warps x 24 KB = 43..58 MB of the 126 MB L2), so residency is bounded by
 //   registers only and the FP64 pipe sees 3-4 warps per scheduler instead of 2.
-template <bool kGlobal, int kMinBlocks>
-__global__ void __launch_bounds__(128, kMinBlocks)
+template <bool kGlobal, int kThreads, int kMaxRegs>
+__global__ void __maxnreg__(kMaxRegs)
 k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const double* __restrict__ beta,
            const double* __restrict__ rho, const double* __restrict__ t, const double* __restrict__ c,
            const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp, int total_vblocks,
@@ -216,8 +216,9 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
         const double ic = 1.0 / c[(size_t)s * K + k];
         const Sample z = make_sample(omega0, ic);
         const size_t idx = ((size_t)s * K + k) * NF + fc;
-        const double seed = gdet ? gdet[idx] : 1.0;
-        ReduceSink sink{acc, L, lane, active};
+        // inactive lanes (period tile overhang) replay a valid sample with a zero seed
+        const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
+        ReduceSink sink{acc, L, lane};
         double v;
         if (kGlobal) {
           const GlobalStore st{estp};
@@ -372,8 +373,8 @@ __global__ void __launch_bounds__(128) k_points_bwd(const double* __restrict__ d
                      Jrho ? Jrho + idx * L : nullptr, active};
         gk = sample_adjoint(par, L, z, seed, store, sink);
       } else {
-        ReduceSink sink{acc, L, lane, active};
-        gk = sample_adjoint(par, L, z, seed, store, sink);
+        ReduceSink sink{acc, L, lane};
+        gk = sample_adjoint(par, L, z, active ? seed : 0.0, store, sink);  // overhang lanes: zero seed
       }
       if (gc && active) gc[idx] = -z.k * ic * gk;  // k = omega0 / c
     }
@@ -453,7 +454,7 @@ inline size_t adj_smem(int L, int wpb) {
 // Where the dense adjoint keeps its per-layer row vectors: 0 = shared memory (2 blocks of 4 warps per
 // SM at 20 layers), 1 / 2 = L2-resident global slab with 3 / 4 blocks of 4 warps per SM.
 // Overridable for experiments with ADSURF_GRID_BWD=smem|g3|g4 (read once).
-enum { kBwdSmem = 0, kBwdG3 = 1, kBwdG4 = 2 };
+enum { kBwdSmem = 0, kBwdG3 = 1, kBwdG4 = 2, kBwdH6 = 3, kBwdH7 = 4, kBwdH8 = 5 };
 inline int bwd_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -462,19 +463,24 @@ inline int bwd_mode() {
     if (e && !strcmp(e, "g3")) mode = kBwdG3;
     if (e && !strcmp(e, "g4")) mode = kBwdG4;
     if (e && !strcmp(e, "smem")) mode = kBwdSmem;
+    if (e && !strcmp(e, "h6")) mode = kBwdH6;
+    if (e && !strcmp(e, "h7")) mode = kBwdH7;
+    if (e && !strcmp(e, "h8")) mode = kBwdH8;
   }
   return mode;
 }
-constexpr int kMaxResidentBlocks = 160 * 4;  // upper bound on co-resident adjoint blocks (global E-store slabs)
+constexpr int kMaxResidentWarps = 160 * 16;  // upper bound on co-resident adjoint warps (global store slabs)
+
+inline int bwd_wpb_global() { return bwd_mode() >= kBwdH6 ? 2 : 4; }
 
 inline size_t bwd_estore_bytes(int L) {
-  return bwd_mode() == kBwdSmem ? 0 : (size_t)kMaxResidentBlocks * 4 * est_bytes_per_warp(L);
+  return bwd_mode() == kBwdSmem ? 0 : (size_t)kMaxResidentWarps * est_bytes_per_warp(L);
 }
 
 inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
   GridPlan gp;
   gp.nft = (NF + kWarp - 1) / kWarp;
-  gp.wpb = adjoint ? (bwd_mode() == kBwdSmem ? adj_wpb(L) : 4) : 8;
+  gp.wpb = adjoint ? (bwd_mode() == kBwdSmem ? adj_wpb(L) : bwd_wpb_global()) : 8;
   const long long target = (long long)kNumSM * 8 * 24;  // ~24 waves of 8 warps per SM
   long long nchunk = (target + (long long)S * gp.nft - 1) / ((long long)S * gp.nft);
   const int maxchunks = K >= 16 ? K / 8 : 1;
@@ -705,14 +711,17 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
       return ADSURF_E_CUDA;                                                                                      \
     }                                                                                                            \
     long long grid = (long long)occ * nsm;                                                                       \
-    if (grid > kMaxResidentBlocks) grid = kMaxResidentBlocks;                                                    \
+    if (grid * gp.wpb > kMaxResidentWarps) grid = kMaxResidentWarps / gp.wpb;                                    \
     if (grid > total_vb) grid = total_vb;                                                                        \
     KERN<<<(unsigned)grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gdet, L, NF, K, gp, (int)total_vb,    \
                                                 det, (double*)ws, estore);                                       \
   } while (0)
-  if (mode == kBwdG3) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 3>));
-  else if (mode == kBwdG4) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 4>));
-  else ADSURF_LAUNCH_BWD((k_grid_bwd<false, 1>));
+  if (mode == kBwdG3) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 128, 168>));        // 3 x 4 = 12 warps / SM
+  else if (mode == kBwdG4) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 128, 128>));   // 16 warps / SM
+  else if (mode == kBwdH6) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 64, 168>));    // 6 x 2 = 12
+  else if (mode == kBwdH7) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 64, 144>));    // 7 x 2 = 14
+  else if (mode == kBwdH8) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 64, 152>));    // 6 x 2 = 12 (fewer regs)
+  else ADSURF_LAUNCH_BWD((k_grid_bwd<false, 128, 232>));
 #undef ADSURF_LAUNCH_BWD
   if (check_launch()) return ADSURF_E_CUDA;
   k_grad_reduce<<<S, 128, 0, st>>>((const double*)ws, L, gp.bpm, gd, galpha, gbeta, grho);

@@ -193,6 +193,32 @@ ADSURF_HD void eig_trans(Eig& e) {
   }
 }
 
+// forward sweep: transcendental + derived terms inside one (warp-uniform) branch, no selects
+ADSURF_HD void eig_forward(Eig& e, double dm) {
+  if (e.lt) {
+    sincos_fast(e.p, &e.c0, &e.c1);
+    e.sn = e.c0;
+    e.cs = e.c1;
+    e.dcs = -e.c0;
+    e.dsn = e.c1;
+    e.ex = 0.0;
+    e.eh = 1.0;
+    e.x = -e.r * e.sn;
+  } else {
+    e.c0 = exp_neg(e.p);
+    e.c1 = 0.0;
+    const double fac = (e.p < 16.0) ? e.c0 * e.c0 : 0.0;
+    e.cs = 0.5 + 0.5 * fac;
+    e.sn = 0.5 - 0.5 * fac;
+    e.dcs = -fac;
+    e.dsn = fac;
+    e.ex = e.p;  // p = 0 when k == kx
+    e.eh = (e.p < 60.0) ? e.c0 : 0.0;
+    e.x = e.r * e.sn;
+  }
+  e.w = e.pos ? e.sn * e.ir : dm;  // k == kx: w = d (reference :135)
+}
+
 ADSURF_HD void eig_finish(Eig& e, double dm) {
   if (e.lt) {
     e.sn = e.c0;
@@ -227,20 +253,20 @@ struct Layer {
 ADSURF_HD void layer_eig_forward(Layer& y, double k) {
   eig_setup(y.P, k, y.ka, y.dm);
   eig_setup(y.S, k, y.kb, y.dm);
-  eig_trans(y.P);
-  eig_trans(y.S);
+  eig_forward(y.P, y.dm);
+  eig_forward(y.S, y.dm);
 }
 
 // adjoint sweep: restore them from the store (c0, c1 already set by the caller)
 ADSURF_HD void layer_eig_restore(Layer& y, double k) {
   eig_setup(y.P, k, y.ka, y.dm);
   eig_setup(y.S, k, y.kb, y.dm);
-}
-
-// t2 = -2 k2 (hoisted per sample); needs P, S set up (layer_eig_forward / layer_eig_restore)
-ADSURF_HD void layer_terms(Layer& y, double k, double k2, double t2) {
   eig_finish(y.P, y.dm);
   eig_finish(y.S, y.dm);
+}
+
+// t2 = -2 k2 (hoisted per sample); needs P, S complete (layer_eig_forward / layer_eig_restore)
+ADSURF_HD void layer_terms(Layer& y, double k, double k2, double t2) {
   y.a0 = (y.P.ex + y.S.ex < 60.0) ? y.P.eh * y.S.eh : 0.0;
   y.gam = y.gk * k2;
   y.g1 = y.gam - 1.0;
@@ -504,8 +530,10 @@ constexpr int kSlot = 9;
 template <int kStride>
 struct PlainStore {
   double* p;
-  ADSURF_HD double ld(int i) const { return p[i * kStride]; }
-  ADSURF_HD void st(int i, double v) const { p[i * kStride] = v; }
+  typedef double* Slot;
+  ADSURF_HD Slot slot(int m) const { return p + (size_t)m * (kSlot * kStride); }
+  ADSURF_HD static double ld(Slot q, int j) { return q[j * kStride]; }
+  ADSURF_HD static void st(Slot q, int j, double v) { q[j * kStride] = v; }
 };
 
 // forward keeping E_{m+1} of every layer: slot m holds the row vector that multiplies CA_m.
@@ -519,12 +547,13 @@ ADSURF_HD double sample_forward_store(const double* __restrict__ par, int L, con
   for (int m = L - 2; m >= 0; --m) {
     load_layer(y, par, L, m, z);
     layer_eig_forward(y, z.k);
+    const typename Store::Slot q = est.slot(m);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) est.st(m * kSlot + i, e[i]);
-    est.st(m * kSlot + 5, y.P.c0);
-    est.st(m * kSlot + 6, y.P.c1);
-    est.st(m * kSlot + 7, y.S.c0);
-    est.st(m * kSlot + 8, y.S.c1);
+    for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
+    Store::st(q, 5, y.P.c0);
+    Store::st(q, 6, y.P.c1);
+    Store::st(q, 7, y.S.c0);
+    Store::st(q, 8, y.S.c1);
     layer_terms(y, z.k, z.k2, z.t2);
     row_apply(e, y);
   }
@@ -533,26 +562,24 @@ ADSURF_HD double sample_forward_store(const double* __restrict__ par, int L, con
 
 // Top-down adjoint sweep.  s_0 = seed * e_0; for every layer m (and finally the half-space, m = L-1)
 // hands (m, dDelta/dd_m, /dalpha_m, /dbeta_m, /drho_m) * seed to `sink`.  Returns dDelta/dk * seed.
-// The row vector of the next layer is fetched one iteration ahead (software prefetch).
+// The stored values of the next layer are fetched one iteration ahead into the other of two
+// register buffers (the loop is unrolled by two so the buffers swap without copies).
 template <typename Store, typename Sink>
 ADSURF_HD double sample_adjoint(const double* __restrict__ par, int L, const Sample& z, double seed, const Store& est,
                                 Sink& sink) {
   double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
-  double e[5], en[kSlot];
+  double bufA[kSlot], bufB[kSlot];
   double gk = 0.0;
-  Layer y;
-  if (L > 1) {
+  auto fetch = [&](int m, double (&buf)[kSlot]) {
+    const typename Store::Slot q = est.slot(m);
 #pragma unroll
-    for (int i = 0; i < kSlot; ++i) en[i] = est.ld(i);
-  }
-  for (int m = 0; m <= L - 2; ++m) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i) e[i] = en[i];
-    y.P.c0 = en[5]; y.P.c1 = en[6]; y.S.c0 = en[7]; y.S.c1 = en[8];
-    if (m + 1 <= L - 2) {
-#pragma unroll
-      for (int i = 0; i < kSlot; ++i) en[i] = est.ld((m + 1) * kSlot + i);
-    }
+    for (int i = 0; i < kSlot; ++i) buf[i] = Store::ld(q, i);
+  };
+  auto layer = [&](int m, const double (&cur)[kSlot], double (&nxt)[kSlot]) {
+    if (m + 1 <= L - 2) fetch(m + 1, nxt);
+    Layer y;
+    const double e[5] = {cur[0], cur[1], cur[2], cur[3], cur[4]};
+    y.P.c0 = cur[5]; y.P.c1 = cur[6]; y.S.c0 = cur[7]; y.S.c1 = cur[8];
     load_layer(y, par, L, m, z);
     layer_eig_restore(y, z.k);
     layer_terms(y, z.k, z.k2, z.t2);
@@ -562,16 +589,24 @@ ADSURF_HD double sample_adjoint(const double* __restrict__ par, int L, const Sam
     const double ia = par[P_IA * L + m], ib = par[P_IB * L + m];
     // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2
     sink(m, g.d, -y.ka * ia * g.ka, -y.kb * ib * g.kb + 2.0 * y.gk * ib * g.gammk, g.rho);
+  };
+  if (L > 1) fetch(0, bufA);
+  int m = 0;
+  for (; m + 1 <= L - 2; m += 2) {
+    layer(m, bufA, bufB);
+    layer(m + 1, bufB, bufA);
   }
+  if (m <= L - 2) layer(m, bufA, bufB);
   // half-space: dDelta/dE_hs = s_{L-1}
+  double e[5];
   Half h;
   load_half(h, par, L, z);
   half_space(h, z.k, z.k2, e);
   const LayerGrad g = half_adjoint(h, e, s, z.k, z.k2);
   gk += g.k;
-  const int m = L - 1;
-  const double ia = par[P_IA * L + m], ib = par[P_IB * L + m];
-  sink(m, 0.0, -h.ka * ia * g.ka, -h.kb * ib * g.kb + 2.0 * h.gammk * ib * g.gammk, g.rho);
+  const int mh = L - 1;
+  const double ia = par[P_IA * L + mh], ib = par[P_IB * L + mh];
+  sink(mh, 0.0, -h.ka * ia * g.ka, -h.kb * ib * g.kb + 2.0 * h.gammk * ib * g.gammk, g.rho);
   return gk;
 }
 
