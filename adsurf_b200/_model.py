@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import ops
+from . import _dist, ops
 from ._utils import gen_model, gen_model1, ifunc_list, list2numpy, numpy2tensor
 
 try:  # progress bars are optional
@@ -119,6 +119,8 @@ class multi_cal_grad(_cal_grad_base):
         self.damp_horizontal = damp_horizontal
         self.L_vertical = _second_difference(self.b.shape[1], self.device)
         self.L_horizontal = _second_difference(self.b.shape[0], self.device)
+        self.shard = None      # (lo, hi, S) when this module holds rows lo:hi of a sharded ensemble
+        self.coupling = None   # horizontal-damping rows owned by other ranks (added to the backward seed)
         self.normalized = normalized
         self.compress = compress
         self.compress_method = compress_method
@@ -137,8 +139,21 @@ class multi_cal_grad(_cal_grad_base):
             mv = self.damp_vertical * torch.matmul(self.b, self.L_vertical.T) / nL
             out = out + torch.sum(torch.abs(mv), dim=1)
         if self.damp_horizontal > 0:
-            mh = self.damp_horizontal * torch.matmul(self.L_horizontal, self.b) / nL
-            out = out + torch.sum(torch.abs(mh), dim=1)
+            if self.shard is None:
+                mh = self.damp_horizontal * torch.matmul(self.L_horizontal, self.b) / nL
+                out = out + torch.sum(torch.abs(mh), dim=1)
+            else:
+                # sharded ensemble: the second difference across models needs the neighbours' Vs.
+                # All ranks hold the same full operator; the other ranks' rows enter as constants and
+                # the rows owned elsewhere are returned through `self.coupling` so that backward
+                # still sees d(sum_r |L_h b|_r)/d(b_local) for every r this rank touches.
+                lo, hi, S = self.shard
+                with torch.no_grad():
+                    b_all = _dist.all_gather_rows(self.b.detach(), S)
+                b_full = torch.cat((b_all[:lo], self.b, b_all[hi:]), dim=0)
+                mh = torch.sum(torch.abs(self.damp_horizontal * torch.matmul(self.L_horizontal, b_full) / nL), dim=1)
+                out = out + mh[lo:hi]
+                self.coupling = torch.sum(mh[:lo]) + torch.sum(mh[hi:])
         return out
 
 
@@ -342,9 +357,15 @@ class multi_inversion:
         t64 = lambda x: numpy2tensor(list2numpy(x)).to(dev)
         init_vs = list2numpy(im["vs"])
         b, a, rho, d = t64(init_vs), t64(im["vp"]), t64(im["rho"]), t64(im["thick"])
-        S, L = b.shape
+        S_all, L = b.shape
         obs = list2numpy(self.pvs_obs)
         tlist, vlist = t64(obs[:, :, 0]).contiguous(), t64(obs[:, :, 1]).contiguous()
+        # one process per GPU: this rank owns models lo:hi of the ensemble
+        sharded = _dist.is_sharded() and S_all >= _dist.rank_world()[1]
+        lo, hi = _dist.shard_bounds(S_all) if sharded else (0, S_all)
+        b_first = b[0].clone()
+        b, a, rho, d, tlist, vlist = (x[lo:hi].contiguous() for x in (b, a, rho, d, tlist, vlist))
+        S = hi - lo
         ip, mp = self.inv_param, self.model_param
         clist = t64(mp.clist).reshape(1, -1)
         Clist = clist.expand(S, -1).contiguous()
@@ -355,6 +376,9 @@ class multi_inversion:
         calculator = multi_cal_grad(d, a, b, rho, Clist, ip.damp_vertical, ip.damp_horizontal, ip.compress,
                                     ip.normalized, ip.compress_method, inversion_method, mp.initialize_method,
                                     mp.vp_vs_ratio, self.AK135_data, device=dev)
+        if sharded:
+            calculator.shard = (lo, hi, S_all)
+            calculator.L_horizontal = _second_difference(S_all, dev)
         if ip.optimizer != "Adam":
             raise NameError("The input optimizer {} can not find in Pytorch".format(ip.optimizer))
         optimizer = torch.optim.Adam(calculator.parameters(), lr=ip.lr)
@@ -366,15 +390,18 @@ class multi_inversion:
         if self.vsrange_sign == "mul":
             lower_b, upper_b = self.vsrange[0] * b, self.vsrange[1] * b
         else:  # the reference offsets the FIRST model's Vs for every model (_model.py:577-578)
-            lower_b = b[0] * torch.ones_like(b) + self.vsrange[0]
-            upper_b = b[0] * torch.ones_like(b) + self.vsrange[1]
+            lower_b = b_first * torch.ones_like(b) + self.vsrange[0]
+            upper_b = b_first * torch.ones_like(b) + self.vsrange[1]
         vs_and_thick = inversion_method.lower() == "vs-and-thick"
         b0 = b.clone()
         ones = torch.ones(S, dtype=torch.float64, device=dev)
         for j in tqdm(range(iteration), disable=not getattr(ip, "progress", False)):
             loss = calculator(vlist, tlist)
             optimizer.zero_grad()
-            loss.backward(ones)
+            if calculator.coupling is not None:  # horizontal-damping rows owned by other ranks
+                (loss.sum() + calculator.coupling).backward()
+            else:
+                loss.backward(ones)
             with torch.no_grad():
                 pb = calculator.b
                 if not vs_and_thick:  # NaN repair exists only on this branch in the reference (:624-626)
@@ -390,6 +417,11 @@ class multi_inversion:
             scheduler.step()
             loss_list[j] = loss.detach()
         loss_list = torch.where(torch.isnan(loss_list), torch.full_like(loss_list, 10.0), loss_list)
+        if sharded:  # the only exchange of the run: per-model losses and iterates of every rank
+            loss_list = _dist.all_gather_rows(loss_list, S_all, dim=1)
+            iter_vs = _dist.all_gather_rows(iter_vs, S_all, dim=1)
+            iter_thick = _dist.all_gather_rows(iter_thick, S_all, dim=1)
+            S = S_all
         loss_np = loss_list.cpu().numpy()
         iter_vs = iter_vs.cpu().numpy()
         iter_thick = iter_thick.cpu().numpy()
