@@ -1,0 +1,134 @@
+"""GPU tests of the reference-facing API (BASELINE configs 1-4 at their real sizes, short runs):
+`inversion(...)`, `init_model_MonteCarlo`, `cal_determinant`, through adsurf_b200._ADsurf."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import assert_det_close, load
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    import adsurf_b200._ADsurf as A
+    return A
+
+
+def _mp6(A):
+    return A.Model_param(dc=0.001, vmin=2, vmax=3.2, tmin=1 / 10, tmax=5, layering_method="LN",
+                         initialize_method="Brocher", layering_ratio=1.2, depth_factor=3.8, layer_number=6,
+                         vp_vs_ratio=2.45, rho=2)
+
+
+def test_config1_determinant_image(api):
+    """cal_determinant on the 6-layer model: [1201 x 500] image, sign pattern vs the oracle on a sub-grid"""
+    from oracle import dltar_oracle as O
+    g = load("grid_single_m6")
+    true_model = api.True_model(_mp6(api), thick=g["d"], vs=g["b"], vp=g["a"], rho=g["rho"])
+    F = true_model._cal_determinant(sampling_method="log-wavelength", sampling_num=500)
+    assert tuple(F.shape) == (1200, 500) or tuple(F.shape) == (1201, 500)
+    vl, tl = np.asarray(true_model.vlist), np.asarray(true_model.tlist)
+    ks, fs = np.arange(5, len(vl), 40), np.arange(0, 500, 25)   # off the layer velocities (k % 10 == 5)
+    ref = O.det_grid(vl[ks], tl[fs], g["d"], g["a"], g["b"], g["rho"]).numpy()
+    sub = F.numpy()[np.ix_(ks, fs)]
+    assert_det_close(sub, ref, axis=0)
+    assert np.array_equal(np.sign(sub), np.sign(ref))
+
+
+def test_config2_single_model_inversion_head(api):
+    """full-size config 2 (N=500 picks, K=1200 trial c, vs-and-thick, LN clipping): first iterations
+    against the reference's shipped float32 trajectory (examples/data/00_increase_layer/output/data/model.json)"""
+    s = load("shipped_fixtures")
+    obs = s["disper_00"]
+    mp = _mp6(api)
+    ip = api.inv_param(inversion_method="vs-and-thick", compress=True, compress_method="exp", normalized=True, lr=0.005,
+                       damp_vertical=0.002, damp_horizontal=0, iteration=8, step_size=400, gamma=0.75)
+    init = api.Init_model(model_param=mp, pvs_obs=obs, thick=[0.4, 0.5, 0.5, 0.5, 0.5, 0.5])
+    np.testing.assert_allclose(init.init_model["vs"], s["c2_init_vs"], rtol=1e-6)
+    np.testing.assert_allclose(init.init_model["thick"], s["c2_init_thick"], rtol=1e-6)
+    inv = api.inversion(model_param=mp, inv_param=ip, init_model=init, pvs_obs=obs, vsrange_sign="mul",
+                        vsrange=[0.1, 2], AK135_data=[], device="Cuda")
+    np.testing.assert_allclose(inv.inv_process["loss"][:8], s["c2_loss_head"][:8], atol=3e-5)
+    np.testing.assert_allclose(np.asarray(inv.inv_process["iter_vs"])[:8], s["c2_iter_vs_head"][:8], atol=3e-5)
+    np.testing.assert_allclose(np.asarray(inv.inv_process["iter_thick"])[:8], s["c2_iter_thick_head"][:8], atol=3e-5)
+
+
+def test_config3_ensemble_inversion_and_prescreen(api):
+    """100-model multimodal sandwich inversion (3 layers, 174 unlabelled picks, 200 trial c): Monte-Carlo
+    pre-screen and the first DMF losses against the oracle; loss decreases over a short run."""
+    from oracle import dltar_oracle as O
+    s = load("shipped_fixtures")
+    obs = s["disper_01_obs"]
+    mp = api.Model_param(dc=0.001, vmin=0.2, vmax=0.4, tmin=1 / 100, tmax=1 / 5, layering_method="LN",
+                         initialize_method="Constant", layering_ratio=2.5, depth_factor=2.5, layer_number=3,
+                         vp_vs_ratio=2.45, rho=2, fundamental_range=[1 / 37, 1 / 8])
+    ip = api.inv_param(inversion_method="vs-and-thick", compress=True, compress_method="exp", normalized=True, lr=0.001,
+                       damp_vertical=0.0, damp_horizontal=0.0, iteration=12, step_size=200, gamma=0.75)
+    init = api.Init_model(model_param=mp, pvs_obs=obs, thick=np.array([0.005, 0.005, 0.005]))
+    np.random.seed(123)
+    mc = api.init_model_MonteCarlo(mp, init, sampling_num=100, sampling_method="normal", vsrange_sign="plus",
+                                   vsrange=[-0.1, 0.2], sigma_vs=20, sigma_thick=20)
+    M = mc.MonteCarlo_model
+    assert M["vs"].shape == (100, 3) and len(M["loss"]) == 100
+    # pre-screen value of three models against the oracle: mean |F / (max - min)|
+    for i in (0, 7, 99):
+        F = O.det_points(obs[:, 1], obs[:, 0], M["thick"][i], M["vp"][i], M["vs"][i], M["rho"][i])
+        det = O.det_grid(mp.clist, obs[:, 0], M["thick"][i], M["vp"][i], M["vs"][i], M["rho"][i])
+        ref = float(torch.mean(torch.abs(F / (det.max(0).values - det.min(0).values))))
+        assert abs(M["loss"][i] - ref) <= 1e-9 * max(ref, 1.0)
+    for key in ("vs", "vp", "thick", "rho"):
+        init.init_model[key] = M[key]
+    S = 100
+    pvs = np.ones((S, obs.shape[0], 2)) * obs[:, :2]
+    inv = api.inversion(model_param=mp, inv_param=ip, init_model=init, pvs_obs=pvs, vsrange_sign="plus",
+                        vsrange=[-0.8, 0.8], AK135_data=[], device="cuda")
+    loss = np.asarray(inv.inv_process["loss"])
+    assert loss.shape == (12, S) and np.isfinite(loss).all()
+    ref0 = O.dmf_loss(pvs[:3, :, 1], pvs[:3, :, 0], np.tile(mp.clist, (3, 1)), torch.tensor(M["thick"][:3]),
+                      torch.tensor(M["vs"][:3]), a=torch.tensor(M["vp"][:3]), rho=torch.tensor(M["rho"][:3]),
+                      initial_method="Constant", vp_vs_ratio=2.45).numpy()
+    np.testing.assert_allclose(loss[0, :3], ref0, rtol=1e-9)
+    assert np.median(loss[-1]) < np.median(loss[0])
+    assert np.asarray(inv.inv_model["vs"]).shape == (S, 3)
+
+
+def test_config4_friul_ensemble_step_and_sensitivity(api):
+    """FRIUL7W 20-layer ensemble of 1024 models, N=300 picks, compress=False: one optimiser step; plus the
+    30-layer sensitivity kernels at the 300 shipped picks (notebook 02_2)."""
+    from oracle import dltar_oracle as O
+    from adsurf_b200 import ops
+    from adsurf_b200.workload import config5_ensemble, friul7w
+    s = load("shipped_fixtures")
+    obs = s["disper_02"]
+    d, a, b, rho = config5_ensemble(1024, 20, seed=0)
+    mp = api.Model_param(dc=0.01, vmin=0.5, vmax=5.0, tmin=1 / 20, tmax=5, layering_method="None",
+                         initialize_method="Brocher", layering_ratio=1.2, depth_factor=2, layer_number=6,
+                         vp_vs_ratio=2.45, rho=2)
+    ip = api.inv_param(inversion_method="vs", compress=False, compress_method="exp", normalized=True, lr=0.03,
+                       damp_vertical=0.0, damp_horizontal=0.0, iteration=3, step_size=200, gamma=0.75)
+    init = api.Init_model(model_param=mp, pvs_obs=obs, vp=a[0], vs=b[0], rho=rho[0], thick=d[0])
+    for key, val in (("vs", b), ("vp", a), ("thick", d), ("rho", rho)):
+        init.init_model[key] = val
+    pvs = np.ones((1024, obs.shape[0], 2)) * obs[:, :2]
+    inv = api.inversion(model_param=mp, inv_param=ip, init_model=init, pvs_obs=pvs, vsrange_sign="mul",
+                        vsrange=[0.1, 2.5], device="cuda:0")
+    loss = np.asarray(inv.inv_process["loss"])
+    assert loss.shape == (3, 1024) and np.isfinite(loss).all()
+    ref = O.dmf_loss(pvs[:2, :, 1], pvs[:2, :, 0], None, torch.tensor(d[:2]), torch.tensor(b[:2]), compress=False).numpy()
+    np.testing.assert_allclose(loss[0, :2], ref, rtol=1e-9)
+    # sensitivity kernels dc/dVs on the 30-layer model
+    th, vp, vs, rr = friul7w(30)
+    out = ops.sensitivity(obs[:, 1], obs[:, 0], th, vp, vs, rr)
+    assert tuple(out["dc_dvs"].shape) == (300, 30) and torch.isfinite(out["dc_dvs"]).all()
+    tv, tc = torch.tensor(vs, requires_grad=True), torch.tensor(obs[:40, 1].copy(), requires_grad=True)
+    F = O.det_points(tc, obs[:40, 0], th, vp, tv, rr)
+    eye = torch.eye(40, dtype=torch.float64)
+    Jb = torch.autograd.grad(F, tv, grad_outputs=(eye,), retain_graph=True, is_grads_batched=True)[0]
+    Jc = torch.diagonal(torch.autograd.grad(F, tc, grad_outputs=(eye,), is_grads_batched=True)[0])
+    kern = (-Jb / Jc[:, None]).numpy()
+    got = out["dc_dvs"][:40].cpu().numpy()
+    scale = np.max(np.abs(kern), axis=1, keepdims=True)
+    assert np.max(np.abs(got - kern) / scale) < 1e-6   # roots are float32-accurate: dF/dc is well away from 0
