@@ -260,6 +260,30 @@ def main():
     # sustained FP64 peak right after the sweep (clocks settled under load)
     peak_tf_after, _ = _capi.fp64_peak_probe(iters=4096, repeats=3, device=dev)
 
+    # ---------------- secondary: forward-only dense sweep with fused max/min (what every DMF iteration runs
+    # K times more often than the pointwise adjoint), same grid, det not materialised
+    ws_f = torch.empty(max(lib.adsurf_workspace_bytes(_capi.OP_GRID_FWD, S, L, NF, K_TRIAL), 8), dtype=torch.uint8,
+                       device=dev)
+    cmax = torch.empty((S, NF), dtype=torch.float64, device=dev)
+    cmin = torch.empty((S, NF), dtype=torch.float64, device=dev)
+
+    def fwd_step():
+        rc = lib.adsurf_det_grid_fwd(P(d), P(a), P(b), P(rho), P(t), P(c), S, L, NF, K_TRIAL, None, P(cmax), P(cmin),
+                                     None, P(ws_f), ws_f.numel(), sp)
+        if rc != 0:
+            raise RuntimeError(f"adsurf_det_grid_fwd failed: {rc}")
+
+    for _ in range(2):
+        fwd_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        fwd_step()
+    e1.record(stream)
+    barrier()
+    ms_fwd = max_over_ranks(e0.elapsed_time(e1))
+    fwd_value = world * n_samples * args.steps / (ms_fwd * 1e-3)
+
     # ---------------- end-to-end leg: host buffers -> C ABI -> host results
     hgr = [torch.empty((S, L), dtype=torch.float64).pin_memory() for _ in range(4)]
     dbuf = [torch.empty_like(x, device=dev) for x in host]
@@ -310,6 +334,11 @@ def main():
                          "hbm_bytes_per_sample_algorithmic": 8,
                          "note": "FP64-pipe bound (~600 FLOP/B); HBM and tensor rooflines do not bind this path"},
             "clocks": clocks,
+            "forward_only": {"value": fwd_value, "unit": UNIT, "ms_per_step": ms_fwd / args.steps,
+                             "call": "adsurf_det_grid_fwd with fused max/min over c (det not materialised)",
+                             "flop_per_sample": flop_per_sample(L) // 3,
+                             "achieved_tflops": fwd_value / world * (flop_per_sample(L) // 3) / 1e12,
+                             "frac_of_measured_fp64_peak": fwd_value / world * (flop_per_sample(L) // 3) / 1e12 / peak_tf},
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = time_cpu()
