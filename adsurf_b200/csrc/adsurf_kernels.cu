@@ -95,12 +95,42 @@ __device__ __forceinline__ void stage_params(double* __restrict__ par, const dou
 // ------------------------------------------------------------------------------------------
 struct GridPlan {
   int nft;     // period tiles of 32 per model
+  int wpb;     // warps per block = period tiles handled by one block
+  int nfg;     // period-tile groups per model = ceil(nft / wpb)
   int nchunk;  // trial-velocity chunks per model
   int chunk;   // trial velocities per chunk
-  int units;   // nft * nchunk warp work units per model
-  int wpb;     // warps per block
-  int bpm;     // blocks per model
+  int bpm;     // blocks per model = nchunk * nfg
+  int tc;      // trial velocities per shared-memory table fill
 };
+
+// Block = (model s, velocity chunk ch, period group fg); warp w owns period tile fg*wpb + w (32 periods,
+// one per lane) and walks the chunk's trial velocities.  Every tc velocities the block refills the
+// shared table of per-(velocity, layer) quantities (TableSource in adsurf_math.cuh).
+struct BlockCoord {
+  int s, ch, fg, blk;
+};
+__device__ __forceinline__ BlockCoord block_coord(int vb, const GridPlan& gp) {
+  BlockCoord bc;
+  bc.s = vb / gp.bpm;
+  bc.blk = vb - bc.s * gp.bpm;
+  bc.ch = bc.blk / gp.nfg;
+  bc.fg = bc.blk - bc.ch * gp.nfg;
+  return bc;
+}
+
+__device__ __forceinline__ void fill_table(double* __restrict__ tab, int* __restrict__ flags, double* __restrict__ ics,
+                                           const double* __restrict__ par, int L, const double* __restrict__ cs,
+                                           int n) {
+  const int per = L - 1;
+  for (int e = threadIdx.x; e < n * per; e += blockDim.x) {
+    const int cc = e / per, m = e - cc * per;
+    const double ic = 1.0 / cs[cc];
+    if (m == 0) ics[cc] = ic;
+    flags[e] = table_entry(tab + (size_t)e * kTab, par, L, m, ic);
+  }
+  if (per == 0)
+    for (int cc = threadIdx.x; cc < n; cc += blockDim.x) ics[cc] = 1.0 / cs[cc];
+}
 
 // Dense grid, forward only: det / fused max,min over k / sign bitmap.
 __global__ void __launch_bounds__(256) k_grid_fwd(const double* __restrict__ d, const double* __restrict__ alpha,
@@ -111,40 +141,49 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const double* __restrict__ d, 
                                                   uint32_t* __restrict__ signbits) {
   extern __shared__ double smem[];
   double* par = smem;
-  const int s = blockIdx.x / gp.bpm;
-  const int blk = blockIdx.x - s * gp.bpm;
+  double* tab = par + par_doubles(L);                   // [tc][L-1][kTab]
+  double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
+  int* flags = (int*)(ics + gp.tc);                     // [tc][L-1]
+  const BlockCoord bc = block_coord(blockIdx.x, gp);
+  const int s = bc.s;
   stage_params(par, d, alpha, beta, rho, s, L);
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blk * gp.wpb + warp;
-  if (unit >= gp.units) return;
-  const int ft = unit % gp.nft, ch = unit / gp.nft;
+  const int ft = bc.fg * gp.wpb + warp;
+  const bool live = ft < gp.nft;  // warps beyond the last period tile only help filling the table
   const int f = ft * kWarp + lane;
-  const bool active = f < NF;
+  const bool active = live && f < NF;
   const int fc = active ? f : NF - 1;
   const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
-  const int k0 = ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
+  const int k0 = bc.ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
   double vmax = -INFINITY, vmin = INFINITY;
   bool anynan = false;
   const int nw = (NF + 31) / 32;
-  for (int k = k0; k < k1; ++k) {
-    const double ic = 1.0 / c[(size_t)s * K + k];
-    const Sample z = make_sample(omega0, ic);
-    const double v = sample_forward(par, L, z);
-    if (det && active) det[((size_t)s * K + k) * NF + f] = v;
-    vmax = fmax(vmax, v);
-    vmin = fmin(vmin, v);
-    anynan |= (v != v);
-    if (signbits) {
-      const uint32_t bits = __ballot_sync(0xffffffffu, active && (v < 0.0));
-      if (lane == 0) signbits[((size_t)s * K + k) * nw + ft] = bits;
+  for (int kb = k0; kb < k1; kb += gp.tc) {
+    const int n = min(gp.tc, k1 - kb);
+    __syncthreads();  // staged parameters visible / previous table consumed
+    fill_table(tab, flags, ics, par, L, c + (size_t)s * K + kb, n);
+    __syncthreads();
+    if (!live) continue;
+    for (int cc = 0; cc < n; ++cc) {
+      const int k = kb + cc;
+      const Sample z = make_sample(omega0, ics[cc]);
+      const TableSource src{par, L, tab + (size_t)cc * (L - 1) * kTab, flags + cc * (L - 1)};
+      const double v = sample_forward(src, z);
+      if (det && active) det[((size_t)s * K + k) * NF + f] = v;
+      vmax = fmax(vmax, v);
+      vmin = fmin(vmin, v);
+      anynan |= (v != v);
+      if (signbits) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, active && (v < 0.0));
+        if (lane == 0) signbits[((size_t)s * K + k) * nw + ft] = bits;
+      }
     }
   }
   if (pmax && active) {
     // torch.max/min propagate NaN; fmax/fmin do not
     if (anynan) { vmax = NAN; vmin = NAN; }
-    pmax[((size_t)s * gp.nchunk + ch) * NF + f] = vmax;
-    pmin[((size_t)s * gp.nchunk + ch) * NF + f] = vmin;
+    pmax[((size_t)s * gp.nchunk + bc.ch) * NF + f] = vmax;
+    pmin[((size_t)s * gp.nchunk + bc.ch) * NF + f] = vmin;
   }
 }
 
@@ -189,32 +228,40 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
            const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp, int total_vblocks,
            double* __restrict__ det, double* __restrict__ part, double* __restrict__ estore) {
   extern __shared__ double smem[];
-  double* par = smem;                               // staged layer constants
-  double* accs = par + par_doubles(L);              // [wpb][4][L]
-  double* ests = accs + (size_t)gp.wpb * 4 * L;     // [wpb][L-1][kSlot][32] (shared-memory variant only)
+  double* par = smem;                                   // staged layer constants
+  double* accs = par + par_doubles(L);                  // [wpb][4][L]
+  double* tab = accs + (size_t)gp.wpb * 4 * L;          // [tc][L-1][kTab]
+  double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
+  int* flags = (int*)(ics + gp.tc);                     // [tc][L-1]
+  double* ests = (double*)(flags + ((gp.tc * (L - 1) + 1) & ~1));  // [wpb][L-1][kSlot][32] (shared variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
   double* acc = accs + (size_t)warp * 4 * L;
   double* estp = kGlobal ? estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + lane
                          : ests + (size_t)warp * slab + lane;
   for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
-    const int s = vb / gp.bpm;
-    const int blk = vb - s * gp.bpm;
+    const BlockCoord bc = block_coord(vb, gp);
+    const int s = bc.s;
     __syncthreads();  // previous virtual block has flushed its accumulators
     stage_params(par, d, alpha, beta, rho, s, L);
     for (int i = threadIdx.x; i < gp.wpb * 4 * L; i += blockDim.x) accs[i] = 0.0;
-    __syncthreads();
-    const int unit = blk * gp.wpb + warp;
-    if (unit < gp.units) {
-      const int ft = unit % gp.nft, ch = unit / gp.nft;
-      const int f = ft * kWarp + lane;
-      const bool active = f < NF;
-      const int fc = active ? f : NF - 1;
-      const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
-      const int k0 = ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
-      for (int k = k0; k < k1; ++k) {
-        const double ic = 1.0 / c[(size_t)s * K + k];
-        const Sample z = make_sample(omega0, ic);
+    const int ft = bc.fg * gp.wpb + warp;
+    const bool live = ft < gp.nft;
+    const int f = ft * kWarp + lane;
+    const bool active = live && f < NF;
+    const int fc = active ? f : NF - 1;
+    const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
+    const int k0 = bc.ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
+    for (int kb = k0; kb < k1; kb += gp.tc) {
+      const int n = min(gp.tc, k1 - kb);
+      __syncthreads();
+      fill_table(tab, flags, ics, par, L, c + (size_t)s * K + kb, n);
+      __syncthreads();
+      if (!live) continue;
+      for (int cc = 0; cc < n; ++cc) {
+        const int k = kb + cc;
+        const Sample z = make_sample(omega0, ics[cc]);
+        const TableSource src{par, L, tab + (size_t)cc * (L - 1) * kTab, flags + cc * (L - 1)};
         const size_t idx = ((size_t)s * K + k) * NF + fc;
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
@@ -222,21 +269,21 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
         double v;
         if (kGlobal) {
           const GlobalStore st{estp};
-          v = sample_forward_store(par, L, z, st);
-          sample_adjoint(par, L, z, seed, st, sink);
+          v = sample_forward_store(src, z, st);
+          sample_adjoint(src, z, seed, st, sink);
         } else {
           const PlainStore<kWarp> st{estp};
-          v = sample_forward_store(par, L, z, st);
-          sample_adjoint(par, L, z, seed, st, sink);
+          v = sample_forward_store(src, z, st);
+          sample_adjoint(src, z, seed, st, sink);
         }
-        if (det && active) __stcs(det + idx, v);  // streaming store: keep the E-store lines in L2
+        if (det && active) __stcs(det + idx, v);  // streaming store: keep the store slabs in L2
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
       double v = 0.0;
       for (int w = 0; w < gp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
-      part[((size_t)s * gp.bpm + blk) * 4 * L + i] = v;
+      part[((size_t)s * gp.bpm + bc.blk) * 4 * L + i] = v;
     }
   }
 }
@@ -275,7 +322,7 @@ __global__ void __launch_bounds__(128) k_points_fwd(const double* __restrict__ d
   if (i >= N) return;
   const double omega0 = omega_of_period(t[(size_t)s * N + i]);
   const Sample z = make_sample(omega0, 1.0 / c[(size_t)s * N + i]);
-  F[(size_t)s * N + i] = sample_forward(par, L, z);
+  F[(size_t)s * N + i] = sample_forward(DirectSource{par, L}, z);
 }
 
 // DMF compression: returns |G| and d|G|/dF (reference _model.py:455-464)
@@ -342,7 +389,8 @@ __global__ void __launch_bounds__(128) k_points_bwd(const double* __restrict__ d
     const double ic = 1.0 / cc;
     const Sample z = make_sample(omega_of_period(t[idx]), ic);
     const PlainStore<kWarp> store{est};
-    const double v = sample_forward_store(par, L, z, store);
+    const DirectSource src{par, L};
+    const double v = sample_forward_store(src, z, store);
     if (F && active) F[idx] = v;
     double seed = 1.0;
     if (kKind == 0) seed = gF[idx];
@@ -371,10 +419,10 @@ __global__ void __launch_bounds__(128) k_points_bwd(const double* __restrict__ d
       if (kKind == 1) {
         JacSink sink{Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
                      Jrho ? Jrho + idx * L : nullptr, active};
-        gk = sample_adjoint(par, L, z, seed, store, sink);
+        gk = sample_adjoint(src, z, seed, store, sink);
       } else {
         ReduceSink sink{acc, L, lane};
-        gk = sample_adjoint(par, L, z, active ? seed : 0.0, store, sink);  // overhang lanes: zero seed
+        gk = sample_adjoint(src, z, active ? seed : 0.0, store, sink);  // overhang lanes: zero seed
       }
       if (gc && active) gc[idx] = -z.k * ic * gk;  // k = omega0 / c
     }
@@ -477,19 +525,40 @@ inline size_t bwd_estore_bytes(int L) {
   return bwd_mode() == kBwdSmem ? 0 : (size_t)kMaxResidentWarps * est_bytes_per_warp(L);
 }
 
+inline size_t table_bytes(int L, int tc) {
+  const size_t per = (size_t)(L > 1 ? L - 1 : 0);
+  return (size_t)tc * per * kTab * sizeof(double) + (size_t)tc * sizeof(double) + (((size_t)tc * per + 1) & ~(size_t)1) * sizeof(int);
+}
+
 inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
   GridPlan gp;
   gp.nft = (NF + kWarp - 1) / kWarp;
-  gp.wpb = adjoint ? (bwd_mode() == kBwdSmem ? adj_wpb(L) : bwd_wpb_global()) : 8;
-  const long long target = (long long)kNumSM * 8 * 24;  // ~24 waves of 8 warps per SM
-  long long nchunk = (target + (long long)S * gp.nft - 1) / ((long long)S * gp.nft);
-  const int maxchunks = K >= 16 ? K / 8 : 1;
+  int want = 8;
+  if (adjoint) {
+    want = bwd_wpb_global();
+    if (bwd_mode() == kBwdSmem) {  // slabs in shared memory: as many warps as fit beside the table
+      want = 0;
+      for (int w = 4; w >= 1 && !want; w >>= 1)
+        if (adj_smem(L, w) + table_bytes(L, 8) <= (w > 1 ? kSmemBudget : kSmemMax)) want = w;
+    }
+  }
+  gp.wpb = want < gp.nft ? want : gp.nft;
+  if (gp.wpb < 1) gp.wpb = adjoint && want <= 0 ? 0 : 1;
+  gp.nfg = gp.wpb > 0 ? (gp.nft + gp.wpb - 1) / gp.wpb : 0;
+  // table fills of up to 8 velocities, fewer for very deep models (keeps the table under ~24 KB)
+  gp.tc = 8;
+  while (gp.tc > 1 && table_bytes(L, gp.tc) > 24 * 1024) gp.tc >>= 1;
+  // enough blocks for ~16 waves of a full machine, chunks not shorter than 2 table fills
+  const long long target = (long long)kNumSM * 4 * 16;
+  const long long base = (long long)S * (gp.nfg > 0 ? gp.nfg : 1);
+  long long nchunk = (target + base - 1) / base;
+  const long long maxchunks = K >= 2 * gp.tc ? K / (2 * gp.tc) : 1;
   if (nchunk > maxchunks) nchunk = maxchunks;
   if (nchunk < 1) nchunk = 1;
   gp.chunk = (K + (int)nchunk - 1) / (int)nchunk;
+  gp.chunk = ((gp.chunk + gp.tc - 1) / gp.tc) * gp.tc;  // whole table fills
   gp.nchunk = (K + gp.chunk - 1) / gp.chunk;
-  gp.units = gp.nft * gp.nchunk;
-  gp.bpm = gp.wpb > 0 ? (gp.units + gp.wpb - 1) / gp.wpb : 0;
+  gp.bpm = gp.nchunk * gp.nfg;
   return gp;
 }
 
@@ -648,7 +717,7 @@ int adsurf_det_points_jac(const double* d, const double* alpha, const double* be
 static int grid_fwd_launch(const double* d, const double* alpha, const double* beta, const double* rho,
                            const double* t, const double* c, int S, int L, int NF, int K, double* det, double* pmax,
                            double* pmin, uint32_t* signbits, const GridPlan& gp, cudaStream_t st) {
-  const size_t smem = (size_t)par_doubles(L) * sizeof(double);
+  const size_t smem = (size_t)par_doubles(L) * sizeof(double) + table_bytes(L, gp.tc);
   if (set_smem(k_grid_fwd, smem)) return ADSURF_E_CUDA;
   k_grid_fwd<<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K, gp,
                                                                             det, pmax, pmin, signbits);
@@ -694,8 +763,8 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = bwd_mode();
-  const size_t smem = mode == kBwdSmem ? adj_smem(L, gp.wpb)
-                                       : (size_t)par_doubles(L) * sizeof(double) + (size_t)gp.wpb * 4 * L * sizeof(double);
+  const size_t smem = (size_t)par_doubles(L) * sizeof(double) + (size_t)gp.wpb * 4 * L * sizeof(double) +
+                      table_bytes(L, gp.tc) + (mode == kBwdSmem ? (size_t)gp.wpb * est_bytes_per_warp(L) : 0);
   double* estore = mode == kBwdSmem ? nullptr : (double*)((char*)ws + part_bytes);
   const long long total_vb = (long long)S * gp.bpm;
   if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;

@@ -249,25 +249,22 @@ struct Layer {
   double a0;
 };
 
-// forward sweep: evaluate the transcendentals
-ADSURF_HD void layer_eig_forward(Layer& y, double k) {
-  eig_setup(y.P, k, y.ka, y.dm);
-  eig_setup(y.S, k, y.kb, y.dm);
+// forward sweep: evaluate the transcendentals (P, S set up by the layer source)
+ADSURF_HD void layer_eig_forward(Layer& y) {
   eig_forward(y.P, y.dm);
   eig_forward(y.S, y.dm);
+  y.a0 = (y.P.ex + y.S.ex < 60.0) ? y.P.eh * y.S.eh : 0.0;
 }
 
 // adjoint sweep: restore them from the store (c0, c1 already set by the caller)
-ADSURF_HD void layer_eig_restore(Layer& y, double k) {
-  eig_setup(y.P, k, y.ka, y.dm);
-  eig_setup(y.S, k, y.kb, y.dm);
+ADSURF_HD void layer_eig_restore(Layer& y) {
   eig_finish(y.P, y.dm);
   eig_finish(y.S, y.dm);
+  y.a0 = (y.P.ex + y.S.ex < 60.0) ? y.P.eh * y.S.eh : 0.0;
 }
 
-// t2 = -2 k2 (hoisted per sample); needs P, S complete (layer_eig_forward / layer_eig_restore)
-ADSURF_HD void layer_terms(Layer& y, double k, double k2, double t2) {
-  y.a0 = (y.P.ex + y.S.ex < 60.0) ? y.P.eh * y.S.eh : 0.0;
+// coefficient scalars from (gk, k2); t2 = -2 k2 (hoisted per sample)
+ADSURF_HD void layer_coefs(Layer& y, double k2, double t2) {
   y.gam = y.gk * k2;
   y.g1 = y.gam - 1.0;
   y.gg = y.gam * y.gk;
@@ -463,7 +460,7 @@ ADSURF_HD LayerGrad half_adjoint(const Half& h, const double (&e)[5], const doub
 // Sample-level drivers
 // ------------------------------------------------------------------------------------------
 struct Sample {
-  double k, k2, omega, iw2, t2;  // wavenumber, its square, clamped angular frequency, 1/omega^2, -2 k^2
+  double k, k2, omega, iw, iw2, t2;  // wavenumber, its square, clamped angular frequency, 1/omega, 1/omega^2, -2 k^2
 };
 
 // omega = twopi / t as torch evaluates `python_float / tensor` (Tensor.__rtruediv__ ==
@@ -477,20 +474,94 @@ ADSURF_HD Sample make_sample(double omega0, double ic) {
   z.k = ic * omega0;                          // (1/c) * omega   (reference :319, unclamped omega)
   z.omega = fmax(omega0, 1.0e-4);             // reference :326
   z.k2 = z.k * z.k;
-  const double iw = 1.0 / z.omega;
-  z.iw2 = iw * iw;
+  z.iw = 1.0 / z.omega;
+  z.iw2 = z.iw * z.iw;
   z.t2 = -2.0 * z.k2;
   return z;
 }
 
-ADSURF_HD void load_layer(Layer& y, const double* __restrict__ par, int L, int m, const Sample& z) {
-  y.ka = z.omega * par[P_IA * L + m];
-  y.kb = z.omega * par[P_IB * L + m];
-  y.gk = par[P_TB2 * L + m] * z.iw2;
-  y.rho = par[P_RHO * L + m];
-  y.ir = par[P_IR * L + m];
-  y.dm = par[P_D * L + m];
+// ---- layer sources: fill the inputs, the eigenfunction set-up and the coefficient scalars of layer m
+// DirectSource: everything per sample from (k, omega) — pointwise kernels, arbitrary (t, c) pairs.
+struct DirectSource {
+  const double* __restrict__ par;
+  int L;
+  ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
+    y.ka = z.omega * par[P_IA * L + m];
+    y.kb = z.omega * par[P_IB * L + m];
+    y.gk = par[P_TB2 * L + m] * z.iw2;
+    y.rho = par[P_RHO * L + m];
+    y.ir = par[P_IR * L + m];
+    y.dm = par[P_D * L + m];
+    eig_setup(y.P, z.k, y.ka, y.dm);
+    eig_setup(y.S, z.k, y.kb, y.dm);
+    layer_coefs(y, z.k2, z.t2);
+  }
+};
+
+// TableSource: dense kernels.  Everything that depends on (trial velocity, layer) but not on the
+// period is computed once per block into a shared-memory table and read as a broadcast:
+//   r = sqrt(|k^2 - kx^2|) = omega * n,  n = sqrt(|1/c^2 - 1/v^2|);   p = omega * (n d);
+//   gam = gk k^2 = 2 (beta/c)^2;  g1 = gam - 1;  br = g1^2 rho;   branch flags (c vs v).
+// Per lane that leaves 6 multiplies for both eigenfunction set-ups (instead of 2 rsqrt sequences,
+// the differences of squares and their selects) and 6 for the coefficient scalars.
+constexpr int kTab = 9;
+enum { T_PDA = 0, T_PDB = 1, T_NA = 2, T_NB = 3, T_INA = 4, T_INB = 5, T_GAM = 6, T_G1 = 7, T_BR = 8 };
+enum { F_LTP = 1, F_POSP = 2, F_LTS = 4, F_POSS = 8 };
+
+// one table entry: trial slowness ic = 1/c against layer m of the staged model
+ADSURF_HD int table_entry(double* __restrict__ tab, const double* __restrict__ par, int L, int m, double ic) {
+  const double sa = par[P_IA * L + m], sb = par[P_IB * L + m], dm = par[P_D * L + m];
+  const double da = (ic + sa) * fabs(ic - sa), db = (ic + sb) * fabs(ic - sb);
+  const double na = sqrt(da), nb = sqrt(db);
+  tab[T_PDA] = na * dm;
+  tab[T_PDB] = nb * dm;
+  tab[T_NA] = na;
+  tab[T_NB] = nb;
+  tab[T_INA] = 1.0 / na;
+  tab[T_INB] = 1.0 / nb;
+  const double gam = par[P_TB2 * L + m] * (ic * ic);
+  const double g1 = gam - 1.0;
+  tab[T_GAM] = gam;
+  tab[T_G1] = g1;
+  tab[T_BR] = g1 * g1 * par[P_RHO * L + m];
+  return (ic < sa ? F_LTP : 0) | (da > 0.0 ? F_POSP : 0) | (ic < sb ? F_LTS : 0) | (db > 0.0 ? F_POSS : 0);
 }
+
+struct TableSource {
+  const double* __restrict__ par;
+  int L;
+  const double* __restrict__ tab;  // [L-1][kTab] for the current trial velocity
+  const int* __restrict__ flags;   // [L-1]
+  ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
+    const double* __restrict__ q = tab + m * kTab;
+    const int fl = flags[m];
+    y.rho = par[P_RHO * L + m];
+    y.ir = par[P_IR * L + m];
+    y.dm = par[P_D * L + m];
+    y.ka = z.omega * par[P_IA * L + m];  // adjoint only
+    y.kb = z.omega * par[P_IB * L + m];
+    y.gk = par[P_TB2 * L + m] * z.iw2;
+    y.gam = q[T_GAM];
+    y.g1 = q[T_G1];
+    y.br = q[T_BR];
+    y.gg = y.gam * y.gk;
+    y.q1 = y.g1 * y.g1;                  // adjoint only
+    y.ar = y.gg * y.rho;
+    y.kr = z.k2 * y.ir;
+    y.tg = z.t2 * y.gk;
+    y.t1 = z.t2 * y.g1;
+    y.P.r = z.omega * q[T_NA];
+    y.P.ir = z.iw * q[T_INA];
+    y.P.p = z.omega * q[T_PDA];
+    y.P.lt = fl & F_LTP;
+    y.P.pos = fl & F_POSP;
+    y.S.r = z.omega * q[T_NB];
+    y.S.ir = z.iw * q[T_INB];
+    y.S.p = z.omega * q[T_PDB];
+    y.S.lt = fl & F_LTS;
+    y.S.pos = fl & F_POSS;
+  }
+};
 
 // The half-space vector is linear in ra, rb = sqrt((k+kx)|k-kx|): at a trial velocity that coincides
 // with the half-space velocity the result depends on the last bit of kx, so kx is formed with the
@@ -506,16 +577,18 @@ ADSURF_HD void load_half(Half& h, const double* __restrict__ par, int L, const S
 }
 
 // forward only
-ADSURF_HD double sample_forward(const double* __restrict__ par, int L, const Sample& z) {
+template <typename Source>
+ADSURF_HD double sample_forward(const Source& src, const Sample& z) {
+  const double* __restrict__ par = src.par;
+  const int L = src.L;
   double e[5];
   Half h;
   load_half(h, par, L, z);
   half_space(h, z.k, z.k2, e);
   Layer y;
   for (int m = L - 2; m >= 0; --m) {
-    load_layer(y, par, L, m, z);
-    layer_eig_forward(y, z.k);
-    layer_terms(y, z.k, z.k2, z.t2);
+    src.prep(y, m, z);
+    layer_eig_forward(y);
     row_apply(e, y);
   }
   return e[0];
@@ -537,16 +610,18 @@ struct PlainStore {
 };
 
 // forward keeping E_{m+1} of every layer: slot m holds the row vector that multiplies CA_m.
-template <typename Store>
-ADSURF_HD double sample_forward_store(const double* __restrict__ par, int L, const Sample& z, const Store& est) {
+template <typename Source, typename Store>
+ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const Store& est) {
+  const double* __restrict__ par = src.par;
+  const int L = src.L;
   double e[5];
   Half h;
   load_half(h, par, L, z);
   half_space(h, z.k, z.k2, e);
   Layer y;
   for (int m = L - 2; m >= 0; --m) {
-    load_layer(y, par, L, m, z);
-    layer_eig_forward(y, z.k);
+    src.prep(y, m, z);
+    layer_eig_forward(y);
     const typename Store::Slot q = est.slot(m);
 #pragma unroll
     for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
@@ -554,7 +629,6 @@ ADSURF_HD double sample_forward_store(const double* __restrict__ par, int L, con
     Store::st(q, 6, y.P.c1);
     Store::st(q, 7, y.S.c0);
     Store::st(q, 8, y.S.c1);
-    layer_terms(y, z.k, z.k2, z.t2);
     row_apply(e, y);
   }
   return e[0];
@@ -564,9 +638,10 @@ ADSURF_HD double sample_forward_store(const double* __restrict__ par, int L, con
 // hands (m, dDelta/dd_m, /dalpha_m, /dbeta_m, /drho_m) * seed to `sink`.  Returns dDelta/dk * seed.
 // The stored values of the next layer are fetched one iteration ahead into the other of two
 // register buffers (the loop is unrolled by two so the buffers swap without copies).
-template <typename Store, typename Sink>
-ADSURF_HD double sample_adjoint(const double* __restrict__ par, int L, const Sample& z, double seed, const Store& est,
-                                Sink& sink) {
+template <typename Source, typename Store, typename Sink>
+ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed, const Store& est, Sink& sink) {
+  const double* __restrict__ par = src.par;
+  const int L = src.L;
   double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
   double bufA[kSlot], bufB[kSlot];
   double gk = 0.0;
@@ -580,9 +655,8 @@ ADSURF_HD double sample_adjoint(const double* __restrict__ par, int L, const Sam
     Layer y;
     const double e[5] = {cur[0], cur[1], cur[2], cur[3], cur[4]};
     y.P.c0 = cur[5]; y.P.c1 = cur[6]; y.S.c0 = cur[7]; y.S.c1 = cur[8];
-    load_layer(y, par, L, m, z);
-    layer_eig_restore(y, z.k);
-    layer_terms(y, z.k, z.k2, z.t2);
+    src.prep(y, m, z);
+    layer_eig_restore(y);
     const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2, z.t2);
     col_apply(s, y);
     gk += g.k;

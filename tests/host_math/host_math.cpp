@@ -43,14 +43,14 @@ int host_points(const double* d, const double* alpha, const double* beta, const 
       const size_t idx = (size_t)s * N + i;
       const double ic = 1.0 / c[idx];
       const Sample z = make_sample(omega_of_period(t[idx]), ic);
-      const double v = sample_forward_store(par.data(), L, z, PlainStore<1>{est.data()});
-      const double v2 = sample_forward(par.data(), L, z);
+      const double v = sample_forward_store(DirectSource{par.data(), L}, z, PlainStore<1>{est.data()});
+      const double v2 = sample_forward(DirectSource{par.data(), L}, z);
       if (v != v2 && !(v != v && v2 != v2)) return -1;
       F[idx] = v;
       HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L,
                     Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
                     Jrho ? Jrho + idx * L : nullptr};
-      const double gk = sample_adjoint(par.data(), L, z, gF ? gF[idx] : 1.0, PlainStore<1>{est.data()}, sink);
+      const double gk = sample_adjoint(DirectSource{par.data(), L}, z, gF ? gF[idx] : 1.0, PlainStore<1>{est.data()}, sink);
       if (gc) gc[idx] = -z.k * ic * gk;
     }
   }
@@ -66,14 +66,23 @@ int host_grid(const double* d, const double* alpha, const double* beta, const do
     for (int m = 0; m < L; ++m)
       stage_one(par.data(), L, m, d[s * L + m], alpha[s * L + m], beta[s * L + m], rho[s * L + m]);
     for (int m = 0; m < L; ++m) gd[s * L + m] = ga[s * L + m] = gb[s * L + m] = grho[s * L + m] = 0.0;
-    for (int k = 0; k < K; ++k)
+    // dense path: per-(velocity, layer) table + per-period lanes, as the dense kernels do
+    std::vector<double> tab((size_t)kTab * (L > 1 ? L - 1 : 1));
+    std::vector<int> flags(L > 1 ? L - 1 : 1);
+    for (int k = 0; k < K; ++k) {
+      const double ic = 1.0 / c[s * K + k];
+      for (int m = 0; m < L - 1; ++m) flags[m] = table_entry(tab.data() + (size_t)m * kTab, par.data(), L, m, ic);
+      const TableSource src{par.data(), L, tab.data(), flags.data()};
       for (int f = 0; f < NF; ++f) {
         const size_t idx = ((size_t)s * K + k) * NF + f;
-        const Sample z = make_sample(omega_of_period(t[s * NF + f]), 1.0 / c[s * K + k]);
-        det[idx] = sample_forward_store(par.data(), L, z, PlainStore<1>{est.data()});
+        const Sample z = make_sample(omega_of_period(t[s * NF + f]), ic);
+        det[idx] = sample_forward_store(src, z, PlainStore<1>{est.data()});
+        const double v2 = sample_forward(src, z);
+        if (det[idx] != v2 && !(det[idx] != det[idx] && v2 != v2)) return -1;
         HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L, nullptr, nullptr, nullptr, nullptr};
-        sample_adjoint(par.data(), L, z, gdet ? gdet[idx] : 1.0, PlainStore<1>{est.data()}, sink);
+        sample_adjoint(src, z, gdet ? gdet[idx] : 1.0, PlainStore<1>{est.data()}, sink);
       }
+    }
   }
   return 0;
 }
