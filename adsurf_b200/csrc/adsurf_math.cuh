@@ -117,11 +117,18 @@ ADSURF_HD double exp_neg(double p) {
 // sin and cos of q for |q| < 1e5: Cody-Waite reduction by pi/2 in three FMA steps, then the fdlibm
 // kernel polynomials on |r| <= pi/4 (coefficients of __kernel_sin/__kernel_cos, (C) 1993 Sun
 // Microsystems, freely usable with this notice; < 1 ulp).  Larger arguments take the library path.
+ADSURF_HD void sincos_core(double q, double* sn, double* cs);
+
 ADSURF_HD void sincos_fast(double q, double* sn, double* cs) {
   if (!(fabs(q) < 1.0e5)) {
     sincos(q, sn, cs);
     return;
   }
+  sincos_core(q, sn, cs);
+}
+
+// branch-free core, valid for |q| < 1e5
+ADSURF_HD void sincos_core(double q, double* sn, double* cs) {
   const double t = fma(q, ADSURF_K(kRedC, 3), kShifter);
   const double fn = t - kShifter;
   double r = fma(fn, ADSURF_K(kRedC, 4), q);
@@ -193,6 +200,31 @@ ADSURF_HD void eig_trans(Eig& e) {
   }
 }
 
+// branch-free bodies of the two regimes (oscillatory valid for |p| < 1e5)
+ADSURF_HD void eig_osc(Eig& e) {
+  sincos_core(e.p, &e.c0, &e.c1);
+  e.sn = e.c0;
+  e.cs = e.c1;
+  e.dcs = -e.c0;
+  e.dsn = e.c1;
+  e.ex = 0.0;
+  e.eh = 1.0;
+  e.x = -e.r * e.sn;
+}
+
+ADSURF_HD void eig_evan(Eig& e) {
+  e.c0 = exp_neg(e.p);
+  e.c1 = 0.0;
+  const double fac = (e.p < 16.0) ? e.c0 * e.c0 : 0.0;
+  e.cs = 0.5 + 0.5 * fac;
+  e.sn = 0.5 - 0.5 * fac;
+  e.dcs = -fac;
+  e.dsn = fac;
+  e.ex = e.p;  // p = 0 when k == kx
+  e.eh = (e.p < 60.0) ? e.c0 : 0.0;
+  e.x = e.r * e.sn;
+}
+
 // forward sweep: transcendental + derived terms inside one (warp-uniform) branch, no selects
 ADSURF_HD void eig_forward(Eig& e, double dm) {
   if (e.lt) {
@@ -249,10 +281,33 @@ struct Layer {
   double a0;
 };
 
-// forward sweep: evaluate the transcendentals (P, S set up by the layer source)
+// forward sweep: evaluate the transcendentals (P, S set up by the layer source).  The four regime
+// combinations get their own straight-line block so that the P and the S polynomial chains (each a
+// ~16-deep dependent FP64 sequence, 8 cycles per link) are scheduled interleaved instead of one
+// after the other behind separate branches.  The regime is warp-uniform in the dense kernels.
 ADSURF_HD void layer_eig_forward(Layer& y) {
-  eig_forward(y.P, y.dm);
-  eig_forward(y.S, y.dm);
+  const bool lp = y.P.lt, ls = y.S.lt;
+  const bool small = (fabs(y.P.p) < 1.0e5) && (fabs(y.S.p) < 1.0e5);
+  if (!small) {  // huge phase (or NaN): generic path with the library fallback
+    eig_forward(y.P, y.dm);
+    eig_forward(y.S, y.dm);
+  } else {
+    if (!lp && ls) {         // c between the S and the P velocity of the layer: the common case
+      eig_evan(y.P);
+      eig_osc(y.S);
+    } else if (!lp && !ls) { // slower than both: fully evanescent
+      eig_evan(y.P);
+      eig_evan(y.S);
+    } else if (lp && ls) {   // faster than both
+      eig_osc(y.P);
+      eig_osc(y.S);
+    } else {
+      eig_osc(y.P);
+      eig_evan(y.S);
+    }
+    y.P.w = y.P.pos ? y.P.sn * y.P.ir : y.dm;  // k == kx: w = d (reference :135)
+    y.S.w = y.S.pos ? y.S.sn * y.S.ir : y.dm;
+  }
   y.a0 = (y.P.ex + y.S.ex < 60.0) ? y.P.eh * y.S.eh : 0.0;
 }
 
@@ -643,18 +698,26 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   const double* __restrict__ par = src.par;
   const int L = src.L;
   double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
-  double bufA[kSlot], bufB[kSlot];
+  // software pipeline: the transcendental results of the next layer (needed first) are fetched one
+  // layer ahead into ping-pong registers; the row vector E (needed ~60 instructions later) is fetched
+  // at the top of its own layer.  Keeps 10 fewer registers live than prefetching the whole slot.
+  double bufA[4], bufB[4];
   double gk = 0.0;
-  auto fetch = [&](int m, double (&buf)[kSlot]) {
+  auto fetch = [&](int m, double (&buf)[4]) {
     const typename Store::Slot q = est.slot(m);
 #pragma unroll
-    for (int i = 0; i < kSlot; ++i) buf[i] = Store::ld(q, i);
+    for (int i = 0; i < 4; ++i) buf[i] = Store::ld(q, 5 + i);
   };
-  auto layer = [&](int m, const double (&cur)[kSlot], double (&nxt)[kSlot]) {
+  auto layer = [&](int m, const double (&cur)[4], double (&nxt)[4]) {
+    double e[5];
+    {
+      const typename Store::Slot q = est.slot(m);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) e[i] = Store::ld(q, i);
+    }
     if (m + 1 <= L - 2) fetch(m + 1, nxt);
     Layer y;
-    const double e[5] = {cur[0], cur[1], cur[2], cur[3], cur[4]};
-    y.P.c0 = cur[5]; y.P.c1 = cur[6]; y.S.c0 = cur[7]; y.S.c1 = cur[8];
+    y.P.c0 = cur[0]; y.P.c1 = cur[1]; y.S.c0 = cur[2]; y.S.c1 = cur[3];
     src.prep(y, m, z);
     layer_eig_restore(y);
     const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2, z.t2);
