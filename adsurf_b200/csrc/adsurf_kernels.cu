@@ -68,6 +68,25 @@ struct ReduceSink {
   }
 };
 
+// Dense adjoint with the slabs in global memory (shared memory is free): fold the warp once
+// (lane l with lane l^16) and keep 16 per-lane partial sums per (layer, gradient) in shared memory:
+// acc[L][4][16].  2 exchanges + 2 read-modify-writes per layer, no dependent shuffle chain; the 16
+// lanes x warps are summed once per virtual block.
+struct FoldSink {
+  double* acc;  // this warp's [L][4][16]
+  int lane;
+  __device__ __forceinline__ void operator()(int m, double gd, double ga, double gb, double gr) const {
+    const bool hi = lane & 16;
+    const double k0 = hi ? gb : gd, k1 = hi ? gr : ga;  // lower half owns (gd, ga), upper half (gb, grho)
+    const double x0 = hi ? gd : gb, x1 = hi ? ga : gr;
+    const double a0 = k0 + __shfl_xor_sync(0xffffffffu, x0, 16);
+    const double a1 = k1 + __shfl_xor_sync(0xffffffffu, x1, 16);
+    double* q = acc + ((m * 4 + ((lane >> 4) << 1)) << 4) + (lane & 15);
+    q[0] += a0;
+    q[16] += a1;
+  }
+};
+
 struct JacSink {  // write this sample's Jacobian rows
   double *jd, *ja, *jb, *jr;
   bool active;
@@ -228,15 +247,16 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
            const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp, int total_vblocks,
            double* __restrict__ det, double* __restrict__ part, double* __restrict__ estore) {
   extern __shared__ double smem[];
+  constexpr int kAccPer = kGlobal ? 64 : 4;             // accumulator doubles per (warp, layer)
   double* par = smem;                                   // staged layer constants
-  double* accs = par + par_doubles(L);                  // [wpb][4][L]
-  double* tab = accs + (size_t)gp.wpb * 4 * L;          // [tc][L-1][kTab]
+  double* accs = par + par_doubles(L);                  // [wpb][L][4][16] (global slabs) or [wpb][4][L]
+  double* tab = accs + (size_t)gp.wpb * kAccPer * L;    // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
   int* flags = (int*)(ics + gp.tc);                     // [tc][L-1]
   double* ests = (double*)(flags + ((gp.tc * (L - 1) + 1) & ~1));  // [wpb][L-1][kSlot][32] (shared variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
-  double* acc = accs + (size_t)warp * 4 * L;
+  double* acc = accs + (size_t)warp * kAccPer * L;
   double* estp = kGlobal ? estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + lane
                          : ests + (size_t)warp * slab + lane;
   for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
@@ -244,7 +264,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
     const int s = bc.s;
     __syncthreads();  // previous virtual block has flushed its accumulators
     stage_params(par, d, alpha, beta, rho, s, L);
-    for (int i = threadIdx.x; i < gp.wpb * 4 * L; i += blockDim.x) accs[i] = 0.0;
+    for (int i = threadIdx.x; i < gp.wpb * kAccPer * L; i += blockDim.x) accs[i] = 0.0;
     const int ft = bc.fg * gp.wpb + warp;
     const bool live = ft < gp.nft;
     const int f = ft * kWarp + lane;
@@ -265,14 +285,15 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
         const size_t idx = ((size_t)s * K + k) * NF + fc;
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
-        ReduceSink sink{acc, L, lane};
         double v;
         if (kGlobal) {
           const GlobalStore st{estp};
+          FoldSink sink{acc, lane};
           v = sample_forward_store(src, z, st);
           sample_adjoint(src, z, seed, st, sink);
         } else {
           const PlainStore<kWarp> st{estp};
+          ReduceSink sink{acc, L, lane};
           v = sample_forward_store(src, z, st);
           sample_adjoint(src, z, seed, st, sink);
         }
@@ -282,7 +303,16 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
       double v = 0.0;
-      for (int w = 0; w < gp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
+      if (kGlobal) {
+        const int which = i / L, m = i - which * L;  // output order [4][L]
+        for (int w = 0; w < gp.wpb; ++w) {
+          const double* q = accs + (size_t)w * kAccPer * L + ((m * 4 + which) << 4);
+#pragma unroll
+          for (int l = 0; l < 16; ++l) v += q[l];
+        }
+      } else {
+        for (int w = 0; w < gp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
+      }
       part[((size_t)s * gp.bpm + bc.blk) * 4 * L + i] = v;
     }
   }
@@ -763,8 +793,9 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = bwd_mode();
-  const size_t smem = (size_t)par_doubles(L) * sizeof(double) + (size_t)gp.wpb * 4 * L * sizeof(double) +
-                      table_bytes(L, gp.tc) + (mode == kBwdSmem ? (size_t)gp.wpb * est_bytes_per_warp(L) : 0);
+  const size_t smem = (size_t)par_doubles(L) * sizeof(double) +
+                      (size_t)gp.wpb * (mode == kBwdSmem ? 4 : 64) * L * sizeof(double) + table_bytes(L, gp.tc) +
+                      (mode == kBwdSmem ? (size_t)gp.wpb * est_bytes_per_warp(L) : 0);
   double* estore = mode == kBwdSmem ? nullptr : (double*)((char*)ws + part_bytes);
   const long long total_vb = (long long)S * gp.bpm;
   if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;

@@ -541,12 +541,12 @@ struct DirectSource {
   const double* __restrict__ par;
   int L;
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
-    y.ka = z.omega * par[P_IA * L + m];
-    y.kb = z.omega * par[P_IB * L + m];
-    y.gk = par[P_TB2 * L + m] * z.iw2;
-    y.rho = par[P_RHO * L + m];
-    y.ir = par[P_IR * L + m];
-    y.dm = par[P_D * L + m];
+    y.ka = z.omega * par[m * kNumPar + P_IA];
+    y.kb = z.omega * par[m * kNumPar + P_IB];
+    y.gk = par[m * kNumPar + P_TB2] * z.iw2;
+    y.rho = par[m * kNumPar + P_RHO];
+    y.ir = par[m * kNumPar + P_IR];
+    y.dm = par[m * kNumPar + P_D];
     eig_setup(y.P, z.k, y.ka, y.dm);
     eig_setup(y.S, z.k, y.kb, y.dm);
     layer_coefs(y, z.k2, z.t2);
@@ -565,7 +565,7 @@ enum { F_LTP = 1, F_POSP = 2, F_LTS = 4, F_POSS = 8 };
 
 // one table entry: trial slowness ic = 1/c against layer m of the staged model
 ADSURF_HD int table_entry(double* __restrict__ tab, const double* __restrict__ par, int L, int m, double ic) {
-  const double sa = par[P_IA * L + m], sb = par[P_IB * L + m], dm = par[P_D * L + m];
+  const double sa = par[m * kNumPar + P_IA], sb = par[m * kNumPar + P_IB], dm = par[m * kNumPar + P_D];
   const double da = (ic + sa) * fabs(ic - sa), db = (ic + sb) * fabs(ic - sb);
   const double na = sqrt(da), nb = sqrt(db);
   tab[T_PDA] = na * dm;
@@ -574,11 +574,11 @@ ADSURF_HD int table_entry(double* __restrict__ tab, const double* __restrict__ p
   tab[T_NB] = nb;
   tab[T_INA] = 1.0 / na;
   tab[T_INB] = 1.0 / nb;
-  const double gam = par[P_TB2 * L + m] * (ic * ic);
+  const double gam = par[m * kNumPar + P_TB2] * (ic * ic);
   const double g1 = gam - 1.0;
   tab[T_GAM] = gam;
   tab[T_G1] = g1;
-  tab[T_BR] = g1 * g1 * par[P_RHO * L + m];
+  tab[T_BR] = g1 * g1 * par[m * kNumPar + P_RHO];
   return (ic < sa ? F_LTP : 0) | (da > 0.0 ? F_POSP : 0) | (ic < sb ? F_LTS : 0) | (db > 0.0 ? F_POSS : 0);
 }
 
@@ -590,12 +590,12 @@ struct TableSource {
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     const double* __restrict__ q = tab + m * kTab;
     const int fl = flags[m];
-    y.rho = par[P_RHO * L + m];
-    y.ir = par[P_IR * L + m];
-    y.dm = par[P_D * L + m];
-    y.ka = z.omega * par[P_IA * L + m];  // adjoint only
-    y.kb = z.omega * par[P_IB * L + m];
-    y.gk = par[P_TB2 * L + m] * z.iw2;
+    y.rho = par[m * kNumPar + P_RHO];
+    y.ir = par[m * kNumPar + P_IR];
+    y.dm = par[m * kNumPar + P_D];
+    y.ka = z.omega * par[m * kNumPar + P_IA];  // adjoint only
+    y.kb = z.omega * par[m * kNumPar + P_IB];
+    y.gk = par[m * kNumPar + P_TB2] * z.iw2;
     y.gam = q[T_GAM];
     y.g1 = q[T_G1];
     y.br = q[T_BR];
@@ -627,8 +627,8 @@ ADSURF_HD void load_half(Half& h, const double* __restrict__ par, int L, const S
   const int m = L - 1;
   h.ka = z.omega / par[kNumPar * L + 0];
   h.kb = z.omega / par[kNumPar * L + 1];
-  h.gammk = par[P_TB2 * L + m] * z.iw2;
-  h.rho = par[P_RHO * L + m];
+  h.gammk = par[m * kNumPar + P_TB2] * z.iw2;
+  h.rho = par[m * kNumPar + P_RHO];
 }
 
 // forward only
@@ -723,7 +723,7 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2, z.t2);
     col_apply(s, y);
     gk += g.k;
-    const double ia = par[P_IA * L + m], ib = par[P_IB * L + m];
+    const double ia = par[m * kNumPar + P_IA], ib = par[m * kNumPar + P_IB];
     // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2
     sink(m, g.d, -y.ka * ia * g.ka, -y.kb * ib * g.kb + 2.0 * y.gk * ib * g.gammk, g.rho);
   };
@@ -742,19 +742,20 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   const LayerGrad g = half_adjoint(h, e, s, z.k, z.k2);
   gk += g.k;
   const int mh = L - 1;
-  const double ia = par[P_IA * L + mh], ib = par[P_IB * L + mh];
+  const double ia = par[mh * kNumPar + P_IA], ib = par[mh * kNumPar + P_IB];
   sink(mh, 0.0, -h.ka * ia * g.ka, -h.kb * ib * g.kb + 2.0 * h.gammk * ib * g.gammk, g.rho);
   return gk;
 }
 
-// per-model layer constants staged for the kernels: par[P_*][L]
+// per-model layer constants staged for the kernels: par[L][kNumPar] (one 48-byte record per layer,
+// so a layer needs one address computation), then the raw half-space velocities
 ADSURF_HD void stage_one(double* __restrict__ par, int L, int m, double dm, double a, double b, double r) {
-  par[P_IA * L + m] = 1.0 / a;
-  par[P_IB * L + m] = 1.0 / b;
-  par[P_TB2 * L + m] = 2.0 * b * b;
-  par[P_RHO * L + m] = r;
-  par[P_IR * L + m] = 1.0 / r;
-  par[P_D * L + m] = dm;
+  par[m * kNumPar + P_IA] = 1.0 / a;
+  par[m * kNumPar + P_IB] = 1.0 / b;
+  par[m * kNumPar + P_TB2] = 2.0 * b * b;
+  par[m * kNumPar + P_RHO] = r;
+  par[m * kNumPar + P_IR] = 1.0 / r;
+  par[m * kNumPar + P_D] = dm;
   if (m == L - 1) {
     par[kNumPar * L + 0] = a;
     par[kNumPar * L + 1] = b;
