@@ -225,12 +225,40 @@ __global__ void k_minmax_reduce(const double* __restrict__ pmax, const double* _
 }
 
 // E-store in global memory (L2-resident working set): cache-global loads/stores, lane-interleaved
+// ADSURF_SLAB_HINT=1 (compile-time): tag slab accesses with an L2 evict_last policy so the write-back
+// cache keeps them resident while det streams through with evict-first stores.
+#ifndef ADSURF_SLAB_HINT
+#define ADSURF_SLAB_HINT 1
+#endif
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 struct GlobalStore {
   double* p;
-  typedef double* Slot;
-  __device__ __forceinline__ Slot slot(int m) const { return p + (size_t)m * (kSlot * kWarp); }
-  __device__ __forceinline__ static double ld(Slot q, int j) { return __ldcg(q + j * kWarp); }
-  __device__ __forceinline__ static void st(Slot q, int j, double v) { __stcg(q + j * kWarp, v); }
+  struct Slot {
+    double* q;
+    unsigned long long pol;
+  };
+  unsigned long long pol;
+  __device__ __forceinline__ Slot slot(int m) const { return Slot{p + (size_t)m * (kSlot * kWarp), pol}; }
+  __device__ __forceinline__ static double ld(Slot s, int j) {
+#if ADSURF_SLAB_HINT
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(s.q + j * kWarp), "l"(s.pol));
+    return v;
+#else
+    return __ldcg(s.q + j * kWarp);
+#endif
+  }
+  __device__ __forceinline__ static void st(Slot s, int j, double v) {
+#if ADSURF_SLAB_HINT
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(s.q + j * kWarp), "d"(v), "l"(s.pol) : "memory");
+#else
+    __stcg(s.q + j * kWarp, v);
+#endif
+  }
 };
 
 // Dense grid, fused forward + adjoint with per-model gradient reduction.  Persistent: each block
@@ -256,6 +284,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
   double* ests = (double*)(flags + ((gp.tc * (L - 1) + 1) & ~1));  // [wpb][L-1][kSlot][32] (shared variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
+  const unsigned long long slab_policy = kGlobal ? l2_evict_last_policy() : 0ull;
   double* acc = accs + (size_t)warp * kAccPer * L;
   double* estp = kGlobal ? estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + lane
                          : ests + (size_t)warp * slab + lane;
@@ -287,7 +316,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
         double v;
         if (kGlobal) {
-          const GlobalStore st{estp};
+          const GlobalStore st{estp, slab_policy};
           FoldSink sink{acc, lane};
           v = sample_forward_store(src, z, st);
           sample_adjoint(src, z, seed, st, sink);
