@@ -132,3 +132,23 @@ def test_config4_friul_ensemble_step_and_sensitivity(api):
     got = out["dc_dvs"][:40].cpu().numpy()
     scale = np.max(np.abs(kern), axis=1, keepdims=True)
     assert np.max(np.abs(got - kern) / scale) < 1e-6   # roots are float32-accurate: dF/dc is well away from 0
+
+
+@pytest.mark.parametrize("tag,modes,dc", [("m6", (0,), 0.001), ("m3", (0, 1, 2), 0.001), ("m20", (0,), 0.01)])
+def test_gpu_dispersion_curves_match_reference_solver(api, tag, modes, dc):
+    """all modes at once from the dense kernel + batched refinement vs the reference's sequential solver"""
+    from adsurf_b200.dispersion import dispersion_curves
+    g = load("surf96_roots")
+    t, d, a, b, rho = (g[f"{tag}_{k}"] for k in ("t", "d", "a", "b", "rho"))
+    c = dispersion_curves(t, d, a, b, rho, modes=modes, dc=dc)
+    for i, mode in enumerate(modes):
+        ref = g[f"{tag}_mode{mode}_c"]
+        both = (c[i] > 0) & (ref > 0)
+        assert both.sum() >= 0.9 * (ref > 0).sum()
+        assert np.max(np.abs(c[i][both] - ref[both])) < 5e-6
+    # converged roots are zeros of the secular function to rounding
+    from adsurf_b200 import ops
+    has = c[0] > 0
+    F = ops.det_points(c[0][has], t[has], d, a, b, rho).cpu().numpy()
+    cmax, cmin = ops.det_grid_minmax(np.linspace(c[0][has].min() * 0.9, b.max(), 200), t[has], d, a, b, rho)
+    assert np.max(np.abs(F) / (cmax - cmin).cpu().numpy()) < 1e-9

@@ -129,3 +129,18 @@ def test_config2_trajectory_head(ab):
     np.testing.assert_allclose(np.asarray(inv.inv_process["iter_vs"])[:n_it], s["c2_iter_vs_head"][:n_it], atol=2e-5)
     np.testing.assert_allclose(np.asarray(inv.inv_process["iter_thick"])[:n_it], s["c2_iter_thick_head"][:n_it], atol=2e-5)
     assert set(inv.inv_model) == {"thick", "vp", "vs", "rho"}
+
+
+def test_gpu_dispersion_extraction_logic(ab):
+    """dense-grid bracketing + batched regula falsi (adsurf_b200.dispersion) against the reference solver's
+    roots; kernels served by the oracle here, the real kernels in tests/test_gpu_api.py."""
+    from adsurf_b200.dispersion import dispersion_curves
+    g = load("surf96_roots")
+    t, d, a, b, rho = (g[f"m3_{k}"] for k in ("t", "d", "a", "b", "rho"))
+    sel = slice(0, 60, 4)
+    c = dispersion_curves(t[sel], d, a, b, rho, modes=(0, 1, 2), dc=0.001)
+    for i in range(3):
+        ref = g[f"m3_mode{i}_c"][sel]
+        both = (c[i] > 0) & (ref > 0)
+        assert both.sum() >= 0.8 * (ref > 0).sum()
+        assert np.max(np.abs(c[i][both] - ref[both])) < 5e-6  # the reference stops at 1e-6 relative
