@@ -103,6 +103,7 @@ struct JacSink {  // write this sample's Jacobian rows
 __device__ __forceinline__ void stage_params(double* __restrict__ par, const double* __restrict__ d,
                                              const double* __restrict__ alpha, const double* __restrict__ beta,
                                              const double* __restrict__ rho, int s, int L) {
+  stage_exp_table();
   for (int m = threadIdx.x; m < L; m += blockDim.x) {
     stage_one(par, L, m, d[(size_t)s * L + m], alpha[(size_t)s * L + m], beta[(size_t)s * L + m],
               rho[(size_t)s * L + m]);
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const double* __restrict__ d, 
                                                   double* __restrict__ pmax, double* __restrict__ pmin,
                                                   uint32_t* __restrict__ signbits) {
   extern __shared__ double smem[];
-  double* par = smem;
+  double* par = smem + kSmemHead;
   double* tab = par + par_doubles(L);                   // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
   int* flags = (int*)(ics + gp.tc);                     // [tc][L-1]
@@ -276,7 +277,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
            double* __restrict__ det, double* __restrict__ part, double* __restrict__ estore) {
   extern __shared__ double smem[];
   constexpr int kAccPer = kGlobal ? 64 : 4;             // accumulator doubles per (warp, layer)
-  double* par = smem;                                   // staged layer constants
+  double* par = smem + kSmemHead;                       // staged layer constants (after the exp table)
   double* accs = par + par_doubles(L);                  // [wpb][L][4][16] (global slabs) or [wpb][4][L]
   double* tab = accs + (size_t)gp.wpb * kAccPer * L;    // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(128) k_points_fwd(const double* __restrict__ d
                                                     const double* __restrict__ t, const double* __restrict__ c, int L,
                                                     int N, PointsPlan pp, double* __restrict__ F) {
   extern __shared__ double smem[];
-  double* par = smem;
+  double* par = smem + kSmemHead;
   const int s = blockIdx.x / pp.bpm;
   const int blk = blockIdx.x - s * pp.bpm;
   stage_params(par, d, alpha, beta, rho, s, L);
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(128) k_points_bwd(const double* __restrict__ d
                                                     int nchunk, int compress, int with_grad, double* __restrict__ norm,
                                                     double* __restrict__ loss_part) {
   extern __shared__ double smem[];
-  double* par = smem;
+  double* par = smem + kSmemHead;
   double* accs = par + par_doubles(L);             // [wpb][4][L]
   double* lossw = accs + (size_t)pp.wpb * 4 * L;  // [wpb]
   double* ests = lossw + pp.wpb;                 // [wpb][L-1][5][32]
@@ -526,6 +527,8 @@ __global__ void __launch_bounds__(256) k_dfma_probe(int iters, double* __restric
 
 __global__ void k_math_probe(const double* __restrict__ x, int n, double* __restrict__ rs, double* __restrict__ ex,
                              double* __restrict__ sn, double* __restrict__ cs) {
+  stage_exp_table();
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   rs[i] = rsqrt_hd(x[i]);
@@ -540,11 +543,13 @@ constexpr int kNumSM = 148;
 constexpr size_t kSmemBudget = 100 * 1024;   // per block, so that two blocks fit an SM
 constexpr size_t kSmemMax = 227 * 1024;
 
+inline size_t par_bytes(int L) { return (size_t)(kSmemHead + par_doubles(L)) * sizeof(double); }
+
 inline size_t est_bytes_per_warp(int L) { return (size_t)(L > 1 ? L - 1 : 0) * kSlot * kWarp * sizeof(double); }
 
 // warps per block for the adjoint kernels; 0 if even one warp does not fit
 inline int adj_wpb(int L) {
-  const size_t fixed = (size_t)par_doubles(L) * sizeof(double) + 64;
+  const size_t fixed = par_bytes(L) + 64;
   const size_t per_warp = est_bytes_per_warp(L) + (size_t)4 * L * sizeof(double) + sizeof(double);
   for (int w = 4; w >= 1; w >>= 1) {
     const size_t need = fixed + (size_t)w * per_warp;
@@ -554,7 +559,7 @@ inline int adj_wpb(int L) {
 }
 
 inline size_t adj_smem(int L, int wpb) {
-  return (size_t)par_doubles(L) * sizeof(double) + (size_t)wpb * ((size_t)4 * L * sizeof(double) + sizeof(double)) +
+  return par_bytes(L) + (size_t)wpb * ((size_t)4 * L * sizeof(double) + sizeof(double)) +
          (size_t)wpb * est_bytes_per_warp(L);
 }
 
@@ -716,7 +721,7 @@ int adsurf_det_points_fwd(const double* d, const double* alpha, const double* be
   pp.units = (N + kWarp - 1) / kWarp;
   pp.wpb = 4;
   pp.bpm = (N + 127) / 128;
-  const size_t smem = (size_t)par_doubles(L) * sizeof(double);
+  const size_t smem = par_bytes(L);
   if (set_smem(k_points_fwd, smem)) return ADSURF_E_CUDA;
   k_points_fwd<<<(unsigned)((size_t)S * pp.bpm), 128, smem, (cudaStream_t)stream>>>(d, alpha, beta, rho, t, c, L, N,
                                                                                       pp, F);
@@ -776,7 +781,7 @@ int adsurf_det_points_jac(const double* d, const double* alpha, const double* be
 static int grid_fwd_launch(const double* d, const double* alpha, const double* beta, const double* rho,
                            const double* t, const double* c, int S, int L, int NF, int K, double* det, double* pmax,
                            double* pmin, uint32_t* signbits, const GridPlan& gp, cudaStream_t st) {
-  const size_t smem = (size_t)par_doubles(L) * sizeof(double) + table_bytes(L, gp.tc);
+  const size_t smem = par_bytes(L) + table_bytes(L, gp.tc);
   if (set_smem(k_grid_fwd, smem)) return ADSURF_E_CUDA;
   k_grid_fwd<<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K, gp,
                                                                             det, pmax, pmin, signbits);
@@ -822,7 +827,7 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = bwd_mode();
-  const size_t smem = (size_t)par_doubles(L) * sizeof(double) +
+  const size_t smem = par_bytes(L) +
                       (size_t)gp.wpb * (mode == kBwdSmem ? 4 : 64) * L * sizeof(double) + table_bytes(L, gp.tc) +
                       (mode == kBwdSmem ? (size_t)gp.wpb * est_bytes_per_warp(L) : 0);
   double* estore = mode == kBwdSmem ? nullptr : (double*)((char*)ws + part_bytes);
@@ -909,7 +914,7 @@ int adsurf_math_probe(const double* x, int n, double* out_rsqrt, double* out_exp
                       double* out_cos, void* stream) {
   if (!x || !out_rsqrt || !out_expneg || !out_sin || !out_cos) return ADSURF_E_NULL;
   if (n <= 0) return ADSURF_E_SHAPE;
-  k_math_probe<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, n, out_rsqrt, out_expneg, out_sin, out_cos);
+  k_math_probe<<<(n + 255) / 256, 256, kSmemHead * sizeof(double), (cudaStream_t)stream>>>(x, n, out_rsqrt, out_expneg, out_sin, out_cos);
   return check_launch();
 }
 

@@ -62,11 +62,6 @@ constexpr double kShifter = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-ne
 
 // Polynomial coefficients live in constant memory on the device so that DFMA reads them as
 // c[bank][offset] operands instead of materialising each 64-bit literal with two UMOVs.
-#define ADSURF_EXP_COEFS                                                                              \
-  { 1.1470745597729725e-11, 2.08767569878681e-09, 2.755731922398589e-07, 2.48015873015873e-05,          \
-    0.001388888888888889, 0.041666666666666664, 0.5, /* even: 1/14! ... 1/2! */                         \
-    1.6059043836821613e-10, 2.505210838544172e-08, 2.7557319223985893e-06, 0.0001984126984126984,      \
-    0.008333333333333333, 0.16666666666666666 /* odd: 1/13! ... 1/3! */ }
 #define ADSURF_SIN_COEFS                                                                              \
   { 1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,               \
     -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01 }
@@ -76,12 +71,10 @@ constexpr double kShifter = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-ne
 #define ADSURF_RED_CONSTS                                                                             \
   { 1.4426950408889634, -0.6931471805599453, -2.3190468138462996e-17, /* log2 e, -ln2 hi, -ln2 lo */    \
     0.6366197723675814, -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33 /* 2/pi, -pi/2 x3 */ }
-static const double kExpCH[13] = ADSURF_EXP_COEFS;
 static const double kSinCH[6] = ADSURF_SIN_COEFS;
 static const double kCosCH[6] = ADSURF_COS_COEFS;
 static const double kRedCH[7] = ADSURF_RED_CONSTS;
 #if defined(__CUDACC__)
-__constant__ double kExpCD[13] = ADSURF_EXP_COEFS;
 __constant__ double kSinCD[6] = ADSURF_SIN_COEFS;
 __constant__ double kCosCD[6] = ADSURF_COS_COEFS;
 __constant__ double kRedCD[7] = ADSURF_RED_CONSTS;
@@ -92,26 +85,50 @@ __constant__ double kRedCD[7] = ADSURF_RED_CONSTS;
 #define ADSURF_K(tab, i) tab##H[i]
 #endif
 
-// exp(-p) for 0 <= p (< ~700): n = rint(-p log2 e), r = -p - n ln2 (two-term), Taylor polynomial in
-// even/odd halves (|r| <= ln2/2, truncation 4e-18), scaled by 2^n through the exponent field.
+// 2^(j/32), j = 0..31 (correctly rounded).  On the device the table lives in the first kSmemHead
+// doubles of every kernel's dynamic shared memory (per-lane indices: a constant-memory table would
+// serialise); every kernel that evaluates exp_neg stages it with stage_exp_table().
+constexpr int kSmemHead = 32;
+#define ADSURF_EXP2_TABLE                                                                                     \
+  { 1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,    \
+    1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484,            \
+    1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,          \
+    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, 1.5422108254079407,         \
+    1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429, 1.718619298122478,            \
+    1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,            \
+    1.9571441241754002 }
+static const double kExp2TabH[32] = ADSURF_EXP2_TABLE;
+#if defined(__CUDACC__)
+__constant__ double kExp2TabD[32] = ADSURF_EXP2_TABLE;
+extern __shared__ double adsurf_smem_head[];
+__device__ __forceinline__ void stage_exp_table() {
+  for (int j = threadIdx.x; j < kSmemHead; j += blockDim.x) adsurf_smem_head[j] = kExp2TabD[j];
+}
+#endif
+#if defined(__CUDA_ARCH__)
+#define ADSURF_EXP2_TAB(j) adsurf_smem_head[j]
+#else
+#define ADSURF_EXP2_TAB(j) kExp2TabH[j]
+#endif
+
+// exp(-p) for 0 <= p (< ~700): n = rint(-p 32/ln2), r = -p - n ln2/32 (two-term, |r| <= ln2/64),
+// e^r by a degree-6 Taylor polynomial (truncation 3.5e-18), times 2^(j/32) from the table (j = n mod 32)
+// scaled by 2^(n div 32) through the exponent field.  11 FP64 instructions, <= 2 ulp.
 ADSURF_HD double exp_neg(double p) {
   const double x = -fmin(p, 700.0);
-  const double t = fma(x, ADSURF_K(kRedC, 0), kShifter);
+  const double t = fma(x, 46.16624130844683, kShifter);
   const double fn = t - kShifter;
-  double r = fma(fn, ADSURF_K(kRedC, 1), x);
-  r = fma(fn, ADSURF_K(kRedC, 2), r);
-  const double r2 = r * r;
-  double ev = ADSURF_K(kExpC, 0);
-#pragma unroll
-  for (int i = 1; i < 7; ++i) ev = fma(ev, r2, ADSURF_K(kExpC, i));
-  double od = ADSURF_K(kExpC, 7);
-#pragma unroll
-  for (int i = 8; i < 13; ++i) od = fma(od, r2, ADSURF_K(kExpC, i));
-  // exp(r) = 1 + r + r2*(ev + r*od)
-  const double q = fma(r, od, ev);
-  const double er = fma(r2, q, r) + 1.0;
-  const long long n = (long long)(int)dbl_bits(t);    // low 32 bits hold the (two's complement) integer
-  return bits_dbl(dbl_bits(er) + (n << 52));
+  double r = fma(fn, -0.02166084939249829, x);
+  r = fma(fn, -7.247021293269686e-19, r);
+  const int n = (int)dbl_bits(t);  // low 32 bits hold the (two's complement) integer
+  double q = fma(0.001388888888888889, r, 0.008333333333333333);
+  q = fma(q, r, 0.041666666666666664);
+  q = fma(q, r, 0.16666666666666666);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  const double tj = bits_dbl(dbl_bits(ADSURF_EXP2_TAB(n & 31)) + ((long long)(n >> 5) << 52));
+  return tj * q;
 }
 
 // sin and cos of q for |q| < 1e5: Cody-Waite reduction by pi/2 in three FMA steps, then the fdlibm
