@@ -29,6 +29,7 @@ EXPORTS = (
     "adsurf_dmf_step",
     "adsurf_fp64_peak_probe",
     "adsurf_math_probe",
+    "adsurf_ensemble_adam_step",
 )
 
 _lib = None
@@ -61,6 +62,10 @@ def lib():
         L.adsurf_det_grid_bwd.argtypes = [vp] * 7 + [ci] * 4 + [vp] * 5 + [vp, sz, vp]
         L.adsurf_dmf_step.argtypes = [vp] * 7 + [ci] * 6 + [vp] * 7 + [vp, sz, vp]
         L.adsurf_fp64_peak_probe.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]
+        cd = ctypes.c_double
+        L.adsurf_ensemble_adam_step.argtypes = ([vp] * 20 + [ci, ci, ci, cd, ci, ci, cd, cd, cd, cd, cd, cd, ci]
+                                                + [vp, vp, vp, sz, vp])
+        L.adsurf_ensemble_adam_step.restype = ci
         L.adsurf_math_probe.argtypes = [vp, ci, vp, vp, vp, vp, vp]
         L.adsurf_math_probe.restype = ci
         for name in EXPORTS:
@@ -195,8 +200,11 @@ def grid_bwd(d, a, b, rho, t, c, gdet=None, want_det=False, out=None, ws=None):
     return (det,) + tuple(out)
 
 
-def dmf_step(d, a, b, rho, t, c, C, compress, with_grad=True, want_F=False, want_norm=False):
-    """(loss [S], F | None, norm | None, gd, ga, gb, grho | None x4)"""
+def dmf_step(d, a, b, rho, t, c, C, compress, with_grad=True, want_F=False, want_norm=False, loss=None, grads=None,
+             ws=None):
+    """(loss [S], F | None, norm | None, gd, ga, gb, grho | None x4)
+
+    `loss`, `grads` (4 x [S,L]) and `ws` (uint8 scratch) may be passed to reuse buffers across iterations."""
     global launch_count
     _req(d, a, b, rho, t, c, C)
     S, L = d.shape
@@ -204,11 +212,15 @@ def dmf_step(d, a, b, rho, t, c, C, compress, with_grad=True, want_F=False, want
     K = C.shape[1] if C is not None else 0
     dev = d.device
     normalised = compress in (COMPRESS_EXP, COMPRESS_LOG, COMPRESS_NORM)
-    loss = torch.empty((S,), dtype=torch.float64, device=dev)
+    if loss is None:
+        loss = torch.empty((S,), dtype=torch.float64, device=dev)
     F = torch.empty((S, N), dtype=torch.float64, device=dev) if want_F else None
     norm = torch.empty((S, N), dtype=torch.float64, device=dev) if (want_norm and normalised) else None
-    grads = tuple(torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4)) if with_grad else (None,) * 4
-    ws, nbytes = _workspace(OP_DMF_STEP, S, L, N, K if normalised else 0, d)
+    if grads is None:
+        grads = tuple(torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4)) if with_grad else (None,) * 4
+    nbytes = lib().adsurf_workspace_bytes(OP_DMF_STEP, S, L, N, K if normalised else 0)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _check(lib().adsurf_dmf_step(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), _ptr(c), _ptr(C), S, L, N, K,
                                      int(compress), int(bool(with_grad)), _ptr(loss), _ptr(F), _ptr(norm),
@@ -235,3 +247,33 @@ def math_probe(x):
     with torch.cuda.device(x.device):
         _check(lib().adsurf_math_probe(_ptr(x), x.numel(), *(_ptr(o) for o in outs), _stream(x)))
     return tuple(outs)
+
+
+VP_MODE = {"": 0, None: 0, "none": 0, "Brocher": 1, "Constant": 2, "USArray": 3}
+LAYERING = {"LR": 1, "LN": 2}
+
+
+def ensemble_adam_step(state, grads, loss, consts, *, vp_mode, vp_vs_ratio, invert_thick, layering, damp_vertical,
+                       damp_horizontal, lr, beta1, beta2, eps, step, iter_b=None, iter_d=None, ws=None):
+    """In-place optimiser step of the ensemble inversion (C ABI adsurf_ensemble_adam_step).
+
+    state  = dict(b, d, alpha, rho, mb, vb, md, vd)          [S,L] float64 CUDA, updated in place
+    grads  = (gd, ga, gb, grho) from dmf_step;  loss [S] gets the Tikhonov terms added
+    consts = dict(b0, alpha0, rho0, lower_b, upper_b, mindepth, maxdepth)"""
+    global launch_count
+    b = state["b"]
+    S, L = b.shape
+    _req(*state.values(), *grads, loss, *consts.values(), iter_b, iter_d)
+    if ws is None:
+        ws = torch.empty(3 * S * L * 8, dtype=torch.uint8, device=b.device)
+    gd, ga, gb, gr = grads
+    with torch.cuda.device(b.device):
+        _check(lib().adsurf_ensemble_adam_step(
+            _ptr(b), _ptr(state["d"]), _ptr(state["alpha"]), _ptr(state["rho"]), _ptr(gd), _ptr(ga), _ptr(gb), _ptr(gr),
+            _ptr(loss), _ptr(state["mb"]), _ptr(state["vb"]), _ptr(state["md"]), _ptr(state["vd"]), _ptr(consts["b0"]),
+            _ptr(consts["alpha0"]), _ptr(consts["rho0"]), _ptr(consts["lower_b"]), _ptr(consts["upper_b"]),
+            _ptr(consts["mindepth"]), _ptr(consts["maxdepth"]), S, L, int(vp_mode), float(vp_vs_ratio or 0.0),
+            int(bool(invert_thick)), int(layering), float(damp_vertical), float(damp_horizontal), float(lr),
+            float(beta1), float(beta2), float(eps), int(step), _ptr(iter_b), _ptr(iter_d), _ptr(ws), ws.numel(),
+            _stream(b)))
+    launch_count += 2

@@ -21,7 +21,9 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _dist, ops
+import os
+
+from . import _capi, _dist, ops
 from ._utils import gen_model, gen_model1, ifunc_list, list2numpy, numpy2tensor
 
 try:  # progress bars are optional
@@ -311,6 +313,49 @@ class iter_inversion:
         self.inv_process = {"iter_vs": iter_vs.tolist(), "iter_thick": iter_thick.tolist(), "loss": loss_np.tolist()}
 
 
+def _fused_ensemble_loop(self, calculator, vlist, tlist, Clist, a_init, rho_init, lower_b, upper_b, mindepth, maxdepth,
+                         iter_vs, iter_thick, loss_list, vs_and_thick):
+    """Iterations of multi_inversion with everything on the device: per iteration one fused
+    DMF evaluation with gradient (`adsurf_dmf_step`) and one optimiser step (`adsurf_ensemble_adam_step`:
+    velocity chain, Tikhonov terms, projection, Adam, next Vp/rho).  Same order of operations as the torch loop
+    below (loss -> gradient -> projection -> record -> Adam -> StepLR); tests compare the two trajectories."""
+    ip, mp = self.inv_param, self.model_param
+    c64 = lambda x: x.detach().to(torch.float64).contiguous().clone()
+    b, d = c64(calculator.b), c64(calculator.d)
+    S, L = b.shape
+    method = mp.initialize_method if mp.initialize_method in _capi.VP_MODE else ""
+    vp_mode = _capi.VP_MODE[method]
+    a0, r0 = c64(a_init), c64(rho_init)
+    with torch.no_grad():  # Vp / rho of the first evaluation come from the velocity chain, like forward() does
+        calculator_a, calculator_r = calculator._velocities()
+    state = {"b": b, "d": d, "alpha": c64(calculator_a), "rho": c64(calculator_r)}
+    for key in ("mb", "vb", "md", "vd"):
+        state[key] = torch.zeros_like(b)
+    full = lambda x: (torch.ones_like(b) * x).contiguous()
+    consts = {"b0": c64(calculator.b), "alpha0": a0, "rho0": r0, "lower_b": full(lower_b), "upper_b": full(upper_b),
+              "mindepth": full(mindepth), "maxdepth": full(maxdepth)}
+    mode = ops.COMPRESS[_compress_mode(ip.compress, ip.normalized, ip.compress_method)]
+    layering = _capi.LAYERING.get(mp.layering_method, 0)
+    grads = tuple(torch.empty_like(b) for _ in range(4))
+    ws_step = torch.empty(3 * S * L * 8, dtype=torch.uint8, device=b.device)
+    ws_dmf = None
+    vlist, tlist, Clist = (x.contiguous() for x in (vlist, tlist, Clist))
+    for j in range(ip.iteration):
+        lr = ip.lr * ip.gamma ** (j // ip.step_size)  # StepLR: scheduler.step() follows optimizer.step()
+        loss = loss_list[j]
+        out = _capi.dmf_step(state["d"], state["alpha"], state["b"], state["rho"], tlist, vlist, Clist, mode,
+                             with_grad=True, loss=loss, grads=grads, ws=ws_dmf)
+        _capi.ensemble_adam_step(state, grads, loss, consts, vp_mode=vp_mode, vp_vs_ratio=mp.vp_vs_ratio,
+                                 invert_thick=vs_and_thick, layering=layering, damp_vertical=ip.damp_vertical,
+                                 damp_horizontal=ip.damp_horizontal, lr=lr, beta1=0.9, beta2=0.999, eps=1e-8,
+                                 step=j + 1, iter_b=iter_vs[j], iter_d=iter_thick[j] if vs_and_thick else None,
+                                 ws=ws_step)
+    with torch.no_grad():
+        calculator.b.data.copy_(state["b"])
+        if vs_and_thick:
+            calculator.d.data.copy_(state["d"])
+
+
 def _final_model(model_param, thick, vs, AK135_data):
     method = model_param.initialize_method
     if method == "Brocher":
@@ -336,6 +381,8 @@ class multi_inversion:
     With torch.distributed initialised (one process per GPU) the model axis is sharded across the
     ranks; the per-model losses and iterates are all-gathered at the end (and neighbouring rows
     of Vs every iteration when damp_horizontal > 0) — see adsurf_b200/_dist.py."""
+
+    _fused_loop = _fused_ensemble_loop
 
     def __init__(self, model_param, inv_param, init_model, pvs_obs, vsrange_sign="mul", vsrange=[0.1, 2],
                  AK135_data=[], device="cuda"):
@@ -395,7 +442,13 @@ class multi_inversion:
         vs_and_thick = inversion_method.lower() == "vs-and-thick"
         b0 = b.clone()
         ones = torch.ones(S, dtype=torch.float64, device=dev)
-        for j in tqdm(range(iteration), disable=not getattr(ip, "progress", False)):
+        fused = (os.environ.get("ADSURF_FUSED_OPT", "1") != "0" and dev.type == "cuda"
+                 and not (sharded and ip.damp_horizontal > 0))
+        if fused:
+            # whole iteration on the device: adsurf_dmf_step + adsurf_ensemble_adam_step, no torch autograd
+            self._fused_loop(calculator, vlist, tlist, Clist, a, rho, lower_b, upper_b, layer_mindepth, layer_maxdepth,
+                             iter_vs, iter_thick, loss_list, vs_and_thick)
+        for j in tqdm(range(0 if not fused else iteration, iteration), disable=not getattr(ip, "progress", False)):
             loss = calculator(vlist, tlist)
             optimizer.zero_grad()
             if calculator.coupling is not None:  # horizontal-damping rows owned by other ranks

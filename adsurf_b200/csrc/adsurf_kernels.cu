@@ -525,6 +525,146 @@ __global__ void __launch_bounds__(256) k_dfma_probe(int iters, double* __restric
   if (r == 12345.678) out[0] = r;  // never true; keeps the chains alive
 }
 
+// ---- ensemble optimiser step (N3) -----------------------------------------------------------------------
+__device__ __forceinline__ double sgn(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : (v == 0.0 ? 0.0 : NAN)); }
+__device__ __forceinline__ double brocher_vp(double b) {
+  return 0.9409 + 2.0947 * b - 0.8206 * b * b + 0.2683 * b * b * b - 0.0251 * b * b * b * b;
+}
+__device__ __forceinline__ double brocher_dvp(double b) {
+  return 2.0947 - 2.0 * 0.8206 * b + 3.0 * 0.2683 * b * b - 4.0 * 0.0251 * b * b * b;
+}
+__device__ __forceinline__ double brocher_rho(double a) {
+  return 1.6612 * a - 0.4721 * a * a + 0.0671 * a * a * a - 0.0043 * a * a * a * a + 0.000106 * a * a * a * a * a;
+}
+__device__ __forceinline__ double brocher_drho(double a) {
+  return 1.6612 - 2.0 * 0.4721 * a + 3.0 * 0.0671 * a * a - 4.0 * 0.0043 * a * a * a + 5.0 * 0.000106 * a * a * a * a;
+}
+// second-difference operator tridiag(-1, 2, -1) with corner entries 1 applied along an axis of length n
+__device__ __forceinline__ double lap(double xm, double x0, double xp, int i, int n) {
+  if (n == 1) return x0;
+  if (i == 0) return x0 - xp;
+  if (i == n - 1) return x0 - xm;
+  return 2.0 * x0 - xm - xp;
+}
+
+// phase 1 (reads the CURRENT, not yet projected, b — the point where the misfit was evaluated): gradient of
+// the data term w.r.t. b through the velocity chain, sign fields of the two Tikhonov terms, total loss
+__global__ void k_ens_prepare(const double* __restrict__ b, const double* __restrict__ alpha,
+                              const double* __restrict__ ga, const double* __restrict__ gb,
+                              const double* __restrict__ gr, int S, int L, int vp_mode, double ratio, double dv,
+                              double dh, double* __restrict__ gt, double* __restrict__ sv, double* __restrict__ sh,
+                              double* __restrict__ loss) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double add = 0.0;
+  for (int l = 0; l < L; ++l) {
+    const size_t i = (size_t)s * L + l;
+    const double x0 = b[i];
+    double g = gb[i];
+    if (vp_mode == 1 || (vp_mode == 3 && x0 <= 4.6)) {
+      g += (ga[i] + gr[i] * brocher_drho(alpha[i])) * brocher_dvp(x0);
+    } else if (vp_mode == 2) {
+      g += ga[i] * ratio;
+    }
+    gt[i] = g;
+    if (dv > 0.0) {
+      const double mv = dv * lap(l > 0 ? b[i - 1] : 0.0, x0, l < L - 1 ? b[i + 1] : 0.0, l, L) / L;
+      add += fabs(mv);
+      sv[i] = sgn(mv);
+    }
+    if (dh > 0.0) {
+      const double mh = dh * lap(s > 0 ? b[i - L] : 0.0, x0, s < S - 1 ? b[i + L] : 0.0, s, S) / L;
+      add += fabs(mh);
+      sh[i] = sgn(mh);
+    }
+  }
+  loss[s] += add;
+}
+
+struct EnsArgs {
+  double *b, *d, *alpha, *rho, *mb, *vb, *md, *vd, *iter_b, *iter_d;
+  const double *gd, *gt, *b0, *a0, *r0, *lob, *upb, *mind, *maxd, *sv, *sh;
+  int S, L, vp_mode, invert_thick, layering;
+  double ratio, dv, dh, lr, beta1, beta2, eps, bc1, bc2s;
+};
+
+__device__ __forceinline__ double adam(double p, double g, double& m, double& v, const EnsArgs& A) {
+  m = m + (1.0 - A.beta1) * (g - m);                // exp_avg.lerp_(grad, 1 - beta1)
+  v = A.beta2 * v + (1.0 - A.beta2) * g * g;        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const double denom = sqrt(v) / A.bc2s + A.eps;    // bias_correction2_sqrt
+  return p - (A.lr / A.bc1) * (m / denom);
+}
+
+// phase 2: one thread per model
+__global__ void k_ens_adam(EnsArgs A) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= A.S) return;
+  const int L = A.L, S = A.S;
+  const size_t o = (size_t)s * L;
+  // --- projection of Vs (before the optimiser step, as the reference orders it); torch.clamp keeps NaN
+  double prev = 0.0;
+  for (int l = 0; l < L; ++l) {
+    double x = A.b[o + l];
+    if (x != x && !A.invert_thick) x = A.b0[o + l];                 // NaN repair exists on the vs-only branch (:624-626)
+    if (x == x) x = fmin(fmax(x, A.lob[o + l]), A.upb[o + l]);       // clip_(min, max): max wins when min > max
+    if (l == L - 1 && L > 1 && x == x && prev == prev) x = fmax(x, prev);  // half-space >= layer above (:599/:631)
+    prev = x;
+    A.b[o + l] = x;
+    if (A.iter_b) A.iter_b[o + l] = x;
+  }
+  // --- projection of the depths
+  if (A.invert_thick) {
+    const double floor_t = A.mind[0];
+    double depth = 0.0, pdepth = 0.0;  // running cumulative depth (raw) and previous projected depth
+    for (int l = 0; l < L; ++l) {
+      depth += A.d[o + l];
+      double z = depth;
+      if (A.layering == 1) {
+        z = fmin(fmax(z, A.mind[o + l]), A.maxd[o + l]);
+      } else if (A.layering == 2) {
+        const double lo = l == 0 ? A.mind[o + l] : pdepth + A.mind[o + l];
+        z = fmin(fmax(z, lo), A.maxd[o + l]);
+      }
+      const double th = fmax(z - pdepth, floor_t);
+      pdepth = z;
+      A.d[o + l] = th;
+      if (A.iter_d) A.iter_d[o + l] = th;
+    }
+  }
+  // --- Tikhonov subgradients on top of the chain gradient of phase 1, Adam, next alpha / rho
+  for (int l = 0; l < L; ++l) {
+    const double x = A.b[o + l];
+    double g = A.gt[o + l];
+    if (A.dv > 0.0) {
+      const double c = lap(l > 0 ? A.sv[o + l - 1] : 0.0, A.sv[o + l], l < L - 1 ? A.sv[o + l + 1] : 0.0, l, L);
+      g += A.dv / L * c;
+    }
+    if (A.dh > 0.0) {
+      const double c = lap(s > 0 ? A.sh[o - L + l] : 0.0, A.sh[o + l], s < S - 1 ? A.sh[o + L + l] : 0.0, s, S);
+      g += A.dh / L * c;
+    }
+    double m = A.mb[o + l], v = A.vb[o + l];
+    const double xn = adam(x, g, m, v, A);
+    A.mb[o + l] = m;
+    A.vb[o + l] = v;
+    A.b[o + l] = xn;
+    if (A.vp_mode == 1 || A.vp_mode == 3) {
+      const bool low = A.vp_mode == 1 || xn <= 4.6;
+      const double an = low ? brocher_vp(xn) : A.a0[o + l];
+      A.alpha[o + l] = an;
+      A.rho[o + l] = low ? brocher_rho(an) : A.r0[o + l];
+    } else if (A.vp_mode == 2) {
+      A.alpha[o + l] = xn * A.ratio;
+    }
+    if (A.invert_thick) {
+      double m2 = A.md[o + l], v2 = A.vd[o + l];
+      A.d[o + l] = adam(A.d[o + l], A.gd[o + l], m2, v2, A);
+      A.md[o + l] = m2;
+      A.vd[o + l] = v2;
+    }
+  }
+}
+
 __global__ void k_math_probe(const double* __restrict__ x, int n, double* __restrict__ rs, double* __restrict__ ex,
                              double* __restrict__ sn, double* __restrict__ cs) {
   stage_exp_table();
@@ -908,6 +1048,43 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
     return check_launch();
   }
   return ADSURF_OK;
+}
+
+int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho, const double* gd,
+                              const double* galpha, const double* gbeta, const double* grho, double* loss, double* mb,
+                              double* vb, double* md, double* vd, const double* b0, const double* alpha0,
+                              const double* rho0, const double* lower_b, const double* upper_b,
+                              const double* layer_mindepth, const double* layer_maxdepth, int S, int L, int vp_mode,
+                              double vp_vs_ratio, int invert_thick, int layering, double damp_vertical,
+                              double damp_horizontal, double lr, double beta1, double beta2, double eps, int step,
+                              double* iter_b, double* iter_d, void* ws, size_t ws_bytes, void* stream) {
+  if (!b || !d || !alpha || !rho || !galpha || !gbeta || !grho || !loss || !mb || !vb || !b0 || !alpha0 || !rho0 ||
+      !lower_b || !upper_b)
+    return ADSURF_E_NULL;
+  if (invert_thick && (!gd || !md || !vd || !layer_mindepth || !layer_maxdepth)) return ADSURF_E_NULL;
+  if (S <= 0 || L <= 0 || step < 1) return ADSURF_E_SHAPE;
+  if (vp_mode < 0 || vp_mode > 3 || layering < 0 || layering > 2) return ADSURF_E_ARG;
+  if (!ws || ws_bytes < (size_t)3 * S * L * sizeof(double)) return ADSURF_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* gt = (double*)ws;
+  double* sv = gt + (size_t)S * L;
+  double* sh = sv + (size_t)S * L;
+  const int threads = 128, blocks = (S + threads - 1) / threads;
+  k_ens_prepare<<<blocks, threads, 0, st>>>(b, alpha, galpha, gbeta, grho, S, L, vp_mode, vp_vs_ratio, damp_vertical,
+                                            damp_horizontal, gt, sv, sh, loss);
+  if (check_launch()) return ADSURF_E_CUDA;
+  EnsArgs A;
+  A.b = b; A.d = d; A.alpha = alpha; A.rho = rho; A.mb = mb; A.vb = vb; A.md = md; A.vd = vd;
+  A.iter_b = iter_b; A.iter_d = iter_d;
+  A.gd = gd; A.gt = gt; A.b0 = b0; A.a0 = alpha0; A.r0 = rho0;
+  A.lob = lower_b; A.upb = upper_b; A.mind = layer_mindepth; A.maxd = layer_maxdepth; A.sv = sv; A.sh = sh;
+  A.S = S; A.L = L; A.vp_mode = vp_mode; A.invert_thick = invert_thick; A.layering = layering;
+  A.ratio = vp_vs_ratio; A.dv = damp_vertical; A.dh = damp_horizontal; A.lr = lr; A.beta1 = beta1; A.beta2 = beta2;
+  A.eps = eps;
+  A.bc1 = 1.0 - pow(beta1, (double)step);
+  A.bc2s = sqrt(1.0 - pow(beta2, (double)step));
+  k_ens_adam<<<blocks, threads, 0, st>>>(A);
+  return check_launch();
 }
 
 int adsurf_math_probe(const double* x, int n, double* out_rsqrt, double* out_expneg, double* out_sin,

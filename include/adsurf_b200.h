@@ -128,6 +128,33 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
  * Used by bench.py for the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
 int adsurf_fp64_peak_probe(int iters, int repeats, double* tflops, double* ms, void* stream);
 
+/* Velocity-model chain and optimiser step of the ensemble inversion loop, on the device.
+ * One call finishes iteration j after adsurf_dmf_step produced the data misfit `loss` [S] and its gradients
+ * gd, galpha, gbeta, grho [S,L] at the current (d, alpha, beta, rho):
+ *   1. total misfit: loss[s] += damp_v sum_l |(L_v b_s)_l| / L + damp_h sum_l |(L_h b)_{s,l}| / L   (_model.py:466-477)
+ *   2. dloss/db through the velocity chain (vp_mode 1 Brocher: alpha = P4(b), rho = P5(alpha); 2 Constant:
+ *      alpha = ratio b; 3 USArray: Brocher where b <= 4.6; 0: alpha, rho fixed) plus the Tikhonov subgradients
+ *   3. parameter projection done by the reference BEFORE the optimiser step (_model.py:593-632): NaN repair
+ *      (vs-only), clip b to [lower_b, upper_b], b[:,L-1] >= b[:,L-2]; with invert_thick the cumulative depths
+ *      are clipped (layering 1 = LR, 2 = LN, 0 = none) and turned back into thicknesses >= min_thick;
+ *      the projected iterates are recorded in iter_b / iter_d (may be NULL)
+ *   4. Adam (torch.optim.Adam semantics, no weight decay/amsgrad) with learning rate `lr` and step count
+ *      `step` (1-based) on b, and on d when invert_thick
+ *   5. alpha, rho for the next iteration from the updated b.
+ * b, d, alpha, rho and the Adam moments mb, vb, md, vd [S,L] are updated in place; b0, alpha0, rho0 are the
+ * initial model (NaN repair / fixed values); ws >= 3*S*L doubles.  Replaces the torch autograd chain,
+ * torch.optim.Adam and the numpy clipping round trip of multi_inversion (_model.py:589-636). */
+int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho,
+                              const double* gd, const double* galpha, const double* gbeta, const double* grho,
+                              double* loss, double* mb, double* vb, double* md, double* vd,
+                              const double* b0, const double* alpha0, const double* rho0,
+                              const double* lower_b, const double* upper_b,
+                              const double* layer_mindepth, const double* layer_maxdepth,
+                              int S, int L, int vp_mode, double vp_vs_ratio, int invert_thick, int layering,
+                              double damp_vertical, double damp_horizontal,
+                              double lr, double beta1, double beta2, double eps, int step,
+                              double* iter_b, double* iter_d, void* ws, size_t ws_bytes, void* stream);
+
 /* Validation hook: evaluates the kernels' inline elementary functions on the device,
  * out_rsqrt[i] = 1/sqrt(x[i]), out_expneg[i] = exp(-x[i]), out_sin/out_cos[i] = sin/cos(x[i]).
  * Used by the GPU tests to bound their error against libm (no reference counterpart). */

@@ -152,3 +152,48 @@ def test_gpu_dispersion_curves_match_reference_solver(api, tag, modes, dc):
     F = ops.det_points(c[0][has], t[has], d, a, b, rho).cpu().numpy()
     cmax, cmin = ops.det_grid_minmax(np.linspace(c[0][has].min() * 0.9, b.max(), 200), t[has], d, a, b, rho)
     assert np.max(np.abs(F) / (cmax - cmin).cpu().numpy()) < 1e-9
+
+
+@pytest.mark.parametrize("case", ["brocher_thick_damped", "constant_thick", "brocher_vs_raw"])
+def test_fused_optimiser_loop_matches_torch_loop(api, case, monkeypatch):
+    """adsurf_ensemble_adam_step (velocity chain + Tikhonov + projection + Adam on the device) against the
+    torch-autograd / torch.optim.Adam loop, same order of operations as the reference (_model.py:589-636)."""
+    import types
+    from adsurf_b200._model import multi_inversion
+    from tests.golden_models import brocher_np
+    rng = np.random.default_rng(8)
+    S, iters = 12, 25
+    if case == "constant_thick":
+        g = load("dmf_const_m3")
+        b = np.tile(g["b"][0], (S, 1)) * (1 + rng.normal(0, 0.03, (S, 3)))
+        a, rho, d = b * 2.45, np.full_like(b, 2.0), np.tile(g["d"][0], (S, 1))
+        clist, init_method, inv_method, lm = np.arange(0.2, 0.4, 0.002), "Constant", "vs-and-thick", "LN"
+        lo, hi, dv, dh, compress, lr = np.full(3, 0.0005), np.full(3, 0.02), 0.0, 0.0, True, 0.001
+    else:
+        g = load("dmf_exp_m6")
+        b = np.tile(g["b"][0], (S, 1)) * (1 + rng.normal(0, 0.03, (S, 6)))
+        a, rho = brocher_np(b)
+        d = np.tile(g["d"][0], (S, 1))
+        clist, init_method = np.arange(2, 3.2, 0.01), "Brocher"
+        lo, hi = np.full(6, 0.05), np.full(6, 4.0)
+        if case == "brocher_thick_damped":
+            inv_method, lm, dv, dh, compress, lr = "vs-and-thick", "LR", 0.002, 0.001, True, 0.005
+            lo, hi = np.cumsum(d[0]) * 0.8, np.cumsum(d[0]) * 1.2
+        else:
+            inv_method, lm, dv, dh, compress, lr = "vs", "None", 0.0, 0.0, False, 0.03
+    obs = np.stack([np.column_stack((g["t"][0], g["c"][0]))] * S)
+    mp_ = types.SimpleNamespace(clist=clist, layering_method=lm, initialize_method=init_method, vp_vs_ratio=2.45, rho=2)
+    ip = types.SimpleNamespace(damp_vertical=dv, damp_horizontal=dh, compress=compress, normalized=True,
+                               compress_method="exp", inversion_method=inv_method, lr=lr, iteration=iters,
+                               step_size=10, gamma=0.5, optimizer="Adam")
+    init = types.SimpleNamespace(init_model={"vs": b, "vp": a, "rho": rho, "thick": d, "layer_mindepth": lo,
+                                             "layer_maxdepth": hi})
+    runs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ADSURF_FUSED_OPT", flag)
+        inv = multi_inversion(mp_, ip, init, obs, vsrange_sign="mul", vsrange=[0.7, 1.3], device="cuda")
+        runs[flag] = (np.asarray(inv.inv_process["loss"]), np.asarray(inv.inv_process["iter_vs"]),
+                      np.asarray(inv.inv_process["iter_thick"]), np.asarray(inv.inv_model["vs"]))
+    for x, y in zip(runs["1"], runs["0"]):
+        np.testing.assert_allclose(x, y, rtol=1e-8, atol=1e-12)
+    assert np.isfinite(runs["1"][0]).all()
