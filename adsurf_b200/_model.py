@@ -444,6 +444,10 @@ class multi_inversion:
         ones = torch.ones(S, dtype=torch.float64, device=dev)
         fused = (os.environ.get("ADSURF_FUSED_OPT", "1") != "0" and dev.type == "cuda"
                  and not (sharded and ip.damp_horizontal > 0))
+        import time
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        t_loop = time.perf_counter()
         if fused:
             # whole iteration on the device: adsurf_dmf_step + adsurf_ensemble_adam_step, no torch autograd
             self._fused_loop(calculator, vlist, tlist, Clist, a, rho, lower_b, upper_b, layer_mindepth, layer_maxdepth,
@@ -469,6 +473,10 @@ class multi_inversion:
             optimizer.step()
             scheduler.step()
             loss_list[j] = loss.detach()
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        # seconds spent in the optimisation loop proper (what the reference's tqdm bar times)
+        self.timing = {"loop_s": time.perf_counter() - t_loop, "iterations": iteration, "fused": bool(fused)}
         loss_list = torch.where(torch.isnan(loss_list), torch.full_like(loss_list, 10.0), loss_list)
         if sharded:  # the only exchange of the run: per-model losses and iterates of every rank
             loss_list = _dist.all_gather_rows(loss_list, S_all, dim=1)

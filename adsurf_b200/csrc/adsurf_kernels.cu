@@ -29,6 +29,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "adsurf_b200.h"
 #include "adsurf_math.cuh"
 
@@ -362,9 +364,10 @@ __global__ void k_grad_reduce(const double* __restrict__ part, int L, int bpm, d
 }
 
 struct PointsPlan {
-  int units;  // ceil(N/32) warp units per model
+  int units;   // ceil(N/32) warp units per model
   int wpb;
   int bpm;
+  int global;  // 1: persistent blocks with the store slabs in the global (L2) slab
 };
 
 // Pointwise forward at the observed picks.
@@ -413,91 +416,110 @@ __device__ __forceinline__ void dmf_compress(int mode, double F, double n, doubl
 
 // Pointwise forward + adjoint.  kind 0: upstream gF given; kind 1: Jacobian rows; kind 2: fused DMF
 // (normalisation read from the dense pass partials, loss partial written per block).
-template <int kKind>
-__global__ void __launch_bounds__(128) k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha,
-                                                    const double* __restrict__ beta, const double* __restrict__ rho,
-                                                    const double* __restrict__ t, const double* __restrict__ c,
-                                                    const double* __restrict__ gF, int L, int N, PointsPlan pp,
-                                                    double* __restrict__ F, double* __restrict__ gc,
-                                                    double* __restrict__ part,
-                                                    // Jacobian outputs
-                                                    double* __restrict__ Jd, double* __restrict__ Ja,
-                                                    double* __restrict__ Jb, double* __restrict__ Jrho,
-                                                    // DMF
-                                                    const double* __restrict__ pmax, const double* __restrict__ pmin,
-                                                    int nchunk, int compress, int with_grad, double* __restrict__ norm,
-                                                    double* __restrict__ loss_part) {
+template <int kKind, bool kGlobal>
+__global__ void __maxnreg__(kGlobal ? 168 : 232)
+k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const double* __restrict__ beta,
+             const double* __restrict__ rho, const double* __restrict__ t, const double* __restrict__ c,
+             const double* __restrict__ gF, int L, int N, PointsPlan pp, int total_vblocks, double* __restrict__ F,
+             double* __restrict__ gc, double* __restrict__ part, double* __restrict__ estore,
+             // Jacobian outputs
+             double* __restrict__ Jd, double* __restrict__ Ja, double* __restrict__ Jb, double* __restrict__ Jrho,
+             // DMF
+             const double* __restrict__ pmax, const double* __restrict__ pmin, int nchunk, int compress, int with_grad,
+             double* __restrict__ norm, double* __restrict__ loss_part) {
+  // kGlobal: persistent blocks, store slabs in the L2-resident global slab, per-lane fold accumulators (large
+  // ensembles); otherwise one block per (model, 32*wpb picks) with the slabs in shared memory (small problems).
   extern __shared__ double smem[];
+  constexpr int kAccPer = kGlobal ? 64 : 4;
   double* par = smem + kSmemHead;
-  double* accs = par + par_doubles(L);             // [wpb][4][L]
-  double* lossw = accs + (size_t)pp.wpb * 4 * L;  // [wpb]
-  double* ests = lossw + pp.wpb;                 // [wpb][L-1][5][32]
-  const int s = blockIdx.x / pp.bpm;
-  const int blk = blockIdx.x - s * pp.bpm;
-  stage_params(par, d, alpha, beta, rho, s, L);
-  for (int i = threadIdx.x; i < pp.wpb * 4 * L + pp.wpb; i += blockDim.x) accs[i] = 0.0;
-  __syncthreads();
+  double* accs = par + par_doubles(L);                  // [wpb][L][4][16] or [wpb][4][L]
+  double* lossw = accs + (size_t)pp.wpb * kAccPer * L;  // [wpb]
+  double* ests = lossw + pp.wpb;                        // [wpb][L-1][kSlot][32] (shared variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blk * pp.wpb + warp;
-  if (unit < pp.units) {
-    double* acc = accs + (size_t)warp * 4 * L;
-    double* est = ests + (size_t)warp * (L - 1) * kSlot * kWarp + lane;
-    const int i = unit * kWarp + lane;
-    const bool active = i < N;
-    const size_t idx = (size_t)s * N + (active ? i : N - 1);
-    const double cc = c[idx];
-    const double ic = 1.0 / cc;
-    const Sample z = make_sample(omega_of_period(t[idx]), ic);
-    const PlainStore<kWarp> store{est};
-    const DirectSource src{par, L};
-    const double v = sample_forward_store(src, z, store);
-    if (F && active) F[idx] = v;
-    double seed = 1.0;
-    if (kKind == 0) seed = gF[idx];
-    if (kKind == 2) {
-      double n = 1.0;
-      if (compress == ADSURF_COMPRESS_EXP || compress == ADSURF_COMPRESS_LOG || compress == ADSURF_COMPRESS_NORM) {
-        double vmax = -INFINITY, vmin = INFINITY;
-        bool anynan = false;
-        const int ii = active ? i : N - 1;
-        for (int ch = 0; ch < nchunk; ++ch) {
-          const double a = pmax[((size_t)s * nchunk + ch) * N + ii], b = pmin[((size_t)s * nchunk + ch) * N + ii];
-          anynan |= (a != a) | (b != b);
-          vmax = fmax(vmax, a);
-          vmin = fmin(vmin, b);
+  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
+  double* acc = accs + (size_t)warp * kAccPer * L;
+  const unsigned long long slab_policy = kGlobal ? l2_evict_last_policy() : 0ull;
+  double* estp = kGlobal ? estore + ((size_t)blockIdx.x * pp.wpb + warp) * slab + lane : ests + (size_t)warp * slab + lane;
+  for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
+    const int s = vb / pp.bpm;
+    const int blk = vb - s * pp.bpm;
+    __syncthreads();
+    stage_params(par, d, alpha, beta, rho, s, L);
+    for (int i = threadIdx.x; i < pp.wpb * kAccPer * L + pp.wpb; i += blockDim.x) accs[i] = 0.0;
+    __syncthreads();
+    const int unit = blk * pp.wpb + warp;
+    if (unit < pp.units) {
+      const int i = unit * kWarp + lane;
+      const bool active = i < N;
+      const size_t idx = (size_t)s * N + (active ? i : N - 1);
+      const double cc = c[idx];
+      const double ic = 1.0 / cc;
+      const Sample z = make_sample(omega_of_period(t[idx]), ic);
+      const DirectSource src{par, L};
+      typename std::conditional<kGlobal, GlobalStore, PlainStore<kWarp>>::type store;
+      store.p = estp;
+      if constexpr (kGlobal) store.pol = slab_policy;
+      const double v = sample_forward_store(src, z, store);
+      if (F && active) F[idx] = v;
+      double seed = 1.0;
+      if (kKind == 0) seed = gF[idx];
+      if (kKind == 2) {
+        double n = 1.0;
+        if (compress == ADSURF_COMPRESS_EXP || compress == ADSURF_COMPRESS_LOG || compress == ADSURF_COMPRESS_NORM) {
+          double vmax = -INFINITY, vmin = INFINITY;
+          bool anynan = false;
+          const int ii = active ? i : N - 1;
+          for (int ch = 0; ch < nchunk; ++ch) {
+            const double a = pmax[((size_t)s * nchunk + ch) * N + ii], b = pmin[((size_t)s * nchunk + ch) * N + ii];
+            anynan |= (a != a) | (b != b);
+            vmax = fmax(vmax, a);
+            vmin = fmin(vmin, b);
+          }
+          n = anynan ? NAN : (vmax - vmin);
+          if (norm && active) norm[idx] = n;
         }
-        n = anynan ? NAN : (vmax - vmin);
-        if (norm && active) norm[idx] = n;
+        double absG;
+        dmf_compress(compress, v, n, 1.0 / (double)N, absG, seed);
+        double lsum = warp_sum(active ? absG : 0.0);
+        if (lane == 0) lossw[warp] = lsum;
       }
-      double absG;
-      dmf_compress(compress, v, n, 1.0 / (double)N, absG, seed);
-      double lsum = warp_sum(active ? absG : 0.0);
-      if (lane == 0) lossw[warp] = lsum;
-    }
-    if (kKind != 2 || with_grad) {
-      double gk;
-      if (kKind == 1) {
-        JacSink sink{Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
-                     Jrho ? Jrho + idx * L : nullptr, active};
-        gk = sample_adjoint(src, z, seed, store, sink);
-      } else {
-        ReduceSink sink{acc, L, lane};
-        gk = sample_adjoint(src, z, active ? seed : 0.0, store, sink);  // overhang lanes: zero seed
+      if (kKind != 2 || with_grad) {
+        double gk;
+        if (kKind == 1) {
+          JacSink sink{Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
+                       Jrho ? Jrho + idx * L : nullptr, active};
+          gk = sample_adjoint(src, z, seed, store, sink);
+        } else if (kGlobal) {
+          FoldSink sink{acc, lane};
+          gk = sample_adjoint(src, z, active ? seed : 0.0, store, sink);  // overhang lanes: zero seed
+        } else {
+          ReduceSink sink{acc, L, lane};
+          gk = sample_adjoint(src, z, active ? seed : 0.0, store, sink);
+        }
+        if (gc && active) gc[idx] = -z.k * ic * gk;  // k = omega0 / c
       }
-      if (gc && active) gc[idx] = -z.k * ic * gk;  // k = omega0 / c
     }
-  }
-  __syncthreads();
-  if (kKind != 1) {
-    for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
-      double v = 0.0;
-      for (int w = 0; w < pp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
-      part[((size_t)s * pp.bpm + blk) * 4 * L + i] = v;
-    }
-    if (kKind == 2 && threadIdx.x == 0) {
-      double v = 0.0;
-      for (int w = 0; w < pp.wpb; ++w) v += lossw[w];
-      loss_part[(size_t)s * pp.bpm + blk] = v;
+    __syncthreads();
+    if (kKind != 1) {
+      for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
+        double v = 0.0;
+        if (kGlobal) {
+          const int which = i / L, m = i - which * L;
+          for (int w = 0; w < pp.wpb; ++w) {
+            const double* q = accs + (size_t)w * kAccPer * L + ((m * 4 + which) << 4);
+#pragma unroll
+            for (int l = 0; l < 16; ++l) v += q[l];
+          }
+        } else {
+          for (int w = 0; w < pp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
+        }
+        part[((size_t)s * pp.bpm + blk) * 4 * L + i] = v;
+      }
+      if (kKind == 2 && threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < pp.wpb; ++w) v += lossw[w];
+        loss_part[(size_t)s * pp.bpm + blk] = v;
+      }
     }
   }
 }
@@ -766,10 +788,12 @@ inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
   return gp;
 }
 
-inline PointsPlan plan_points(int L, int N) {
+inline PointsPlan plan_points(int S, int L, int N, bool allow_global) {
   PointsPlan pp;
   pp.units = (N + kWarp - 1) / kWarp;
-  pp.wpb = adj_wpb(L);
+  // large ensembles: 12 resident warps per SM with the slabs in L2; small problems: slabs in shared memory
+  pp.global = allow_global && (long long)S * pp.units >= (long long)kNumSM * 8;
+  pp.wpb = pp.global ? 4 : adj_wpb(L);
   if (pp.wpb > pp.units) {
     int w = 1;
     while (w < pp.units) w <<= 1;
@@ -777,6 +801,14 @@ inline PointsPlan plan_points(int L, int N) {
   }
   pp.bpm = pp.wpb > 0 ? (pp.units + pp.wpb - 1) / pp.wpb : 0;
   return pp;
+}
+
+inline size_t points_estore_bytes(const PointsPlan& pp, int L) {
+  return pp.global ? (size_t)kMaxResidentWarps * est_bytes_per_warp(L) : 0;
+}
+
+inline size_t points_smem(const PointsPlan& pp, int L) {
+  return pp.global ? par_bytes(L) + (size_t)pp.wpb * (64 * L + 1) * sizeof(double) : adj_smem(L, pp.wpb);
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -795,6 +827,43 @@ inline int set_smem(Kern kern, size_t bytes) {
     }
   }
   return ADSURF_OK;
+}
+
+// launch k_points_bwd<kKind, global?> (persistent when the slabs live in global memory)
+template <int kKind>
+inline int launch_points_bwd(const PointsPlan& pp, int S, int L, int N, const double* d, const double* alpha,
+                             const double* beta, const double* rho, const double* t, const double* c,
+                             const double* gF, double* F, double* gc, double* part, double* estore, double* Jd,
+                             double* Ja, double* Jb, double* Jrho, const double* pmax, const double* pmin, int nchunk,
+                             int compress, int with_grad, double* norm, double* loss_part, cudaStream_t st) {
+  const size_t smem = points_smem(pp, L);
+  const long long total_vb = (long long)S * pp.bpm;
+  if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;
+  const int threads = pp.wpb * kWarp;
+  if (pp.global) {
+    auto kern = k_points_bwd<kKind, true>;
+    if (set_smem(kern, smem)) return ADSURF_E_CUDA;
+    int dev = 0, nsm = kNumSM, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      return ADSURF_E_CUDA;
+    }
+    long long grid = (long long)occ * nsm;
+    if (grid * pp.wpb > kMaxResidentWarps) grid = kMaxResidentWarps / pp.wpb;
+    if (grid > total_vb) grid = total_vb;
+    kern<<<(unsigned)grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F, gc, part,
+                                                estore, Jd, Ja, Jb, Jrho, pmax, pmin, nchunk, compress, with_grad,
+                                                norm, loss_part);
+  } else {
+    auto kern = k_points_bwd<kKind, false>;
+    if (set_smem(kern, smem)) return ADSURF_E_CUDA;
+    kern<<<(unsigned)total_vb, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F, gc,
+                                                    part, nullptr, Jd, Ja, Jb, Jrho, pmax, pmin, nchunk, compress,
+                                                    with_grad, norm, loss_part);
+  }
+  return check_launch();
 }
 
 }  // namespace
@@ -826,8 +895,8 @@ size_t adsurf_workspace_bytes(int op, int S, int L, int n, int K) {
     case ADSURF_OP_POINTS_JAC:
       return 0;
     case ADSURF_OP_POINTS_BWD: {
-      const PointsPlan pp = plan_points(L, n);
-      return align256((size_t)S * pp.bpm * 4 * L * sizeof(double));
+      const PointsPlan pp = plan_points(S, L, n, true);
+      return align256((size_t)S * pp.bpm * 4 * L * sizeof(double)) + align256(points_estore_bytes(pp, L));
     }
     case ADSURF_OP_GRID_FWD: {
       if (K <= 0) return 0;
@@ -840,8 +909,9 @@ size_t adsurf_workspace_bytes(int op, int S, int L, int n, int K) {
       return align256((size_t)S * gp.bpm * 4 * L * sizeof(double)) + align256(bwd_estore_bytes(L));
     }
     case ADSURF_OP_DMF_STEP: {
-      const PointsPlan pp = plan_points(L, n);
-      size_t b = align256((size_t)S * pp.bpm * 4 * L * sizeof(double)) + align256((size_t)S * pp.bpm * sizeof(double));
+      const PointsPlan pp = plan_points(S, L, n, true);
+      size_t b = align256((size_t)S * pp.bpm * 4 * L * sizeof(double)) + align256((size_t)S * pp.bpm * sizeof(double)) +
+                 align256(points_estore_bytes(pp, L));
       if (K > 0) {
         const GridPlan gp = plan_grid(S, L, n, K, false);
         b += 2 * align256((size_t)S * gp.nchunk * n * sizeof(double));
@@ -876,30 +946,21 @@ static int points_adjoint_common(int kind, const double* d, const double* alpha,
   if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
   if (S <= 0 || L <= 0 || N <= 0) return ADSURF_E_SHAPE;
   if (L - 1 > ADSURF_MAX_ADJ_LAYERS) return ADSURF_E_LAYERS;
-  const PointsPlan pp = plan_points(L, N);
+  const PointsPlan pp = plan_points(S, L, N, kind == 0);  // the Jacobian entry has no workspace: shared slabs
   if (pp.wpb <= 0) return ADSURF_E_LAYERS;
-  const size_t smem = adj_smem(L, pp.wpb);
-  double* part = nullptr;
   if (kind == 0) {
-    const size_t need = align256((size_t)S * pp.bpm * 4 * L * sizeof(double));
-    if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
-    part = (double*)ws;
-  }
-  const unsigned grid = (unsigned)((size_t)S * pp.bpm);
-  const unsigned threads = pp.wpb * kWarp;
-  if (kind == 0) {
-    if (set_smem(k_points_bwd<0>, smem)) return ADSURF_E_CUDA;
-    k_points_bwd<0><<<grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, F, gc, part, nullptr,
-                                                 nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, nullptr,
-                                                 nullptr);
-    if (check_launch()) return ADSURF_E_CUDA;
+    const size_t part_bytes = align256((size_t)S * pp.bpm * 4 * L * sizeof(double));
+    if (!ws || ws_bytes < part_bytes + align256(points_estore_bytes(pp, L))) return ADSURF_E_WORKSPACE;
+    double* part = (double*)ws;
+    double* estore = pp.global ? (double*)((char*)ws + part_bytes) : nullptr;
+    const int rc = launch_points_bwd<0>(pp, S, L, N, d, alpha, beta, rho, t, c, gF, F, gc, part, estore, nullptr,
+                                        nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, nullptr, nullptr, st);
+    if (rc) return rc;
     k_grad_reduce<<<S, 128, 0, st>>>(part, L, pp.bpm, gd, ga, gb, grho);
-  } else {
-    if (set_smem(k_points_bwd<1>, smem)) return ADSURF_E_CUDA;
-    k_points_bwd<1><<<grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, nullptr, L, N, pp, F, gc, nullptr, Jd, Ja,
-                                                 Jb, Jrho, nullptr, nullptr, 0, 0, 1, nullptr, nullptr);
+    return check_launch();
   }
-  return check_launch();
+  return launch_points_bwd<1>(pp, S, L, N, d, alpha, beta, rho, t, c, nullptr, F, gc, nullptr, nullptr, Jd, Ja, Jb,
+                              Jrho, nullptr, nullptr, 0, 0, 1, nullptr, nullptr, st);
 }
 
 int adsurf_det_points_bwd(const double* d, const double* alpha, const double* beta, const double* rho,
@@ -1013,7 +1074,7 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
   if (normalised && !C) return ADSURF_E_NULL;
   if (S <= 0 || L <= 0 || N <= 0 || (normalised && K <= 0)) return ADSURF_E_SHAPE;
   if (L - 1 > ADSURF_MAX_ADJ_LAYERS) return ADSURF_E_LAYERS;
-  const PointsPlan pp = plan_points(L, N);
+  const PointsPlan pp = plan_points(S, L, N, true);
   if (pp.wpb <= 0) return ADSURF_E_LAYERS;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t need = adsurf_workspace_bytes(ADSURF_OP_DMF_STEP, S, L, N, normalised ? K : 0);
@@ -1023,6 +1084,8 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
   w += align256((size_t)S * pp.bpm * 4 * L * sizeof(double));
   double* loss_part = (double*)w;
   w += align256((size_t)S * pp.bpm * sizeof(double));
+  double* estore = pp.global ? (double*)w : nullptr;
+  w += align256(points_estore_bytes(pp, L));
   double *pmax = nullptr, *pmin = nullptr;
   int nchunk = 0;
   if (normalised) {
@@ -1035,12 +1098,10 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
     const int rc = grid_fwd_launch(d, alpha, beta, rho, t, C, S, L, N, K, nullptr, pmax, pmin, nullptr, gp, st);
     if (rc) return rc;
   }
-  const size_t smem = adj_smem(L, pp.wpb);
-  if (set_smem(k_points_bwd<2>, smem)) return ADSURF_E_CUDA;
-  k_points_bwd<2><<<(unsigned)((size_t)S * pp.bpm), pp.wpb * kWarp, smem, st>>>(
-      d, alpha, beta, rho, t, c, nullptr, L, N, pp, F, nullptr, part, nullptr, nullptr, nullptr, nullptr, pmax, pmin,
-      nchunk, compress, with_grad, norm, loss_part);
-  if (check_launch()) return ADSURF_E_CUDA;
+  const int rc2 = launch_points_bwd<2>(pp, S, L, N, d, alpha, beta, rho, t, c, nullptr, F, nullptr, part, estore,
+                                       nullptr, nullptr, nullptr, nullptr, pmax, pmin, nchunk, compress, with_grad,
+                                       norm, loss_part, st);
+  if (rc2) return rc2;
   k_loss_reduce<<<(S + 127) / 128, 128, 0, st>>>(loss_part, pp.bpm, N, loss, S);
   if (check_launch()) return ADSURF_E_CUDA;
   if (with_grad) {
