@@ -555,6 +555,7 @@ ADSURF_HD Sample make_sample(double omega0, double ic) {
 // ---- layer sources: fill the inputs, the eigenfunction set-up and the coefficient scalars of layer m
 // DirectSource: everything per sample from (k, omega) — pointwise kernels, arbitrary (t, c) pairs.
 struct DirectSource {
+  static constexpr bool kUniformFlags = false;  // per-sample (t, c): regimes may differ between lanes
   const double* __restrict__ par;
   int L;
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
@@ -600,6 +601,7 @@ ADSURF_HD int table_entry(double* __restrict__ tab, const double* __restrict__ p
 }
 
 struct TableSource {
+  static constexpr bool kUniformFlags = true;   // flags come from the shared (velocity, layer) table
   const double* __restrict__ par;
   int L;
   const double* __restrict__ tab;  // [L-1][kTab] for the current trial velocity
@@ -736,21 +738,36 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     Layer y;
     y.P.c0 = cur[0]; y.P.c1 = cur[1]; y.S.c0 = cur[2]; y.S.c1 = cur[3];
     src.prep(y, m, z);
-    layer_eig_restore(y);
-    const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2, z.t2);
-    col_apply(s, y);
-    gk += g.k;
-    const double ia = par[m * kNumPar + P_IA], ib = par[m * kNumPar + P_IB];
-    // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2
-    sink(m, g.d, -y.ka * ia * g.ka, -y.kb * ib * g.kb + 2.0 * y.gk * ib * g.gammk, g.rho);
+    auto body = [&]() {
+      layer_eig_restore(y);
+      const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2, z.t2);
+      col_apply(s, y);
+      gk += g.k;
+      const double ia = par[m * kNumPar + P_IA], ib = par[m * kNumPar + P_IB];
+      // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2
+      sink(m, g.d, -y.ka * ia * g.ka, -y.kb * ib * g.kb + 2.0 * y.gk * ib * g.gammk, g.rho);
+    };
+    // Regime specialisation (dense kernels: the flags are warp-uniform table entries).  Re-stating the flags
+    // as constants inside each branch lets the compiler fold every "lt ? a : b" / "pos ? a : b" select of
+    // eig_finish / eig_adjoint away in the two regimes that cover ~95 % of (velocity, layer) pairs.
+    if (Source::kUniformFlags && y.P.pos && y.S.pos && !y.P.lt) {
+      if (y.S.lt) {  // P evanescent, S oscillatory
+        y.P.lt = false; y.S.lt = true; y.P.pos = true; y.S.pos = true;
+        body();
+      } else {       // both evanescent
+        y.P.lt = false; y.S.lt = false; y.P.pos = true; y.S.pos = true;
+        body();
+      }
+    } else {
+      body();
+    }
   };
   if (L > 1) fetch(0, bufA);
-  int m = 0;
-  for (; m + 1 <= L - 2; m += 2) {
+  for (int m = 0; m <= L - 2; ++m) {
     layer(m, bufA, bufB);
-    layer(m + 1, bufB, bufA);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bufA[i] = bufB[i];
   }
-  if (m <= L - 2) layer(m, bufA, bufB);
   // half-space: dDelta/dE_hs = s_{L-1}
   double e[5];
   Half h;
