@@ -717,30 +717,31 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   const double* __restrict__ par = src.par;
   const int L = src.L;
   double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
-  // software pipeline: the transcendental results of the next layer (needed first) are fetched one
-  // layer ahead into ping-pong registers; the row vector E (needed ~60 instructions later) is fetched
-  // at the top of its own layer.  Keeps 10 fewer registers live than prefetching the whole slot.
-  double bufA[4], bufB[4];
+  // software pipeline over the stored values: each group of registers is re-loaded for layer m+1 right
+  // after its last use in layer m — the transcendental results once eig_finish has consumed them, the row
+  // vector E once layer_adjoint is done — so the L2 latency of the slab hides behind the rest of the layer
+  // (col_apply, the gradient sink, the next layer's set-up) without a second register buffer.
+  double e[5], cv[4];
   double gk = 0.0;
-  auto fetch = [&](int m, double (&buf)[4]) {
+  auto fetch_c = [&](int m) {
     const typename Store::Slot q = est.slot(m);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) buf[i] = Store::ld(q, 5 + i);
+    for (int i = 0; i < 4; ++i) cv[i] = Store::ld(q, 5 + i);
   };
-  auto layer = [&](int m, const double (&cur)[4], double (&nxt)[4]) {
-    double e[5];
-    {
-      const typename Store::Slot q = est.slot(m);
+  auto fetch_e = [&](int m) {
+    const typename Store::Slot q = est.slot(m);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) e[i] = Store::ld(q, i);
-    }
-    if (m + 1 <= L - 2) fetch(m + 1, nxt);
+    for (int i = 0; i < 5; ++i) e[i] = Store::ld(q, i);
+  };
+  auto layer = [&](int m) {
     Layer y;
-    y.P.c0 = cur[0]; y.P.c1 = cur[1]; y.S.c0 = cur[2]; y.S.c1 = cur[3];
+    y.P.c0 = cv[0]; y.P.c1 = cv[1]; y.S.c0 = cv[2]; y.S.c1 = cv[3];
     src.prep(y, m, z);
     auto body = [&]() {
       layer_eig_restore(y);
+      if (m + 1 <= L - 2) fetch_c(m + 1);
       const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2, z.t2);
+      if (m + 1 <= L - 2) fetch_e(m + 1);
       col_apply(s, y);
       gk += g.k;
       const double ia = par[m * kNumPar + P_IA], ib = par[m * kNumPar + P_IB];
@@ -762,14 +763,12 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
       body();
     }
   };
-  if (L > 1) fetch(0, bufA);
-  for (int m = 0; m <= L - 2; ++m) {
-    layer(m, bufA, bufB);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) bufA[i] = bufB[i];
+  if (L > 1) {
+    fetch_c(0);
+    fetch_e(0);
   }
+  for (int m = 0; m <= L - 2; ++m) layer(m);
   // half-space: dDelta/dE_hs = s_{L-1}
-  double e[5];
   Half h;
   load_half(h, par, L, z);
   half_space(h, z.k, z.k2, e);
