@@ -58,6 +58,20 @@ ADSURF_HD double rsqrt_hd(double u) {
 #endif
 }
 
+// "v < T" for a threshold T whose low 32 bits are zero (16, 60, 1e5) and v >= 0 (or NaN): compare the high
+// words as integers — one ALU instruction instead of a DSETP that occupies the half-rate FP64 pipe.
+// NaN (high word 0x7ff8....) compares false like the floating-point test.
+ADSURF_HD int hi_word(double v) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(v);
+#else
+  return (int)(dbl_bits(v) >> 32);
+#endif
+}
+ADSURF_HD bool below16(double v) { return hi_word(v) < 0x40300000; }
+ADSURF_HD bool below60(double v) { return hi_word(v) < 0x404E0000; }
+ADSURF_HD bool below1e5(double v) { return hi_word(v) < 0x40F86A00; }
+
 constexpr double kShifter = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest integer into the low mantissa bits
 
 // Polynomial coefficients live in constant memory on the device so that DFMA reads them as
@@ -232,13 +246,13 @@ ADSURF_HD void eig_osc(Eig& e) {
 ADSURF_HD void eig_evan(Eig& e) {
   e.c0 = exp_neg(e.p);
   e.c1 = 0.0;
-  const double fac = (e.p < 16.0) ? e.c0 * e.c0 : 0.0;
+  const double fac = below16(e.p) ? e.c0 * e.c0 : 0.0;
   e.cs = 0.5 + 0.5 * fac;
   e.sn = 0.5 - 0.5 * fac;
   e.dcs = -fac;
   e.dsn = fac;
   e.ex = e.p;  // p = 0 when k == kx
-  e.eh = (e.p < 60.0) ? e.c0 : 0.0;
+  e.eh = below60(e.p) ? e.c0 : 0.0;
   e.x = e.r * e.sn;
 }
 
@@ -256,13 +270,13 @@ ADSURF_HD void eig_forward(Eig& e, double dm) {
   } else {
     e.c0 = exp_neg(e.p);
     e.c1 = 0.0;
-    const double fac = (e.p < 16.0) ? e.c0 * e.c0 : 0.0;
+    const double fac = below16(e.p) ? e.c0 * e.c0 : 0.0;
     e.cs = 0.5 + 0.5 * fac;
     e.sn = 0.5 - 0.5 * fac;
     e.dcs = -fac;
     e.dsn = fac;
     e.ex = e.p;  // p = 0 when k == kx
-    e.eh = (e.p < 60.0) ? e.c0 : 0.0;
+    e.eh = below60(e.p) ? e.c0 : 0.0;
     e.x = e.r * e.sn;
   }
   e.w = e.pos ? e.sn * e.ir : dm;  // k == kx: w = d (reference :135)
@@ -277,13 +291,13 @@ ADSURF_HD void eig_finish(Eig& e, double dm) {
     e.ex = 0.0;
     e.eh = 1.0;
   } else {
-    const double fac = (e.p < 16.0) ? e.c0 * e.c0 : 0.0;
+    const double fac = below16(e.p) ? e.c0 * e.c0 : 0.0;
     e.cs = 0.5 + 0.5 * fac;
     e.sn = 0.5 - 0.5 * fac;
     e.dcs = -fac;
     e.dsn = fac;
     e.ex = e.p;  // p = 0 when k == kx
-    e.eh = (e.p < 60.0) ? e.c0 : 0.0;
+    e.eh = below60(e.p) ? e.c0 : 0.0;
   }
   e.w = e.pos ? e.sn * e.ir : dm;  // k == kx: w = d (reference :135)
   e.x = (e.lt ? -e.r : e.r) * e.sn;
@@ -304,7 +318,7 @@ struct Layer {
 // after the other behind separate branches.  The regime is warp-uniform in the dense kernels.
 ADSURF_HD void layer_eig_forward(Layer& y) {
   const bool lp = y.P.lt, ls = y.S.lt;
-  const bool small = (fabs(y.P.p) < 1.0e5) && (fabs(y.S.p) < 1.0e5);
+  const bool small = below1e5(fabs(y.P.p)) && below1e5(fabs(y.S.p));
   if (!small) {  // huge phase (or NaN): generic path with the library fallback
     eig_forward(y.P, y.dm);
     eig_forward(y.S, y.dm);
@@ -325,14 +339,14 @@ ADSURF_HD void layer_eig_forward(Layer& y) {
     y.P.w = y.P.pos ? y.P.sn * y.P.ir : y.dm;  // k == kx: w = d (reference :135)
     y.S.w = y.S.pos ? y.S.sn * y.S.ir : y.dm;
   }
-  y.a0 = (y.P.ex + y.S.ex < 60.0) ? y.P.eh * y.S.eh : 0.0;
+  y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
 }
 
 // adjoint sweep: restore them from the store (c0, c1 already set by the caller)
 ADSURF_HD void layer_eig_restore(Layer& y) {
   eig_finish(y.P, y.dm);
   eig_finish(y.S, y.dm);
-  y.a0 = (y.P.ex + y.S.ex < 60.0) ? y.P.eh * y.S.eh : 0.0;
+  y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
 }
 
 // coefficient scalars from (gk, k2); t2 = -2 k2 (hoisted per sample)
@@ -577,8 +591,12 @@ struct DirectSource {
 //   gam = gk k^2 = 2 (beta/c)^2;  g1 = gam - 1;  br = g1^2 rho;   branch flags (c vs v).
 // Per lane that leaves 6 multiplies for both eigenfunction set-ups (instead of 2 rsqrt sequences,
 // the differences of squares and their selects) and 6 for the coefficient scalars.
-constexpr int kTab = 9;
-enum { T_PDA = 0, T_PDB = 1, T_NA = 2, T_NB = 3, T_INA = 4, T_INB = 5, T_GAM = 6, T_G1 = 7, T_BR = 8 };
+constexpr int kTab = 10;  // 80-byte entries: five 16-byte loads; the last slot carries the flag bits
+enum { T_PDA = 0, T_PDB = 1, T_NA = 2, T_NB = 3, T_INA = 4, T_INB = 5, T_GAM = 6, T_G1 = 7, T_BR = 8, T_FL = 9 };
+struct alignas(16) Dbl2 {
+  double x, y;
+};
+ADSURF_HD Dbl2 ld2(const double* p) { return *reinterpret_cast<const Dbl2*>(p); }
 enum { F_LTP = 1, F_POSP = 2, F_LTS = 4, F_POSS = 8 };
 
 // one table entry: trial slowness ic = 1/c against layer m of the staged model
@@ -597,7 +615,9 @@ ADSURF_HD int table_entry(double* __restrict__ tab, const double* __restrict__ p
   tab[T_GAM] = gam;
   tab[T_G1] = g1;
   tab[T_BR] = g1 * g1 * par[m * kNumPar + P_RHO];
-  return (ic < sa ? F_LTP : 0) | (da > 0.0 ? F_POSP : 0) | (ic < sb ? F_LTS : 0) | (db > 0.0 ? F_POSS : 0);
+  const int fl = (ic < sa ? F_LTP : 0) | (da > 0.0 ? F_POSP : 0) | (ic < sb ? F_LTS : 0) | (db > 0.0 ? F_POSS : 0);
+  tab[T_FL] = bits_dbl((long long)fl);  // raw bits, read back with dbl_bits()
+  return fl;
 }
 
 struct TableSource {
@@ -607,31 +627,36 @@ struct TableSource {
   const double* __restrict__ tab;  // [L-1][kTab] for the current trial velocity
   const int* __restrict__ flags;   // [L-1]
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
+    // 16-byte broadcast loads: 3 for the layer record, 5 for the table entry
+    const double* __restrict__ pr = par + m * kNumPar;
+    const Dbl2 p01 = ld2(pr + P_IA), p23 = ld2(pr + P_TB2), p45 = ld2(pr + P_IR);
     const double* __restrict__ q = tab + m * kTab;
-    const int fl = flags[m];
-    y.rho = par[m * kNumPar + P_RHO];
-    y.ir = par[m * kNumPar + P_IR];
-    y.dm = par[m * kNumPar + P_D];
-    y.ka = z.omega * par[m * kNumPar + P_IA];  // adjoint only
-    y.kb = z.omega * par[m * kNumPar + P_IB];
-    y.gk = par[m * kNumPar + P_TB2] * z.iw2;
-    y.gam = q[T_GAM];
-    y.g1 = q[T_G1];
-    y.br = q[T_BR];
+    const Dbl2 t01 = ld2(q + T_PDA), t23 = ld2(q + T_NA), t45 = ld2(q + T_INA), t67 = ld2(q + T_GAM),
+               t89 = ld2(q + T_BR);
+    const int fl = (int)dbl_bits(t89.y);
+    y.rho = p23.y;
+    y.ir = p45.x;
+    y.dm = p45.y;
+    y.ka = z.omega * p01.x;  // adjoint only
+    y.kb = z.omega * p01.y;
+    y.gk = p23.x * z.iw2;
+    y.gam = t67.x;
+    y.g1 = t67.y;
+    y.br = t89.x;
     y.gg = y.gam * y.gk;
-    y.q1 = y.g1 * y.g1;                  // adjoint only
+    y.q1 = y.g1 * y.g1;      // adjoint only
     y.ar = y.gg * y.rho;
     y.kr = z.k2 * y.ir;
     y.tg = z.t2 * y.gk;
     y.t1 = z.t2 * y.g1;
-    y.P.r = z.omega * q[T_NA];
-    y.P.ir = z.iw * q[T_INA];
-    y.P.p = z.omega * q[T_PDA];
+    y.P.r = z.omega * t23.x;
+    y.P.ir = z.iw * t45.x;
+    y.P.p = z.omega * t01.x;
     y.P.lt = fl & F_LTP;
     y.P.pos = fl & F_POSP;
-    y.S.r = z.omega * q[T_NB];
-    y.S.ir = z.iw * q[T_INB];
-    y.S.p = z.omega * q[T_PDB];
+    y.S.r = z.omega * t23.y;
+    y.S.ir = z.iw * t45.y;
+    y.S.p = z.omega * t01.y;
     y.S.lt = fl & F_LTS;
     y.S.pos = fl & F_POSS;
   }
