@@ -140,7 +140,7 @@ __device__ __forceinline__ BlockCoord block_coord(int vb, const GridPlan& gp) {
   return bc;
 }
 
-__device__ __forceinline__ void fill_table(double* __restrict__ tab, int* __restrict__ flags, double* __restrict__ ics,
+__device__ __forceinline__ void fill_table(double* __restrict__ tab, double* __restrict__ ics,
                                            const double* __restrict__ par, int L, const double* __restrict__ cs,
                                            int n) {
   const int per = L - 1;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void fill_table(double* __restrict__ tab, int* __rest
     const int cc = e / per, m = e - cc * per;
     const double ic = 1.0 / cs[cc];
     if (m == 0) ics[cc] = ic;
-    flags[e] = table_entry(tab + (size_t)e * kTab, par, L, m, ic);
+    table_entry(tab + (size_t)e * kTab, par, L, m, ic);
   }
   if (per == 0)
     for (int cc = threadIdx.x; cc < n; cc += blockDim.x) ics[cc] = 1.0 / cs[cc];
@@ -165,7 +165,6 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const double* __restrict__ d, 
   double* par = smem + kSmemHead;
   double* tab = par + par_doubles(L);                   // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
-  int* flags = (int*)(ics + gp.tc);                     // [tc][L-1]
   const BlockCoord bc = block_coord(blockIdx.x, gp);
   const int s = bc.s;
   stage_params(par, d, alpha, beta, rho, s, L);
@@ -183,13 +182,13 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const double* __restrict__ d, 
   for (int kb = k0; kb < k1; kb += gp.tc) {
     const int n = min(gp.tc, k1 - kb);
     __syncthreads();  // staged parameters visible / previous table consumed
-    fill_table(tab, flags, ics, par, L, c + (size_t)s * K + kb, n);
+    fill_table(tab, ics, par, L, c + (size_t)s * K + kb, n);
     __syncthreads();
     if (!live) continue;
     for (int cc = 0; cc < n; ++cc) {
       const int k = kb + cc;
       const Sample z = make_sample(omega0, ics[cc]);
-      const TableSource src{par, L, tab + (size_t)cc * (L - 1) * kTab, flags + cc * (L - 1)};
+      const TableSource src{par, L, tab + (size_t)cc * (L - 1) * kTab};
       const double v = sample_forward(src, z);
       if (det && active) det[((size_t)s * K + k) * NF + f] = v;
       vmax = fmax(vmax, v);
@@ -283,8 +282,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
   double* accs = par + par_doubles(L);                  // [wpb][L][4][16] (global slabs) or [wpb][4][L]
   double* tab = accs + (size_t)gp.wpb * kAccPer * L;    // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
-  int* flags = (int*)(ics + gp.tc);                     // [tc][L-1]
-  double* ests = (double*)(flags + ((gp.tc * (L - 1) + 1) & ~1));  // [wpb][L-1][kSlot][32] (shared variant only)
+  double* ests = ics + ((gp.tc + 1) & ~1);              // [wpb][L-1][kSlot][32] (shared variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
   const unsigned long long slab_policy = kGlobal ? l2_evict_last_policy() : 0ull;
@@ -307,13 +305,13 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
     for (int kb = k0; kb < k1; kb += gp.tc) {
       const int n = min(gp.tc, k1 - kb);
       __syncthreads();
-      fill_table(tab, flags, ics, par, L, c + (size_t)s * K + kb, n);
+      fill_table(tab, ics, par, L, c + (size_t)s * K + kb, n);
       __syncthreads();
       if (!live) continue;
       for (int cc = 0; cc < n; ++cc) {
         const int k = kb + cc;
         const Sample z = make_sample(omega0, ics[cc]);
-        const TableSource src{par, L, tab + (size_t)cc * (L - 1) * kTab, flags + cc * (L - 1)};
+        const TableSource src{par, L, tab + (size_t)cc * (L - 1) * kTab};
         const size_t idx = ((size_t)s * K + k) * NF + fc;
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
@@ -753,7 +751,7 @@ inline size_t bwd_estore_bytes(int L) {
 
 inline size_t table_bytes(int L, int tc) {
   const size_t per = (size_t)(L > 1 ? L - 1 : 0);
-  return (size_t)tc * per * kTab * sizeof(double) + (size_t)tc * sizeof(double) + (((size_t)tc * per + 1) & ~(size_t)1) * sizeof(int);
+  return (size_t)tc * per * kTab * sizeof(double) + (size_t)((tc + 1) & ~1) * sizeof(double);
 }
 
 inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {

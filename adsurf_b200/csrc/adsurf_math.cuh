@@ -318,8 +318,8 @@ struct Layer {
 // after the other behind separate branches.  The regime is warp-uniform in the dense kernels.
 ADSURF_HD void layer_eig_forward(Layer& y) {
   const bool lp = y.P.lt, ls = y.S.lt;
-  const bool small = below1e5(fabs(y.P.p)) && below1e5(fabs(y.S.p));
-  if (!small) {  // huge phase (or NaN): generic path with the library fallback
+  const bool small = below1e5(fabs(y.P.p)) && below1e5(fabs(y.S.p)) && y.P.pos && y.S.pos;
+  if (!small) {  // huge phase, NaN, or c exactly on a layer velocity: generic path
     eig_forward(y.P, y.dm);
     eig_forward(y.S, y.dm);
   } else {
@@ -336,8 +336,8 @@ ADSURF_HD void layer_eig_forward(Layer& y) {
       eig_osc(y.P);
       eig_evan(y.S);
     }
-    y.P.w = y.P.pos ? y.P.sn * y.P.ir : y.dm;  // k == kx: w = d (reference :135)
-    y.S.w = y.S.pos ? y.S.sn * y.S.ir : y.dm;
+    y.P.w = y.P.sn * y.P.ir;
+    y.S.w = y.S.sn * y.S.ir;
   }
   y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
 }
@@ -600,7 +600,7 @@ ADSURF_HD Dbl2 ld2(const double* p) { return *reinterpret_cast<const Dbl2*>(p); 
 enum { F_LTP = 1, F_POSP = 2, F_LTS = 4, F_POSS = 8 };
 
 // one table entry: trial slowness ic = 1/c against layer m of the staged model
-ADSURF_HD int table_entry(double* __restrict__ tab, const double* __restrict__ par, int L, int m, double ic) {
+ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ par, int L, int m, double ic) {
   const double sa = par[m * kNumPar + P_IA], sb = par[m * kNumPar + P_IB], dm = par[m * kNumPar + P_D];
   const double da = (ic + sa) * fabs(ic - sa), db = (ic + sb) * fabs(ic - sb);
   const double na = sqrt(da), nb = sqrt(db);
@@ -617,15 +617,13 @@ ADSURF_HD int table_entry(double* __restrict__ tab, const double* __restrict__ p
   tab[T_BR] = g1 * g1 * par[m * kNumPar + P_RHO];
   const int fl = (ic < sa ? F_LTP : 0) | (da > 0.0 ? F_POSP : 0) | (ic < sb ? F_LTS : 0) | (db > 0.0 ? F_POSS : 0);
   tab[T_FL] = bits_dbl((long long)fl);  // raw bits, read back with dbl_bits()
-  return fl;
 }
 
 struct TableSource {
   static constexpr bool kUniformFlags = true;   // flags come from the shared (velocity, layer) table
   const double* __restrict__ par;
   int L;
-  const double* __restrict__ tab;  // [L-1][kTab] for the current trial velocity
-  const int* __restrict__ flags;   // [L-1]
+  const double* __restrict__ tab;  // [L-1][kTab] for the current trial velocity (16-byte aligned)
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     // 16-byte broadcast loads: 3 for the layer record, 5 for the table entry
     const double* __restrict__ pr = par + m * kNumPar;

@@ -326,7 +326,11 @@ def main():
                     "call": "adsurf_det_grid_bwd (C ABI) with pinned host inputs copied H2D and gradients read D2H every step"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "frac": achieved_tf / peak_tf,
+                         # DRAM bytes per launch of the dominant kernel, scaled from the ncu --set full capture in
+                         # profiles/r1_ncu_full_final.txt (7.23 GB for 67 108 864 samples = 107.7 B/sample; the
+                         # algorithmic 8 B/sample is the det output, the rest is write-back of the L2-resident slabs)
+                         "traffic": 107.7 * n_samples, "traffic_source": "profiles/r1_ncu_full_final.txt",
                          "peak_source": "measured in-process: register-resident DFMA loop (adsurf_fp64_peak_probe), burst",
                          "peak_after_sweep": peak_tf_after, "peak_nominal": nominal,
                          "frac_of_nominal": achieved_tf / nominal,

@@ -68,11 +68,10 @@ int host_grid(const double* d, const double* alpha, const double* beta, const do
     for (int m = 0; m < L; ++m) gd[s * L + m] = ga[s * L + m] = gb[s * L + m] = grho[s * L + m] = 0.0;
     // dense path: per-(velocity, layer) table + per-period lanes, as the dense kernels do
     std::vector<double> tab((size_t)kTab * (L > 1 ? L - 1 : 1));
-    std::vector<int> flags(L > 1 ? L - 1 : 1);
     for (int k = 0; k < K; ++k) {
       const double ic = 1.0 / c[s * K + k];
-      for (int m = 0; m < L - 1; ++m) flags[m] = table_entry(tab.data() + (size_t)m * kTab, par.data(), L, m, ic);
-      const TableSource src{par.data(), L, tab.data(), flags.data()};
+      for (int m = 0; m < L - 1; ++m) table_entry(tab.data() + (size_t)m * kTab, par.data(), L, m, ic);
+      const TableSource src{par.data(), L, tab.data()};
       for (int f = 0; f < NF; ++f) {
         const size_t idx = ((size_t)s * K + k) * NF + f;
         const Sample z = make_sample(omega_of_period(t[s * NF + f]), ic);
