@@ -21,8 +21,9 @@ namespace adsurf {
 constexpr double kTwoPi = 6.283185307179586;  // 2.0 * np.pi
 constexpr double kLn10 = 2.302585092994046;
 constexpr int kWarp = 32;
-constexpr int kNumPar = 6;  // staged per-layer constants
-enum { P_IA = 0, P_IB = 1, P_TB2 = 2, P_RHO = 3, P_IR = 4, P_D = 5 };
+constexpr int kNumPar = 10;  // staged per-layer record (80 bytes: five 16-byte loads)
+// 1/alpha, 1/beta, 2 beta^2, rho, 1/rho, d | adjoint only: 1/alpha^3, 1/beta^3, 4 beta, (pad)
+enum { P_IA = 0, P_IB = 1, P_TB2 = 2, P_RHO = 3, P_IR = 4, P_D = 5, P_IA3 = 6, P_IB3 = 7, P_CB = 8 };
 
 // ---- inline elementary functions -------------------------------------------------------------
 // Straight-line (call-free, branch-free on the common path) so that the P and S terms of a layer
@@ -305,7 +306,7 @@ ADSURF_HD void eig_finish(Eig& e, double dm) {
 
 struct Layer {
   // inputs
-  double ka, kb, gk, rho, ir, dm;
+  double gk, rho, ir, dm;
   // coefficient scalars
   double gam, g1, gg, q1, ar, br, kr, tg, t1;
   Eig P, S;
@@ -401,22 +402,24 @@ ADSURF_HD void col_apply(double (&s)[5], const Layer& y) {
 }
 
 struct LayerGrad {
-  double d, ka, kb, gammk, rho, k;  // dDelta/d(each input of the layer), k includes the k2 path
+  // dDelta/d(thickness, gammk, rho, k) and, for each wave type, h = (dDelta/dr) / r * sign(k - kx):
+  // dDelta/dk += k h, dDelta/dkx = -kx h  =>  dDelta/dalpha = omega^2 / alpha^3 * hp (kx = omega/alpha).
+  double d, hp, hs, gammk, rho, k;
 };
 
-// adjoint of one eigenfunction block: (bcs, bw, bx, bex) -> (bd, bk, bkx).  Both branches share
-// one formula through dcs = d cs/dp, dsn = d sn/dp and the sign of (k - kx).
-ADSURF_HD void eig_adjoint(const Eig& e, double k, double kx, double dm, double bcs, double bw, double bx,
-                           double bex, double& bd, double& bk, double& bkx) {
-  const double sg = e.lt ? -1.0 : 1.0;
-  const double bsn = bw * e.ir + sg * e.r * bx;
+// adjoint of one eigenfunction block: (bcs, bw, bx, bex) -> bd += ..., bk += k h, returns h.  Both branches
+// share one formula through dcs = d cs/dp, dsn = d sn/dp and the sign of (k - kx):
+//   w = sn/r, x = sg r sn  =>  d/dr = (x bx - w bw)/r ;  d u/d k = 2 sg k, d r/d u = 1/(2 r).
+ADSURF_HD double eig_adjoint(const Eig& e, double k, double dm, double bcs, double bw, double bx, double bex,
+                             double& bd, double& bk) {
+  const double bsn = bw * e.ir + (e.lt ? -e.r : e.r) * bx;
   const double bp = e.dcs * bcs + e.dsn * bsn + (e.lt ? 0.0 : bex);
-  const double br = sg * e.sn * bx - e.w * e.ir * bw + dm * bp;
-  const double h = sg * br * e.ir;  // d u / d k = 2 sg k, d r / d u = 1 / (2 r)
+  const double br = e.ir * (e.x * bx - e.w * bw) + dm * bp;
+  const double h = (e.lt ? -e.ir : e.ir) * br;
   // k == kx: w = d and the (measure-zero) dependence through r is dropped (finite one-sided value)
   bd += e.pos ? e.r * bp : bw;
   bk += e.pos ? k * h : 0.0;
-  bkx -= e.pos ? kx * h : 0.0;
+  return e.pos ? h : 0.0;
 }
 
 // Reverse sweep through one layer: given row vector e (= E_{m+1}) and column s (= s_m, already
@@ -471,12 +474,12 @@ ADSURF_HD LayerGrad layer_adjoint(const Layer& y, const double (&e)[5], const do
   const double bex = -a0 * ba0;
 
   LayerGrad g;
-  g.d = 0.0; g.ka = 0.0; g.kb = 0.0;
+  g.d = 0.0;
   g.k = 2.0 * k * b_k2;
   g.gammk = b_gk;
   g.rho = b_rho;
-  eig_adjoint(y.P, k, y.ka, y.dm, bcp, bw, bx, bex, g.d, g.k, g.ka);
-  eig_adjoint(y.S, k, y.kb, y.dm, bcq, by, bz, bex, g.d, g.k, g.kb);
+  g.hp = eig_adjoint(y.P, k, y.dm, bcp, bw, bx, bex, g.d, g.k);
+  g.hs = eig_adjoint(y.S, k, y.dm, bcq, by, bz, bex, g.d, g.k);
   return g;
 }
 
@@ -528,16 +531,14 @@ ADSURF_HD LayerGrad half_adjoint(const Half& h, const double (&e)[5], const doub
   g.rho = (2.0 * e[0] * s[0] + e[1] * s[1] + e[2] * s[2] + e[3] * s[3]) * ir;
   g.gammk = bgk;
   g.k = 2.0 * k * bk2;
-  g.ka = 0.0; g.kb = 0.0;
+  g.hp = 0.0; g.hs = 0.0;
   if (h.bra < 2) {
-    const double hh = (h.bra ? 1.0 : -1.0) * bra * h.ira;
-    g.k += k * hh;
-    g.ka -= h.ka * hh;
+    g.hp = (h.bra ? 1.0 : -1.0) * bra * h.ira;
+    g.k += k * g.hp;
   }
   if (h.brb < 2) {
-    const double hh = (h.brb ? 1.0 : -1.0) * brb * h.irb;
-    g.k += k * hh;
-    g.kb -= h.kb * hh;
+    g.hs = (h.brb ? 1.0 : -1.0) * brb * h.irb;
+    g.k += k * g.hs;
   }
   return g;
 }
@@ -546,7 +547,7 @@ ADSURF_HD LayerGrad half_adjoint(const Half& h, const double (&e)[5], const doub
 // Sample-level drivers
 // ------------------------------------------------------------------------------------------
 struct Sample {
-  double k, k2, omega, iw, iw2, t2;  // wavenumber, its square, clamped angular frequency, 1/omega, 1/omega^2, -2 k^2
+  double k, k2, omega, iw, iw2, t2, w2;  // wavenumber, k^2, clamped angular frequency, 1/omega, 1/omega^2, -2 k^2, omega^2
 };
 
 // omega = twopi / t as torch evaluates `python_float / tensor` (Tensor.__rtruediv__ ==
@@ -563,6 +564,7 @@ ADSURF_HD Sample make_sample(double omega0, double ic) {
   z.iw = 1.0 / z.omega;
   z.iw2 = z.iw * z.iw;
   z.t2 = -2.0 * z.k2;
+  z.w2 = z.omega * z.omega;
   return z;
 }
 
@@ -573,14 +575,12 @@ struct DirectSource {
   const double* __restrict__ par;
   int L;
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
-    y.ka = z.omega * par[m * kNumPar + P_IA];
-    y.kb = z.omega * par[m * kNumPar + P_IB];
     y.gk = par[m * kNumPar + P_TB2] * z.iw2;
     y.rho = par[m * kNumPar + P_RHO];
     y.ir = par[m * kNumPar + P_IR];
     y.dm = par[m * kNumPar + P_D];
-    eig_setup(y.P, z.k, y.ka, y.dm);
-    eig_setup(y.S, z.k, y.kb, y.dm);
+    eig_setup(y.P, z.k, z.omega * par[m * kNumPar + P_IA], y.dm);
+    eig_setup(y.S, z.k, z.omega * par[m * kNumPar + P_IB], y.dm);
     layer_coefs(y, z.k2, z.t2);
   }
 };
@@ -625,9 +625,9 @@ struct TableSource {
   int L;
   const double* __restrict__ tab;  // [L-1][kTab] for the current trial velocity (16-byte aligned)
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
-    // 16-byte broadcast loads: 3 for the layer record, 5 for the table entry
+    // 16-byte broadcast loads: 2 for the layer record, 5 for the table entry
     const double* __restrict__ pr = par + m * kNumPar;
-    const Dbl2 p01 = ld2(pr + P_IA), p23 = ld2(pr + P_TB2), p45 = ld2(pr + P_IR);
+    const Dbl2 p23 = ld2(pr + P_TB2), p45 = ld2(pr + P_IR);
     const double* __restrict__ q = tab + m * kTab;
     const Dbl2 t01 = ld2(q + T_PDA), t23 = ld2(q + T_NA), t45 = ld2(q + T_INA), t67 = ld2(q + T_GAM),
                t89 = ld2(q + T_BR);
@@ -635,8 +635,6 @@ struct TableSource {
     y.rho = p23.y;
     y.ir = p45.x;
     y.dm = p45.y;
-    y.ka = z.omega * p01.x;  // adjoint only
-    y.kb = z.omega * p01.y;
     y.gk = p23.x * z.iw2;
     y.gam = t67.x;
     y.g1 = t67.y;
@@ -767,9 +765,10 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
       if (m + 1 <= L - 2) fetch_e(m + 1);
       col_apply(s, y);
       gk += g.k;
-      const double ia = par[m * kNumPar + P_IA], ib = par[m * kNumPar + P_IB];
-      // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2
-      sink(m, g.d, -y.ka * ia * g.ka, -y.kb * ib * g.kb + 2.0 * y.gk * ib * g.gammk, g.rho);
+      // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2:
+      //   d/dalpha = omega^2/alpha^3 hp,  d/dbeta = omega^2/beta^3 hs + 4 beta/omega^2 dDelta/dgammk
+      const double* __restrict__ pr = par + m * kNumPar;
+      sink(m, g.d, (z.w2 * pr[P_IA3]) * g.hp, (z.w2 * pr[P_IB3]) * g.hs + (pr[P_CB] * z.iw2) * g.gammk, g.rho);
     };
     // Regime specialisation (dense kernels: the flags are warp-uniform table entries).  Re-stating the flags
     // as constants inside each branch lets the compiler fold every "lt ? a : b" / "pos ? a : b" select of
@@ -798,8 +797,8 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   const LayerGrad g = half_adjoint(h, e, s, z.k, z.k2);
   gk += g.k;
   const int mh = L - 1;
-  const double ia = par[mh * kNumPar + P_IA], ib = par[mh * kNumPar + P_IB];
-  sink(mh, 0.0, -h.ka * ia * g.ka, -h.kb * ib * g.kb + 2.0 * h.gammk * ib * g.gammk, g.rho);
+  const double* __restrict__ prh = par + mh * kNumPar;
+  sink(mh, 0.0, (z.w2 * prh[P_IA3]) * g.hp, (z.w2 * prh[P_IB3]) * g.hs + (prh[P_CB] * z.iw2) * g.gammk, g.rho);
   return gk;
 }
 
@@ -812,6 +811,10 @@ ADSURF_HD void stage_one(double* __restrict__ par, int L, int m, double dm, doub
   par[m * kNumPar + P_RHO] = r;
   par[m * kNumPar + P_IR] = 1.0 / r;
   par[m * kNumPar + P_D] = dm;
+  par[m * kNumPar + P_IA3] = 1.0 / (a * a * a);
+  par[m * kNumPar + P_IB3] = 1.0 / (b * b * b);
+  par[m * kNumPar + P_CB] = 4.0 * b;
+  par[m * kNumPar + 9] = 0.0;
   if (m == L - 1) {
     par[kNumPar * L + 0] = a;
     par[kNumPar * L + 1] = b;
