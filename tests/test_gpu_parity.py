@@ -298,3 +298,37 @@ def test_device_elementary_functions(ab):
     assert ulp(ex[m], np.exp(-x[m])).max() <= 2
     err = np.maximum(np.abs(sn - np.sin(x)), np.abs(cs - np.cos(x))) / np.spacing(1.0)
     assert err.max() <= 2
+
+
+def test_full_size_config5_properties(ab):
+    """BASELINE config 5 at its full size (4096 models x 128 f x 1024 c x 20 layers = 536 870 912 samples):
+    size-independent properties of the fused forward+adjoint sweep.
+      * batch independence: models 0..7 swept alone give the same det and gradients as inside the 4096 batch
+        (and those 8 models are checked against the oracle by test_config5_subset_against_oracle);
+      * exact linearity in the upstream gradient (gdet = 1 vs gdet = 2, power of two);
+      * determinism (two runs bit-identical); fused max/min == max/min of the materialised grid;
+      * row 0 of the ensemble is the unperturbed model: its column-wise sign-change count is >= 1 everywhere."""
+    from adsurf_b200 import _capi
+    from tests.workload import config5
+    S, NF, K = 4096, 128, 1024
+    d, a, b, rho, t, c = (G(x) for x in config5(S, NF, K))
+    det, gd, ga, gb, gr = _capi.grid_bwd(d, a, b, rho, t, c, None, want_det=True)
+    assert torch.isfinite(det).all() and all(torch.isfinite(x).all() for x in (gd, ga, gb, gr))
+    again = _capi.grid_bwd(d, a, b, rho, t, c, None, want_det=False)[1:]
+    for x, y in zip((gd, ga, gb, gr), again):
+        assert torch.equal(x, y)
+    sub = slice(0, 8)
+    det8, gd8, ga8, gb8, gr8 = _capi.grid_bwd(*(x[sub].contiguous() for x in (d, a, b, rho, t, c)), None, want_det=True)
+    assert torch.equal(det8, det[sub])
+    for x, y in zip((gd8, ga8, gb8, gr8), (gd, ga, gb, gr)):
+        assert_grad_close(N(x), N(y[sub]), rtol=1e-12)  # block partials are summed in a different order
+    _, cmax, cmin, _ = _capi.grid_fwd(d, a, b, rho, t, c, want_det=False, want_minmax=True)
+    assert_det_close(N(cmax[:64]), N(det[:64].max(1).values), axis=-1, rtol=SAME)
+    assert_det_close(N(cmin[:64]), N(det[:64].min(1).values), axis=-1, rtol=SAME)
+    sgn = torch.sign(det[0])
+    assert int((sgn[:-1] != sgn[1:]).sum(0).min()) >= 1
+    del det, det8
+    two = torch.full((S, K, NF), 2.0, dtype=torch.float64, device="cuda")
+    g2 = _capi.grid_bwd(d, a, b, rho, t, c, two)[1:]
+    for x, y in zip((gd, ga, gb, gr), g2):
+        assert torch.equal(2.0 * x, y)
