@@ -809,6 +809,22 @@ inline size_t points_smem(const PointsPlan& pp, int L) {
   return pp.global ? par_bytes(L) + (size_t)pp.wpb * (64 * L + 1) * sizeof(double) : adj_smem(L, pp.wpb);
 }
 
+// The slabs are tagged evict_last; L2 honours that only inside its persisting carve-out, which is 0 bytes by
+// default.  Ask once per device for the largest carve-out the part allows (a context-wide limit, like a
+// shared-memory carve-out preference: it changes nothing for code that does not use persisting accesses).
+// ADSURF_PERSIST_L2=0 disables the request.
+inline void reserve_persisting_l2(int dev) {
+  static int done[64] = {0};
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  done[dev] = 1;
+  const char* e = getenv("ADSURF_PERSIST_L2");
+  if (e && !strcmp(e, "0")) return;
+  int maxb = 0;
+  if (cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && maxb > 0)
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxb);
+  cudaGetLastError();
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 inline int check_launch() {
@@ -1035,6 +1051,7 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   int dev = 0, nsm = kNumSM, occ = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  reserve_persisting_l2(dev);
   const int threads = gp.wpb * kWarp;
 #define ADSURF_LAUNCH_BWD(KERN)                                                                                  \
   do {                                                                                                           \
