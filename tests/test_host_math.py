@@ -120,3 +120,47 @@ def test_inline_elementary_functions_accuracy(hm):
     # sin/cos: error measured against the larger of the two (the reduction error is absolute)
     err = np.maximum(np.abs(sn - np.sin(x)), np.abs(cs - np.cos(x))) / np.spacing(1.0)
     assert err.max() <= 2
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_models_against_oracle(hm, seed):
+    """Seeded random layered models (2-14 layers, low-velocity zones allowed, trial velocities in every regime:
+    below all Vs, between Vs and Vp, above Vp of the top layers) — kernel arithmetic (host build) vs the oracle's
+    autograd, dense (table) path and pointwise (direct) path."""
+    import torch
+    from oracle import dltar_oracle as O
+    rng = np.random.default_rng(1000 + seed)
+    S, L = 2, int(rng.integers(2, 15))
+    b = rng.uniform(0.3, 4.5, (S, L))
+    a = b * rng.uniform(1.5, 2.2, (S, L))
+    rho = rng.uniform(1.5, 3.3, (S, L))
+    d = rng.uniform(0.02, 0.8, (S, L))  # phases up to ~250 rad; beyond that 1-ulp input noise alone exceeds 1e-9
+    K, NF = 24, 7
+    c = np.sort(rng.uniform(0.25, 8.0, (S, K)), axis=1)
+    t = np.exp(rng.uniform(np.log(0.1), np.log(8.0), (S, NF)))
+    gdet = rng.standard_normal((S, K, NF))
+    td, ta, tb, tr = (torch.tensor(x, requires_grad=True) for x in (d, a, b, rho))
+    det_o = O.det_grid(torch.tensor(c), torch.tensor(t), td, ta, tb, tr)
+    go = torch.autograd.grad(det_o, (td, ta, tb, tr), grad_outputs=torch.tensor(gdet))
+    det = np.empty((S, K, NF))
+    outs = [np.empty((S, L)) for _ in range(4)]
+    assert hm.host_grid(P(C(d)), P(C(a)), P(C(b)), P(C(rho)), P(C(t)), P(C(c)), P(C(gdet)), S, L, NF, K, P(det),
+                        *(P(o) for o in outs)) == 0
+    assert_det_close(det, det_o.detach().numpy(), axis=1)
+    assert np.array_equal(np.sign(det), np.sign(det_o.detach().numpy()))
+    for new, ref, key in zip(outs, go, ("gd", "ga", "gb", "grho")):
+        assert_grad_close(new, ref.numpy(), what=key)
+    # pointwise path on the flattened grid of model 0, including dF/dc
+    cc = np.repeat(c[:1], NF, axis=0).T.reshape(1, -1)
+    tt = np.tile(t[:1], (K, 1)).reshape(1, -1)
+    tc = torch.tensor(cc, requires_grad=True)
+    td, ta, tb, tr = (torch.tensor(x[:1], requires_grad=True) for x in (d, a, b, rho))
+    Fo = O.det_points(tc, torch.tensor(tt), td, ta, tb, tr)
+    gF = rng.standard_normal(cc.shape)
+    go = torch.autograd.grad(Fo, (td, ta, tb, tr, tc), grad_outputs=torch.tensor(gF))
+    g = {"d": d[:1], "a": a[:1], "b": b[:1], "rho": rho[:1], "t": tt, "c": cc, "gF": gF}
+    F, gd, ga, gb, gr, gc, _ = run_points(hm, g)
+    assert_det_close(F.reshape(K, NF), Fo.detach().numpy().reshape(K, NF), axis=0)
+    for new, ref, key in zip((gd, ga, gb, gr), go[:4], ("gd", "ga", "gb", "grho")):
+        assert_grad_close(new, ref.numpy(), what="points " + key)
+    assert_grad_close(gc.reshape(K, NF).T, go[4].numpy().reshape(K, NF).T, what="gc")
