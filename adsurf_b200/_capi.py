@@ -63,7 +63,7 @@ def lib():
         L.adsurf_dmf_step.argtypes = [vp] * 7 + [ci] * 6 + [vp] * 7 + [vp, sz, vp]
         L.adsurf_fp64_peak_probe.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]
         cd = ctypes.c_double
-        L.adsurf_ensemble_adam_step.argtypes = ([vp] * 20 + [ci, ci, ci, cd, ci, ci, cd, cd, cd, cd, cd, cd, ci]
+        L.adsurf_ensemble_adam_step.argtypes = ([vp] * 20 + [ci, ci, ci, cd, ci, ci, ci, cd, cd, cd, cd, cd, cd, ci]
                                                 + [vp, vp, vp, sz, vp])
         L.adsurf_ensemble_adam_step.restype = ci
         L.adsurf_math_probe.argtypes = [vp, ci, vp, vp, vp, vp, vp]
@@ -253,8 +253,11 @@ VP_MODE = {"": 0, None: 0, "none": 0, "Brocher": 1, "Constant": 2, "USArray": 3}
 LAYERING = {"LR": 1, "LN": 2}
 
 
+PROJ_LAST_LAYER, PROJ_NAN_REPAIR = 1, 2
+
+
 def ensemble_adam_step(state, grads, loss, consts, *, vp_mode, vp_vs_ratio, invert_thick, layering, damp_vertical,
-                       damp_horizontal, lr, beta1, beta2, eps, step, iter_b=None, iter_d=None, ws=None):
+                       damp_horizontal, lr, beta1, beta2, eps, step, iter_b=None, iter_d=None, ws=None, proj_flags=None):
     """In-place optimiser step of the ensemble inversion (C ABI adsurf_ensemble_adam_step).
 
     state  = dict(b, d, alpha, rho, mb, vb, md, vd)          [S,L] float64 CUDA, updated in place
@@ -267,13 +270,16 @@ def ensemble_adam_step(state, grads, loss, consts, *, vp_mode, vp_vs_ratio, inve
     if ws is None:
         ws = torch.empty(3 * S * L * 8, dtype=torch.uint8, device=b.device)
     gd, ga, gb, gr = grads
+    if proj_flags is None:  # the ensemble loops of the reference
+        proj_flags = PROJ_LAST_LAYER | (0 if invert_thick else PROJ_NAN_REPAIR)
     with torch.cuda.device(b.device):
         _check(lib().adsurf_ensemble_adam_step(
             _ptr(b), _ptr(state["d"]), _ptr(state["alpha"]), _ptr(state["rho"]), _ptr(gd), _ptr(ga), _ptr(gb), _ptr(gr),
             _ptr(loss), _ptr(state["mb"]), _ptr(state["vb"]), _ptr(state["md"]), _ptr(state["vd"]), _ptr(consts["b0"]),
             _ptr(consts["alpha0"]), _ptr(consts["rho0"]), _ptr(consts["lower_b"]), _ptr(consts["upper_b"]),
             _ptr(consts["mindepth"]), _ptr(consts["maxdepth"]), S, L, int(vp_mode), float(vp_vs_ratio or 0.0),
-            int(bool(invert_thick)), int(layering), float(damp_vertical), float(damp_horizontal), float(lr),
+            int(bool(invert_thick)), int(layering), int(proj_flags), float(damp_vertical), float(damp_horizontal),
+            float(lr),
             float(beta1), float(beta2), float(eps), int(step), _ptr(iter_b), _ptr(iter_d), _ptr(ws), ws.numel(),
             _stream(b)))
     launch_count += 2

@@ -267,25 +267,58 @@ class iter_inversion:
         vs_and_thick = inversion_method.lower() == "vs-and-thick"
         last = iteration
         prev = None
-        for j in tqdm(range(iteration), disable=not getattr(ip, "progress", False)):
-            loss = calculator(vlist, tlist)
-            optimizer.zero_grad()
-            loss.backward()
+        fused = os.environ.get("ADSURF_FUSED_OPT", "1") != "0" and dev.type == "cuda"
+        if fused:
+            # device-resident iteration (one fused DMF evaluation + one optimiser-step launch, S = 1); the loss is
+            # read back every iteration because the reference's early stopping looks at it (_model.py:168-186)
+            method = mp.initialize_method if mp.initialize_method in _capi.VP_MODE else ""
             with torch.no_grad():
-                pb = calculator.b
-                pb.data = torch.minimum(torch.maximum(pb.data, lower_b), upper_b)
-                if vs_and_thick:
-                    pb.data[-1] = torch.maximum(pb.data[-1], pb.data[-2])  # half-space >= layer above (:129)
-                    iter_vs[j] = pb.data
-                    pd = calculator.d
-                    pd.data = _clip_depths(pd.data, layer_mindepth, layer_maxdepth, mp.layering_method)
-                    iter_thick[j] = pd.data
-                else:
-                    iter_vs[j] = pb.data
-            optimizer.step()
-            scheduler.step()
-            cur = float(loss.detach())  # the reference syncs every iteration for its progress bar (:164)
-            loss_list[j] = cur
+                a_now, r_now = calculator._velocities()
+            c64 = lambda x: x.detach().to(torch.float64).reshape(1, -1).contiguous().clone()
+            state = {"b": c64(calculator.b), "d": c64(calculator.d), "alpha": c64(a_now), "rho": c64(r_now)}
+            for key in ("mb", "vb", "md", "vd"):
+                state[key] = torch.zeros_like(state["b"])
+            consts = {"b0": c64(calculator.b), "alpha0": c64(a), "rho0": c64(rho), "lower_b": c64(lower_b),
+                      "upper_b": c64(upper_b), "mindepth": c64(layer_mindepth), "maxdepth": c64(layer_maxdepth)}
+            mode = ops.COMPRESS[_compress_mode(ip.compress, ip.normalized, ip.compress_method)]
+            grads = tuple(torch.empty_like(state["b"]) for _ in range(4))
+            ws_step = torch.empty(3 * b.numel() * 8, dtype=torch.uint8, device=dev)
+            vl, tl = vlist.reshape(1, -1).contiguous(), tlist.reshape(1, -1).contiguous()
+            loss_buf = loss_list.reshape(-1, 1)
+            # single-model loops: half-space rule only on the vs-and-thick branch, no NaN repair (:122-159)
+            proj = _capi.PROJ_LAST_LAYER if vs_and_thick else 0
+        for j in tqdm(range(iteration), disable=not getattr(ip, "progress", False)):
+            if fused:
+                lr_j = ip.lr * ip.gamma ** (j // ip.step_size)
+                _capi.dmf_step(state["d"], state["alpha"], state["b"], state["rho"], tl, vl, calculator.Clist, mode,
+                               with_grad=True, loss=loss_buf[j], grads=grads)
+                _capi.ensemble_adam_step(state, grads, loss_buf[j], consts, vp_mode=_capi.VP_MODE[method],
+                                         vp_vs_ratio=mp.vp_vs_ratio, invert_thick=vs_and_thick,
+                                         layering=_capi.LAYERING.get(mp.layering_method, 0),
+                                         damp_vertical=ip.damp_vertical, damp_horizontal=0.0, lr=lr_j, beta1=0.9,
+                                         beta2=0.999, eps=1e-8, step=j + 1, iter_b=iter_vs[j:j + 1],
+                                         iter_d=iter_thick[j:j + 1] if vs_and_thick else None, ws=ws_step,
+                                         proj_flags=proj)
+                cur = float(loss_list[j])
+            else:
+                loss = calculator(vlist, tlist)
+                optimizer.zero_grad()
+                loss.backward()
+                with torch.no_grad():
+                    pb = calculator.b
+                    pb.data = torch.minimum(torch.maximum(pb.data, lower_b), upper_b)
+                    if vs_and_thick:
+                        pb.data[-1] = torch.maximum(pb.data[-1], pb.data[-2])  # half-space >= layer above (:129)
+                        iter_vs[j] = pb.data
+                        pd = calculator.d
+                        pd.data = _clip_depths(pd.data, layer_mindepth, layer_maxdepth, mp.layering_method)
+                        iter_thick[j] = pd.data
+                    else:
+                        iter_vs[j] = pb.data
+                optimizer.step()
+                scheduler.step()
+                cur = float(loss.detach())  # the reference syncs every iteration for its progress bar (:164)
+                loss_list[j] = cur
             if j > 0:
                 if cur > 0.6:
                     trigger_times = 0

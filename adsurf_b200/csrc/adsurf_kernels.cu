@@ -604,7 +604,7 @@ __global__ void k_ens_prepare(const double* __restrict__ b, const double* __rest
 struct EnsArgs {
   double *b, *d, *alpha, *rho, *mb, *vb, *md, *vd, *iter_b, *iter_d;
   const double *gd, *gt, *b0, *a0, *r0, *lob, *upb, *mind, *maxd, *sv, *sh;
-  int S, L, vp_mode, invert_thick, layering;
+  int S, L, vp_mode, invert_thick, layering, proj_flags;
   double ratio, dv, dh, lr, beta1, beta2, eps, bc1, bc2s;
 };
 
@@ -625,9 +625,9 @@ __global__ void k_ens_adam(EnsArgs A) {
   double prev = 0.0;
   for (int l = 0; l < L; ++l) {
     double x = A.b[o + l];
-    if (x != x && !A.invert_thick) x = A.b0[o + l];                 // NaN repair exists on the vs-only branch (:624-626)
+    if (x != x && (A.proj_flags & 2)) x = A.b0[o + l];              // NaN repair of the ensemble vs-only loop (:624-626)
     if (x == x) x = fmin(fmax(x, A.lob[o + l]), A.upb[o + l]);       // clip_(min, max): max wins when min > max
-    if (l == L - 1 && L > 1 && x == x && prev == prev) x = fmax(x, prev);  // half-space >= layer above (:599/:631)
+    if ((A.proj_flags & 1) && l == L - 1 && L > 1 && x == x && prev == prev) x = fmax(x, prev);  // (:129/:599/:631)
     prev = x;
     A.b[o + l] = x;
     if (A.iter_b) A.iter_b[o + l] = x;
@@ -1131,8 +1131,8 @@ int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho, 
                               double* vb, double* md, double* vd, const double* b0, const double* alpha0,
                               const double* rho0, const double* lower_b, const double* upper_b,
                               const double* layer_mindepth, const double* layer_maxdepth, int S, int L, int vp_mode,
-                              double vp_vs_ratio, int invert_thick, int layering, double damp_vertical,
-                              double damp_horizontal, double lr, double beta1, double beta2, double eps, int step,
+                              double vp_vs_ratio, int invert_thick, int layering, int proj_flags,
+                              double damp_vertical, double damp_horizontal, double lr, double beta1, double beta2, double eps, int step,
                               double* iter_b, double* iter_d, void* ws, size_t ws_bytes, void* stream) {
   if (!b || !d || !alpha || !rho || !galpha || !gbeta || !grho || !loss || !mb || !vb || !b0 || !alpha0 || !rho0 ||
       !lower_b || !upper_b)
@@ -1155,6 +1155,7 @@ int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho, 
   A.gd = gd; A.gt = gt; A.b0 = b0; A.a0 = alpha0; A.r0 = rho0;
   A.lob = lower_b; A.upb = upper_b; A.mind = layer_mindepth; A.maxd = layer_maxdepth; A.sv = sv; A.sh = sh;
   A.S = S; A.L = L; A.vp_mode = vp_mode; A.invert_thick = invert_thick; A.layering = layering;
+  A.proj_flags = proj_flags;
   A.ratio = vp_vs_ratio; A.dv = damp_vertical; A.dh = damp_horizontal; A.lr = lr; A.beta1 = beta1; A.beta2 = beta2;
   A.eps = eps;
   A.bc1 = 1.0 - pow(beta1, (double)step);

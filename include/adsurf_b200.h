@@ -134,8 +134,9 @@ int adsurf_fp64_peak_probe(int iters, int repeats, double* tflops, double* ms, v
  *   1. total misfit: loss[s] += damp_v sum_l |(L_v b_s)_l| / L + damp_h sum_l |(L_h b)_{s,l}| / L   (_model.py:466-477)
  *   2. dloss/db through the velocity chain (vp_mode 1 Brocher: alpha = P4(b), rho = P5(alpha); 2 Constant:
  *      alpha = ratio b; 3 USArray: Brocher where b <= 4.6; 0: alpha, rho fixed) plus the Tikhonov subgradients
- *   3. parameter projection done by the reference BEFORE the optimiser step (_model.py:593-632): NaN repair
- *      (vs-only), clip b to [lower_b, upper_b], b[:,L-1] >= b[:,L-2]; with invert_thick the cumulative depths
+ *   3. parameter projection done by the reference BEFORE the optimiser step (_model.py:593-632, :122-159): clip b
+ *      to [lower_b, upper_b]; proj_flags bit 0: b[:,L-1] >= b[:,L-2] (ensemble loops and the single-model
+ *      vs-and-thick loop), bit 1: NaN entries reset to b0 first (ensemble vs-only loop); with invert_thick the cumulative depths
  *      are clipped (layering 1 = LR, 2 = LN, 0 = none) and turned back into thicknesses >= min_thick;
  *      the projected iterates are recorded in iter_b / iter_d (may be NULL)
  *   4. Adam (torch.optim.Adam semantics, no weight decay/amsgrad) with learning rate `lr` and step count
@@ -151,7 +152,7 @@ int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho,
                               const double* lower_b, const double* upper_b,
                               const double* layer_mindepth, const double* layer_maxdepth,
                               int S, int L, int vp_mode, double vp_vs_ratio, int invert_thick, int layering,
-                              double damp_vertical, double damp_horizontal,
+                              int proj_flags, double damp_vertical, double damp_horizontal,
                               double lr, double beta1, double beta2, double eps, int step,
                               double* iter_b, double* iter_d, void* ws, size_t ws_bytes, void* stream);
 

@@ -197,3 +197,29 @@ def test_fused_optimiser_loop_matches_torch_loop(api, case, monkeypatch):
     for x, y in zip(runs["1"], runs["0"]):
         np.testing.assert_allclose(x, y, rtol=1e-8, atol=1e-12)
     assert np.isfinite(runs["1"][0]).all()
+
+
+@pytest.mark.parametrize("inv_method", ["vs-and-thick", "vs"])
+def test_fused_single_model_loop_matches_torch_loop(api, inv_method, monkeypatch):
+    """iter_inversion: device-resident iteration vs the torch-autograd loop (same early-stopping bookkeeping)."""
+    import types
+    from adsurf_b200._model import iter_inversion
+    from adsurf_b200._utils import depth_ln
+    s = load("shipped_fixtures")
+    obs = s["disper_00"][::5]
+    lo, hi = depth_ln(0.2, 16.0, 6, 3.8)
+    mp_ = types.SimpleNamespace(clist=np.arange(2, 3.2, 0.004), layering_method="LN", initialize_method="Brocher",
+                                vp_vs_ratio=2.45, rho=2)
+    ip = types.SimpleNamespace(damp_vertical=0.002, damp_horizontal=0, compress=True, normalized=True,
+                               compress_method="exp", inversion_method=inv_method, lr=0.005, iteration=30, step_size=10,
+                               gamma=0.75, optimizer="Adam")
+    init = types.SimpleNamespace(init_model={"vs": s["c2_init_vs"], "vp": s["c2_init_vp"], "rho": s["c2_init_rho"],
+                                             "thick": s["c2_init_thick"], "layer_mindepth": lo, "layer_maxdepth": hi})
+    runs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ADSURF_FUSED_OPT", flag)
+        inv = iter_inversion(mp_, ip, init, obs, vsrange_sign="mul", vsrange=[0.1, 2], device="cuda")
+        runs[flag] = (np.asarray(inv.inv_process["loss"]), np.asarray(inv.inv_process["iter_vs"]),
+                      np.asarray(inv.inv_process["iter_thick"]), np.asarray(inv.inv_model["vs"]))
+    for x, y in zip(runs["1"], runs["0"]):
+        np.testing.assert_allclose(x, y, rtol=1e-8, atol=1e-12)
