@@ -5,20 +5,27 @@
 // What it computes is specified in SURVEY.md Appendix A, which restates
 // /root/reference/ADsurf/_cps/_surf96_vectorAll_gpu.py:52-100 (Dunkin matrix), :102-192
 // (exponent-scaled eigenfunction terms) and :303-399 (layer recursion, no normalisation).
-// How it computes it is new:
-//   * one thread per (model, period, trial velocity) sample, lanes of a warp run over PERIODS
-//     at a fixed trial velocity so that (a) det[s,k,f] is written coalesced and (b) the three-way
-//     branch "c <,==,> layer velocity" is warp-uniform (it does not depend on the period);
-//   * per-model layer constants (1/alpha, 1/beta, 2 beta^2, rho, 1/rho, d) staged once per block
-//     in shared memory; the 5-component compound state lives in registers; the 5x5 matrix is
-//     never formed;
-//   * the adjoint is a hand-derived reverse sweep: pass 1 (bottom-up) keeps the row vectors
-//     E_{m+1} of each layer in shared memory (40 B per thread per layer), pass 2 (top-down)
-//     carries the column vector s_m = CA_{m-1}...CA_0 e_0, recomputes the layer terms and
-//     contracts dDelta = E_{m+1} . dCA_m . s_m analytically into (d, alpha, beta, rho, c);
-//   * per-model gradient sums: warp shuffle -> per-warp shared accumulators -> one partial per
-//     block -> deterministic second-stage reduce (no atomics);
-//   * the dense pass fuses max/min over the trial velocities (what the DMF needs) and an optional
+// How it computes it is new (DESIGN.md §2, §5):
+//   * one thread per (model, period, trial velocity) sample; lanes of a warp run over PERIODS at a fixed trial
+//     velocity, so det[s,k,f] is written coalesced and the three-way branch "c <,==,> layer velocity" is
+//     warp-uniform (it does not depend on the period);
+//   * a block = (model, velocity chunk, group of <= 4 period tiles).  Per-model layer records (1/alpha, 1/beta,
+//     2 beta^2, rho, 1/rho, d, ...) are staged once per block in shared memory; everything that depends on
+//     (velocity, layer) but not on the period — sqrt(|1/c^2 - 1/v^2|), its reciprocal, the phase per unit omega,
+//     gam, gam-1, (gam-1)^2 rho, the regime flags — is computed once per 8 velocities into a shared table and
+//     read by every lane as 16-byte broadcasts (TableSource);
+//   * the 5-component compound state lives in registers; the 5x5 Dunkin matrix is never formed: the layer
+//     product uses its rank structure (two rank-one couplings around the Kronecker product of the P and S
+//     blocks), 33 FMAs per product; elementary functions are inline (table-driven exp, Cody-Waite sincos);
+//   * the adjoint is a hand-derived reverse sweep: pass 1 (bottom-up) stores, per layer, the row vector
+//     E_{m+1} and the transcendental results (9 doubles per thread) in a per-resident-warp slab of global
+//     memory that stays in the persisting part of L2; pass 2 (top-down) carries the column vector
+//     s_m = CA_{m-1}...CA_0 e_0, reloads the stored values right after their last use, and contracts
+//     dDelta = E_{m+1} . dCA_m . s_m analytically into (d, alpha, beta, rho, c) — no transcendental is
+//     evaluated twice; the kernel is persistent (3 blocks x 4 warps per SM, register-bound);
+//   * per-model gradient sums: one warp fold + per-lane shared accumulators -> one partial per block ->
+//     deterministic second-stage reduce (no atomics);
+//   * the dense forward pass fuses max/min over the trial velocities (what the DMF needs) and an optional
 //     sign bitmap, so det never has to be materialised.
 // No tensor cores (not a contraction), no library calls on the path.
 
