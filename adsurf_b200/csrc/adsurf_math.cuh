@@ -197,6 +197,9 @@ ADSURF_HD void sincos_core(double q, double* sn, double* cs) {
 // i.e. two rank-one couplings around the Kronecker product of the P block [cp w; x cp] and the S block
 // [cq y; z cq].  Row and column products therefore cost ~33 FMAs without ever forming the 13 entries
 // or the 9 eigenfunction products, and the adjoint contracts against the same few scalars.
+// regime flags of a (velocity, layer) pair: oscillatory (k < kx) and regular (k != kx) for P and S
+enum { F_LTP = 1, F_POSP = 2, F_LTS = 4, F_POSS = 8, F_REGULAR = F_POSP | F_POSS };
+
 struct Eig {
   double r, ir;     // sqrt((k+kx)|k-kx|) and its reciprocal
   double p;         // r * d
@@ -311,35 +314,48 @@ struct Layer {
   double gam, g1, gg, q1, ar, br, kr, tg, t1;
   Eig P, S;
   double a0;
+  int fl;  // regime flags F_LTP | F_POSP | F_LTS | F_POSS (set by the layer source)
 };
 
 // forward sweep: evaluate the transcendentals (P, S set up by the layer source).  The four regime
 // combinations get their own straight-line block so that the P and the S polynomial chains (each a
 // ~16-deep dependent FP64 sequence, 8 cycles per link) are scheduled interleaved instead of one
 // after the other behind separate branches.  The regime is warp-uniform in the dense kernels.
+ADSURF_HD void layer_set_flags(Layer& y, int fl) {
+  y.P.lt = fl & F_LTP;
+  y.P.pos = fl & F_POSP;
+  y.S.lt = fl & F_LTS;
+  y.S.pos = fl & F_POSS;
+}
+
 ADSURF_HD void layer_eig_forward(Layer& y) {
-  const bool lp = y.P.lt, ls = y.S.lt;
-  const bool small = below1e5(fabs(y.P.p)) && below1e5(fabs(y.S.p)) && y.P.pos && y.S.pos;
-  if (!small) {  // huge phase, NaN, or c exactly on a layer velocity: generic path
+  const bool small = below1e5(fabs(y.P.p)) && below1e5(fabs(y.S.p));
+  const int fl = small ? y.fl : -1;  // one integer compare per regime instead of four extracted booleans
+  if (fl == (F_REGULAR | F_LTS)) {          // c between the S and the P velocity of the layer: the common case
+    layer_set_flags(y, F_REGULAR | F_LTS);
+    eig_evan(y.P);
+    eig_osc(y.S);
+  } else if (fl == F_REGULAR) {             // slower than both: fully evanescent
+    layer_set_flags(y, F_REGULAR);
+    eig_evan(y.P);
+    eig_evan(y.S);
+  } else if (fl == (F_REGULAR | F_LTP | F_LTS)) {  // faster than both
+    layer_set_flags(y, F_REGULAR | F_LTP | F_LTS);
+    eig_osc(y.P);
+    eig_osc(y.S);
+  } else if (fl == (F_REGULAR | F_LTP)) {
+    layer_set_flags(y, F_REGULAR | F_LTP);
+    eig_osc(y.P);
+    eig_evan(y.S);
+  } else {  // huge phase, NaN, or c exactly on a layer velocity: generic path
+    layer_set_flags(y, y.fl);
     eig_forward(y.P, y.dm);
     eig_forward(y.S, y.dm);
-  } else {
-    if (!lp && ls) {         // c between the S and the P velocity of the layer: the common case
-      eig_evan(y.P);
-      eig_osc(y.S);
-    } else if (!lp && !ls) { // slower than both: fully evanescent
-      eig_evan(y.P);
-      eig_evan(y.S);
-    } else if (lp && ls) {   // faster than both
-      eig_osc(y.P);
-      eig_osc(y.S);
-    } else {
-      eig_osc(y.P);
-      eig_evan(y.S);
-    }
-    y.P.w = y.P.sn * y.P.ir;
-    y.S.w = y.S.sn * y.S.ir;
+    y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
+    return;
   }
+  y.P.w = y.P.sn * y.P.ir;
+  y.S.w = y.S.sn * y.S.ir;
   y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
 }
 
@@ -581,6 +597,7 @@ struct DirectSource {
     y.dm = par[m * kNumPar + P_D];
     eig_setup(y.P, z.k, z.omega * par[m * kNumPar + P_IA], y.dm);
     eig_setup(y.S, z.k, z.omega * par[m * kNumPar + P_IB], y.dm);
+    y.fl = (y.P.lt ? F_LTP : 0) | (y.P.pos ? F_POSP : 0) | (y.S.lt ? F_LTS : 0) | (y.S.pos ? F_POSS : 0);
     layer_coefs(y, z.k2, z.t2);
   }
 };
@@ -597,7 +614,6 @@ struct alignas(16) Dbl2 {
   double x, y;
 };
 ADSURF_HD Dbl2 ld2(const double* p) { return *reinterpret_cast<const Dbl2*>(p); }
-enum { F_LTP = 1, F_POSP = 2, F_LTS = 4, F_POSS = 8 };
 
 // one table entry: trial slowness ic = 1/c against layer m of the staged model
 ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ par, int L, int m, double ic) {
@@ -648,13 +664,10 @@ struct TableSource {
     y.P.r = z.omega * t23.x;
     y.P.ir = z.iw * t45.x;
     y.P.p = z.omega * t01.x;
-    y.P.lt = fl & F_LTP;
-    y.P.pos = fl & F_POSP;
     y.S.r = z.omega * t23.y;
     y.S.ir = z.iw * t45.y;
     y.S.p = z.omega * t01.y;
-    y.S.lt = fl & F_LTS;
-    y.S.pos = fl & F_POSS;
+    y.fl = fl;  // the per-eig booleans are set where a regime is selected (layer_set_flags)
   }
 };
 
@@ -773,15 +786,14 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     // Regime specialisation (dense kernels: the flags are warp-uniform table entries).  Re-stating the flags
     // as constants inside each branch lets the compiler fold every "lt ? a : b" / "pos ? a : b" select of
     // eig_finish / eig_adjoint away in the two regimes that cover ~95 % of (velocity, layer) pairs.
-    if (Source::kUniformFlags && y.P.pos && y.S.pos && !y.P.lt) {
-      if (y.S.lt) {  // P evanescent, S oscillatory
-        y.P.lt = false; y.S.lt = true; y.P.pos = true; y.S.pos = true;
-        body();
-      } else {       // both evanescent
-        y.P.lt = false; y.S.lt = false; y.P.pos = true; y.S.pos = true;
-        body();
-      }
+    if (Source::kUniformFlags && y.fl == (F_REGULAR | F_LTS)) {  // P evanescent, S oscillatory
+      layer_set_flags(y, F_REGULAR | F_LTS);
+      body();
+    } else if (Source::kUniformFlags && y.fl == F_REGULAR) {     // both evanescent
+      layer_set_flags(y, F_REGULAR);
+      body();
     } else {
+      layer_set_flags(y, y.fl);
       body();
     }
   };
