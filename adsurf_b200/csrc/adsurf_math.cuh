@@ -126,11 +126,13 @@ __device__ __forceinline__ void stage_exp_table() {
 #define ADSURF_EXP2_TAB(j) kExp2TabH[j]
 #endif
 
-// exp(-p) for 0 <= p (< ~700): n = rint(-p 32/ln2), r = -p - n ln2/32 (two-term, |r| <= ln2/64),
+// exp(-p) for 0 <= p < ~700: n = rint(-p 32/ln2), r = -p - n ln2/32 (two-term, |r| <= ln2/64),
 // e^r by a degree-6 Taylor polynomial (truncation 3.5e-18), times 2^(j/32) from the table (j = n mod 32)
 // scaled by 2^(n div 32) through the exponent field.  11 FP64 instructions, <= 2 ulp.
+// For p >= ~700 the exponent field wraps and the value is meaningless — every caller discards it there
+// (the e^{-2p} term is used only for p < 16, e^{-p} only for p < 60), so no clamp is spent on it.
 ADSURF_HD double exp_neg(double p) {
-  const double x = -fmin(p, 700.0);
+  const double x = -p;
   const double t = fma(x, 46.16624130844683, kShifter);
   const double fn = t - kShifter;
   double r = fma(fn, -0.02166084939249829, x);
@@ -142,7 +144,8 @@ ADSURF_HD double exp_neg(double p) {
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   q = fma(q, r, 1.0);
-  const double tj = bits_dbl(dbl_bits(ADSURF_EXP2_TAB(n & 31)) + ((long long)(n >> 5) << 52));
+  const double tj = bits_dbl((long long)((unsigned long long)dbl_bits(ADSURF_EXP2_TAB(n & 31)) +
+                                         ((unsigned long long)(long long)(n >> 5) << 52)));
   return tj * q;
 }
 

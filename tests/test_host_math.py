@@ -115,7 +115,7 @@ def test_inline_elementary_functions_accuracy(hm):
     hm.host_elementary(P(C(x)), n, P(rs), P(ex), P(sn), P(cs))
     pos = x > 0
     assert _ulps(rs[pos], 1 / np.sqrt(x[pos])).max() <= 2
-    m = x <= 700
+    m = x <= 690  # beyond ~700 the value is unspecified (callers use it only for p < 60)
     assert _ulps(ex[m], np.exp(-x[m])).max() <= 2
     # sin/cos: error measured against the larger of the two (the reduction error is absolute)
     err = np.maximum(np.abs(sn - np.sin(x)), np.abs(cs - np.cos(x))) / np.spacing(1.0)
