@@ -147,6 +147,7 @@ __device__ __forceinline__ BlockCoord block_coord(int vb, const GridPlan& gp) {
   return bc;
 }
 
+template <int kTab>
 __device__ __forceinline__ void fill_table(double* __restrict__ tab, double* __restrict__ ics,
                                            const double* __restrict__ par, int L, const double* __restrict__ cs,
                                            int n) {
@@ -155,7 +156,7 @@ __device__ __forceinline__ void fill_table(double* __restrict__ tab, double* __r
     const int cc = e / per, m = e - cc * per;
     const double ic = 1.0 / cs[cc];
     if (m == 0) ics[cc] = ic;
-    table_entry(tab + (size_t)e * kTab, par, L, m, ic);
+    table_entry<kTab>(tab + (size_t)e * kTab, par, m, ic);
   }
   if (per == 0)
     for (int cc = threadIdx.x; cc < n; cc += blockDim.x) ics[cc] = 1.0 / cs[cc];
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const double* __restrict__ d, 
                                                   uint32_t* __restrict__ signbits) {
   extern __shared__ double smem[];
   double* par = smem + kSmemHead;
+  constexpr int kTab = kTabFwd;
   double* tab = par + par_doubles(L);                   // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
   const BlockCoord bc = block_coord(blockIdx.x, gp);
@@ -189,13 +191,13 @@ __global__ void __launch_bounds__(256) k_grid_fwd(const double* __restrict__ d, 
   for (int kb = k0; kb < k1; kb += gp.tc) {
     const int n = min(gp.tc, k1 - kb);
     __syncthreads();  // staged parameters visible / previous table consumed
-    fill_table(tab, ics, par, L, c + (size_t)s * K + kb, n);
+    fill_table<kTab>(tab, ics, par, L, c + (size_t)s * K + kb, n);
     __syncthreads();
     if (!live) continue;
     for (int cc = 0; cc < n; ++cc) {
       const int k = kb + cc;
       const Sample z = make_sample(omega0, ics[cc]);
-      const TableSource src{par, L, tab + (size_t)cc * (L - 1) * kTab};
+      const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab};
       const double v = sample_forward(src, z);
       if (det && active) det[((size_t)s * K + k) * NF + f] = v;
       vmax = fmax(vmax, v);
@@ -285,6 +287,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
            double* __restrict__ det, double* __restrict__ part, double* __restrict__ estore) {
   extern __shared__ double smem[];
   constexpr int kAccPer = kGlobal ? 64 : 4;             // accumulator doubles per (warp, layer)
+  constexpr int kTab = kTabAdj;
   double* par = smem + kSmemHead;                       // staged layer constants (after the exp table)
   double* accs = par + par_doubles(L);                  // [wpb][L][4][16] (global slabs) or [wpb][4][L]
   double* tab = accs + (size_t)gp.wpb * kAccPer * L;    // [tc][L-1][kTab]
@@ -312,29 +315,30 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
     for (int kb = k0; kb < k1; kb += gp.tc) {
       const int n = min(gp.tc, k1 - kb);
       __syncthreads();
-      fill_table(tab, ics, par, L, c + (size_t)s * K + kb, n);
+      fill_table<kTab>(tab, ics, par, L, c + (size_t)s * K + kb, n);
       __syncthreads();
       if (!live) continue;
       for (int cc = 0; cc < n; ++cc) {
         const int k = kb + cc;
         const Sample z = make_sample(omega0, ics[cc]);
-        const TableSource src{par, L, tab + (size_t)cc * (L - 1) * kTab};
+        const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab};
         const size_t idx = ((size_t)s * K + k) * NF + fc;
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
-        double v;
+        double v, top4;
         if (kGlobal) {
           const GlobalStore st{estp, slab_policy};
           FoldSink sink{acc, lane};
-          v = sample_forward_store(src, z, st);
-          sample_adjoint(src, z, seed, st, sink);
+          v = sample_forward_store(src, z, st, top4);
+          if (det && active) __stcs(det + idx, v);  // streaming store: keep the store slabs in L2
+          sample_adjoint(src, z, seed, v, top4, st, sink);
         } else {
           const PlainStore<kWarp> st{estp};
           ReduceSink sink{acc, L, lane};
-          v = sample_forward_store(src, z, st);
-          sample_adjoint(src, z, seed, st, sink);
+          v = sample_forward_store(src, z, st, top4);
+          if (det && active) __stcs(det + idx, v);
+          sample_adjoint(src, z, seed, v, top4, st, sink);
         }
-        if (det && active) __stcs(det + idx, v);  // streaming store: keep the store slabs in L2
       }
     }
     __syncthreads();
@@ -464,7 +468,8 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
       typename std::conditional<kGlobal, GlobalStore, PlainStore<kWarp>>::type store;
       store.p = estp;
       if constexpr (kGlobal) store.pol = slab_policy;
-      const double v = sample_forward_store(src, z, store);
+      double top4;
+      const double v = sample_forward_store(src, z, store, top4);
       if (F && active) F[idx] = v;
       double seed = 1.0;
       if (kKind == 0) seed = gF[idx];
@@ -493,15 +498,15 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
         if (kKind == 1) {
           JacSink sink{Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
                        Jrho ? Jrho + idx * L : nullptr, active};
-          gk = sample_adjoint(src, z, seed, store, sink);
+          gk = sample_adjoint(src, z, seed, v, top4, store, sink);
         } else if (kGlobal) {
           FoldSink sink{acc, lane};
-          gk = sample_adjoint(src, z, active ? seed : 0.0, store, sink);  // overhang lanes: zero seed
+          gk = sample_adjoint(src, z, active ? seed : 0.0, v, top4, store, sink);  // overhang lanes: zero seed
         } else {
           ReduceSink sink{acc, L, lane};
-          gk = sample_adjoint(src, z, active ? seed : 0.0, store, sink);
+          gk = sample_adjoint(src, z, active ? seed : 0.0, v, top4, store, sink);
         }
-        if (gc && active) gc[idx] = -z.k * ic * gk;  // k = omega0 / c
+        if (gc && active) gc[idx] = -ic * z.ic * gk;  // gk = dDelta/d(k/omega), k/omega = 1/c
       }
     }
     __syncthreads();
@@ -756,9 +761,9 @@ inline size_t bwd_estore_bytes(int L) {
   return bwd_mode() == kBwdSmem ? 0 : (size_t)kMaxResidentWarps * est_bytes_per_warp(L);
 }
 
-inline size_t table_bytes(int L, int tc) {
+inline size_t table_bytes(int L, int tc, bool adjoint) {
   const size_t per = (size_t)(L > 1 ? L - 1 : 0);
-  return (size_t)tc * per * kTab * sizeof(double) + (size_t)((tc + 1) & ~1) * sizeof(double);
+  return (size_t)tc * per * (adjoint ? kTabAdj : kTabFwd) * sizeof(double) + (size_t)((tc + 1) & ~1) * sizeof(double);
 }
 
 inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
@@ -770,7 +775,7 @@ inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
     if (bwd_mode() == kBwdSmem) {  // slabs in shared memory: as many warps as fit beside the table
       want = 0;
       for (int w = 4; w >= 1 && !want; w >>= 1)
-        if (adj_smem(L, w) + table_bytes(L, 8) <= (w > 1 ? kSmemBudget : kSmemMax)) want = w;
+        if (adj_smem(L, w) + table_bytes(L, 8, true) <= (w > 1 ? kSmemBudget : kSmemMax)) want = w;
     }
   }
   gp.wpb = want < gp.nft ? want : gp.nft;
@@ -778,7 +783,7 @@ inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
   gp.nfg = gp.wpb > 0 ? (gp.nft + gp.wpb - 1) / gp.wpb : 0;
   // table fills of up to 8 velocities, fewer for very deep models (keeps the table under ~24 KB)
   gp.tc = 8;
-  while (gp.tc > 1 && table_bytes(L, gp.tc) > 24 * 1024) gp.tc >>= 1;
+  while (gp.tc > 1 && table_bytes(L, gp.tc, adjoint) > 24 * 1024) gp.tc >>= 1;
   // enough blocks for ~16 waves of a full machine, chunks not shorter than 2 table fills
   const long long target = (long long)kNumSM * 4 * 16;
   const long long base = (long long)S * (gp.nfg > 0 ? gp.nfg : 1);
@@ -1003,7 +1008,7 @@ int adsurf_det_points_jac(const double* d, const double* alpha, const double* be
 static int grid_fwd_launch(const double* d, const double* alpha, const double* beta, const double* rho,
                            const double* t, const double* c, int S, int L, int NF, int K, double* det, double* pmax,
                            double* pmin, uint32_t* signbits, const GridPlan& gp, cudaStream_t st) {
-  const size_t smem = par_bytes(L) + table_bytes(L, gp.tc);
+  const size_t smem = par_bytes(L) + table_bytes(L, gp.tc, false);
   if (set_smem(k_grid_fwd, smem)) return ADSURF_E_CUDA;
   k_grid_fwd<<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K, gp,
                                                                             det, pmax, pmin, signbits);
@@ -1050,7 +1055,7 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   cudaStream_t st = (cudaStream_t)stream;
   const int mode = bwd_mode();
   const size_t smem = par_bytes(L) +
-                      (size_t)gp.wpb * (mode == kBwdSmem ? 4 : 64) * L * sizeof(double) + table_bytes(L, gp.tc) +
+                      (size_t)gp.wpb * (mode == kBwdSmem ? 4 : 64) * L * sizeof(double) + table_bytes(L, gp.tc, true) +
                       (mode == kBwdSmem ? (size_t)gp.wpb * est_bytes_per_warp(L) : 0);
   double* estore = mode == kBwdSmem ? nullptr : (double*)((char*)ws + part_bytes);
   const long long total_vb = (long long)S * gp.bpm;

@@ -200,12 +200,25 @@ ADSURF_HD void sincos_core(double q, double* sn, double* cs) {
 // i.e. two rank-one couplings around the Kronecker product of the P block [cp w; x cp] and the S block
 // [cq y; z cq].  Row and column products therefore cost ~33 FMAs without ever forming the 13 entries
 // or the 9 eigenfunction products, and the adjoint contracts against the same few scalars.
+//
+// Frequency scaling.  Every wavenumber in CA is proportional to omega (k = omega/c, k_v = omega/v,
+// r = omega n with n = sqrt(|1/c^2 - 1/v^2|), gammk = 2 beta^2/omega^2), so
+//   CA(omega) = D^-1 CA~ D,   D = diag(1, omega, 1, omega, omega^2),
+// where CA~ is the same matrix built from the frequency-free quantities (slowness 1/c for k, n for r,
+// 2 beta^2 for gammk) and depends on omega only through the phases p = omega n d.  D is the same for all
+// layers, so the product telescopes: the layer sweep runs on E~ = E D^-1 (and s~ = D s) with coefficient
+// scalars that depend on (trial velocity, layer) only — in the dense kernels they come out of a shared
+// table and a lane spends two multiplies (the two phases) on a layer's set-up instead of thirteen.  The
+// half-space vector is formed as the reference does and converted once per sample.
+// A second similarity, CA = R^-1 CA^ R with R = diag(rho^2, rho, rho, rho, 1) and CA^ free of rho, gives
+// the density gradient of a layer from the vectors on either side of it:
+//   rho dDelta/drho = (E'_0 s_0 - E_0 s'_0) - (E'_4 s_4 - E_4 s'_4),   E' = E.CA, s' = CA.s.
 // regime flags of a (velocity, layer) pair: oscillatory (k < kx) and regular (k != kx) for P and S
 enum { F_LTP = 1, F_POSP = 2, F_LTS = 4, F_POSS = 8, F_REGULAR = F_POSP | F_POSS };
 
 struct Eig {
-  double r, ir;     // sqrt((k+kx)|k-kx|) and its reciprocal
-  double p;         // r * d
+  double r, ir;     // n = sqrt(|1/c^2 - 1/v^2|) and its reciprocal (frequency-free)
+  double p;         // phase omega n d
   double cs, sn;    // cos p / (1+e^-2p)/2   and   sin p / (1-e^-2p)/2
   double w, x;      // sn / r   and   -+ r sn
   double dcs, dsn;  // d cs / dp, d sn / dp
@@ -214,30 +227,9 @@ struct Eig {
   bool lt, pos;     // oscillatory branch (k < kx);  u > 0 (false: k == kx or unordered)
 };
 
-// var_vector, reference :109-136 (P) / :140-167 (S), split in three steps so that the adjoint sweep can
-// re-use the transcendental values of the forward sweep instead of re-evaluating them:
-//   eig_setup  — r, 1/r, p and the branch   (cheap; done in both sweeps)
-//   eig_trans  — sin/cos or e^{-p}          (expensive; forward sweep only, results stored)
-//   eig_finish — everything derived from them.
+// var_vector, reference :109-136 (P) / :140-167 (S).  The transcendental values (sin/cos or e^{-p}) are
+// evaluated in the forward sweep only and stored; eig_finish re-derives everything else from them.
 // e^{-2p} is formed as (e^{-p})^2 and a0 = e^{-(pex+sex)} as e^{-pex} e^{-sex} (thresholds kept).
-ADSURF_HD void eig_setup(Eig& e, double k, double kx, double dm) {
-  const double u = (k + kx) * fabs(k - kx);
-  e.pos = u > 0.0;
-  e.lt = k < kx;
-  e.ir = rsqrt_hd(u);
-  e.r = e.pos ? u * e.ir : u;  // u == 0 -> 0, NaN -> NaN
-  e.p = e.r * dm;
-}
-
-ADSURF_HD void eig_trans(Eig& e) {
-  if (e.lt) {  // warp-uniform in the dense kernels (depends on c and the layer, not on the period)
-    sincos_fast(e.p, &e.c0, &e.c1);
-  } else {
-    e.c0 = exp_neg(e.p);
-    e.c1 = 0.0;
-  }
-}
-
 // branch-free bodies of the two regimes (oscillatory valid for |p| < 1e5)
 ADSURF_HD void eig_osc(Eig& e) {
   sincos_core(e.p, &e.c0, &e.c1);
@@ -263,8 +255,8 @@ ADSURF_HD void eig_evan(Eig& e) {
   e.x = e.r * e.sn;
 }
 
-// forward sweep: transcendental + derived terms inside one (warp-uniform) branch, no selects
-ADSURF_HD void eig_forward(Eig& e, double dm) {
+// generic forward: regime from the flags; wd = omega * thickness is the value of w when k == kx (reference :135)
+ADSURF_HD void eig_forward(Eig& e, double wd) {
   if (e.lt) {
     sincos_fast(e.p, &e.c0, &e.c1);
     e.sn = e.c0;
@@ -275,21 +267,13 @@ ADSURF_HD void eig_forward(Eig& e, double dm) {
     e.eh = 1.0;
     e.x = -e.r * e.sn;
   } else {
-    e.c0 = exp_neg(e.p);
-    e.c1 = 0.0;
-    const double fac = below16(e.p) ? e.c0 * e.c0 : 0.0;
-    e.cs = 0.5 + 0.5 * fac;
-    e.sn = 0.5 - 0.5 * fac;
-    e.dcs = -fac;
-    e.dsn = fac;
-    e.ex = e.p;  // p = 0 when k == kx
-    e.eh = below60(e.p) ? e.c0 : 0.0;
-    e.x = e.r * e.sn;
+    eig_evan(e);
   }
-  e.w = e.pos ? e.sn * e.ir : dm;  // k == kx: w = d (reference :135)
+  e.w = e.pos ? e.sn * e.ir : wd;
 }
 
-ADSURF_HD void eig_finish(Eig& e, double dm) {
+// adjoint sweep: everything derived from the stored (c0, c1)
+ADSURF_HD void eig_finish(Eig& e, double wd) {
   if (e.lt) {
     e.sn = e.c0;
     e.cs = e.c1;
@@ -303,27 +287,23 @@ ADSURF_HD void eig_finish(Eig& e, double dm) {
     e.sn = 0.5 - 0.5 * fac;
     e.dcs = -fac;
     e.dsn = fac;
-    e.ex = e.p;  // p = 0 when k == kx
+    e.ex = e.p;
     e.eh = below60(e.p) ? e.c0 : 0.0;
   }
-  e.w = e.pos ? e.sn * e.ir : dm;  // k == kx: w = d (reference :135)
+  e.w = e.pos ? e.sn * e.ir : wd;
   e.x = (e.lt ? -e.r : e.r) * e.sn;
 }
 
 struct Layer {
-  // inputs
-  double gk, rho, ir, dm;
-  // coefficient scalars
-  double gam, g1, gg, q1, ar, br, kr, tg, t1;
+  double ir, tg, ar, kr, t1, br, gk, g1;  // coefficient scalars: a' = (ir, tg, ar), b' = (kr, t1, br), a = (ar, gk, ir), b = (br, g1, kr)
+  double c1, c3, tqa, tqb, cb;            // adjoint chain constants (table_entry)
+  double rho;                             // pointwise kernels only (d/dc)
+  const double* pr;                       // the layer's staged record (thickness for the k == kx case)
   Eig P, S;
   double a0;
   int fl;  // regime flags F_LTP | F_POSP | F_LTS | F_POSS (set by the layer source)
 };
 
-// forward sweep: evaluate the transcendentals (P, S set up by the layer source).  The four regime
-// combinations get their own straight-line block so that the P and the S polynomial chains (each a
-// ~16-deep dependent FP64 sequence, 8 cycles per link) are scheduled interleaved instead of one
-// after the other behind separate branches.  The regime is warp-uniform in the dense kernels.
 ADSURF_HD void layer_set_flags(Layer& y, int fl) {
   y.P.lt = fl & F_LTP;
   y.P.pos = fl & F_POSP;
@@ -331,55 +311,51 @@ ADSURF_HD void layer_set_flags(Layer& y, int fl) {
   y.S.pos = fl & F_POSS;
 }
 
-ADSURF_HD void layer_eig_forward(Layer& y) {
+// forward sweep: evaluate the transcendentals (phases set up by the layer source).  The four regime
+// combinations get their own straight-line block so that the P and the S polynomial chains (each a
+// ~16-deep dependent FP64 sequence, 8 cycles per link) are scheduled interleaved instead of one
+// after the other behind separate branches.  The regime is warp-uniform in the dense kernels.
+ADSURF_HD void layer_eig_forward(Layer& y, double omega) {
   const bool small = below1e5(fabs(y.P.p)) && below1e5(fabs(y.S.p));
   const int fl = small ? y.fl : -1;  // one integer compare per regime instead of four extracted booleans
   if (fl == (F_REGULAR | F_LTS)) {          // c between the S and the P velocity of the layer: the common case
     layer_set_flags(y, F_REGULAR | F_LTS);
     eig_evan(y.P);
     eig_osc(y.S);
+    y.a0 = y.P.eh;
   } else if (fl == F_REGULAR) {             // slower than both: fully evanescent
     layer_set_flags(y, F_REGULAR);
     eig_evan(y.P);
     eig_evan(y.S);
+    y.a0 = below60(y.P.p + y.S.p) ? y.P.eh * y.S.eh : 0.0;
   } else if (fl == (F_REGULAR | F_LTP | F_LTS)) {  // faster than both
     layer_set_flags(y, F_REGULAR | F_LTP | F_LTS);
     eig_osc(y.P);
     eig_osc(y.S);
+    y.a0 = 1.0;
   } else if (fl == (F_REGULAR | F_LTP)) {
     layer_set_flags(y, F_REGULAR | F_LTP);
     eig_osc(y.P);
     eig_evan(y.S);
+    y.a0 = y.S.eh;
   } else {  // huge phase, NaN, or c exactly on a layer velocity: generic path
     layer_set_flags(y, y.fl);
-    eig_forward(y.P, y.dm);
-    eig_forward(y.S, y.dm);
+    const double wd = omega * y.pr[P_D];
+    eig_forward(y.P, wd);
+    eig_forward(y.S, wd);
     y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
     return;
   }
   y.P.w = y.P.sn * y.P.ir;
   y.S.w = y.S.sn * y.S.ir;
-  y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
 }
 
 // adjoint sweep: restore them from the store (c0, c1 already set by the caller)
-ADSURF_HD void layer_eig_restore(Layer& y) {
-  eig_finish(y.P, y.dm);
-  eig_finish(y.S, y.dm);
+ADSURF_HD void layer_eig_restore(Layer& y, double omega) {
+  const double wd = omega * y.pr[P_D];  // only read when k == kx
+  eig_finish(y.P, wd);
+  eig_finish(y.S, wd);
   y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
-}
-
-// coefficient scalars from (gk, k2); t2 = -2 k2 (hoisted per sample)
-ADSURF_HD void layer_coefs(Layer& y, double k2, double t2) {
-  y.gam = y.gk * k2;
-  y.g1 = y.gam - 1.0;
-  y.gg = y.gam * y.gk;
-  y.q1 = y.g1 * y.g1;
-  y.ar = y.gg * y.rho;
-  y.br = y.q1 * y.rho;
-  y.kr = k2 * y.ir;
-  y.tg = t2 * y.gk;
-  y.t1 = t2 * y.g1;
 }
 
 // E <- E . CA   (row vector times Dunkin matrix, reference :376-383)
@@ -401,50 +377,27 @@ ADSURF_HD void row_apply(double (&e)[5], const Layer& y) {
   e[4] = y.a0 * e4 + y.ir * Ca + y.kr * Cb;
 }
 
-// s <- CA . s   (column vector of the layers above)
-ADSURF_HD void col_apply(double (&s)[5], const Layer& y) {
-  const double s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3], s4 = s[4];
-  const double cp = y.P.cs, w = y.P.w, x = y.P.x, cq = y.S.cs, yy = y.S.w, z = y.S.x;
-  const double ta = y.ar * s0 + y.gk * s2 + y.ir * s4;
-  const double tb = y.br * s0 + y.g1 * s2 + y.kr * s4;
-  const double m1 = z * ta + cq * s1;
-  const double m2 = cq * tb + z * s3;
-  const double m3 = yy * tb + cq * s3;
-  const double m4 = cq * ta + yy * s1;
-  const double Da = cp * m2 - x * m1 - y.a0 * tb;
-  const double Db = cp * m4 - w * m3 - y.a0 * ta;
-  s[1] = cp * m1 - w * m2;
-  s[3] = cp * m3 - x * m4;
-  s[0] = y.a0 * s0 + y.ir * Da + y.kr * Db;
-  s[2] = y.a0 * s2 + y.tg * Da + y.t1 * Db;
-  s[4] = y.a0 * s4 + y.ar * Da + y.br * Db;
-}
-
+// what one layer contributes to the gradient: dDelta/d(thickness, alpha, beta, rho) and, for the pointwise
+// kernels, dDelta/d(1/c) through this layer
 struct LayerGrad {
-  // dDelta/d(thickness, gammk, rho, k) and, for each wave type, h = (dDelta/dr) / r * sign(k - kx):
-  // dDelta/dk += k h, dDelta/dkx = -kx h  =>  dDelta/dalpha = omega^2 / alpha^3 * hp (kx = omega/alpha).
-  double d, hp, hs, gammk, rho, k;
+  double d, a, b, rho, ic;
 };
 
-// adjoint of one eigenfunction block: (bcs, bw, bx, bex) -> bd += ..., bk += k h, returns h.  Both branches
-// share one formula through dcs = d cs/dp, dsn = d sn/dp and the sign of (k - kx):
-//   w = sn/r, x = sg r sn  =>  d/dr = (x bx - w bw)/r ;  d u/d k = 2 sg k, d r/d u = 1/(2 r).
-ADSURF_HD double eig_adjoint(const Eig& e, double k, double dm, double bcs, double bw, double bx, double bex,
-                             double& bd, double& bk) {
+// adjoint of one eigenfunction block: (bcs, bw, bx, bex) -> bp = dDelta/dp and the return value
+// t = r dDelta/dr = x bx - w bw + p bp   (w = sn/r, x = -+ r sn, p = omega r d)
+ADSURF_HD double eig_adjoint(const Eig& e, double bcs, double bw, double bx, double bex, double& bp) {
   const double bsn = bw * e.ir + (e.lt ? -e.r : e.r) * bx;
-  const double bp = e.dcs * bcs + e.dsn * bsn + (e.lt ? 0.0 : bex);
-  const double br = e.ir * (e.x * bx - e.w * bw) + dm * bp;
-  const double h = (e.lt ? -e.ir : e.ir) * br;
-  // k == kx: w = d and the (measure-zero) dependence through r is dropped (finite one-sided value)
-  bd += e.pos ? e.r * bp : bw;
-  bk += e.pos ? k * h : 0.0;
-  return e.pos ? h : 0.0;
+  bp = e.dcs * bcs + e.dsn * bsn + (e.lt ? 0.0 : bex);
+  return e.x * bx - e.w * bw + e.p * bp;
 }
 
-// Reverse sweep through one layer: given row vector e (= E_{m+1}) and column s (= s_m, already
-// scaled by the upstream seed) returns dDelta/d(layer inputs), Delta = e . CA . s.
-ADSURF_HD LayerGrad layer_adjoint(const Layer& y, const double (&e)[5], const double (&s)[5],
-                                                   double k, double k2, double t2) {
+// Reverse sweep through one layer: row vector e (= E_{m+1}), column s (= s_m, already scaled by the upstream
+// seed) and the row vector on the other side of the layer (ep0, ep4 = components 0 and 4 of E_m = E_{m+1}.CA).
+// Returns dDelta/d(layer inputs), Delta = e . CA . s, and advances s <- CA . s on the way (the column
+// product shares the contractions ta, tb, g1..g4, Da, Db with the adjoint: 13 extra FMAs instead of 33).
+template <bool kWantIc>
+ADSURF_HD LayerGrad layer_adjoint(const Layer& y, const double (&e)[5], double (&s)[5], double ep0, double ep4,
+                                  double omega, double ic, double ic2, double t2) {
   const double e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3], e4 = e[4];
   const double s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3], s4 = s[4];
   const double cp = y.P.cs, w = y.P.w, x = y.P.x, cq = y.S.cs, yy = y.S.w, z = y.S.x;
@@ -471,42 +424,58 @@ ADSURF_HD LayerGrad layer_adjoint(const Layer& y, const double (&e)[5], const do
   const double by = sb * g1_ + e3 * g2_;
   const double bz = sa * g3_ + e1 * g4_;
   const double bcq = e1 * g1_ + sa * g2_ + e3 * g3_ + sb * g4_;
-  // adjoints of the contractions
-  const double Dsa = cq * g2_ + z * g3_ - a0 * tb;
-  const double Dsb = yy * g1_ + cq * g4_ - a0 * ta;
+  // adjoints of the contractions: Da = dDelta/dsa = the a-part of CA.s, Ca = dDelta/dta = the a-part of e.CA
+  const double Da = cq * g2_ + z * g3_ - a0 * tb;
+  const double Db = yy * g1_ + cq * g4_ - a0 * ta;
   const double Ca = cp * h4 - x * h3 - sb * a0;
   const double Cb = cp * h2 - w * h1 - sa * a0;
-  // coefficient scalars
-  const double b_ir = Dsa * e0 + Ca * s4;
-  const double b_tg = Dsa * e2;
-  const double b_ar = Dsa * e4 + Ca * s0;
-  const double b_kr = Dsb * e0 + Cb * s4;
-  const double b_t1 = Dsb * e2;
-  const double b_br = Dsb * e4 + Cb * s0;
-  const double b_gg = y.rho * b_ar;
-  const double b_q1 = y.rho * b_br;
-  const double b_g1 = Cb * s2 + t2 * b_t1 + 2.0 * y.g1 * b_q1;
-  const double b_gam = b_g1 + y.gk * b_gg;
-  const double b_gk = Ca * s2 + t2 * b_tg + y.gam * b_gg + k2 * b_gam;
-  const double b_k2 = y.ir * b_kr + y.gk * b_gam - 2.0 * (y.gk * b_tg + y.g1 * b_t1);
-  const double b_rho = y.gg * b_ar + y.q1 * b_br - y.ir * y.ir * (b_ir + k2 * b_kr);
+  // s <- CA . s
+  s[1] = cq * g1_ + z * g4_;
+  s[3] = cq * g3_ + yy * g2_;
+  s[0] = a0 * s0 + y.ir * Da + y.kr * Db;
+  s[2] = a0 * s2 + y.tg * Da + y.t1 * Db;
+  s[4] = a0 * s4 + y.ar * Da + y.br * Db;
+  // coefficient scalars -> 2 beta^2 (the only coefficient input besides rho and 1/c):
+  //   d/dgk = s2 (Ca + ic2 Cb) + t2 e2 (Da + ic2 Db) + 2 gam rho b_ar + 2 g1 ic2 rho b_br
+  const double b_ar = Da * e4 + Ca * s0;
+  const double b_br = Db * e4 + Cb * s0;
+  const double X1 = Ca + ic2 * Cb;
+  const double X2 = Da + ic2 * Db;
+  const double b_gk = s2 * X1 + (t2 * e2) * X2 + y.c1 * b_ar + y.c3 * b_br;
   const double bex = -a0 * ba0;
-
+  double bpP, bpS;
+  const double tP = eig_adjoint(y.P, bcp, bw, bx, bex, bpP);
+  const double tS = eig_adjoint(y.S, bcq, by, bz, bex, bpS);
   LayerGrad g;
-  g.d = 0.0;
-  g.k = 2.0 * k * b_k2;
-  g.gammk = b_gk;
-  g.rho = b_rho;
-  g.hp = eig_adjoint(y.P, k, y.dm, bcp, bw, bx, bex, g.d, g.k);
-  g.hs = eig_adjoint(y.S, k, y.dm, bcq, by, bz, bex, g.d, g.k);
+  // k == kx: w = omega d and the (measure-zero) dependence through r is dropped (finite one-sided value)
+  g.d = omega * ((y.P.pos ? y.P.r * bpP : bw) + (y.S.pos ? y.S.r * bpS : by));
+  g.a = y.P.pos ? y.tqa * tP : 0.0;
+  g.b = (y.S.pos ? y.tqb * tS : 0.0) + y.cb * b_gk;
+  g.rho = y.ir * (ep0 * s0 - e0 * s[0] - ep4 * s4 + e4 * s[4]);
+  g.ic = 0.0;
+  if (kWantIc) {
+    // d/d(1/c): through n^2 = +-(ic2 - 1/v^2) and through ic2 in the coefficients
+    const double b_kr = Db * e0 + Cb * s4;
+    const double b_tg = Da * e2, b_t1 = Db * e2;
+    const double gam = y.g1 + 1.0;
+    const double b_ic2 = y.gk * (Cb * s2) + (y.gk * y.gk * y.rho) * b_ar + (2.0 * y.g1 * y.gk * y.rho) * b_br +
+                         y.ir * b_kr - 2.0 * (y.gk * b_tg + (y.g1 + gam) * b_t1);
+    const double hp = y.P.pos ? (y.P.lt ? -y.P.ir : y.P.ir) * y.P.ir * tP : 0.0;
+    const double hs = y.S.pos ? (y.S.lt ? -y.S.ir : y.S.ir) * y.S.ir * tS : 0.0;
+    g.ic = ic * (hp + hs + 2.0 * b_ic2);
+  }
   return g;
 }
 
-// Half-space start vector (reference :328-347)
+// Half-space start vector (reference :328-347), in the reference's own (unscaled) variables
 struct Half {
   double ka, kb, gammk, rho;
   double ra, ira, rb, irb, gam, gamm1, R;
   int bra, brb;  // 0 osc (k<kx), 1 evan (k>kx), 2 equal/unordered
+};
+
+struct HalfGrad {
+  double hp, hs, gammk, rho, k;  // h = (dDelta/dr)/r * sign(k - kx):  dDelta/dalpha = omega^2/alpha^3 hp
 };
 
 ADSURF_HD void sqrt_pair(double k, double kx, double& r, double& ir, int& br) {
@@ -531,8 +500,7 @@ ADSURF_HD void half_space(Half& h, double k, double k2, double (&e)[5]) {
   e[4] = k2 - h.R;
 }
 
-ADSURF_HD LayerGrad half_adjoint(const Half& h, const double (&e)[5], const double (&s)[5], double k,
-                                                  double k2) {
+ADSURF_HD HalfGrad half_adjoint(const Half& h, const double (&e)[5], const double (&s)[5], double k, double k2) {
   const double rho = h.rho, ir = 1.0 / rho;
   const double rho2s0 = rho * rho * s[0];
   const double bq1 = rho2s0;
@@ -545,8 +513,7 @@ ADSURF_HD LayerGrad half_adjoint(const Half& h, const double (&e)[5], const doub
   const double bgam = 2.0 * h.gamm1 * bq1 + h.gammk * bgg + bgm1;
   bgk += h.gam * bgg + k2 * bgam;
   const double bk2 = s[4] + h.gammk * bgam;
-  LayerGrad g;
-  g.d = 0.0;
+  HalfGrad g;
   g.rho = (2.0 * e[0] * s[0] + e[1] * s[1] + e[2] * s[2] + e[3] * s[3]) * ir;
   g.gammk = bgk;
   g.k = 2.0 * k * bk2;
@@ -566,7 +533,8 @@ ADSURF_HD LayerGrad half_adjoint(const Half& h, const double (&e)[5], const doub
 // Sample-level drivers
 // ------------------------------------------------------------------------------------------
 struct Sample {
-  double k, k2, omega, iw, iw2, t2, w2;  // wavenumber, k^2, clamped angular frequency, 1/omega, 1/omega^2, -2 k^2, omega^2
+  double k, k2, omega, iw, iw2;  // wavenumber, k^2, clamped angular frequency, 1/omega, 1/omega^2: half-space
+  double ic, ic2, t2;            // k / omega (= 1/c unless omega is clamped), its square, -2 ic^2: the layers
 };
 
 // omega = twopi / t as torch evaluates `python_float / tensor` (Tensor.__rtruediv__ ==
@@ -582,103 +550,126 @@ ADSURF_HD Sample make_sample(double omega0, double ic) {
   z.k2 = z.k * z.k;
   z.iw = 1.0 / z.omega;
   z.iw2 = z.iw * z.iw;
-  z.t2 = -2.0 * z.k2;
-  z.w2 = z.omega * z.omega;
+  z.ic = (omega0 >= 1.0e-4) ? ic : z.k * z.iw;  // periods beyond 2 pi 1e4 s: k / omega differs from 1/c
+  z.ic2 = z.ic * z.ic;
+  z.t2 = -2.0 * z.ic2;
   return z;
 }
 
-// ---- layer sources: fill the inputs, the eigenfunction set-up and the coefficient scalars of layer m
-// DirectSource: everything per sample from (k, omega) — pointwise kernels, arbitrary (t, c) pairs.
-struct DirectSource {
-  static constexpr bool kUniformFlags = false;  // per-sample (t, c): regimes may differ between lanes
-  const double* __restrict__ par;
-  int L;
-  ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
-    y.gk = par[m * kNumPar + P_TB2] * z.iw2;
-    y.rho = par[m * kNumPar + P_RHO];
-    y.ir = par[m * kNumPar + P_IR];
-    y.dm = par[m * kNumPar + P_D];
-    eig_setup(y.P, z.k, z.omega * par[m * kNumPar + P_IA], y.dm);
-    eig_setup(y.S, z.k, z.omega * par[m * kNumPar + P_IB], y.dm);
-    y.fl = (y.P.lt ? F_LTP : 0) | (y.P.pos ? F_POSP : 0) | (y.S.lt ? F_LTS : 0) | (y.S.pos ? F_POSS : 0);
-    layer_coefs(y, z.k2, z.t2);
-  }
+// ---- layer sources: fill the frequency-free coefficient scalars, the phases and the regime of layer m.
+// Everything that depends on (trial velocity, layer) but not on the period is one table entry:
+//   n = sqrt(|1/c^2 - 1/v^2|), 1/n, n d (phase per unit omega) for P and S; the coefficient scalars
+//   (1/rho, -2 gam, gam gk rho, ic2/rho, -2 ic2 g1, g1^2 rho, gk = 2 beta^2, g1 = gam - 1, gam = gk ic2);
+//   the regime flags; and for the adjoint the constants that fold the chain rule to (alpha, beta):
+//   1/(alpha^3 (ic2 - 1/alpha^2)), same for beta, 4 beta, 2 gam rho, 2 g1 ic2 rho.
+// TableSource (dense kernels) reads entries that the block computed once per trial velocity into shared
+// memory (16-byte broadcasts); DirectSource (pointwise kernels, arbitrary (t, c) pairs) computes the entry
+// per sample.
+constexpr int kTabFwd = 16, kTabAdj = 20;  // doubles per entry: forward sweep only / with the adjoint constants
+enum {
+  T_PDA = 0, T_PDB = 1, T_NA = 2, T_NB = 3, T_INA = 4, T_INB = 5, T_IR = 6, T_TG = 7, T_AR = 8, T_KR = 9,
+  T_T1 = 10, T_BR = 11, T_GK = 12, T_G1 = 13, T_FL = 14, T_TQA = 15, T_TQB = 16, T_CB = 17, T_C1 = 18, T_C3 = 19
 };
-
-// TableSource: dense kernels.  Everything that depends on (trial velocity, layer) but not on the
-// period is computed once per block into a shared-memory table and read as a broadcast:
-//   r = sqrt(|k^2 - kx^2|) = omega * n,  n = sqrt(|1/c^2 - 1/v^2|);   p = omega * (n d);
-//   gam = gk k^2 = 2 (beta/c)^2;  g1 = gam - 1;  br = g1^2 rho;   branch flags (c vs v).
-// Per lane that leaves 6 multiplies for both eigenfunction set-ups (instead of 2 rsqrt sequences,
-// the differences of squares and their selects) and 6 for the coefficient scalars.
-constexpr int kTab = 10;  // 80-byte entries: five 16-byte loads; the last slot carries the flag bits
-enum { T_PDA = 0, T_PDB = 1, T_NA = 2, T_NB = 3, T_INA = 4, T_INB = 5, T_GAM = 6, T_G1 = 7, T_BR = 8, T_FL = 9 };
 struct alignas(16) Dbl2 {
   double x, y;
 };
 ADSURF_HD Dbl2 ld2(const double* p) { return *reinterpret_cast<const Dbl2*>(p); }
 
 // one table entry: trial slowness ic = 1/c against layer m of the staged model
-ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ par, int L, int m, double ic) {
-  const double sa = par[m * kNumPar + P_IA], sb = par[m * kNumPar + P_IB], dm = par[m * kNumPar + P_D];
+template <int kN>
+ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ par, int m, double ic) {
+  const double* __restrict__ pr = par + m * kNumPar;
+  const double sa = pr[P_IA], sb = pr[P_IB], dm = pr[P_D], rho = pr[P_RHO], ir = pr[P_IR], gk = pr[P_TB2];
   const double da = (ic + sa) * fabs(ic - sa), db = (ic + sb) * fabs(ic - sb);
   const double na = sqrt(da), nb = sqrt(db);
+  const double ic2 = ic * ic;
+  const double gam = gk * ic2;
+  const double g1 = gam - 1.0;
   tab[T_PDA] = na * dm;
   tab[T_PDB] = nb * dm;
   tab[T_NA] = na;
   tab[T_NB] = nb;
   tab[T_INA] = 1.0 / na;
   tab[T_INB] = 1.0 / nb;
-  const double gam = par[m * kNumPar + P_TB2] * (ic * ic);
-  const double g1 = gam - 1.0;
-  tab[T_GAM] = gam;
+  tab[T_IR] = ir;
+  tab[T_TG] = -2.0 * gam;
+  tab[T_AR] = gam * gk * rho;
+  tab[T_KR] = ic2 * ir;
+  tab[T_T1] = -2.0 * ic2 * g1;
+  tab[T_BR] = g1 * g1 * rho;
+  tab[T_GK] = gk;
   tab[T_G1] = g1;
-  tab[T_BR] = g1 * g1 * par[m * kNumPar + P_RHO];
   const int fl = (ic < sa ? F_LTP : 0) | (da > 0.0 ? F_POSP : 0) | (ic < sb ? F_LTS : 0) | (db > 0.0 ? F_POSS : 0);
   tab[T_FL] = bits_dbl((long long)fl);  // raw bits, read back with dbl_bits()
+  tab[T_TQA] = pr[P_IA3] / ((ic + sa) * (ic - sa));
+  if (kN > kTabFwd) {
+    tab[T_TQB] = pr[P_IB3] / ((ic + sb) * (ic - sb));
+    tab[T_CB] = pr[P_CB];
+    tab[T_C1] = 2.0 * gam * rho;
+    tab[T_C3] = 2.0 * g1 * ic2 * rho;
+  }
 }
 
-struct TableSource {
-  static constexpr bool kUniformFlags = true;   // flags come from the shared (velocity, layer) table
+// fill a Layer from a table entry (kN = kTabFwd: the adjoint constants are not there and not read)
+template <int kN>
+ADSURF_HD void layer_from_entry(Layer& y, const double* __restrict__ q, const double* __restrict__ pr, double omega) {
+  const Dbl2 t01 = ld2(q + T_PDA), t23 = ld2(q + T_NA), t45 = ld2(q + T_INA), t67 = ld2(q + T_IR),
+             t89 = ld2(q + T_AR), tab_ = ld2(q + T_T1), tcd = ld2(q + T_GK), tef = ld2(q + T_FL);
+  y.pr = pr;
+  y.P.p = omega * t01.x;
+  y.S.p = omega * t01.y;
+  y.P.r = t23.x;
+  y.S.r = t23.y;
+  y.P.ir = t45.x;
+  y.S.ir = t45.y;
+  y.ir = t67.x;
+  y.tg = t67.y;
+  y.ar = t89.x;
+  y.kr = t89.y;
+  y.t1 = tab_.x;
+  y.br = tab_.y;
+  y.gk = tcd.x;
+  y.g1 = tcd.y;
+  y.fl = (int)dbl_bits(tef.x);  // the per-eig booleans are set where a regime is selected (layer_set_flags)
+  if (kN > kTabFwd) {
+    const Dbl2 tgh = ld2(q + T_TQB), tij = ld2(q + T_C1);
+    y.tqa = tef.y;
+    y.tqb = tgh.x;
+    y.cb = tgh.y;
+    y.c1 = tij.x;
+    y.c3 = tij.y;
+  }
+}
+
+struct DirectSource {
+  static constexpr bool kUniformFlags = false;  // per-sample (t, c): regimes may differ between lanes
+  static constexpr bool kWantIc = true;         // the pointwise kernels return dF/dc
   const double* __restrict__ par;
   int L;
-  const double* __restrict__ tab;  // [L-1][kTab] for the current trial velocity (16-byte aligned)
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
-    // 16-byte broadcast loads: 2 for the layer record, 5 for the table entry
-    const double* __restrict__ pr = par + m * kNumPar;
-    const Dbl2 p23 = ld2(pr + P_TB2), p45 = ld2(pr + P_IR);
-    const double* __restrict__ q = tab + m * kTab;
-    const Dbl2 t01 = ld2(q + T_PDA), t23 = ld2(q + T_NA), t45 = ld2(q + T_INA), t67 = ld2(q + T_GAM),
-               t89 = ld2(q + T_BR);
-    const int fl = (int)dbl_bits(t89.y);
-    y.rho = p23.y;
-    y.ir = p45.x;
-    y.dm = p45.y;
-    y.gk = p23.x * z.iw2;
-    y.gam = t67.x;
-    y.g1 = t67.y;
-    y.br = t89.x;
-    y.gg = y.gam * y.gk;
-    y.q1 = y.g1 * y.g1;      // adjoint only
-    y.ar = y.gg * y.rho;
-    y.kr = z.k2 * y.ir;
-    y.tg = z.t2 * y.gk;
-    y.t1 = z.t2 * y.g1;
-    y.P.r = z.omega * t23.x;
-    y.P.ir = z.iw * t45.x;
-    y.P.p = z.omega * t01.x;
-    y.S.r = z.omega * t23.y;
-    y.S.ir = z.iw * t45.y;
-    y.S.p = z.omega * t01.y;
-    y.fl = fl;  // the per-eig booleans are set where a regime is selected (layer_set_flags)
+    alignas(16) double tab[kTabAdj];
+    table_entry<kTabAdj>(tab, par, m, z.ic);
+    layer_from_entry<kTabAdj>(y, tab, par + m * kNumPar, z.omega);
+    y.rho = par[m * kNumPar + P_RHO];
+  }
+};
+
+template <int kN>
+struct TableSource {
+  static constexpr bool kUniformFlags = true;   // flags come from the shared (velocity, layer) table
+  static constexpr bool kWantIc = false;
+  const double* __restrict__ par;
+  int L;
+  const double* __restrict__ tab;  // [L-1][kN] for the current trial velocity (16-byte aligned)
+  ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
+    layer_from_entry<kN>(y, tab + m * kN, par + m * kNumPar, z.omega);
   }
 };
 
 // The half-space vector is linear in ra, rb = sqrt((k+kx)|k-kx|): at a trial velocity that coincides
 // with the half-space velocity the result depends on the last bit of kx, so kx is formed with the
 // reference's own correctly-rounded division omega/alpha (reference :328-329) from the raw
-// velocities kept at par[kNumPar*L + 0/1].  Inside the layers the dependence on kx is smooth
-// (even in r), and the cheaper omega * (1/alpha) is used.
+// velocities kept at par[kNumPar*L + 0/1].
 ADSURF_HD void load_half(Half& h, const double* __restrict__ par, int L, const Sample& z) {
   const int m = L - 1;
   h.ka = z.omega / par[kNumPar * L + 0];
@@ -687,19 +678,26 @@ ADSURF_HD void load_half(Half& h, const double* __restrict__ par, int L, const S
   h.rho = par[m * kNumPar + P_RHO];
 }
 
-// forward only
-template <typename Source>
-ADSURF_HD double sample_forward(const Source& src, const Sample& z) {
-  const double* __restrict__ par = src.par;
-  const int L = src.L;
-  double e[5];
+// half-space vector in the scaled variables of the layer sweep: E~ = E D^-1, D = diag(1, w, 1, w, w^2)
+ADSURF_HD void half_start(const double* __restrict__ par, int L, const Sample& z, double (&e)[5]) {
   Half h;
   load_half(h, par, L, z);
   half_space(h, z.k, z.k2, e);
+  e[1] *= z.iw;
+  e[3] *= z.iw;
+  e[4] *= z.iw2;
+}
+
+// forward only
+template <typename Source>
+ADSURF_HD double sample_forward(const Source& src, const Sample& z) {
+  const int L = src.L;
+  double e[5];
+  half_start(src.par, L, z, e);
   Layer y;
   for (int m = L - 2; m >= 0; --m) {
     src.prep(y, m, z);
-    layer_eig_forward(y);
+    layer_eig_forward(y, z.omega);
     row_apply(e, y);
   }
   return e[0];
@@ -720,19 +718,17 @@ struct PlainStore {
   ADSURF_HD static void st(Slot q, int j, double v) { q[j * kStride] = v; }
 };
 
-// forward keeping E_{m+1} of every layer: slot m holds the row vector that multiplies CA_m.
+// forward keeping E_{m+1} of every layer: slot m holds the row vector that multiplies CA_m.  Returns
+// E_0[0] (the determinant); top4 = E_0[4], which the adjoint sweep needs next to it.
 template <typename Source, typename Store>
-ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const Store& est) {
-  const double* __restrict__ par = src.par;
+ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const Store& est, double& top4) {
   const int L = src.L;
   double e[5];
-  Half h;
-  load_half(h, par, L, z);
-  half_space(h, z.k, z.k2, e);
+  half_start(src.par, L, z, e);
   Layer y;
   for (int m = L - 2; m >= 0; --m) {
     src.prep(y, m, z);
-    layer_eig_forward(y);
+    layer_eig_forward(y, z.omega);
     const typename Store::Slot q = est.slot(m);
 #pragma unroll
     for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
@@ -742,24 +738,26 @@ ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const 
     Store::st(q, 8, y.S.c1);
     row_apply(e, y);
   }
+  top4 = e[4];
   return e[0];
 }
 
 // Top-down adjoint sweep.  s_0 = seed * e_0; for every layer m (and finally the half-space, m = L-1)
-// hands (m, dDelta/dd_m, /dalpha_m, /dbeta_m, /drho_m) * seed to `sink`.  Returns dDelta/dk * seed.
-// The stored values of the next layer are fetched one iteration ahead into the other of two
-// register buffers (the loop is unrolled by two so the buffers swap without copies).
+// hands (m, dDelta/dd_m, /dalpha_m, /dbeta_m, /drho_m) * seed to `sink`.  (top0, top4) are components 0 and 4
+// of the forward sweep's final row vector.  Returns seed * dDelta/d(k/omega) (pointwise sources; 0 otherwise).
+// Software pipeline over the stored values: each group of registers is re-loaded for layer m+1 right
+// after its last use in layer m — the transcendental results once eig_finish has consumed them, the row
+// vector E once layer_adjoint is done — so the L2 latency of the slab hides behind the rest of the layer
+// without a second register buffer.
 template <typename Source, typename Store, typename Sink>
-ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed, const Store& est, Sink& sink) {
+ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed, double top0, double top4,
+                                const Store& est, Sink& sink) {
   const double* __restrict__ par = src.par;
   const int L = src.L;
   double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
-  // software pipeline over the stored values: each group of registers is re-loaded for layer m+1 right
-  // after its last use in layer m — the transcendental results once eig_finish has consumed them, the row
-  // vector E once layer_adjoint is done — so the L2 latency of the slab hides behind the rest of the layer
-  // (col_apply, the gradient sink, the next layer's set-up) without a second register buffer.
   double e[5], cv[4];
-  double gk = 0.0;
+  double ep0 = top0, ep4 = top4;
+  double gic = 0.0;
   auto fetch_c = [&](int m) {
     const typename Store::Slot q = est.slot(m);
 #pragma unroll
@@ -775,16 +773,14 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     y.P.c0 = cv[0]; y.P.c1 = cv[1]; y.S.c0 = cv[2]; y.S.c1 = cv[3];
     src.prep(y, m, z);
     auto body = [&]() {
-      layer_eig_restore(y);
+      layer_eig_restore(y, z.omega);
       if (m + 1 <= L - 2) fetch_c(m + 1);
-      const LayerGrad g = layer_adjoint(y, e, s, z.k, z.k2, z.t2);
+      const LayerGrad g = layer_adjoint<Source::kWantIc>(y, e, s, ep0, ep4, z.omega, z.ic, z.ic2, z.t2);
+      ep0 = e[0];
+      ep4 = e[4];
       if (m + 1 <= L - 2) fetch_e(m + 1);
-      col_apply(s, y);
-      gk += g.k;
-      // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2:
-      //   d/dalpha = omega^2/alpha^3 hp,  d/dbeta = omega^2/beta^3 hs + 4 beta/omega^2 dDelta/dgammk
-      const double* __restrict__ pr = par + m * kNumPar;
-      sink(m, g.d, (z.w2 * pr[P_IA3]) * g.hp, (z.w2 * pr[P_IB3]) * g.hs + (pr[P_CB] * z.iw2) * g.gammk, g.rho);
+      gic += g.ic;
+      sink(m, g.d, g.a, g.b, g.rho);
     };
     // Regime specialisation (dense kernels: the flags are warp-uniform table entries).  Re-stating the flags
     // as constants inside each branch lets the compiler fold every "lt ? a : b" / "pos ? a : b" select of
@@ -805,20 +801,24 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     fetch_e(0);
   }
   for (int m = 0; m <= L - 2; ++m) layer(m);
-  // half-space: dDelta/dE_hs = s_{L-1}
+  // half-space: dDelta/dE_hs = D^-1 s~_{L-1}, in the reference's variables
   Half h;
   load_half(h, par, L, z);
   half_space(h, z.k, z.k2, e);
-  const LayerGrad g = half_adjoint(h, e, s, z.k, z.k2);
-  gk += g.k;
+  const double su[5] = {s[0], s[1] * z.iw, s[2], s[3] * z.iw, s[4] * z.iw2};
+  const HalfGrad g = half_adjoint(h, e, su, z.k, z.k2);
+  gic += z.omega * g.k;  // k = omega * (k/omega)
   const int mh = L - 1;
   const double* __restrict__ prh = par + mh * kNumPar;
-  sink(mh, 0.0, (z.w2 * prh[P_IA3]) * g.hp, (z.w2 * prh[P_IB3]) * g.hs + (prh[P_CB] * z.iw2) * g.gammk, g.rho);
-  return gk;
+  const double w2 = z.omega * z.omega;
+  // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2:
+  //   d/dalpha = omega^2/alpha^3 hp,  d/dbeta = omega^2/beta^3 hs + 4 beta/omega^2 dDelta/dgammk
+  sink(mh, 0.0, (w2 * prh[P_IA3]) * g.hp, (w2 * prh[P_IB3]) * g.hs + (prh[P_CB] * z.iw2) * g.gammk, g.rho);
+  return gic;
 }
 
-// per-model layer constants staged for the kernels: par[L][kNumPar] (one 48-byte record per layer,
-// so a layer needs one address computation), then the raw half-space velocities
+// per-model layer constants staged for the kernels: par[L][kNumPar] (one 80-byte record per layer),
+// then the raw half-space velocities
 ADSURF_HD void stage_one(double* __restrict__ par, int L, int m, double dm, double a, double b, double r) {
   par[m * kNumPar + P_IA] = 1.0 / a;
   par[m * kNumPar + P_IB] = 1.0 / b;

@@ -43,15 +43,17 @@ int host_points(const double* d, const double* alpha, const double* beta, const 
       const size_t idx = (size_t)s * N + i;
       const double ic = 1.0 / c[idx];
       const Sample z = make_sample(omega_of_period(t[idx]), ic);
-      const double v = sample_forward_store(DirectSource{par.data(), L}, z, PlainStore<1>{est.data()});
+      double top4 = 0.0;
+      const double v = sample_forward_store(DirectSource{par.data(), L}, z, PlainStore<1>{est.data()}, top4);
       const double v2 = sample_forward(DirectSource{par.data(), L}, z);
       if (v != v2 && !(v != v && v2 != v2)) return -1;
       F[idx] = v;
       HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L,
                     Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
                     Jrho ? Jrho + idx * L : nullptr};
-      const double gk = sample_adjoint(DirectSource{par.data(), L}, z, gF ? gF[idx] : 1.0, PlainStore<1>{est.data()}, sink);
-      if (gc) gc[idx] = -z.k * ic * gk;
+      const double gic = sample_adjoint(DirectSource{par.data(), L}, z, gF ? gF[idx] : 1.0, v, top4,
+                                        PlainStore<1>{est.data()}, sink);
+      if (gc) gc[idx] = -ic * z.ic * gic;  // d(k/omega)/dc
     }
   }
   return 0;
@@ -67,19 +69,26 @@ int host_grid(const double* d, const double* alpha, const double* beta, const do
       stage_one(par.data(), L, m, d[s * L + m], alpha[s * L + m], beta[s * L + m], rho[s * L + m]);
     for (int m = 0; m < L; ++m) gd[s * L + m] = ga[s * L + m] = gb[s * L + m] = grho[s * L + m] = 0.0;
     // dense path: per-(velocity, layer) table + per-period lanes, as the dense kernels do
-    std::vector<double> tab((size_t)kTab * (L > 1 ? L - 1 : 1));
+    std::vector<double> tab((size_t)kTabAdj * (L > 1 ? L - 1 : 1) + 2);
+    double* tb = tab.data() + (((size_t)tab.data() & 15) ? 1 : 0);  // 16-byte aligned like the shared table
     for (int k = 0; k < K; ++k) {
       const double ic = 1.0 / c[s * K + k];
-      for (int m = 0; m < L - 1; ++m) table_entry(tab.data() + (size_t)m * kTab, par.data(), L, m, ic);
-      const TableSource src{par.data(), L, tab.data()};
+      for (int m = 0; m < L - 1; ++m) table_entry<kTabAdj>(tb + (size_t)m * kTabAdj, par.data(), m, ic);
+      const TableSource<kTabAdj> src{par.data(), L, tb};
+      // the forward-only kernel reads 16-double entries
+      std::vector<double> tabf((size_t)kTabFwd * (L > 1 ? L - 1 : 1) + 2);
+      double* tf = tabf.data() + (((size_t)tabf.data() & 15) ? 1 : 0);
+      for (int m = 0; m < L - 1; ++m) table_entry<kTabFwd>(tf + (size_t)m * kTabFwd, par.data(), m, ic);
+      const TableSource<kTabFwd> srcf{par.data(), L, tf};
       for (int f = 0; f < NF; ++f) {
         const size_t idx = ((size_t)s * K + k) * NF + f;
         const Sample z = make_sample(omega_of_period(t[s * NF + f]), ic);
-        det[idx] = sample_forward_store(src, z, PlainStore<1>{est.data()});
-        const double v2 = sample_forward(src, z);
+        double top4 = 0.0;
+        det[idx] = sample_forward_store(src, z, PlainStore<1>{est.data()}, top4);
+        const double v2 = sample_forward(srcf, z);
         if (det[idx] != v2 && !(det[idx] != det[idx] && v2 != v2)) return -1;
         HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L, nullptr, nullptr, nullptr, nullptr};
-        sample_adjoint(src, z, gdet ? gdet[idx] : 1.0, PlainStore<1>{est.data()}, sink);
+        sample_adjoint(src, z, gdet ? gdet[idx] : 1.0, det[idx], top4, PlainStore<1>{est.data()}, sink);
       }
     }
   }

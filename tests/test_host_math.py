@@ -11,7 +11,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from tests.helpers import COINCIDENT_RTOL, RTOL, assert_det_close, assert_grad_close, coincident_rows, load
+from tests.helpers import (COINCIDENT_RTOL, RTOL, assert_det_close, assert_grad_close, coincident_rows,
+                           col_scaled_err, load)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -158,9 +159,16 @@ def test_random_models_against_oracle(hm, seed):
     Fo = O.det_points(tc, torch.tensor(tt), td, ta, tb, tr)
     gF = rng.standard_normal(cc.shape)
     go = torch.autograd.grad(Fo, (td, ta, tb, tr, tc), grad_outputs=torch.tensor(gF))
+    # conditioning of this random case: what a 1-ulp change of the thicknesses alone does to the oracle's own
+    # gradients.  Where that exceeds the tolerance the comparison is bounded by it (x4) instead of by 1e-9.
+    td1 = torch.tensor(np.nextafter(d[:1], np.inf), requires_grad=True)
+    Fn = O.det_points(tc, torch.tensor(tt), td1, ta, tb, tr)
+    gn = torch.autograd.grad(Fn, (td1, ta, tb, tr, tc), grad_outputs=torch.tensor(gF))
+    shp = lambda x, i: x.numpy().reshape(K, NF).T if i == 4 else x.numpy()
+    tol = [max(RTOL, 4.0 * col_scaled_err(shp(x, i), shp(y, i), axis=-1)) for i, (x, y) in enumerate(zip(gn, go))]
     g = {"d": d[:1], "a": a[:1], "b": b[:1], "rho": rho[:1], "t": tt, "c": cc, "gF": gF}
     F, gd, ga, gb, gr, gc, _ = run_points(hm, g)
     assert_det_close(F.reshape(K, NF), Fo.detach().numpy().reshape(K, NF), axis=0)
-    for new, ref, key in zip((gd, ga, gb, gr), go[:4], ("gd", "ga", "gb", "grho")):
-        assert_grad_close(new, ref.numpy(), what="points " + key)
-    assert_grad_close(gc.reshape(K, NF).T, go[4].numpy().reshape(K, NF).T, what="gc")
+    for i, (new, ref, key) in enumerate(zip((gd, ga, gb, gr), go[:4], ("gd", "ga", "gb", "grho"))):
+        assert_grad_close(new, ref.numpy(), rtol=tol[i], what="points " + key)
+    assert_grad_close(gc.reshape(K, NF).T, go[4].numpy().reshape(K, NF).T, rtol=tol[4], what="gc")
