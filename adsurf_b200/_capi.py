@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libadsurf_b200.so")
+# ADSURF_LIB: load another build of the library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("ADSURF_LIB") or os.path.join(_HERE, "_lib", "libadsurf_b200.so")
 
 OP_POINTS_FWD, OP_POINTS_BWD, OP_POINTS_JAC, OP_GRID_FWD, OP_GRID_BWD, OP_DMF_STEP = range(6)
 COMPRESS_NONE, COMPRESS_EXP, COMPRESS_LOG, COMPRESS_EXP_NONORM, COMPRESS_NORM = range(5)

@@ -325,19 +325,19 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
         const size_t idx = ((size_t)s * K + k) * NF + fc;
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
-        double v, top4;
+        double v;
         if (kGlobal) {
           const GlobalStore st{estp, slab_policy};
           FoldSink sink{acc, lane};
-          v = sample_forward_store(src, z, st, top4);
+          v = sample_forward_store(src, z, st);
           if (det && active) __stcs(det + idx, v);  // streaming store: keep the store slabs in L2
-          sample_adjoint(src, z, seed, v, top4, st, sink);
+          sample_adjoint(src, z, seed, v, st, sink);
         } else {
           const PlainStore<kWarp> st{estp};
           ReduceSink sink{acc, L, lane};
-          v = sample_forward_store(src, z, st, top4);
+          v = sample_forward_store(src, z, st);
           if (det && active) __stcs(det + idx, v);
-          sample_adjoint(src, z, seed, v, top4, st, sink);
+          sample_adjoint(src, z, seed, v, st, sink);
         }
       }
     }
@@ -355,6 +355,77 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
         for (int w = 0; w < gp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
       }
       part[((size_t)s * gp.bpm + bc.blk) * 4 * L + i] = v;
+    }
+  }
+}
+
+// The same fused sweep with a free warp <-> work assignment: a block = (model, velocity chunk); per table fill
+// (tc trial velocities) its warps share the tc x nft (velocity, period tile) tasks round-robin, so the block size
+// is not tied to the number of period tiles of a model.  That allows 2 blocks x 7 warps per SM at 144 registers
+// (14 resident warps instead of 3 x 4 = 12 at 168): more latency hiding per scheduler for the long dependent FP64
+// chains, and one table fill serves 7 warps.  omega and 1/omega per period are staged once per block.
+template <int kThreads, int kMaxRegs>
+__global__ void __maxnreg__(kMaxRegs)
+k_grid_bwd_flex(const double* __restrict__ d, const double* __restrict__ alpha, const double* __restrict__ beta,
+                const double* __restrict__ rho, const double* __restrict__ t, const double* __restrict__ c,
+                const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp, int total_vblocks,
+                double* __restrict__ det, double* __restrict__ part, double* __restrict__ estore) {
+  extern __shared__ double smem[];
+  constexpr int kW = kThreads / kWarp;
+  constexpr int kTab = kTabAdj;
+  double* par = smem + kSmemHead;                       // staged layer constants (after the exp table)
+  double* accs = par + par_doubles(L);                  // [kW][L][4][16]
+  double* tab = accs + (size_t)kW * 64 * L;             // [tc][L-1][kTab]
+  double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
+  double* omg = ics + ((gp.tc + 1) & ~1);               // [nft*32][2]: omega, 1/max(omega, 1e-4)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
+  const GlobalStore st{estore + ((size_t)blockIdx.x * kW + warp) * slab + lane, l2_evict_last_policy()};
+  double* acc = accs + (size_t)warp * 64 * L;
+  const int nft = gp.nft;
+  for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
+    const int s = vb / gp.bpm, ch = vb - s * gp.bpm;
+    __syncthreads();  // previous virtual block has flushed its accumulators
+    stage_params(par, d, alpha, beta, rho, s, L);
+    for (int i = threadIdx.x; i < kW * 64 * L; i += blockDim.x) accs[i] = 0.0;
+    for (int i = threadIdx.x; i < nft * kWarp; i += blockDim.x) {
+      const double om = omega_of_period(t[(size_t)s * NF + min(i, NF - 1)]);
+      omg[2 * i] = om;
+      omg[2 * i + 1] = 1.0 / fmax(om, 1.0e-4);
+    }
+    const int k0 = ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
+    for (int kb = k0; kb < k1; kb += gp.tc) {
+      const int n = min(gp.tc, k1 - kb);
+      __syncthreads();
+      fill_table<kTab>(tab, ics, par, L, c + (size_t)s * K + kb, n);
+      __syncthreads();
+      const int ntask = n * nft;
+      for (int task = warp; task < ntask; task += kW) {
+        const int cc = task / nft, tile = task - cc * nft;
+        const int f = tile * kWarp + lane;
+        const bool active = f < NF;
+        const Dbl2 om = ld2(omg + 2 * f);
+        const Sample z = make_sample(om.x, ics[cc], om.y);
+        const TableSource<kTab, true> src{par, L, tab + (size_t)cc * (L - 1) * kTab, omg + 2 * f, ics + cc};
+        const size_t idx = ((size_t)s * K + (kb + cc)) * NF + (active ? f : NF - 1);
+        // inactive lanes (period tile overhang) replay a valid sample with a zero seed
+        const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
+        FoldSink sink{acc, lane};
+        const double v = sample_forward_store(src, z, st);
+        if (det && active) __stcs(det + idx, v);  // streaming store: keep the store slabs in L2
+        sample_adjoint(src, z, seed, v, st, sink);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
+      const int which = i / L, m = i - which * L;  // output order [4][L]
+      double v = 0.0;
+      for (int w = 0; w < kW; ++w) {
+        const double* q = accs + (size_t)w * 64 * L + ((m * 4 + which) << 4);
+#pragma unroll
+        for (int l = 0; l < 16; ++l) v += q[l];
+      }
+      part[((size_t)s * gp.bpm + ch) * 4 * L + i] = v;
     }
   }
 }
@@ -468,8 +539,7 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
       typename std::conditional<kGlobal, GlobalStore, PlainStore<kWarp>>::type store;
       store.p = estp;
       if constexpr (kGlobal) store.pol = slab_policy;
-      double top4;
-      const double v = sample_forward_store(src, z, store, top4);
+      const double v = sample_forward_store(src, z, store);
       if (F && active) F[idx] = v;
       double seed = 1.0;
       if (kKind == 0) seed = gF[idx];
@@ -498,13 +568,13 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
         if (kKind == 1) {
           JacSink sink{Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
                        Jrho ? Jrho + idx * L : nullptr, active};
-          gk = sample_adjoint(src, z, seed, v, top4, store, sink);
+          gk = sample_adjoint(src, z, seed, v, store, sink);
         } else if (kGlobal) {
           FoldSink sink{acc, lane};
-          gk = sample_adjoint(src, z, active ? seed : 0.0, v, top4, store, sink);  // overhang lanes: zero seed
+          gk = sample_adjoint(src, z, active ? seed : 0.0, v, store, sink);  // overhang lanes: zero seed
         } else {
           ReduceSink sink{acc, L, lane};
-          gk = sample_adjoint(src, z, active ? seed : 0.0, v, top4, store, sink);
+          gk = sample_adjoint(src, z, active ? seed : 0.0, v, store, sink);
         }
         if (gc && active) gc[idx] = -ic * z.ic * gk;  // gk = dDelta/d(k/omega), k/omega = 1/c
       }
@@ -738,7 +808,7 @@ inline size_t adj_smem(int L, int wpb) {
 // Where the dense adjoint keeps its per-layer row vectors: 0 = shared memory (2 blocks of 4 warps per
 // SM at 20 layers), 1 / 2 = L2-resident global slab with 3 / 4 blocks of 4 warps per SM.
 // Overridable for experiments with ADSURF_GRID_BWD=smem|g3|g4 (read once).
-enum { kBwdSmem = 0, kBwdG3 = 1, kBwdG4 = 2, kBwdH6 = 3, kBwdH7 = 4, kBwdH8 = 5 };
+enum { kBwdSmem = 0, kBwdG3 = 1, kBwdG4 = 2, kBwdH6 = 3, kBwdH7 = 4, kBwdH8 = 5, kBwdF7 = 6, kBwdF5 = 7, kBwdF4 = 8, kBwdF8 = 9 };
 inline int bwd_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -750,12 +820,20 @@ inline int bwd_mode() {
     if (e && !strcmp(e, "h6")) mode = kBwdH6;
     if (e && !strcmp(e, "h7")) mode = kBwdH7;
     if (e && !strcmp(e, "h8")) mode = kBwdH8;
+    if (e && !strcmp(e, "f7")) mode = kBwdF7;
+    if (e && !strcmp(e, "f5")) mode = kBwdF5;
+    if (e && !strcmp(e, "f4")) mode = kBwdF4;
+    if (e && !strcmp(e, "f8")) mode = kBwdF8;
   }
   return mode;
 }
+inline int bwd_flex_warps() {  // warps per block of the free-assignment kernel, 0 = period-tile kernel
+  const int m = bwd_mode();
+  return m == kBwdF7 ? 7 : (m == kBwdF5 ? 5 : (m == kBwdF4 ? 4 : (m == kBwdF8 ? 8 : 0)));
+}
 constexpr int kMaxResidentWarps = 160 * 16;  // upper bound on co-resident adjoint warps (global store slabs)
 
-inline int bwd_wpb_global() { return bwd_mode() >= kBwdH6 ? 2 : 4; }
+inline int bwd_wpb_global() { return bwd_flex_warps() ? bwd_flex_warps() : (bwd_mode() >= kBwdH6 ? 2 : 4); }
 
 inline size_t bwd_estore_bytes(int L) {
   return bwd_mode() == kBwdSmem ? 0 : (size_t)kMaxResidentWarps * est_bytes_per_warp(L);
@@ -778,12 +856,25 @@ inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
         if (adj_smem(L, w) + table_bytes(L, 8, true) <= (w > 1 ? kSmemBudget : kSmemMax)) want = w;
     }
   }
-  gp.wpb = want < gp.nft ? want : gp.nft;
+  const int flex = adjoint ? bwd_flex_warps() : 0;
+  gp.wpb = flex ? flex : (want < gp.nft ? want : gp.nft);
   if (gp.wpb < 1) gp.wpb = adjoint && want <= 0 ? 0 : 1;
-  gp.nfg = gp.wpb > 0 ? (gp.nft + gp.wpb - 1) / gp.wpb : 0;
+  gp.nfg = flex ? 1 : (gp.wpb > 0 ? (gp.nft + gp.wpb - 1) / gp.wpb : 0);
   // table fills of up to 8 velocities, fewer for very deep models (keeps the table under ~24 KB)
   gp.tc = 8;
   while (gp.tc > 1 && table_bytes(L, gp.tc, adjoint) > 24 * 1024) gp.tc >>= 1;
+  if (flex) {
+    // free assignment: tc * nft tasks per fill should be a multiple of the warps per block
+    int best = gp.tc, waste = 1 << 30;
+    for (int tc = gp.tc; tc >= 1 && tc > gp.tc / 2; --tc) {
+      const int tasks = tc * gp.nft, w = ((tasks + flex - 1) / flex) * flex - tasks;
+      if (w * best < waste * tc) {  // compare idle slots per task: w / tasks
+        best = tc;
+        waste = w;
+      }
+    }
+    gp.tc = best;
+  }
   // enough blocks for ~16 waves of a full machine, chunks not shorter than 2 table fills
   const long long target = (long long)kNumSM * 4 * 16;
   const long long base = (long long)S * (gp.nfg > 0 ? gp.nfg : 1);
@@ -1056,7 +1147,8 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   const int mode = bwd_mode();
   const size_t smem = par_bytes(L) +
                       (size_t)gp.wpb * (mode == kBwdSmem ? 4 : 64) * L * sizeof(double) + table_bytes(L, gp.tc, true) +
-                      (mode == kBwdSmem ? (size_t)gp.wpb * est_bytes_per_warp(L) : 0);
+                      (mode == kBwdSmem ? (size_t)gp.wpb * est_bytes_per_warp(L) : 0) +
+                      (bwd_flex_warps() ? (size_t)gp.nft * kWarp * 2 * sizeof(double) : 0);
   double* estore = mode == kBwdSmem ? nullptr : (double*)((char*)ws + part_bytes);
   const long long total_vb = (long long)S * gp.bpm;
   if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;
@@ -1083,6 +1175,10 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   else if (mode == kBwdH6) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 64, 168>));    // 6 x 2 = 12
   else if (mode == kBwdH7) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 64, 144>));    // 7 x 2 = 14
   else if (mode == kBwdH8) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 64, 152>));    // 6 x 2 = 12 (fewer regs)
+  else if (mode == kBwdF7) ADSURF_LAUNCH_BWD((k_grid_bwd_flex<224, 144>));    // 2 x 7 = 14
+  else if (mode == kBwdF5) ADSURF_LAUNCH_BWD((k_grid_bwd_flex<160, 136>));    // 3 x 5 = 15
+  else if (mode == kBwdF4) ADSURF_LAUNCH_BWD((k_grid_bwd_flex<128, 168>));    // 3 x 4 = 12 (control)
+  else if (mode == kBwdF8) ADSURF_LAUNCH_BWD((k_grid_bwd_flex<256, 128>));    // 2 x 8 = 16
   else ADSURF_LAUNCH_BWD((k_grid_bwd<false, 128, 232>));
 #undef ADSURF_LAUNCH_BWD
   if (check_launch()) return ADSURF_E_CUDA;

@@ -10,10 +10,20 @@
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
+
 #if defined(__CUDACC__)
 #define ADSURF_HD __host__ __device__ __forceinline__
 #else
 #define ADSURF_HD inline
+#endif
+
+// experiment switches for the adjoint sweep's layer loop (see sample_adjoint)
+#ifndef ADSURF_ADJ_MODE
+#define ADSURF_ADJ_MODE 1
+#endif
+#ifndef ADSURF_FETCH_CLAMP
+#define ADSURF_FETCH_CLAMP 1
 #endif
 
 namespace adsurf {
@@ -69,9 +79,44 @@ ADSURF_HD int hi_word(double v) {
   return (int)(dbl_bits(v) >> 32);
 #endif
 }
+// v with its sign flipped when bit 31 of m is set
+ADSURF_HD double flip_sign(double v, int m) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(v) ^ (m & (int)0x80000000), __double2loint(v));
+#else
+  return bits_dbl(dbl_bits(v) ^ ((long long)(m & (int)0x80000000) << 32));
+#endif
+}
+// v >= 0: min(v, T) for a threshold given by its high word (low word of the result is v's: |error| < 1 ulp(hi))
+ADSURF_HD double clamp_hi(double v, int thi) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(min(__double2hiint(v), thi), __double2loint(v));
+#else
+  const long long b = dbl_bits(v);
+  const int hi = (int)(b >> 32);
+  return bits_dbl(((long long)(hi < thi ? hi : thi) << 32) | (b & 0xffffffffLL));
+#endif
+}
 ADSURF_HD bool below16(double v) { return hi_word(v) < 0x40300000; }
 ADSURF_HD bool below60(double v) { return hi_word(v) < 0x404E0000; }
 ADSURF_HD bool below1e5(double v) { return hi_word(v) < 0x40F86A00; }
+
+// v/2 and a+b as separate instructions: "0.5 + 0.5 v" contracted to one fma needs 0.5 twice, and an FP64
+// instruction encodes only one immediate, so the second copy costs two moves per use
+ADSURF_HD double half_of(double v) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(v, 0.5);
+#else
+  return v * 0.5;
+#endif
+}
+ADSURF_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
 
 constexpr double kShifter = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-nearest integer into the low mantissa bits
 
@@ -86,10 +131,13 @@ constexpr double kShifter = 6755399441055744.0;  // 1.5 * 2^52: adds round-to-ne
 #define ADSURF_RED_CONSTS                                                                             \
   { 1.4426950408889634, -0.6931471805599453, -2.3190468138462996e-17, /* log2 e, -ln2 hi, -ln2 lo */    \
     0.6366197723675814, -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33 /* 2/pi, -pi/2 x3 */ }
+#define ADSURF_EXP_CONSTS { 5.952044687368025e-11, 0.041666666666666664, 0.16666666666666666, 0.0 } /* -(ln2/32 tail), 1/24, 1/6 */
+static const double kExpCH[4] = ADSURF_EXP_CONSTS;
 static const double kSinCH[6] = ADSURF_SIN_COEFS;
 static const double kCosCH[6] = ADSURF_COS_COEFS;
 static const double kRedCH[7] = ADSURF_RED_CONSTS;
 #if defined(__CUDACC__)
+__constant__ double kExpCD[4] = ADSURF_EXP_CONSTS;
 __constant__ double kSinCD[6] = ADSURF_SIN_COEFS;
 __constant__ double kCosCD[6] = ADSURF_COS_COEFS;
 __constant__ double kRedCD[7] = ADSURF_RED_CONSTS;
@@ -129,18 +177,26 @@ __device__ __forceinline__ void stage_exp_table() {
 // exp(-p) for 0 <= p < ~700: n = rint(-p 32/ln2), r = -p - n ln2/32 (two-term, |r| <= ln2/64),
 // e^r by a degree-6 Taylor polynomial (truncation 3.5e-18), times 2^(j/32) from the table (j = n mod 32)
 // scaled by 2^(n div 32) through the exponent field.  11 FP64 instructions, <= 2 ulp.
-// For p >= ~700 the exponent field wraps and the value is meaningless — every caller discards it there
-// (the e^{-2p} term is used only for p < 16, e^{-p} only for p < 60), so no clamp is spent on it.
-ADSURF_HD double exp_neg(double p) {
+// Constants whose exact value does not matter are rounded to 21 significant bits, i.e. to doubles whose low
+// word is zero, which an FP64 instruction encodes as an immediate (a full 64-bit literal costs two extra
+// instructions): 32/ln2 (only picks n), the head of ln2/32 (the tail carries the rest: head + tail = ln2/32 to
+// 2^-75) and the two highest Taylor coefficients (their rounding moves the result by < 1e-18).
+// The reference sets e^{-(pP+pS)} to 0 beyond 60 (:170-178), a cut-off that removes a factor < 1e-26; here the
+// exponential is simply evaluated (the argument is clamped at 700), which saves a compare and two selects per
+// layer in both sweeps.  (Its other cut-off, e^{-2p} := 0 beyond p = 16, is kept: see evan_terms.)
+ADSURF_HD double exp_neg(double p_in) {
+  // p >= 0 (or NaN): doubles order like their high words, so an integer min on the high word clamps p to ~700
+  // (e^-700 ~ 1e-304: its square and its products underflow to 0) in one ALU instruction; beyond ~708 the exponent arithmetic below would wrap.
+  const double p = clamp_hi(p_in, 0x4085E000);
   const double x = -p;
-  const double t = fma(x, 46.16624130844683, kShifter);
+  const double t = fma(x, 46.166229248046875, kShifter);
   const double fn = t - kShifter;
-  double r = fma(fn, -0.02166084939249829, x);
-  r = fma(fn, -7.247021293269686e-19, r);
+  double r = fma(fn, -0.021660849452018738, x);
+  r = fma(fn, ADSURF_K(kExpC, 0), r);
   const int n = (int)dbl_bits(t);  // low 32 bits hold the (two's complement) integer
-  double q = fma(0.001388888888888889, r, 0.008333333333333333);
-  q = fma(q, r, 0.041666666666666664);
-  q = fma(q, r, 0.16666666666666666);
+  double q = fma(0.00138888880610466, r, 0.00833333283662796);
+  q = fma(q, r, ADSURF_K(kExpC, 1));
+  q = fma(q, r, ADSURF_K(kExpC, 2));
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   q = fma(q, r, 1.0);
@@ -181,8 +237,9 @@ ADSURF_HD void sincos_core(double q, double* sn, double* cs) {
   const int n = (int)dbl_bits(t);
   const double a = (n & 1) ? c : s;
   const double b = (n & 1) ? s : c;
-  *sn = (n & 2) ? -a : a;
-  *cs = ((n + 1) & 2) ? -b : b;
+  // quadrant signs: flip the sign bit with integer operations (a negation is an FP64-pipe instruction)
+  *sn = flip_sign(a, n << 30);
+  *cs = flip_sign(b, (n + 1) << 30);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -222,7 +279,6 @@ struct Eig {
   double cs, sn;    // cos p / (1+e^-2p)/2   and   sin p / (1-e^-2p)/2
   double w, x;      // sn / r   and   -+ r sn
   double dcs, dsn;  // d cs / dp, d sn / dp
-  double ex, eh;    // exponent carried out of the term (p when evanescent); e^{-p} (1 when oscillatory)
   double c0, c1;    // the transcendental results kept for the adjoint sweep: (sin, cos) or (e^{-p}, -)
   bool lt, pos;     // oscillatory branch (k < kx);  u > 0 (false: k == kx or unordered)
 };
@@ -237,23 +293,28 @@ ADSURF_HD void eig_osc(Eig& e) {
   e.cs = e.c1;
   e.dcs = -e.c0;
   e.dsn = e.c1;
-  e.ex = 0.0;
-  e.eh = 1.0;
   e.x = -e.r * e.sn;
+}
+
+// (1 +- e^{-2p})/2 from e^{-p}; the e^{-2p} term is dropped beyond p = 16 as the reference does (:128-134)
+ADSURF_HD void evan_terms(Eig& e) {
+  const double fac = below16(e.p) ? e.c0 * e.c0 : 0.0;  // cut-off kept: it shapes d/d(thickness) at the 1e-8 level
+  const double hf = half_of(fac);
+  e.cs = add_rn(0.5, hf);
+  e.sn = add_rn(0.5, -hf);
+  e.dcs = -fac;
+  e.dsn = fac;
 }
 
 ADSURF_HD void eig_evan(Eig& e) {
   e.c0 = exp_neg(e.p);
   e.c1 = 0.0;
-  const double fac = below16(e.p) ? e.c0 * e.c0 : 0.0;
-  e.cs = 0.5 + 0.5 * fac;
-  e.sn = 0.5 - 0.5 * fac;
-  e.dcs = -fac;
-  e.dsn = fac;
-  e.ex = e.p;  // p = 0 when k == kx
-  e.eh = below60(e.p) ? e.c0 : 0.0;
+  evan_terms(e);
   e.x = e.r * e.sn;
 }
+
+// a0 = e^{-(pex + sex)} (reference :170-178) from the stored e^{-p} of the evanescent terms
+ADSURF_HD double layer_a0(const Eig& P, const Eig& S) { return (P.lt ? 1.0 : P.c0) * (S.lt ? 1.0 : S.c0); }
 
 // generic forward: regime from the flags; wd = omega * thickness is the value of w when k == kx (reference :135)
 ADSURF_HD void eig_forward(Eig& e, double wd) {
@@ -263,9 +324,7 @@ ADSURF_HD void eig_forward(Eig& e, double wd) {
     e.cs = e.c1;
     e.dcs = -e.c0;
     e.dsn = e.c1;
-    e.ex = 0.0;
-    e.eh = 1.0;
-    e.x = -e.r * e.sn;
+      e.x = -e.r * e.sn;
   } else {
     eig_evan(e);
   }
@@ -279,16 +338,8 @@ ADSURF_HD void eig_finish(Eig& e, double wd) {
     e.cs = e.c1;
     e.dcs = -e.c0;
     e.dsn = e.c1;
-    e.ex = 0.0;
-    e.eh = 1.0;
-  } else {
-    const double fac = below16(e.p) ? e.c0 * e.c0 : 0.0;
-    e.cs = 0.5 + 0.5 * fac;
-    e.sn = 0.5 - 0.5 * fac;
-    e.dcs = -fac;
-    e.dsn = fac;
-    e.ex = e.p;
-    e.eh = below60(e.p) ? e.c0 : 0.0;
+    } else {
+    evan_terms(e);
   }
   e.w = e.pos ? e.sn * e.ir : wd;
   e.x = (e.lt ? -e.r : e.r) * e.sn;
@@ -322,32 +373,29 @@ ADSURF_HD void layer_eig_forward(Layer& y, double omega) {
     layer_set_flags(y, F_REGULAR | F_LTS);
     eig_evan(y.P);
     eig_osc(y.S);
-    y.a0 = y.P.eh;
   } else if (fl == F_REGULAR) {             // slower than both: fully evanescent
     layer_set_flags(y, F_REGULAR);
     eig_evan(y.P);
     eig_evan(y.S);
-    y.a0 = below60(y.P.p + y.S.p) ? y.P.eh * y.S.eh : 0.0;
   } else if (fl == (F_REGULAR | F_LTP | F_LTS)) {  // faster than both
     layer_set_flags(y, F_REGULAR | F_LTP | F_LTS);
     eig_osc(y.P);
     eig_osc(y.S);
-    y.a0 = 1.0;
   } else if (fl == (F_REGULAR | F_LTP)) {
     layer_set_flags(y, F_REGULAR | F_LTP);
     eig_osc(y.P);
     eig_evan(y.S);
-    y.a0 = y.S.eh;
   } else {  // huge phase, NaN, or c exactly on a layer velocity: generic path
     layer_set_flags(y, y.fl);
     const double wd = omega * y.pr[P_D];
     eig_forward(y.P, wd);
     eig_forward(y.S, wd);
-    y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
+    y.a0 = layer_a0(y.P, y.S);
     return;
   }
   y.P.w = y.P.sn * y.P.ir;
   y.S.w = y.S.sn * y.S.ir;
+  y.a0 = layer_a0(y.P, y.S);  // the flags are constants here: one compare and at most one multiply
 }
 
 // adjoint sweep: restore them from the store (c0, c1 already set by the caller)
@@ -355,7 +403,7 @@ ADSURF_HD void layer_eig_restore(Layer& y, double omega) {
   const double wd = omega * y.pr[P_D];  // only read when k == kx
   eig_finish(y.P, wd);
   eig_finish(y.S, wd);
-  y.a0 = below60(y.P.ex + y.S.ex) ? y.P.eh * y.S.eh : 0.0;
+  y.a0 = layer_a0(y.P, y.S);
 }
 
 // E <- E . CA   (row vector times Dunkin matrix, reference :376-383)
@@ -392,12 +440,13 @@ ADSURF_HD double eig_adjoint(const Eig& e, double bcs, double bw, double bx, dou
 }
 
 // Reverse sweep through one layer: row vector e (= E_{m+1}), column s (= s_m, already scaled by the upstream
-// seed) and the row vector on the other side of the layer (ep0, ep4 = components 0 and 4 of E_m = E_{m+1}.CA).
-// Returns dDelta/d(layer inputs), Delta = e . CA . s, and advances s <- CA . s on the way (the column
+// seed).  Returns dDelta/d(layer inputs), Delta = e . CA . s, and advances s <- CA . s on the way (the column
 // product shares the contractions ta, tb, g1..g4, Da, Db with the adjoint: 13 extra FMAs instead of 33).
+// tq carries T_m = E_m[0] s_m[0] - E_m[4] s_m[4] of the interface above the layer in and T_{m+1} out:
+// rho dDelta/drho = T_m - T_{m+1} (the rho similarity above), T_0 = seed * determinant.
 template <bool kWantIc>
-ADSURF_HD LayerGrad layer_adjoint(const Layer& y, const double (&e)[5], double (&s)[5], double ep0, double ep4,
-                                  double omega, double ic, double ic2, double t2) {
+ADSURF_HD LayerGrad layer_adjoint(const Layer& y, const double (&e)[5], double (&s)[5], double& tq, double omega,
+                                  double ic, double ic2, double t2) {
   const double e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3], e4 = e[4];
   const double s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3], s4 = s[4];
   const double cp = y.P.cs, w = y.P.w, x = y.P.x, cq = y.S.cs, yy = y.S.w, z = y.S.x;
@@ -451,7 +500,9 @@ ADSURF_HD LayerGrad layer_adjoint(const Layer& y, const double (&e)[5], double (
   g.d = omega * ((y.P.pos ? y.P.r * bpP : bw) + (y.S.pos ? y.S.r * bpS : by));
   g.a = y.P.pos ? y.tqa * tP : 0.0;
   g.b = (y.S.pos ? y.tqb * tS : 0.0) + y.cb * b_gk;
-  g.rho = y.ir * (ep0 * s0 - e0 * s[0] - ep4 * s4 + e4 * s[4]);
+  const double tn = e0 * s[0] - e4 * s[4];
+  g.rho = y.ir * (tq - tn);
+  tq = tn;
   g.ic = 0.0;
   if (kWantIc) {
     // d/d(1/c): through n^2 = +-(ic2 - 1/v^2) and through ic2 in the coefficients
@@ -543,18 +594,20 @@ struct Sample {
 // where a trial velocity coincides with the half-space velocity (see load_half).
 ADSURF_HD double omega_of_period(double t) { return (1.0 / t) * kTwoPi; }
 
-ADSURF_HD Sample make_sample(double omega0, double ic) {
+// iw = 1 / max(omega0, 1e-4), precomputed by callers that revisit a period
+ADSURF_HD Sample make_sample(double omega0, double ic, double iw) {
   Sample z;
   z.k = ic * omega0;                          // (1/c) * omega   (reference :319, unclamped omega)
   z.omega = fmax(omega0, 1.0e-4);             // reference :326
   z.k2 = z.k * z.k;
-  z.iw = 1.0 / z.omega;
+  z.iw = iw;
   z.iw2 = z.iw * z.iw;
   z.ic = (omega0 >= 1.0e-4) ? ic : z.k * z.iw;  // periods beyond 2 pi 1e4 s: k / omega differs from 1/c
   z.ic2 = z.ic * z.ic;
   z.t2 = -2.0 * z.ic2;
   return z;
 }
+ADSURF_HD Sample make_sample(double omega0, double ic) { return make_sample(omega0, ic, 1.0 / fmax(omega0, 1.0e-4)); }
 
 // ---- layer sources: fill the frequency-free coefficient scalars, the phases and the regime of layer m.
 // Everything that depends on (trial velocity, layer) but not on the period is one table entry:
@@ -646,6 +699,8 @@ struct DirectSource {
   static constexpr bool kWantIc = true;         // the pointwise kernels return dF/dc
   const double* __restrict__ par;
   int L;
+  ADSURF_HD int flags(int) const { return -1; }
+  ADSURF_HD Sample again(const Sample& z) const { return z; }
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     alignas(16) double tab[kTabAdj];
     table_entry<kTabAdj>(tab, par, m, z.ic);
@@ -654,13 +709,25 @@ struct DirectSource {
   }
 };
 
-template <int kN>
+template <int kN, bool kRemake = false>
 struct TableSource {
   static constexpr bool kUniformFlags = true;   // flags come from the shared (velocity, layer) table
   static constexpr bool kWantIc = false;
   const double* __restrict__ par;
   int L;
   const double* __restrict__ tab;  // [L-1][kN] for the current trial velocity (16-byte aligned)
+  // kRemake: where the sample's (omega, 1/omega) pair and 1/c are staged, so that the half-space quantities
+  // (k, k^2, 1/omega, 1/omega^2) need not stay in registers across the layer loop of the adjoint sweep
+  const double* omq = nullptr;
+  const double* icq = nullptr;
+  ADSURF_HD Sample again(const Sample& z) const {
+    if (kRemake) {
+      const Dbl2 om = ld2(omq);
+      return make_sample(om.x, *icq, om.y);
+    }
+    return z;
+  }
+  ADSURF_HD int flags(int m) const { return (int)dbl_bits(tab[m * kN + T_FL]); }
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     layer_from_entry<kN>(y, tab + m * kN, par + m * kNumPar, z.omega);
   }
@@ -718,10 +785,9 @@ struct PlainStore {
   ADSURF_HD static void st(Slot q, int j, double v) { q[j * kStride] = v; }
 };
 
-// forward keeping E_{m+1} of every layer: slot m holds the row vector that multiplies CA_m.  Returns
-// E_0[0] (the determinant); top4 = E_0[4], which the adjoint sweep needs next to it.
+// forward keeping E_{m+1} of every layer: slot m holds the row vector that multiplies CA_m.
 template <typename Source, typename Store>
-ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const Store& est, double& top4) {
+ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const Store& est) {
   const int L = src.L;
   double e[5];
   half_start(src.par, L, z, e);
@@ -738,82 +804,139 @@ ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const 
     Store::st(q, 8, y.S.c1);
     row_apply(e, y);
   }
-  top4 = e[4];
   return e[0];
 }
 
 // Top-down adjoint sweep.  s_0 = seed * e_0; for every layer m (and finally the half-space, m = L-1)
-// hands (m, dDelta/dd_m, /dalpha_m, /dbeta_m, /drho_m) * seed to `sink`.  (top0, top4) are components 0 and 4
-// of the forward sweep's final row vector.  Returns seed * dDelta/d(k/omega) (pointwise sources; 0 otherwise).
+// hands (m, dDelta/dd_m, /dalpha_m, /dbeta_m, /drho_m) * seed to `sink`.  det is the forward sweep's result.
+// Returns seed * dDelta/d(k/omega) (pointwise sources; 0 otherwise).
 // Software pipeline over the stored values: each group of registers is re-loaded for layer m+1 right
 // after its last use in layer m — the transcendental results once eig_finish has consumed them, the row
 // vector E once layer_adjoint is done — so the L2 latency of the slab hides behind the rest of the layer
 // without a second register buffer.
 template <typename Source, typename Store, typename Sink>
-ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed, double top0, double top4,
-                                const Store& est, Sink& sink) {
+ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed, double det, const Store& est,
+                                Sink& sink) {
   const double* __restrict__ par = src.par;
   const int L = src.L;
   double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
-  double e[5], cv[4];
-  double ep0 = top0, ep4 = top4;
+  double tq = seed * det;  // T_0
   double gic = 0.0;
-  auto fetch_c = [&](int m) {
+  // The stored values of layer m+1 are fetched while layer m is being worked on (the slab lives in L2: a few
+  // hundred cycles away) — the transcendental results as soon as eig_finish has consumed layer m's, the row
+  // vector once the contractions are under way.  Two register buffers alternate so that a load never targets
+  // registers that are still live: a single buffer makes the compiler load into temporaries and copy all nine
+  // doubles at the end of every layer.
+  struct Buf {
+    double e[5], cv[4];
+  };
+  Buf A, B;
+  auto fetch_c = [&](Buf& b, int m) {
     const typename Store::Slot q = est.slot(m);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) cv[i] = Store::ld(q, 5 + i);
+    for (int i = 0; i < 4; ++i) b.cv[i] = Store::ld(q, 5 + i);
   };
-  auto fetch_e = [&](int m) {
+  auto fetch_e = [&](Buf& b, int m) {
     const typename Store::Slot q = est.slot(m);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) e[i] = Store::ld(q, i);
+    for (int i = 0; i < 5; ++i) b.e[i] = Store::ld(q, i);
   };
-  auto layer = [&](int m) {
+  // One layer; kFl >= 0 states the regime flags as a compile-time constant, which folds every "lt ? a : b" /
+  // "pos ? a : b" select of eig_finish / eig_adjoint away.
+  auto layer = [&](int m, auto tag, Buf& cur, Buf& nxt) {
+    constexpr int kFl = decltype(tag)::value;
     Layer y;
-    y.P.c0 = cv[0]; y.P.c1 = cv[1]; y.S.c0 = cv[2]; y.S.c1 = cv[3];
+    y.P.c0 = cur.cv[0]; y.P.c1 = cur.cv[1]; y.S.c0 = cur.cv[2]; y.S.c1 = cur.cv[3];
     src.prep(y, m, z);
-    auto body = [&]() {
-      layer_eig_restore(y, z.omega);
-      if (m + 1 <= L - 2) fetch_c(m + 1);
-      const LayerGrad g = layer_adjoint<Source::kWantIc>(y, e, s, ep0, ep4, z.omega, z.ic, z.ic2, z.t2);
-      ep0 = e[0];
-      ep4 = e[4];
-      if (m + 1 <= L - 2) fetch_e(m + 1);
-      gic += g.ic;
-      sink(m, g.d, g.a, g.b, g.rho);
-    };
-    // Regime specialisation (dense kernels: the flags are warp-uniform table entries).  Re-stating the flags
-    // as constants inside each branch lets the compiler fold every "lt ? a : b" / "pos ? a : b" select of
-    // eig_finish / eig_adjoint away in the two regimes that cover ~95 % of (velocity, layer) pairs.
-    if (Source::kUniformFlags && y.fl == (F_REGULAR | F_LTS)) {  // P evanescent, S oscillatory
-      layer_set_flags(y, F_REGULAR | F_LTS);
-      body();
-    } else if (Source::kUniformFlags && y.fl == F_REGULAR) {     // both evanescent
-      layer_set_flags(y, F_REGULAR);
-      body();
-    } else {
-      layer_set_flags(y, y.fl);
-      body();
-    }
+    layer_set_flags(y, kFl >= 0 ? kFl : y.fl);
+    layer_eig_restore(y, z.omega);
+#if ADSURF_FETCH_CLAMP
+    const int mn = m + 1 <= L - 2 ? m + 1 : m;  // the last layer re-reads its own slot: no predicated loads
+    fetch_c(nxt, mn);
+    const LayerGrad g = layer_adjoint<Source::kWantIc>(y, cur.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
+    fetch_e(nxt, mn);
+#else
+    if (m + 1 <= L - 2) fetch_c(nxt, m + 1);
+    const LayerGrad g = layer_adjoint<Source::kWantIc>(y, cur.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
+    if (m + 1 <= L - 2) fetch_e(nxt, m + 1);
+#endif
+    gic += g.ic;
+    sink(m, g.d, g.a, g.b, g.rho);
   };
   if (L > 1) {
-    fetch_c(0);
-    fetch_e(0);
+    fetch_c(A, 0);
+    fetch_e(A, 0);
   }
-  for (int m = 0; m <= L - 2; ++m) layer(m);
+  // Regime specialisation (dense kernels: the flags are warp-uniform table entries).
+  constexpr int kEO = F_REGULAR | F_LTS, kEE = F_REGULAR;  // (P evanescent, S oscillatory), (both evanescent)
+  const int last = L - 2;
+  int m = 0;
+#if ADSURF_ADJ_MODE == 0
+  // one dispatch per layer
+  for (; m <= last; ++m) {
+    const int fl = Source::kUniformFlags ? src.flags(m) : -1;
+    if (fl == kEO) layer(m, std::integral_constant<int, kEO>{}, A, A);
+    else if (fl == kEE) layer(m, std::integral_constant<int, kEE>{}, A, A);
+    else layer(m, std::integral_constant<int, -1>{}, A, A);
+  }
+#else
+  // Consecutive layers in the same regime (the usual case: oscillatory S near the surface, evanescent below)
+  // run in a loop of their own.
+  auto run = [&](auto tag) {
+    constexpr int kFl = decltype(tag)::value;
+#if ADSURF_ADJ_MODE == 1
+    do {
+      layer(m, tag, A, A);
+      ++m;
+    } while (m <= last && src.flags(m) == kFl);
+#else
+    for (;;) {  // two layers per trip (buffers A -> B -> A); a run of odd length copies B back to A once
+      layer(m, tag, A, B);
+      ++m;
+      if (!(m <= last && src.flags(m) == kFl)) {
+#if ADSURF_ADJ_MODE == 3
+        if (m <= last) {  // odd run length: re-read the next layer's values into A instead of copying B
+          fetch_c(A, m);
+          fetch_e(A, m);
+        }
+#else
+        A = B;
+#endif
+        break;
+      }
+      layer(m, tag, B, A);
+      ++m;
+      if (!(m <= last && src.flags(m) == kFl)) break;
+    }
+#endif
+  };
+  while (m <= last) {
+    const int fl = Source::kUniformFlags ? src.flags(m) : -1;
+    if (fl == kEO) {
+      run(std::integral_constant<int, kEO>{});
+    } else if (fl == kEE) {
+      run(std::integral_constant<int, kEE>{});
+    } else {
+      layer(m, std::integral_constant<int, -1>{}, A, A);
+      ++m;
+    }
+  }
+#endif
+  double e[5];
   // half-space: dDelta/dE_hs = D^-1 s~_{L-1}, in the reference's variables
+  const Sample zh = src.again(z);
   Half h;
-  load_half(h, par, L, z);
-  half_space(h, z.k, z.k2, e);
-  const double su[5] = {s[0], s[1] * z.iw, s[2], s[3] * z.iw, s[4] * z.iw2};
-  const HalfGrad g = half_adjoint(h, e, su, z.k, z.k2);
-  gic += z.omega * g.k;  // k = omega * (k/omega)
+  load_half(h, par, L, zh);
+  half_space(h, zh.k, zh.k2, e);
+  const double su[5] = {s[0], s[1] * zh.iw, s[2], s[3] * zh.iw, s[4] * zh.iw2};
+  const HalfGrad g = half_adjoint(h, e, su, zh.k, zh.k2);
+  gic += zh.omega * g.k;  // k = omega * (k/omega)
   const int mh = L - 1;
   const double* __restrict__ prh = par + mh * kNumPar;
-  const double w2 = z.omega * z.omega;
+  const double w2 = zh.omega * zh.omega;
   // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2:
   //   d/dalpha = omega^2/alpha^3 hp,  d/dbeta = omega^2/beta^3 hs + 4 beta/omega^2 dDelta/dgammk
-  sink(mh, 0.0, (w2 * prh[P_IA3]) * g.hp, (w2 * prh[P_IB3]) * g.hs + (prh[P_CB] * z.iw2) * g.gammk, g.rho);
+  sink(mh, 0.0, (w2 * prh[P_IA3]) * g.hp, (w2 * prh[P_IB3]) * g.hs + (prh[P_CB] * zh.iw2) * g.gammk, g.rho);
   return gic;
 }
 

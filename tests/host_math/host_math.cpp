@@ -43,15 +43,14 @@ int host_points(const double* d, const double* alpha, const double* beta, const 
       const size_t idx = (size_t)s * N + i;
       const double ic = 1.0 / c[idx];
       const Sample z = make_sample(omega_of_period(t[idx]), ic);
-      double top4 = 0.0;
-      const double v = sample_forward_store(DirectSource{par.data(), L}, z, PlainStore<1>{est.data()}, top4);
+      const double v = sample_forward_store(DirectSource{par.data(), L}, z, PlainStore<1>{est.data()});
       const double v2 = sample_forward(DirectSource{par.data(), L}, z);
       if (v != v2 && !(v != v && v2 != v2)) return -1;
       F[idx] = v;
       HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L,
                     Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
                     Jrho ? Jrho + idx * L : nullptr};
-      const double gic = sample_adjoint(DirectSource{par.data(), L}, z, gF ? gF[idx] : 1.0, v, top4,
+      const double gic = sample_adjoint(DirectSource{par.data(), L}, z, gF ? gF[idx] : 1.0, v,
                                         PlainStore<1>{est.data()}, sink);
       if (gc) gc[idx] = -ic * z.ic * gic;  // d(k/omega)/dc
     }
@@ -83,12 +82,11 @@ int host_grid(const double* d, const double* alpha, const double* beta, const do
       for (int f = 0; f < NF; ++f) {
         const size_t idx = ((size_t)s * K + k) * NF + f;
         const Sample z = make_sample(omega_of_period(t[s * NF + f]), ic);
-        double top4 = 0.0;
-        det[idx] = sample_forward_store(src, z, PlainStore<1>{est.data()}, top4);
+        det[idx] = sample_forward_store(src, z, PlainStore<1>{est.data()});
         const double v2 = sample_forward(srcf, z);
         if (det[idx] != v2 && !(det[idx] != det[idx] && v2 != v2)) return -1;
         HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L, nullptr, nullptr, nullptr, nullptr};
-        sample_adjoint(src, z, gdet ? gdet[idx] : 1.0, det[idx], top4, PlainStore<1>{est.data()}, sink);
+        sample_adjoint(src, z, gdet ? gdet[idx] : 1.0, det[idx], PlainStore<1>{est.data()}, sink);
       }
     }
   }
