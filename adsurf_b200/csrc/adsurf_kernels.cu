@@ -117,6 +117,7 @@ __device__ __forceinline__ void stage_params(double* __restrict__ par, const dou
     stage_one(par, L, m, d[(size_t)s * L + m], alpha[(size_t)s * L + m], beta[(size_t)s * L + m],
               rho[(size_t)s * L + m]);
   }
+  if (threadIdx.x == blockDim.x - 1) stage_bounds(par, L, d + (size_t)s * L, beta + (size_t)s * L);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@
 
 // experiment switches for the adjoint sweep's layer loop (see sample_adjoint)
 #ifndef ADSURF_ADJ_MODE
-#define ADSURF_ADJ_MODE 1
+#define ADSURF_ADJ_MODE 3
 #endif
 #ifndef ADSURF_FETCH_CLAMP
 #define ADSURF_FETCH_CLAMP 1
@@ -362,42 +362,6 @@ ADSURF_HD void layer_set_flags(Layer& y, int fl) {
   y.S.pos = fl & F_POSS;
 }
 
-// forward sweep: evaluate the transcendentals (phases set up by the layer source).  The four regime
-// combinations get their own straight-line block so that the P and the S polynomial chains (each a
-// ~16-deep dependent FP64 sequence, 8 cycles per link) are scheduled interleaved instead of one
-// after the other behind separate branches.  The regime is warp-uniform in the dense kernels.
-ADSURF_HD void layer_eig_forward(Layer& y, double omega) {
-  const bool small = below1e5(fabs(y.P.p)) && below1e5(fabs(y.S.p));
-  const int fl = small ? y.fl : -1;  // one integer compare per regime instead of four extracted booleans
-  if (fl == (F_REGULAR | F_LTS)) {          // c between the S and the P velocity of the layer: the common case
-    layer_set_flags(y, F_REGULAR | F_LTS);
-    eig_evan(y.P);
-    eig_osc(y.S);
-  } else if (fl == F_REGULAR) {             // slower than both: fully evanescent
-    layer_set_flags(y, F_REGULAR);
-    eig_evan(y.P);
-    eig_evan(y.S);
-  } else if (fl == (F_REGULAR | F_LTP | F_LTS)) {  // faster than both
-    layer_set_flags(y, F_REGULAR | F_LTP | F_LTS);
-    eig_osc(y.P);
-    eig_osc(y.S);
-  } else if (fl == (F_REGULAR | F_LTP)) {
-    layer_set_flags(y, F_REGULAR | F_LTP);
-    eig_osc(y.P);
-    eig_evan(y.S);
-  } else {  // huge phase, NaN, or c exactly on a layer velocity: generic path
-    layer_set_flags(y, y.fl);
-    const double wd = omega * y.pr[P_D];
-    eig_forward(y.P, wd);
-    eig_forward(y.S, wd);
-    y.a0 = layer_a0(y.P, y.S);
-    return;
-  }
-  y.P.w = y.P.sn * y.P.ir;
-  y.S.w = y.S.sn * y.S.ir;
-  y.a0 = layer_a0(y.P, y.S);  // the flags are constants here: one compare and at most one multiply
-}
-
 // adjoint sweep: restore them from the store (c0, c1 already set by the caller)
 ADSURF_HD void layer_eig_restore(Layer& y, double omega) {
   const double wd = omega * y.pr[P_D];  // only read when k == kx
@@ -700,6 +664,7 @@ struct DirectSource {
   const double* __restrict__ par;
   int L;
   ADSURF_HD int flags(int) const { return -1; }
+  ADSURF_HD bool small_phases(const Sample&) const { return false; }
   ADSURF_HD Sample again(const Sample& z) const { return z; }
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     alignas(16) double tab[kTabAdj];
@@ -728,6 +693,10 @@ struct TableSource {
     return z;
   }
   ADSURF_HD int flags(int m) const { return (int)dbl_bits(tab[m * kN + T_FL]); }
+  // every phase of the sample below 1e5 (the inline sincos's range): p = omega n d, n <= max(1/c, 1/beta)
+  ADSURF_HD bool small_phases(const Sample& z) const {
+    return z.omega * fmax(z.ic, par[kNumPar * L + 2]) * par[kNumPar * L + 3] < 1.0e5;
+  }
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     layer_from_entry<kN>(y, tab + m * kN, par + m * kNumPar, z.omega);
   }
@@ -755,21 +724,6 @@ ADSURF_HD void half_start(const double* __restrict__ par, int L, const Sample& z
   e[4] *= z.iw2;
 }
 
-// forward only
-template <typename Source>
-ADSURF_HD double sample_forward(const Source& src, const Sample& z) {
-  const int L = src.L;
-  double e[5];
-  half_start(src.par, L, z, e);
-  Layer y;
-  for (int m = L - 2; m >= 0; --m) {
-    src.prep(y, m, z);
-    layer_eig_forward(y, z.omega);
-    row_apply(e, y);
-  }
-  return e[0];
-}
-
 // Storage policy for what the forward sweep keeps for the adjoint sweep, kSlot = 9 doubles per layer:
 // the row vector E_{m+1} (5) and the transcendental results of the P and S terms (2 + 2).  Element
 // (m, j) of this thread lives at p[(m*kSlot+j)*kStride] (kStride = 32: lane-interleaved, i.e.
@@ -784,27 +738,88 @@ struct PlainStore {
   ADSURF_HD static double ld(Slot q, int j) { return q[j * kStride]; }
   ADSURF_HD static void st(Slot q, int j, double v) { q[j * kStride] = v; }
 };
+struct NoStore {
+  typedef int Slot;
+  ADSURF_HD Slot slot(int) const { return 0; }
+  ADSURF_HD static void st(Slot, int, double) {}
+};
 
-// forward keeping E_{m+1} of every layer: slot m holds the row vector that multiplies CA_m.
-template <typename Source, typename Store>
-ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const Store& est) {
+constexpr int kEO = F_REGULAR | F_LTS;          // P evanescent, S oscillatory: c between the S and P velocity
+constexpr int kEE = F_REGULAR;                  // both evanescent: c below both
+constexpr int kOO = F_REGULAR | F_LTP | F_LTS;  // both oscillatory: c above both
+constexpr int kOE = F_REGULAR | F_LTP;
+
+// Bottom-up sweep E <- E . CA_m, m = L-2 .. 0, from the half-space vector; kStore keeps E_{m+1} and the
+// transcendental results of every layer in slot m for the adjoint sweep.
+// Dense kernels (warp-uniform regime flags from the table): consecutive layers in the same regime run in a
+// straight-line loop of their own — no selects, the P and S polynomial chains (each a ~16-deep dependent FP64
+// sequence, 8 cycles per link) interleaved by the scheduler — and the next layer's flags are read one layer
+// ahead, so the branch that closes a run never waits for shared memory.
+template <bool kStore, typename Source, typename Store>
+ADSURF_HD double forward_sweep(const Source& src, const Sample& z, const Store& est) {
   const int L = src.L;
   double e[5];
   half_start(src.par, L, z, e);
-  Layer y;
-  for (int m = L - 2; m >= 0; --m) {
+  auto step = [&](int m, auto tag) {
+    constexpr int kFl = decltype(tag)::value;
+    Layer y;
     src.prep(y, m, z);
-    layer_eig_forward(y, z.omega);
-    const typename Store::Slot q = est.slot(m);
+    if (kFl >= 0) {  // regular regime, |phase| < 1e5: branch-free bodies
+      layer_set_flags(y, kFl);
+      if (kFl & F_LTP) eig_osc(y.P); else eig_evan(y.P);
+      if (kFl & F_LTS) eig_osc(y.S); else eig_evan(y.S);
+      y.P.w = y.P.sn * y.P.ir;
+      y.S.w = y.S.sn * y.S.ir;
+    } else {         // huge phase, NaN, or c exactly on a layer velocity
+      layer_set_flags(y, y.fl);
+      const double wd = z.omega * y.pr[P_D];
+      eig_forward(y.P, wd);
+      eig_forward(y.S, wd);
+    }
+    y.a0 = layer_a0(y.P, y.S);
+    if (kStore) {
+      const typename Store::Slot q = est.slot(m);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
-    Store::st(q, 5, y.P.c0);
-    Store::st(q, 6, y.P.c1);
-    Store::st(q, 7, y.S.c0);
-    Store::st(q, 8, y.S.c1);
+      for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
+      Store::st(q, 5, y.P.c0);
+      Store::st(q, 6, y.P.c1);
+      Store::st(q, 7, y.S.c0);
+      Store::st(q, 8, y.S.c1);
+    }
     row_apply(e, y);
+  };
+  int m = L - 2;
+  if (Source::kUniformFlags && src.small_phases(z)) {
+    int fl = m >= 0 ? src.flags(m) : -2;
+    auto run = [&](auto tag) {
+      constexpr int kFl = decltype(tag)::value;
+      do {
+        const int fln = m > 0 ? src.flags(m - 1) : -2;
+        step(m, tag);
+        --m;
+        fl = fln;
+      } while (kFl >= 0 && fl == kFl);
+    };
+    while (m >= 0) {
+      if (fl == kEO) run(std::integral_constant<int, kEO>{});
+      else if (fl == kEE) run(std::integral_constant<int, kEE>{});
+      else if (fl == kOO) run(std::integral_constant<int, kOO>{});
+      else if (fl == kOE) run(std::integral_constant<int, kOE>{});
+      else run(std::integral_constant<int, -1>{});
+    }
+  } else {
+    for (; m >= 0; --m) step(m, std::integral_constant<int, -1>{});
   }
   return e[0];
+}
+
+template <typename Source>
+ADSURF_HD double sample_forward(const Source& src, const Sample& z) {
+  return forward_sweep<false>(src, z, NoStore{});
+}
+template <typename Source, typename Store>
+ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const Store& est) {
+  return forward_sweep<true>(src, z, est);
 }
 
 // Top-down adjoint sweep.  s_0 = seed * e_0; for every layer m (and finally the half-space, m = L-1)
@@ -843,13 +858,21 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   };
   // One layer; kFl >= 0 states the regime flags as a compile-time constant, which folds every "lt ? a : b" /
   // "pos ? a : b" select of eig_finish / eig_adjoint away.
+  // The gradient of layer m goes to the sink while layer m+1 is being worked on: the sink's exchange and
+  // shared-memory round trips (short-scoreboard latencies in a dependent chain) then overlap FP64 work instead
+  // of stalling the warp at the end of every layer.
+  LayerGrad pend;
+  pend.d = pend.a = pend.b = pend.rho = 0.0;
+  int fl = -2;  // flags of layer m (read one layer ahead)
   auto layer = [&](int m, auto tag, Buf& cur, Buf& nxt) {
     constexpr int kFl = decltype(tag)::value;
+    const int fln = (Source::kUniformFlags && m < L - 2) ? src.flags(m + 1) : -2;
     Layer y;
     y.P.c0 = cur.cv[0]; y.P.c1 = cur.cv[1]; y.S.c0 = cur.cv[2]; y.S.c1 = cur.cv[3];
     src.prep(y, m, z);
     layer_set_flags(y, kFl >= 0 ? kFl : y.fl);
     layer_eig_restore(y, z.omega);
+    sink(m > 0 ? m - 1 : 0, pend.d, pend.a, pend.b, pend.rho);  // layer m-1 (zeros before layer 0)
 #if ADSURF_FETCH_CLAMP
     const int mn = m + 1 <= L - 2 ? m + 1 : m;  // the last layer re-reads its own slot: no predicated loads
     fetch_c(nxt, mn);
@@ -861,20 +884,20 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     if (m + 1 <= L - 2) fetch_e(nxt, m + 1);
 #endif
     gic += g.ic;
-    sink(m, g.d, g.a, g.b, g.rho);
+    pend = g;
+    fl = fln;
   };
   if (L > 1) {
     fetch_c(A, 0);
     fetch_e(A, 0);
+    if (Source::kUniformFlags) fl = src.flags(0);
   }
   // Regime specialisation (dense kernels: the flags are warp-uniform table entries).
-  constexpr int kEO = F_REGULAR | F_LTS, kEE = F_REGULAR;  // (P evanescent, S oscillatory), (both evanescent)
   const int last = L - 2;
   int m = 0;
 #if ADSURF_ADJ_MODE == 0
   // one dispatch per layer
   for (; m <= last; ++m) {
-    const int fl = Source::kUniformFlags ? src.flags(m) : -1;
     if (fl == kEO) layer(m, std::integral_constant<int, kEO>{}, A, A);
     else if (fl == kEE) layer(m, std::integral_constant<int, kEE>{}, A, A);
     else layer(m, std::integral_constant<int, -1>{}, A, A);
@@ -888,12 +911,12 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     do {
       layer(m, tag, A, A);
       ++m;
-    } while (m <= last && src.flags(m) == kFl);
+    } while (fl == kFl);
 #else
-    for (;;) {  // two layers per trip (buffers A -> B -> A); a run of odd length copies B back to A once
+    for (;;) {  // two layers per trip (buffers A -> B -> A)
       layer(m, tag, A, B);
       ++m;
-      if (!(m <= last && src.flags(m) == kFl)) {
+      if (fl != kFl) {
 #if ADSURF_ADJ_MODE == 3
         if (m <= last) {  // odd run length: re-read the next layer's values into A instead of copying B
           fetch_c(A, m);
@@ -906,12 +929,11 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
       }
       layer(m, tag, B, A);
       ++m;
-      if (!(m <= last && src.flags(m) == kFl)) break;
+      if (fl != kFl) break;
     }
 #endif
   };
   while (m <= last) {
-    const int fl = Source::kUniformFlags ? src.flags(m) : -1;
     if (fl == kEO) {
       run(std::integral_constant<int, kEO>{});
     } else if (fl == kEE) {
@@ -922,6 +944,7 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     }
   }
 #endif
+  if (L > 1) sink(last, pend.d, pend.a, pend.b, pend.rho);
   double e[5];
   // half-space: dDelta/dE_hs = D^-1 s~_{L-1}, in the reference's variables
   const Sample zh = src.again(z);
@@ -959,7 +982,19 @@ ADSURF_HD void stage_one(double* __restrict__ par, int L, int m, double dm, doub
   }
 }
 
+// bounds used by TableSource::small_phases: max_m 1/beta_m and max_m d_m over the layers above the half-space
+ADSURF_HD void stage_bounds(double* __restrict__ par, int L, const double* __restrict__ d,
+                            const double* __restrict__ beta) {
+  double smax = 0.0, dmax = 0.0;
+  for (int m = 0; m < L - 1; ++m) {
+    smax = fmax(smax, 1.0 / beta[m]);
+    dmax = fmax(dmax, d[m]);
+  }
+  par[kNumPar * L + 2] = smax;
+  par[kNumPar * L + 3] = dmax;
+}
+
 // doubles of staged constants per model
-ADSURF_HD int par_doubles(int L) { return kNumPar * L + 2; }
+ADSURF_HD int par_doubles(int L) { return kNumPar * L + 4; }
 
 }  // namespace adsurf

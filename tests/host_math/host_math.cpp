@@ -66,6 +66,7 @@ int host_grid(const double* d, const double* alpha, const double* beta, const do
   for (int s = 0; s < S; ++s) {
     for (int m = 0; m < L; ++m)
       stage_one(par.data(), L, m, d[s * L + m], alpha[s * L + m], beta[s * L + m], rho[s * L + m]);
+    stage_bounds(par.data(), L, d + s * L, beta + s * L);
     for (int m = 0; m < L; ++m) gd[s * L + m] = ga[s * L + m] = gb[s * L + m] = grho[s * L + m] = 0.0;
     // dense path: per-(velocity, layer) table + per-period lanes, as the dense kernels do
     std::vector<double> tab((size_t)kTabAdj * (L > 1 ? L - 1 : 1) + 2);
