@@ -164,7 +164,8 @@ __device__ __forceinline__ void fill_table(double* __restrict__ tab, double* __r
 }
 
 // Dense grid, forward only: det / fused max,min over k / sign bitmap.
-__global__ void __launch_bounds__(256) k_grid_fwd(const double* __restrict__ d, const double* __restrict__ alpha,
+template <int kMaxRegs>
+__global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, const double* __restrict__ alpha,
                                                   const double* __restrict__ beta, const double* __restrict__ rho,
                                                   const double* __restrict__ t, const double* __restrict__ c, int L,
                                                   int NF, int K, GridPlan gp, double* __restrict__ det,
@@ -1101,9 +1102,22 @@ static int grid_fwd_launch(const double* d, const double* alpha, const double* b
                            const double* t, const double* c, int S, int L, int NF, int K, double* det, double* pmax,
                            double* pmin, uint32_t* signbits, const GridPlan& gp, cudaStream_t st) {
   const size_t smem = par_bytes(L) + table_bytes(L, gp.tc, false);
-  if (set_smem(k_grid_fwd, smem)) return ADSURF_E_CUDA;
-  k_grid_fwd<<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K, gp,
-                                                                            det, pmax, pmin, signbits);
+  // register cap: 128 leaves the compiler free (it uses ~108: 4 warps per scheduler); ADSURF_GRID_FWD=r96 trades
+  // registers for a fifth warp per scheduler (experiments)
+  static int cap = -1;
+  if (cap < 0) {
+    const char* e = getenv("ADSURF_GRID_FWD");
+    cap = (e && !strcmp(e, "r96")) ? 96 : 128;
+  }
+  if (cap == 96) {
+    if (set_smem(k_grid_fwd<96>, smem)) return ADSURF_E_CUDA;
+    k_grid_fwd<96><<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K,
+                                                                                  gp, det, pmax, pmin, signbits);
+  } else {
+    if (set_smem(k_grid_fwd<128>, smem)) return ADSURF_E_CUDA;
+    k_grid_fwd<128><<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K,
+                                                                                   gp, det, pmax, pmin, signbits);
+  }
   return check_launch();
 }
 

@@ -20,10 +20,13 @@
 
 // experiment switches for the adjoint sweep's layer loop (see sample_adjoint)
 #ifndef ADSURF_ADJ_MODE
-#define ADSURF_ADJ_MODE 3
+#define ADSURF_ADJ_MODE 1
 #endif
 #ifndef ADSURF_FETCH_CLAMP
 #define ADSURF_FETCH_CLAMP 1
+#endif
+#ifndef ADSURF_E_FETCH_SELF
+#define ADSURF_E_FETCH_SELF 0
 #endif
 
 namespace adsurf {
@@ -629,8 +632,9 @@ ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ 
 
 // fill a Layer from a table entry (kN = kTabFwd: the adjoint constants are not there and not read)
 template <int kN>
-ADSURF_HD void layer_from_entry(Layer& y, const double* __restrict__ q, const double* __restrict__ pr, double omega) {
-  const Dbl2 t01 = ld2(q + T_PDA), t23 = ld2(q + T_NA), t45 = ld2(q + T_INA), t67 = ld2(q + T_IR),
+ADSURF_HD void layer_from_entry(Layer& y, const double* __restrict__ q, const double* __restrict__ pr, double omega,
+                                const Dbl2 t01) {
+  const Dbl2 t23 = ld2(q + T_NA), t45 = ld2(q + T_INA), t67 = ld2(q + T_IR),
              t89 = ld2(q + T_AR), tab_ = ld2(q + T_T1), tcd = ld2(q + T_GK), tef = ld2(q + T_FL);
   y.pr = pr;
   y.P.p = omega * t01.x;
@@ -669,9 +673,11 @@ struct DirectSource {
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     alignas(16) double tab[kTabAdj];
     table_entry<kTabAdj>(tab, par, m, z.ic);
-    layer_from_entry<kTabAdj>(y, tab, par + m * kNumPar, z.omega);
+    layer_from_entry<kTabAdj>(y, tab, par + m * kNumPar, z.omega, Dbl2{tab[T_PDA], tab[T_PDB]});
     y.rho = par[m * kNumPar + P_RHO];
   }
+  ADSURF_HD Dbl2 phases(int) const { return Dbl2{0.0, 0.0}; }
+  ADSURF_HD void prep(Layer& y, int m, const Sample& z, const Dbl2&) const { prep(y, m, z); }
 };
 
 template <int kN, bool kRemake = false>
@@ -698,7 +704,13 @@ struct TableSource {
     return z.omega * fmax(z.ic, par[kNumPar * L + 2]) * par[kNumPar * L + 3] < 1.0e5;
   }
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
-    layer_from_entry<kN>(y, tab + m * kN, par + m * kNumPar, z.omega);
+    layer_from_entry<kN>(y, tab + m * kN, par + m * kNumPar, z.omega, ld2(tab + m * kN + T_PDA));
+  }
+  // the phase pair (n d for P and S) of layer m, which the dense sweeps read one layer ahead: it heads the
+  // layer's longest dependent chain (phase -> exp / sincos -> ...)
+  ADSURF_HD Dbl2 phases(int m) const { return ld2(tab + m * kN + T_PDA); }
+  ADSURF_HD void prep(Layer& y, int m, const Sample& z, const Dbl2& ph) const {
+    layer_from_entry<kN>(y, tab + m * kN, par + m * kNumPar, z.omega, ph);
   }
 };
 
@@ -760,10 +772,11 @@ ADSURF_HD double forward_sweep(const Source& src, const Sample& z, const Store& 
   const int L = src.L;
   double e[5];
   half_start(src.par, L, z, e);
+  Dbl2 ph{0.0, 0.0};  // phase pair of layer m (dense sweeps: read one layer ahead)
   auto step = [&](int m, auto tag) {
     constexpr int kFl = decltype(tag)::value;
     Layer y;
-    src.prep(y, m, z);
+    if (Source::kUniformFlags) src.prep(y, m, z, ph); else src.prep(y, m, z);
     if (kFl >= 0) {  // regular regime, |phase| < 1e5: branch-free bodies
       layer_set_flags(y, kFl);
       if (kFl & F_LTP) eig_osc(y.P); else eig_evan(y.P);
@@ -791,13 +804,17 @@ ADSURF_HD double forward_sweep(const Source& src, const Sample& z, const Store& 
   int m = L - 2;
   if (Source::kUniformFlags && src.small_phases(z)) {
     int fl = m >= 0 ? src.flags(m) : -2;
+    if (m >= 0) ph = src.phases(m);
     auto run = [&](auto tag) {
       constexpr int kFl = decltype(tag)::value;
       do {
-        const int fln = m > 0 ? src.flags(m - 1) : -2;
+        const int mp = m > 0 ? m - 1 : 0;
+        const int fln = m > 0 ? src.flags(mp) : -2;
+        const Dbl2 phn = src.phases(mp);
         step(m, tag);
         --m;
         fl = fln;
+        ph = phn;
       } while (kFl >= 0 && fl == kFl);
     };
     while (m >= 0) {
@@ -808,7 +825,10 @@ ADSURF_HD double forward_sweep(const Source& src, const Sample& z, const Store& 
       else run(std::integral_constant<int, -1>{});
     }
   } else {
-    for (; m >= 0; --m) step(m, std::integral_constant<int, -1>{});
+    for (; m >= 0; --m) {
+      ph = src.phases(m);
+      step(m, std::integral_constant<int, -1>{});
+    }
   }
   return e[0];
 }
@@ -867,6 +887,9 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   auto layer = [&](int m, auto tag, Buf& cur, Buf& nxt) {
     constexpr int kFl = decltype(tag)::value;
     const int fln = (Source::kUniformFlags && m < L - 2) ? src.flags(m + 1) : -2;
+#if ADSURF_E_FETCH_SELF
+    fetch_e(cur, m);  // needed after the restore, the column-side contractions and the deferred sink
+#endif
     Layer y;
     y.P.c0 = cur.cv[0]; y.P.c1 = cur.cv[1]; y.S.c0 = cur.cv[2]; y.S.c1 = cur.cv[3];
     src.prep(y, m, z);
@@ -877,7 +900,9 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     const int mn = m + 1 <= L - 2 ? m + 1 : m;  // the last layer re-reads its own slot: no predicated loads
     fetch_c(nxt, mn);
     const LayerGrad g = layer_adjoint<Source::kWantIc>(y, cur.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
+#if !ADSURF_E_FETCH_SELF
     fetch_e(nxt, mn);
+#endif
 #else
     if (m + 1 <= L - 2) fetch_c(nxt, m + 1);
     const LayerGrad g = layer_adjoint<Source::kWantIc>(y, cur.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
@@ -889,7 +914,9 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   };
   if (L > 1) {
     fetch_c(A, 0);
+#if !ADSURF_E_FETCH_SELF
     fetch_e(A, 0);
+#endif
     if (Source::kUniformFlags) fl = src.flags(0);
   }
   // Regime specialisation (dense kernels: the flags are warp-uniform table entries).
@@ -920,7 +947,9 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
 #if ADSURF_ADJ_MODE == 3
         if (m <= last) {  // odd run length: re-read the next layer's values into A instead of copying B
           fetch_c(A, m);
+#if !ADSURF_E_FETCH_SELF
           fetch_e(A, m);
+#endif
         }
 #else
         A = B;
