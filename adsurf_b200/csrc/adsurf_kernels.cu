@@ -363,9 +363,8 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
 
 // The same fused sweep with a free warp <-> work assignment: a block = (model, velocity chunk); per table fill
 // (tc trial velocities) its warps share the tc x nft (velocity, period tile) tasks round-robin, so the block size
-// is not tied to the number of period tiles of a model.  That allows 2 blocks x 7 warps per SM at 144 registers
-// (14 resident warps instead of 3 x 4 = 12 at 168): more latency hiding per scheduler for the long dependent FP64
-// chains, and one table fill serves 7 warps.  omega and 1/omega per period are staged once per block.
+// is not tied to the number of period tiles of a model (ADSURF_GRID_BWD=f8: 2 blocks x 8 warps per SM at 128
+// registers, one table fill serves 8 warps).  omega and 1/omega per period are staged once per block.
 template <int kThreads, int kMaxRegs>
 __global__ void __maxnreg__(kMaxRegs)
 k_grid_bwd_flex(const double* __restrict__ d, const double* __restrict__ alpha, const double* __restrict__ beta,
@@ -807,35 +806,30 @@ inline size_t adj_smem(int L, int wpb) {
          (size_t)wpb * est_bytes_per_warp(L);
 }
 
-// Where the dense adjoint keeps its per-layer row vectors: 0 = shared memory (2 blocks of 4 warps per
-// SM at 20 layers), 1 / 2 = L2-resident global slab with 3 / 4 blocks of 4 warps per SM.
-// Overridable for experiments with ADSURF_GRID_BWD=smem|g3|g4 (read once).
-enum { kBwdSmem = 0, kBwdG3 = 1, kBwdG4 = 2, kBwdH6 = 3, kBwdH7 = 4, kBwdH8 = 5, kBwdF7 = 6, kBwdF5 = 7, kBwdF4 = 8, kBwdF8 = 9 };
+// Where the dense adjoint keeps its per-layer row vectors and how many warps it runs.
+// Overridable for experiments with ADSURF_GRID_BWD (read once):
+//   g3   (default) slabs in the L2-resident global slab, 3 blocks x 4 warps per SM at <= 168 registers.  The
+//        register file is split per scheduler (16384 registers each), so residency goes in steps of one warp
+//        per scheduler: 3 warps up to 170 registers per thread, 4 only at <= 128 — variants with 14 or 15 warps
+//        per SM (2 x 7 at 144, 3 x 5 at 136) do not become resident and were measured 25 % slower;
+//   f8   free warp <-> task assignment, 2 blocks x 8 warps at 128 registers (4 warps per scheduler; the tighter
+//        register budget costs about what the extra warp brings: 2.31 G vs 2.35 G samples/s when measured);
+//   smem slabs in shared memory (2 blocks x 4 warps at 20 layers).
+enum { kBwdSmem = 0, kBwdG3 = 1, kBwdF8 = 2 };
 inline int bwd_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("ADSURF_GRID_BWD");
     mode = kBwdG3;
-    if (e && !strcmp(e, "g3")) mode = kBwdG3;
-    if (e && !strcmp(e, "g4")) mode = kBwdG4;
     if (e && !strcmp(e, "smem")) mode = kBwdSmem;
-    if (e && !strcmp(e, "h6")) mode = kBwdH6;
-    if (e && !strcmp(e, "h7")) mode = kBwdH7;
-    if (e && !strcmp(e, "h8")) mode = kBwdH8;
-    if (e && !strcmp(e, "f7")) mode = kBwdF7;
-    if (e && !strcmp(e, "f5")) mode = kBwdF5;
-    if (e && !strcmp(e, "f4")) mode = kBwdF4;
     if (e && !strcmp(e, "f8")) mode = kBwdF8;
   }
   return mode;
 }
-inline int bwd_flex_warps() {  // warps per block of the free-assignment kernel, 0 = period-tile kernel
-  const int m = bwd_mode();
-  return m == kBwdF7 ? 7 : (m == kBwdF5 ? 5 : (m == kBwdF4 ? 4 : (m == kBwdF8 ? 8 : 0)));
-}
+inline int bwd_flex_warps() { return bwd_mode() == kBwdF8 ? 8 : 0; }  // 0 = period-tile kernel
 constexpr int kMaxResidentWarps = 160 * 16;  // upper bound on co-resident adjoint warps (global store slabs)
 
-inline int bwd_wpb_global() { return bwd_flex_warps() ? bwd_flex_warps() : (bwd_mode() >= kBwdH6 ? 2 : 4); }
+inline int bwd_wpb_global() { return bwd_flex_warps() ? bwd_flex_warps() : 4; }
 
 inline size_t bwd_estore_bytes(int L) {
   return bwd_mode() == kBwdSmem ? 0 : (size_t)kMaxResidentWarps * est_bytes_per_warp(L);
@@ -1186,13 +1180,6 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
                                                 det, (double*)ws, estore);                                       \
   } while (0)
   if (mode == kBwdG3) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 128, 168>));        // 3 x 4 = 12 warps / SM
-  else if (mode == kBwdG4) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 128, 128>));   // 16 warps / SM
-  else if (mode == kBwdH6) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 64, 168>));    // 6 x 2 = 12
-  else if (mode == kBwdH7) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 64, 144>));    // 7 x 2 = 14
-  else if (mode == kBwdH8) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 64, 152>));    // 6 x 2 = 12 (fewer regs)
-  else if (mode == kBwdF7) ADSURF_LAUNCH_BWD((k_grid_bwd_flex<224, 144>));    // 2 x 7 = 14
-  else if (mode == kBwdF5) ADSURF_LAUNCH_BWD((k_grid_bwd_flex<160, 136>));    // 3 x 5 = 15
-  else if (mode == kBwdF4) ADSURF_LAUNCH_BWD((k_grid_bwd_flex<128, 168>));    // 3 x 4 = 12 (control)
   else if (mode == kBwdF8) ADSURF_LAUNCH_BWD((k_grid_bwd_flex<256, 128>));    // 2 x 8 = 16
   else ADSURF_LAUNCH_BWD((k_grid_bwd<false, 128, 232>));
 #undef ADSURF_LAUNCH_BWD

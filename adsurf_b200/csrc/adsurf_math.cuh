@@ -402,7 +402,7 @@ struct LayerGrad {
 // t = r dDelta/dr = x bx - w bw + p bp   (w = sn/r, x = -+ r sn, p = omega r d)
 ADSURF_HD double eig_adjoint(const Eig& e, double bcs, double bw, double bx, double bex, double& bp) {
   const double bsn = bw * e.ir + (e.lt ? -e.r : e.r) * bx;
-  bp = e.dcs * bcs + e.dsn * bsn + (e.lt ? 0.0 : bex);
+  bp = fma(e.dsn, bsn, e.lt ? e.dcs * bcs : fma(e.dcs, bcs, bex));  // two FMAs when bex takes part
   return e.x * bx - e.w * bw + e.p * bp;
 }
 
@@ -791,16 +791,25 @@ ADSURF_HD double forward_sweep(const Source& src, const Sample& z, const Store& 
     }
     y.a0 = layer_a0(y.P, y.S);
     if (kStore) {
+      // the second value (cos) exists only for an oscillatory term; the adjoint sweep loads it on the same rule
       const typename Store::Slot q = est.slot(m);
-#pragma unroll
-      for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
       Store::st(q, 5, y.P.c0);
-      Store::st(q, 6, y.P.c1);
+      if (kFl >= 0 ? (kFl & F_LTP) != 0 : y.P.lt) Store::st(q, 6, y.P.c1);
       Store::st(q, 7, y.S.c0);
-      Store::st(q, 8, y.S.c1);
+      if (kFl >= 0 ? (kFl & F_LTS) != 0 : y.S.lt) Store::st(q, 8, y.S.c1);
     }
     row_apply(e, y);
+    if (kStore && m > 0) {  // E_m multiplies CA_{m-1}: stored right after it is formed, a whole layer before
+      const typename Store::Slot q = est.slot(m - 1);  // its registers are overwritten (no store/overwrite hazard)
+#pragma unroll
+      for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
+    }
   };
+  if (kStore && L >= 2) {
+    const typename Store::Slot q = est.slot(L - 2);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
+  }
   int m = L - 2;
   if (Source::kUniformFlags && src.small_phases(z)) {
     int fl = m >= 0 ? src.flags(m) : -2;
@@ -865,11 +874,13 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   struct Buf {
     double e[5], cv[4];
   };
-  Buf A, B;
-  auto fetch_c = [&](Buf& b, int m) {
+  Buf A{}, B{};
+  auto fetch_c = [&](Buf& b, int m, int flm) {  // flm: regime flags of layer m (-1: unknown, read everything)
     const typename Store::Slot q = est.slot(m);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) b.cv[i] = Store::ld(q, 5 + i);
+    b.cv[0] = Store::ld(q, 5);
+    if (flm & F_LTP) b.cv[1] = Store::ld(q, 6);
+    b.cv[2] = Store::ld(q, 7);
+    if (flm & F_LTS) b.cv[3] = Store::ld(q, 8);
   };
   auto fetch_e = [&](Buf& b, int m) {
     const typename Store::Slot q = est.slot(m);
@@ -883,10 +894,10 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   // of stalling the warp at the end of every layer.
   LayerGrad pend;
   pend.d = pend.a = pend.b = pend.rho = 0.0;
-  int fl = -2;  // flags of layer m (read one layer ahead)
+  int fl = -1;  // flags of layer m (read one layer ahead; -1: pointwise sources, generic path)
   auto layer = [&](int m, auto tag, Buf& cur, Buf& nxt) {
     constexpr int kFl = decltype(tag)::value;
-    const int fln = (Source::kUniformFlags && m < L - 2) ? src.flags(m + 1) : -2;
+    const int fln = Source::kUniformFlags ? (m < L - 2 ? src.flags(m + 1) : 0) : -1;  // 0: no layer
 #if ADSURF_E_FETCH_SELF
     fetch_e(cur, m);  // needed after the restore, the column-side contractions and the deferred sink
 #endif
@@ -898,13 +909,13 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     sink(m > 0 ? m - 1 : 0, pend.d, pend.a, pend.b, pend.rho);  // layer m-1 (zeros before layer 0)
 #if ADSURF_FETCH_CLAMP
     const int mn = m + 1 <= L - 2 ? m + 1 : m;  // the last layer re-reads its own slot: no predicated loads
-    fetch_c(nxt, mn);
+    fetch_c(nxt, mn, fln);
     const LayerGrad g = layer_adjoint<Source::kWantIc>(y, cur.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
 #if !ADSURF_E_FETCH_SELF
     fetch_e(nxt, mn);
 #endif
 #else
-    if (m + 1 <= L - 2) fetch_c(nxt, m + 1);
+    if (m + 1 <= L - 2) fetch_c(nxt, m + 1, fln);
     const LayerGrad g = layer_adjoint<Source::kWantIc>(y, cur.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
     if (m + 1 <= L - 2) fetch_e(nxt, m + 1);
 #endif
@@ -913,11 +924,11 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     fl = fln;
   };
   if (L > 1) {
-    fetch_c(A, 0);
+    if (Source::kUniformFlags) fl = src.flags(0);
+    fetch_c(A, 0, fl);
 #if !ADSURF_E_FETCH_SELF
     fetch_e(A, 0);
 #endif
-    if (Source::kUniformFlags) fl = src.flags(0);
   }
   // Regime specialisation (dense kernels: the flags are warp-uniform table entries).
   const int last = L - 2;
@@ -946,7 +957,7 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
       if (fl != kFl) {
 #if ADSURF_ADJ_MODE == 3
         if (m <= last) {  // odd run length: re-read the next layer's values into A instead of copying B
-          fetch_c(A, m);
+          fetch_c(A, m, fl);
 #if !ADSURF_E_FETCH_SELF
           fetch_e(A, m);
 #endif
