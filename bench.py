@@ -327,10 +327,10 @@ def main():
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
-                         # DRAM bytes per launch of the dominant kernel, scaled from the ncu capture in
-                         # profiles/r1_dram_traffic.csv (554 MB for 67 108 864 samples = 8.26 B/sample: the det
-                         # output; the slabs stay in the persisting L2 carve-out)
-                         "traffic": 8.26 * n_samples, "traffic_source": "profiles/r1_dram_traffic.csv",
+                         # DRAM bytes per launch of the dominant kernel, scaled from the ncu --set full capture
+                         # in profiles/r1_ncu_full_final.txt (9.4 MB read + 536.0 MB written for 67 108 864
+                         # samples = 8.13 B/sample: the det output; the slabs stay in the persisting L2 carve-out)
+                         "traffic": 8.13 * n_samples, "traffic_source": "profiles/r1_ncu_full_final.txt",
                          "peak_source": "measured in-process: register-resident DFMA loop (adsurf_fp64_peak_probe), burst",
                          "peak_after_sweep": peak_tf_after, "peak_nominal": nominal,
                          "frac_of_nominal": achieved_tf / nominal,
