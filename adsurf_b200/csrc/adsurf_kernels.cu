@@ -186,6 +186,7 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
   const bool active = live && f < NF;
   const int fc = active ? f : NF - 1;
   const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
+  const double iw0 = 1.0 / fmax(omega0, 1.0e-4);
   const int k0 = bc.ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
   double vmax = -INFINITY, vmin = INFINITY;
   bool anynan = false;
@@ -198,7 +199,7 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
     if (!live) continue;
     for (int cc = 0; cc < n; ++cc) {
       const int k = kb + cc;
-      const Sample z = make_sample(omega0, ics[cc]);
+      const Sample z = make_sample_dense(omega0, ics[cc], iw0);
       const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab};
       const double v = sample_forward(src, z);
       if (det && active) det[((size_t)s * K + k) * NF + f] = v;
@@ -313,6 +314,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
     const bool active = live && f < NF;
     const int fc = active ? f : NF - 1;
     const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
+    const double iw0 = 1.0 / fmax(omega0, 1.0e-4);
     const int k0 = bc.ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
     for (int kb = k0; kb < k1; kb += gp.tc) {
       const int n = min(gp.tc, k1 - kb);
@@ -322,7 +324,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
       if (!live) continue;
       for (int cc = 0; cc < n; ++cc) {
         const int k = kb + cc;
-        const Sample z = make_sample(omega0, ics[cc]);
+        const Sample z = make_sample_dense(omega0, ics[cc], iw0);
         const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab};
         const size_t idx = ((size_t)s * K + k) * NF + fc;
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
@@ -406,7 +408,7 @@ k_grid_bwd_flex(const double* __restrict__ d, const double* __restrict__ alpha, 
         const int f = tile * kWarp + lane;
         const bool active = f < NF;
         const Dbl2 om = ld2(omg + 2 * f);
-        const Sample z = make_sample(om.x, ics[cc], om.y);
+        const Sample z = make_sample_dense(om.x, ics[cc], om.y);
         const TableSource<kTab, true> src{par, L, tab + (size_t)cc * (L - 1) * kTab, omg + 2 * f, ics + cc};
         const size_t idx = ((size_t)s * K + (kb + cc)) * NF + (active ? f : NF - 1);
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed

@@ -576,6 +576,13 @@ ADSURF_HD Sample make_sample(double omega0, double ic, double iw) {
 }
 ADSURF_HD Sample make_sample(double omega0, double ic) { return make_sample(omega0, ic, 1.0 / fmax(omega0, 1.0e-4)); }
 
+// Dense kernels: the shared (velocity, layer) table is built for k/omega = 1/c, so a period beyond 2 pi 1e4 s
+// (where the reference clamps omega but not k, making k/omega period-dependent) is evaluated with the clamp
+// applied to both, i.e. at the clamped period.  The pointwise kernels follow the reference exactly.
+ADSURF_HD Sample make_sample_dense(double omega0, double ic, double iw) {
+  return make_sample(fmax(omega0, 1.0e-4), ic, iw);
+}
+
 // ---- layer sources: fill the frequency-free coefficient scalars, the phases and the regime of layer m.
 // Everything that depends on (trial velocity, layer) but not on the period is one table entry:
 //   n = sqrt(|1/c^2 - 1/v^2|), 1/n, n d (phase per unit omega) for P and S; the coefficient scalars
@@ -596,12 +603,26 @@ struct alignas(16) Dbl2 {
 ADSURF_HD Dbl2 ld2(const double* p) { return *reinterpret_cast<const Dbl2*>(p); }
 
 // one table entry: trial slowness ic = 1/c against layer m of the staged model
-template <int kN>
+// kFast (pointwise kernels: one entry per sample and layer): n and 1/n from the rsqrt sequence and the
+// alpha/beta chain constants as +-(1/n)^2 / v^3 — no square root and no division; otherwise (dense kernels: one
+// entry per (velocity, layer) and block) correctly rounded sqrt and divisions.
+template <int kN, bool kFast = false>
 ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ par, int m, double ic) {
   const double* __restrict__ pr = par + m * kNumPar;
   const double sa = pr[P_IA], sb = pr[P_IB], dm = pr[P_D], rho = pr[P_RHO], ir = pr[P_IR], gk = pr[P_TB2];
   const double da = (ic + sa) * fabs(ic - sa), db = (ic + sb) * fabs(ic - sb);
-  const double na = sqrt(da), nb = sqrt(db);
+  double na, nb, ina, inb;
+  if (kFast) {
+    ina = rsqrt_hd(da);
+    inb = rsqrt_hd(db);
+    na = da > 0.0 ? da * ina : da;  // 0 -> 0, NaN -> NaN
+    nb = db > 0.0 ? db * inb : db;
+  } else {
+    na = sqrt(da);
+    nb = sqrt(db);
+    ina = 1.0 / na;
+    inb = 1.0 / nb;
+  }
   const double ic2 = ic * ic;
   const double gam = gk * ic2;
   const double g1 = gam - 1.0;
@@ -609,8 +630,8 @@ ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ 
   tab[T_PDB] = nb * dm;
   tab[T_NA] = na;
   tab[T_NB] = nb;
-  tab[T_INA] = 1.0 / na;
-  tab[T_INB] = 1.0 / nb;
+  tab[T_INA] = ina;
+  tab[T_INB] = inb;
   tab[T_IR] = ir;
   tab[T_TG] = -2.0 * gam;
   tab[T_AR] = gam * gk * rho;
@@ -621,9 +642,9 @@ ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ 
   tab[T_G1] = g1;
   const int fl = (ic < sa ? F_LTP : 0) | (da > 0.0 ? F_POSP : 0) | (ic < sb ? F_LTS : 0) | (db > 0.0 ? F_POSS : 0);
   tab[T_FL] = bits_dbl((long long)fl);  // raw bits, read back with dbl_bits()
-  tab[T_TQA] = pr[P_IA3] / ((ic + sa) * (ic - sa));
+  tab[T_TQA] = kFast ? (ic < sa ? -pr[P_IA3] : pr[P_IA3]) * (ina * ina) : pr[P_IA3] / ((ic + sa) * (ic - sa));
   if (kN > kTabFwd) {
-    tab[T_TQB] = pr[P_IB3] / ((ic + sb) * (ic - sb));
+    tab[T_TQB] = kFast ? (ic < sb ? -pr[P_IB3] : pr[P_IB3]) * (inb * inb) : pr[P_IB3] / ((ic + sb) * (ic - sb));
     tab[T_CB] = pr[P_CB];
     tab[T_C1] = 2.0 * gam * rho;
     tab[T_C3] = 2.0 * g1 * ic2 * rho;
@@ -672,7 +693,7 @@ struct DirectSource {
   ADSURF_HD Sample again(const Sample& z) const { return z; }
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     alignas(16) double tab[kTabAdj];
-    table_entry<kTabAdj>(tab, par, m, z.ic);
+    table_entry<kTabAdj, true>(tab, par, m, z.ic);
     layer_from_entry<kTabAdj>(y, tab, par + m * kNumPar, z.omega, Dbl2{tab[T_PDA], tab[T_PDB]});
     y.rho = par[m * kNumPar + P_RHO];
   }

@@ -82,7 +82,8 @@ int host_grid(const double* d, const double* alpha, const double* beta, const do
       const TableSource<kTabFwd> srcf{par.data(), L, tf};
       for (int f = 0; f < NF; ++f) {
         const size_t idx = ((size_t)s * K + k) * NF + f;
-        const Sample z = make_sample(omega_of_period(t[s * NF + f]), ic);
+        const double om0 = omega_of_period(t[s * NF + f]);
+        const Sample z = make_sample_dense(om0, ic, 1.0 / fmax(om0, 1.0e-4));
         det[idx] = sample_forward_store(src, z, PlainStore<1>{est.data()});
         const double v2 = sample_forward(srcf, z);
         if (det[idx] != v2 && !(det[idx] != det[idx] && v2 != v2)) return -1;

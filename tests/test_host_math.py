@@ -172,3 +172,22 @@ def test_random_models_against_oracle(hm, seed):
     for i, (new, ref, key) in enumerate(zip((gd, ga, gb, gr), go[:4], ("gd", "ga", "gb", "grho"))):
         assert_grad_close(new, ref.numpy(), rtol=tol[i], what="points " + key)
     assert_grad_close(gc.reshape(K, NF).T, go[4].numpy().reshape(K, NF).T, rtol=tol[4], what="gc")
+
+
+def test_pointwise_period_beyond_omega_clamp(hm):
+    """periods beyond 2 pi 1e4 s: the reference clamps omega to 1e-4 but not k (_surf96_vectorAll_gpu.py:319,326),
+    so k/omega depends on the period; the pointwise path follows that exactly (value and gradients)."""
+    import torch
+    from oracle import dltar_oracle as O
+    g = load("points_m6")
+    d, a, b, rho = (C(g[k][:1]) for k in ("d", "a", "b", "rho"))
+    t = C(np.array([[1.0, 5.0e4, 7.0e4, 2.0e5, 1.0e6, 3.0]]))
+    c = C(np.array([[2.9, 3.1, 2.95, 3.3, 3.05, 3.2]]))
+    gF = C(np.array([[1.0, -2.0, 0.5, 1.5, -1.0, 2.0]]))
+    td, ta, tb, tr, tc = (torch.tensor(x, requires_grad=True) for x in (d, a, b, rho, c))
+    Fo = O.det_points(tc, torch.tensor(t), td, ta, tb, tr)
+    go = torch.autograd.grad(Fo, (td, ta, tb, tr, tc), grad_outputs=torch.tensor(gF))
+    F, gd, ga, gb, gr, gc, _ = run_points(hm, {"d": d, "a": a, "b": b, "rho": rho, "t": t, "c": c, "gF": gF})
+    np.testing.assert_allclose(F, Fo.detach().numpy(), rtol=1e-9)
+    for new, ref, key in zip((gd, ga, gb, gr, gc), go, ("gd", "ga", "gb", "grho", "gc")):
+        assert_grad_close(new, ref.numpy(), what=key)
