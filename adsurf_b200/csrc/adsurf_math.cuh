@@ -28,6 +28,9 @@
 #ifndef ADSURF_E_FETCH_SELF
 #define ADSURF_E_FETCH_SELF 0
 #endif
+#ifndef ADSURF_SINK_DEFER
+#define ADSURF_SINK_DEFER 1
+#endif
 
 namespace adsurf {
 
@@ -927,7 +930,9 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     src.prep(y, m, z);
     layer_set_flags(y, kFl >= 0 ? kFl : y.fl);
     layer_eig_restore(y, z.omega);
+#if ADSURF_SINK_DEFER
     sink(m > 0 ? m - 1 : 0, pend.d, pend.a, pend.b, pend.rho);  // layer m-1 (zeros before layer 0)
+#endif
 #if ADSURF_FETCH_CLAMP
     const int mn = m + 1 <= L - 2 ? m + 1 : m;  // the last layer re-reads its own slot: no predicated loads
     fetch_c(nxt, mn, fln);
@@ -941,7 +946,11 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     if (m + 1 <= L - 2) fetch_e(nxt, m + 1);
 #endif
     gic += g.ic;
+#if ADSURF_SINK_DEFER
     pend = g;
+#else
+    sink(m, g.d, g.a, g.b, g.rho);
+#endif
     fl = fln;
   };
   if (L > 1) {
@@ -1005,7 +1014,9 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     }
   }
 #endif
+#if ADSURF_SINK_DEFER
   if (L > 1) sink(last, pend.d, pend.a, pend.b, pend.rho);
+#endif
   double e[5];
   // half-space: dDelta/dE_hs = D^-1 s~_{L-1}, in the reference's variables
   const Sample zh = src.again(z);
