@@ -1,3 +1,8 @@
+#!/bin/bash
+# Round artefacts in one GPU call (run from the repo root on the GPU box, e.g. through gpurun):
+# GPU tests, smoke, the full N=1 bench, the reference arm, the per-launch list of the bench command (ncu, only after
+# the same command exited 0 without it) and the end-to-end iteration rates of BASELINE configs 2-4.
+# Outputs go to gpurun_out/; copy what should be judged into profiles/.
 set -x
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo smoke rc=$? >> gpurun_out/smoke.log
