@@ -285,6 +285,27 @@ def test_nan_and_error_codes(ab):
     assert F.shape == (1, c.shape[1])
 
 
+def test_periods_beyond_the_omega_clamp(ab):
+    """omega is clamped at 1e-4 (periods beyond 2 pi 1e4 s).  The pointwise kernels follow the reference (k keeps the
+    unclamped omega); the dense kernels evaluate at the clamped period, consistently in value and gradient."""
+    from adsurf_b200 import _capi
+    from oracle import dltar_oracle as O
+    g = load("points_m6")
+    d, a, b, rho = (g[k][:1] for k in ("d", "a", "b", "rho"))
+    t = np.array([[1.0, 5.0e4, 7.0e4, 2.0e5, 1.0e6, 3.0]])
+    c = np.array([[2.9, 3.1, 2.95, 3.3, 3.05, 3.2]])
+    F = _capi.points_fwd(G(d), G(a), G(b), G(rho), G(t), G(c))
+    Fo = O.det_points(torch.tensor(c), torch.tensor(t), *(torch.tensor(x) for x in (d, a, b, rho)))
+    np.testing.assert_allclose(N(F), Fo.numpy(), rtol=1e-9)
+    tc = np.minimum(t, 2.0 * np.pi / 1.0e-4)
+    out_long = _capi.grid_bwd(G(d), G(a), G(b), G(rho), G(t), G(c), None, want_det=True)
+    out_clamped = _capi.grid_bwd(G(d), G(a), G(b), G(rho), G(tc), G(c), None, want_det=True)
+    for x, y in zip(out_long, out_clamped):
+        np.testing.assert_allclose(N(x), N(y), rtol=1e-12, atol=0)
+    det_o = O.det_grid(torch.tensor(c), torch.tensor(tc), *(torch.tensor(x) for x in (d, a, b, rho)))
+    assert_det_close(N(out_clamped[0]), det_o.numpy(), axis=1)
+
+
 def test_device_elementary_functions(ab):
     """inline rsqrt / exp(-x) / sincos of the kernels (device code paths) against libm: <= 2 ulp"""
     from adsurf_b200 import _capi
