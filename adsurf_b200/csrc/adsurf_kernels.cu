@@ -10,19 +10,24 @@
 //     velocity, so det[s,k,f] is written coalesced and the three-way branch "c <,==,> layer velocity" is
 //     warp-uniform (it does not depend on the period);
 //   * a block = (model, velocity chunk, group of <= 4 period tiles).  Per-model layer records (1/alpha, 1/beta,
-//     2 beta^2, rho, 1/rho, d, ...) are staged once per block in shared memory; everything that depends on
-//     (velocity, layer) but not on the period — sqrt(|1/c^2 - 1/v^2|), its reciprocal, the phase per unit omega,
-//     gam, gam-1, (gam-1)^2 rho, the regime flags — is computed once per 8 velocities into a shared table and
-//     read by every lane as 16-byte broadcasts (TableSource);
+//     2 beta^2, rho, 1/rho, d, ...) are staged once per block in shared memory.  The layers are swept in
+//     frequency-free variables (CA(omega) = D^-1 CA~ D, D = diag(1, w, 1, w, w^2)): everything about a layer
+//     except its two phases depends on (velocity, layer) only — sqrt(|1/c^2 - 1/v^2|), its reciprocal, the
+//     phase per unit omega, the eight coefficient scalars, the regime flags, the adjoint's chain constants —
+//     and is computed once per 8 velocities into a shared table read by every lane as 16-byte broadcasts
+//     (TableSource); a lane spends two multiplies on a layer's set-up;
 //   * the 5-component compound state lives in registers; the 5x5 Dunkin matrix is never formed: the layer
 //     product uses its rank structure (two rank-one couplings around the Kronecker product of the P and S
 //     blocks), 33 FMAs per product; elementary functions are inline (table-driven exp, Cody-Waite sincos);
 //   * the adjoint is a hand-derived reverse sweep: pass 1 (bottom-up) stores, per layer, the row vector
-//     E_{m+1} and the transcendental results (9 doubles per thread) in a per-resident-warp slab of global
+//     E_{m+1} and the transcendental results (up to 9 doubles per thread) in a per-resident-warp slab of global
 //     memory that stays in the persisting part of L2; pass 2 (top-down) carries the column vector
-//     s_m = CA_{m-1}...CA_0 e_0, reloads the stored values right after their last use, and contracts
-//     dDelta = E_{m+1} . dCA_m . s_m analytically into (d, alpha, beta, rho, c) — no transcendental is
-//     evaluated twice; the kernel is persistent (3 blocks x 4 warps per SM, register-bound);
+//     s_m = CA_{m-1}...CA_0 e_0, reloads the stored values one layer ahead, and contracts
+//     dDelta = E_{m+1} . dCA_m . s_m analytically into (d, alpha, beta, rho) while advancing s in the same
+//     expressions — no transcendental is evaluated twice; the kernel is persistent (3 blocks x 4 warps per SM:
+//     the register file allows 3 warps per scheduler up to 170 registers).  In both passes consecutive layers of
+//     one regime run in a straight-line loop, with the values that head a dependent chain (regime flags, phases,
+//     stored transcendentals) read one layer ahead and the gradient sink deferred by one layer;
 //   * per-model gradient sums: one warp fold + per-lane shared accumulators -> one partial per block ->
 //     deterministic second-stage reduce (no atomics);
 //   * the dense forward pass fuses max/min over the trial velocities (what the DMF needs) and an optional
