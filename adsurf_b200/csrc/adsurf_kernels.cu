@@ -181,6 +181,7 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
   constexpr int kTab = kTabFwd;
   double* tab = par + par_doubles(L);                   // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
+  double* hks = ics + ((gp.tc + 1) & ~1);               // [wpb*32][2]: omega/alpha_hs, omega/beta_hs per lane
   const BlockCoord bc = block_coord(blockIdx.x, gp);
   const int s = bc.s;
   stage_params(par, d, alpha, beta, rho, s, L);
@@ -192,6 +193,9 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
   const int fc = active ? f : NF - 1;
   const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
   const double iw0 = 1.0 / fmax(omega0, 1.0e-4);
+  double* hk = hks + 2 * threadIdx.x;
+  __syncthreads();  // staged parameters visible
+  stage_half_k(hk, par, L, omega0);
   const int k0 = bc.ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
   double vmax = -INFINITY, vmin = INFINITY;
   bool anynan = false;
@@ -205,7 +209,7 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
     for (int cc = 0; cc < n; ++cc) {
       const int k = kb + cc;
       const Sample z = make_sample_dense(omega0, ics[cc], iw0);
-      const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab};
+      const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab, nullptr, nullptr, hk};
       const double v = sample_forward(src, z);
       if (det && active) det[((size_t)s * K + k) * NF + f] = v;
       vmax = fmax(vmax, v);
@@ -300,7 +304,8 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
   double* accs = par + par_doubles(L);                  // [wpb][L][4][16] (global slabs) or [wpb][4][L]
   double* tab = accs + (size_t)gp.wpb * kAccPer * L;    // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
-  double* ests = ics + ((gp.tc + 1) & ~1);              // [wpb][L-1][kSlot][32] (shared variant only)
+  double* hks = ics + ((gp.tc + 1) & ~1);               // [wpb*32][2]: omega/alpha_hs, omega/beta_hs per lane
+  double* ests = hks + 2 * kThreads;                    // [wpb][L-1][kSlot][32] (shared variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
   const unsigned long long slab_policy = kGlobal ? l2_evict_last_policy() : 0ull;
@@ -320,6 +325,9 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
     const int fc = active ? f : NF - 1;
     const double omega0 = omega_of_period(t[(size_t)s * NF + fc]);
     const double iw0 = 1.0 / fmax(omega0, 1.0e-4);
+    double* hk = hks + 2 * threadIdx.x;
+    __syncthreads();  // staged parameters visible
+    stage_half_k(hk, par, L, omega0);
     const int k0 = bc.ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
     for (int kb = k0; kb < k1; kb += gp.tc) {
       const int n = min(gp.tc, k1 - kb);
@@ -330,7 +338,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
       for (int cc = 0; cc < n; ++cc) {
         const int k = kb + cc;
         const Sample z = make_sample_dense(omega0, ics[cc], iw0);
-        const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab};
+        const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab, nullptr, nullptr, hk};
         const size_t idx = ((size_t)s * K + k) * NF + fc;
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
@@ -385,7 +393,7 @@ k_grid_bwd_flex(const double* __restrict__ d, const double* __restrict__ alpha, 
   double* accs = par + par_doubles(L);                  // [kW][L][4][16]
   double* tab = accs + (size_t)kW * 64 * L;             // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
-  double* omg = ics + ((gp.tc + 1) & ~1);               // [nft*32][2]: omega, 1/max(omega, 1e-4)
+  double* omg = ics + ((gp.tc + 1) & ~1);               // [nft*32][4]: omega, 1/max(omega, 1e-4), omega/alpha_hs, omega/beta_hs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
   const GlobalStore st{estore + ((size_t)blockIdx.x * kW + warp) * slab + lane, l2_evict_last_policy()};
@@ -396,10 +404,12 @@ k_grid_bwd_flex(const double* __restrict__ d, const double* __restrict__ alpha, 
     __syncthreads();  // previous virtual block has flushed its accumulators
     stage_params(par, d, alpha, beta, rho, s, L);
     for (int i = threadIdx.x; i < kW * 64 * L; i += blockDim.x) accs[i] = 0.0;
+    __syncthreads();  // staged parameters visible
     for (int i = threadIdx.x; i < nft * kWarp; i += blockDim.x) {
       const double om = omega_of_period(t[(size_t)s * NF + min(i, NF - 1)]);
-      omg[2 * i] = om;
-      omg[2 * i + 1] = 1.0 / fmax(om, 1.0e-4);
+      omg[4 * i] = om;
+      omg[4 * i + 1] = 1.0 / fmax(om, 1.0e-4);
+      stage_half_k(omg + 4 * i + 2, par, L, om);
     }
     const int k0 = ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
     for (int kb = k0; kb < k1; kb += gp.tc) {
@@ -412,9 +422,10 @@ k_grid_bwd_flex(const double* __restrict__ d, const double* __restrict__ alpha, 
         const int cc = task / nft, tile = task - cc * nft;
         const int f = tile * kWarp + lane;
         const bool active = f < NF;
-        const Dbl2 om = ld2(omg + 2 * f);
+        const Dbl2 om = ld2(omg + 4 * f);
         const Sample z = make_sample_dense(om.x, ics[cc], om.y);
-        const TableSource<kTab, true> src{par, L, tab + (size_t)cc * (L - 1) * kTab, omg + 2 * f, ics + cc};
+        const TableSource<kTab, true> src{par, L, tab + (size_t)cc * (L - 1) * kTab, omg + 4 * f, ics + cc,
+                                          omg + 4 * f + 2};
         const size_t idx = ((size_t)s * K + (kb + cc)) * NF + (active ? f : NF - 1);
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
@@ -856,7 +867,9 @@ inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
     if (bwd_mode() == kBwdSmem) {  // slabs in shared memory: as many warps as fit beside the table
       want = 0;
       for (int w = 4; w >= 1 && !want; w >>= 1)
-        if (adj_smem(L, w) + table_bytes(L, 8, true) <= (w > 1 ? kSmemBudget : kSmemMax)) want = w;
+        if (adj_smem(L, w) + table_bytes(L, 8, true) + (size_t)w * kWarp * 2 * sizeof(double) <=
+            (w > 1 ? kSmemBudget : kSmemMax))
+          want = w;
     }
   }
   const int flex = adjoint ? bwd_flex_warps() : 0;
@@ -1102,7 +1115,7 @@ int adsurf_det_points_jac(const double* d, const double* alpha, const double* be
 static int grid_fwd_launch(const double* d, const double* alpha, const double* beta, const double* rho,
                            const double* t, const double* c, int S, int L, int NF, int K, double* det, double* pmax,
                            double* pmin, uint32_t* signbits, const GridPlan& gp, cudaStream_t st) {
-  const size_t smem = par_bytes(L) + table_bytes(L, gp.tc, false);
+  const size_t smem = par_bytes(L) + table_bytes(L, gp.tc, false) + (size_t)gp.wpb * kWarp * 2 * sizeof(double);
   // register cap: 128 leaves the compiler free (it uses ~108: 4 warps per scheduler); ADSURF_GRID_FWD=r96 trades
   // registers for a fifth warp per scheduler (experiments)
   static int cap = -1;
@@ -1164,7 +1177,7 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   const size_t smem = par_bytes(L) +
                       (size_t)gp.wpb * (mode == kBwdSmem ? 4 : 64) * L * sizeof(double) + table_bytes(L, gp.tc, true) +
                       (mode == kBwdSmem ? (size_t)gp.wpb * est_bytes_per_warp(L) : 0) +
-                      (bwd_flex_warps() ? (size_t)gp.nft * kWarp * 2 * sizeof(double) : 0);
+                      (bwd_flex_warps() ? (size_t)gp.nft * kWarp * 4 * sizeof(double) : (size_t)gp.wpb * kWarp * 2 * sizeof(double));
   double* estore = mode == kBwdSmem ? nullptr : (double*)((char*)ws + part_bytes);
   const long long total_vb = (long long)S * gp.bpm;
   if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;

@@ -692,6 +692,7 @@ struct DirectSource {
   const double* __restrict__ par;
   int L;
   ADSURF_HD int flags(int) const { return -1; }
+  ADSURF_HD const double* half_k() const { return nullptr; }
   ADSURF_HD bool small_phases(const Sample&) const { return false; }
   ADSURF_HD Sample again(const Sample& z) const { return z; }
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
@@ -715,6 +716,8 @@ struct TableSource {
   // (k, k^2, 1/omega, 1/omega^2) need not stay in registers across the layer loop of the adjoint sweep
   const double* omq = nullptr;
   const double* icq = nullptr;
+  const double* hkq = nullptr;  // this lane's staged (omega/alpha_hs, omega/beta_hs), see load_half
+  ADSURF_HD const double* half_k() const { return hkq; }
   ADSURF_HD Sample again(const Sample& z) const {
     if (kRemake) {
       const Dbl2 om = ld2(omq);
@@ -742,18 +745,34 @@ struct TableSource {
 // with the half-space velocity the result depends on the last bit of kx, so kx is formed with the
 // reference's own correctly-rounded division omega/alpha (reference :328-329) from the raw
 // velocities kept at par[kNumPar*L + 0/1].
-ADSURF_HD void load_half(Half& h, const double* __restrict__ par, int L, const Sample& z) {
+// hk: the sample's (omega/alpha_hs, omega/beta_hs) if the caller staged them per period (dense kernels: two
+// correctly rounded divisions per period and block instead of four per sample), else null.
+ADSURF_HD void load_half(Half& h, const double* __restrict__ par, int L, const Sample& z,
+                         const double* __restrict__ hk) {
   const int m = L - 1;
-  h.ka = z.omega / par[kNumPar * L + 0];
-  h.kb = z.omega / par[kNumPar * L + 1];
+  if (hk) {
+    const Dbl2 k = ld2(hk);
+    h.ka = k.x;
+    h.kb = k.y;
+  } else {
+    h.ka = z.omega / par[kNumPar * L + 0];
+    h.kb = z.omega / par[kNumPar * L + 1];
+  }
   h.gammk = par[m * kNumPar + P_TB2] * z.iw2;
   h.rho = par[m * kNumPar + P_RHO];
 }
+// what a caller stages per period for load_half (omega0 unclamped)
+ADSURF_HD void stage_half_k(double* __restrict__ hk, const double* __restrict__ par, int L, double omega0) {
+  const double w = fmax(omega0, 1.0e-4);
+  hk[0] = w / par[kNumPar * L + 0];
+  hk[1] = w / par[kNumPar * L + 1];
+}
 
 // half-space vector in the scaled variables of the layer sweep: E~ = E D^-1, D = diag(1, w, 1, w, w^2)
-ADSURF_HD void half_start(const double* __restrict__ par, int L, const Sample& z, double (&e)[5]) {
+ADSURF_HD void half_start(const double* __restrict__ par, int L, const Sample& z, const double* __restrict__ hk,
+                          double (&e)[5]) {
   Half h;
-  load_half(h, par, L, z);
+  load_half(h, par, L, z, hk);
   half_space(h, z.k, z.k2, e);
   e[1] *= z.iw;
   e[3] *= z.iw;
@@ -795,7 +814,7 @@ template <bool kStore, typename Source, typename Store>
 ADSURF_HD double forward_sweep(const Source& src, const Sample& z, const Store& est) {
   const int L = src.L;
   double e[5];
-  half_start(src.par, L, z, e);
+  half_start(src.par, L, z, src.half_k(), e);
   Dbl2 ph{0.0, 0.0};  // phase pair of layer m (dense sweeps: read one layer ahead)
   auto step = [&](int m, auto tag) {
     constexpr int kFl = decltype(tag)::value;
@@ -1021,7 +1040,7 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   // half-space: dDelta/dE_hs = D^-1 s~_{L-1}, in the reference's variables
   const Sample zh = src.again(z);
   Half h;
-  load_half(h, par, L, zh);
+  load_half(h, par, L, zh, src.half_k());
   half_space(h, zh.k, zh.k2, e);
   const double su[5] = {s[0], s[1] * zh.iw, s[2], s[3] * zh.iw, s[4] * zh.iw2};
   const HalfGrad g = half_adjoint(h, e, su, zh.k, zh.k2);
