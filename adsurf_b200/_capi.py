@@ -15,13 +15,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # ADSURF_LIB: load another build of the library (kernel experiments); the default is the in-tree build
 LIB_PATH = os.environ.get("ADSURF_LIB") or os.path.join(_HERE, "_lib", "libadsurf_b200.so")
 
-OP_POINTS_FWD, OP_POINTS_BWD, OP_POINTS_JAC, OP_GRID_FWD, OP_GRID_BWD, OP_DMF_STEP = range(6)
+OP_POINTS_FWD, OP_POINTS_BWD, OP_POINTS_JAC, OP_GRID_FWD, OP_GRID_BWD, OP_DMF_STEP, OP_ENSEMBLE_STEP = range(7)
+INIT_PERSIST_L2 = 1
 COMPRESS_NONE, COMPRESS_EXP, COMPRESS_LOG, COMPRESS_EXP_NONORM, COMPRESS_NORM = range(5)
 
 EXPORTS = (
     "adsurf_version",
     "adsurf_error_string",
+    "adsurf_init",
     "adsurf_workspace_bytes",
+    "adsurf_plan_describe",
     "adsurf_det_points_fwd",
     "adsurf_det_points_bwd",
     "adsurf_det_points_jac",
@@ -31,7 +34,26 @@ EXPORTS = (
     "adsurf_fp64_peak_probe",
     "adsurf_math_probe",
     "adsurf_ensemble_adam_step",
+    "adsurf_inversion_workspace_bytes",
+    "adsurf_inversion_step",
 )
+
+
+_INV_FIELDS = ([(k, ctypes.c_int) for k in ("S", "L", "N", "K", "T")]
+               + [(k, ctypes.c_void_p) for k in (
+                   "t", "c", "C", "b", "d", "alpha", "rho", "mb", "vb", "md", "vd", "b0", "alpha0", "rho0", "lower_b",
+                   "upper_b", "layer_mindepth", "layer_maxdepth", "loss", "loss_hist", "iter_b_hist", "iter_d_hist",
+                   "counter", "halo")]
+               + [(k, ctypes.c_int) for k in ("row0", "S_all", "compress", "vp_mode", "invert_thick", "layering",
+                                              "proj_flags", "step_size")]
+               + [(k, ctypes.c_double) for k in ("vp_vs_ratio", "damp_vertical", "damp_horizontal", "lr", "gamma",
+                                                 "beta1", "beta2", "eps")])
+
+
+class InversionStruct(ctypes.Structure):
+    """`adsurf_inversion` of include/adsurf_b200.h (same field order and types)"""
+    _fields_ = _INV_FIELDS
+
 
 _lib = None
 launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
@@ -69,11 +91,41 @@ def lib():
         L.adsurf_ensemble_adam_step.restype = ci
         L.adsurf_math_probe.argtypes = [vp, ci, vp, vp, vp, vp, vp]
         L.adsurf_math_probe.restype = ci
+        L.adsurf_plan_describe.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(ci)]
+        L.adsurf_plan_describe.restype = ci
+        L.adsurf_init.argtypes = [ci, ctypes.c_uint]
+        L.adsurf_init.restype = ci
+        L.adsurf_inversion_workspace_bytes.argtypes = [ctypes.POINTER(InversionStruct)]
+        L.adsurf_inversion_workspace_bytes.restype = sz
+        L.adsurf_inversion_step.argtypes = [ctypes.POINTER(InversionStruct), vp, sz, vp]
+        L.adsurf_inversion_step.restype = ci
         for name in EXPORTS:
             if name.startswith("adsurf_det") or name in ("adsurf_dmf_step", "adsurf_fp64_peak_probe"):
                 getattr(L, name).restype = ci
         _lib = L
     return _lib
+
+
+_inited = set()
+
+
+def init(device=None, persist_l2=True):
+    """Explicit per-device set-up (C ABI `adsurf_init`): reserves the persisting-L2 carve-out the adjoint kernels'
+    evict_last slabs need to stay cache-resident.  A context-wide CUDA limit, hence a visible call; the adjoint
+    entry points of this binding make it once per device unless ADSURF_PERSIST_L2=0 is set."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    _check(lib().adsurf_init(int(idx), INIT_PERSIST_L2 if persist_l2 else 0))
+    _inited.add(idx)
+
+
+def ensure_init(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _inited:
+        if os.environ.get("ADSURF_PERSIST_L2", "1") == "0":
+            _inited.add(idx)
+        else:
+            init(torch.device("cuda", idx))
 
 
 def _check(rc):
@@ -100,9 +152,20 @@ def _req(*tensors):
 
 
 def _workspace(op, S, L, n, K, ref):
-    nbytes = lib().adsurf_workspace_bytes(op, S, L, n, K)
+    with torch.cuda.device(ref.device):  # sizes follow the SM count of the device the launch will use
+        nbytes = lib().adsurf_workspace_bytes(op, S, L, n, K)
     ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=ref.device)
     return ws, nbytes
+
+
+def plan_describe(op, S, L, n, K=0):
+    """how `op` would be split over the current device (see adsurf_plan_describe in the header)"""
+    out = (ctypes.c_int * 8)()
+    _check(lib().adsurf_plan_describe(int(op), int(S), int(L), int(n), int(K), out))
+    v = list(out)
+    if op in (OP_GRID_FWD, OP_GRID_BWD):
+        return dict(zip(("wpb", "nfg", "nchunk", "chunk", "tc", "bpm", "nft", "sms"), v))
+    return {"wpb": v[0], "units": v[1], "bpm": v[5], "l2_slabs": v[6], "sms": v[7]}
 
 
 def version():
@@ -133,6 +196,7 @@ def points_bwd(d, a, b, rho, t, c, gF, want_F=False):
     F = torch.empty((S, N), dtype=torch.float64, device=dev) if want_F else None
     gd, ga, gb, gr = (torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4))
     gc = torch.empty((S, N), dtype=torch.float64, device=dev)
+    ensure_init(dev)
     ws, nbytes = _workspace(OP_POINTS_BWD, S, L, N, 0, d)
     with torch.cuda.device(dev):
         _check(lib().adsurf_det_points_bwd(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), _ptr(c), _ptr(gF), S, L, N,
@@ -190,7 +254,9 @@ def grid_bwd(d, a, b, rho, t, c, gdet=None, want_det=False, out=None, ws=None):
     det = torch.empty((S, K, NF), dtype=torch.float64, device=dev) if want_det else None
     if out is None:
         out = tuple(torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4))
-    nbytes = lib().adsurf_workspace_bytes(OP_GRID_BWD, S, L, NF, K)
+    ensure_init(dev)
+    with torch.cuda.device(dev):
+        nbytes = lib().adsurf_workspace_bytes(OP_GRID_BWD, S, L, NF, K)
     if ws is None:
         ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
@@ -219,7 +285,9 @@ def dmf_step(d, a, b, rho, t, c, C, compress, with_grad=True, want_F=False, want
     norm = torch.empty((S, N), dtype=torch.float64, device=dev) if (want_norm and normalised) else None
     if grads is None:
         grads = tuple(torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4)) if with_grad else (None,) * 4
-    nbytes = lib().adsurf_workspace_bytes(OP_DMF_STEP, S, L, N, K if normalised else 0)
+    ensure_init(dev)
+    with torch.cuda.device(dev):
+        nbytes = lib().adsurf_workspace_bytes(OP_DMF_STEP, S, L, N, K if normalised else 0)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
@@ -250,6 +318,11 @@ def math_probe(x):
     return tuple(outs)
 
 
+def fused_available(device):
+    """the device-resident inversion loops need the CUDA library (tests patch this together with the binding)"""
+    return device.type == "cuda"
+
+
 VP_MODE = {"": 0, None: 0, "none": 0, "Brocher": 1, "Constant": 2, "USArray": 3}
 LAYERING = {"LR": 1, "LN": 2}
 
@@ -268,8 +341,9 @@ def ensemble_adam_step(state, grads, loss, consts, *, vp_mode, vp_vs_ratio, inve
     b = state["b"]
     S, L = b.shape
     _req(*state.values(), *grads, loss, *consts.values(), iter_b, iter_d)
-    if ws is None:
-        ws = torch.empty(3 * S * L * 8, dtype=torch.uint8, device=b.device)
+    need = lib().adsurf_workspace_bytes(OP_ENSEMBLE_STEP, S, L, 1, 0)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=b.device)
     gd, ga, gb, gr = grads
     if proj_flags is None:  # the ensemble loops of the reference
         proj_flags = PROJ_LAST_LAYER | (0 if invert_thick else PROJ_NAN_REPAIR)
@@ -284,3 +358,141 @@ def ensemble_adam_step(state, grads, loss, consts, *, vp_mode, vp_vs_ratio, inve
             float(beta1), float(beta2), float(eps), int(step), _ptr(iter_b), _ptr(iter_d), _ptr(ws), ws.numel(),
             _stream(b)))
     launch_count += 2
+
+
+class InversionLoop:
+    """Device-resident inversion loop over the C ABI `adsurf_inversion_step`.
+
+    One iteration = dense pass (normalised modes) + pointwise forward/adjoint with the DMF seed + the two
+    optimiser-step kernels, with the iteration index in device memory.  `run(n)` replays a CUDA graph of
+    `unroll` iterations (captured once from the ctypes calls on a side stream) — no Python, no host
+    synchronisation and no allocation between iterations.  With `halo_fn` (sharded ensembles with horizontal
+    damping: the neighbours' Vs rows change every iteration and travel through a collective) the iterations are
+    issued one by one instead.
+
+    state  = dict(b, d, alpha, rho [, mb, vb, md, vd])     [S,L] float64 CUDA, updated in place
+    consts = dict(b0, alpha0, rho0, lower_b, upper_b, mindepth, maxdepth)
+    History (`loss_hist` [T,S], `iter_b_hist`, `iter_d_hist` [T,S,L]) is filled row by row on the device."""
+
+    def __init__(self, state, consts, t, c, C, *, compress, vp_mode, vp_vs_ratio, invert_thick, layering, proj_flags,
+                 damp_vertical, damp_horizontal, lr, gamma, step_size, T, beta1=0.9, beta2=0.999, eps=1e-8,
+                 row0=0, S_all=None, halo_fn=None, record_thick=None, unroll=8, use_graph=True):
+        b = state["b"]
+        S, L = b.shape
+        dev = b.device
+        self.dev, self.S, self.L, self.T = dev, S, L, int(T)
+        for key in ("mb", "vb", "md", "vd"):
+            state.setdefault(key, torch.zeros_like(b))
+        self.state, self.consts = state, consts
+        normalised = compress in (COMPRESS_EXP, COMPRESS_LOG, COMPRESS_NORM)
+        self.t, self.c, self.C = t, c, (C if normalised else None)
+        _req(*state.values(), *consts.values(), t, c, self.C)
+        ensure_init(dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.loss = torch.zeros((S,), **f64)
+        self.loss_hist = torch.full((self.T, S), 10.0, **f64)     # the reference pre-fills its loss list with 10
+        self.iter_b_hist = torch.zeros((self.T, S, L), **f64)
+        record_thick = bool(invert_thick) if record_thick is None else record_thick
+        self.iter_d_hist = torch.zeros((self.T, S, L), **f64) if record_thick else None
+        self.counter = torch.zeros((2,), dtype=torch.int32, device=dev)
+        self.halo_fn = halo_fn
+        self.halo = torch.zeros((4, L), **f64) if halo_fn is not None else None
+        self.S_all = S if S_all is None else int(S_all)
+        self.kernels_per_iteration = (1 if normalised else 0) + 3
+        P = InversionStruct()
+        P.S, P.L, P.N, P.K, P.T = S, L, c.shape[1], (C.shape[1] if self.C is not None else 0), self.T
+        P.t, P.c, P.C = t.data_ptr(), c.data_ptr(), (self.C.data_ptr() if self.C is not None else None)
+        for key in ("b", "d", "alpha", "rho", "mb", "vb", "md", "vd"):
+            setattr(P, key, state[key].data_ptr())
+        for key, src in (("b0", "b0"), ("alpha0", "alpha0"), ("rho0", "rho0"), ("lower_b", "lower_b"),
+                         ("upper_b", "upper_b"), ("layer_mindepth", "mindepth"), ("layer_maxdepth", "maxdepth")):
+            setattr(P, key, consts[src].data_ptr())
+        P.loss, P.loss_hist, P.iter_b_hist = self.loss.data_ptr(), self.loss_hist.data_ptr(), self.iter_b_hist.data_ptr()
+        P.iter_d_hist = self.iter_d_hist.data_ptr() if self.iter_d_hist is not None else None
+        P.counter = self.counter.data_ptr()
+        P.halo = self.halo.data_ptr() if self.halo is not None else None
+        P.row0, P.S_all = int(row0), self.S_all
+        P.compress, P.vp_mode, P.invert_thick, P.layering = int(compress), int(vp_mode), int(bool(invert_thick)), int(layering)
+        P.proj_flags, P.step_size = int(proj_flags), int(step_size)
+        P.vp_vs_ratio, P.damp_vertical, P.damp_horizontal = float(vp_vs_ratio or 0.0), float(damp_vertical), float(damp_horizontal)
+        P.lr, P.gamma, P.beta1, P.beta2, P.eps = float(lr), float(gamma), float(beta1), float(beta2), float(eps)
+        self.P = P
+        with torch.cuda.device(dev):
+            nbytes = lib().adsurf_inversion_workspace_bytes(ctypes.byref(P))
+        if nbytes == 0:
+            raise AdsurfError("adsurf_inversion_workspace_bytes: bad problem description")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.unroll = max(1, int(unroll))
+        self.use_graph = bool(use_graph) and halo_fn is None and os.environ.get("ADSURF_GRAPH", "1") != "0"
+        self._graphs = {}
+        self.done = 0
+
+    def _step(self, P=None, ws=None):
+        global launch_count
+        P = self.P if P is None else P
+        ws = self.ws if ws is None else ws
+        _check(lib().adsurf_inversion_step(ctypes.byref(P), ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(self.loss)))
+        launch_count += self.kernels_per_iteration
+
+    def _warm(self):
+        """run the launch sequence once on scratch copies (loads the kernels, sets their attributes) so that the
+        capture below records launches only"""
+        Q = InversionStruct()
+        ctypes.memmove(ctypes.byref(Q), ctypes.byref(self.P), ctypes.sizeof(Q))
+        keep = []
+        for key in ("b", "d", "alpha", "rho", "mb", "vb", "md", "vd"):
+            x = self.state[key].clone()
+            keep.append(x)
+            setattr(Q, key, x.data_ptr())
+        scratch_loss, scratch_cnt = torch.zeros_like(self.loss), torch.zeros_like(self.counter)
+        Q.loss, Q.counter = scratch_loss.data_ptr(), scratch_cnt.data_ptr()
+        Q.loss_hist = Q.iter_b_hist = Q.iter_d_hist = None
+        Q.T = 0
+        self._step(Q, torch.empty_like(self.ws))
+        torch.cuda.synchronize(self.dev)
+
+    def _graph(self, n):
+        g = self._graphs.get(n)
+        if g is None:
+            if not self._graphs:
+                self._warm()
+            global launch_count
+            g, count = torch.cuda.CUDAGraph(), launch_count
+            with torch.cuda.device(self.dev), torch.cuda.graph(g, capture_error_mode="thread_local"):
+                for _ in range(n):
+                    self._step()
+            launch_count = count  # a capture records launches, it does not run them
+            self._graphs[n] = g
+        return g
+
+    def prepare(self, n):
+        """capture the graphs `run(n)` will replay (so that a caller can time the iterations alone)"""
+        if self.use_graph:
+            with torch.cuda.device(self.dev):
+                k = self.unroll
+                if n >= k:
+                    self._graph(k)
+                if n % k:
+                    self._graph(n % k)
+
+    def run(self, n):
+        """advance `n` iterations (asynchronous on the current stream)"""
+        global launch_count
+        n = int(n)
+        with torch.cuda.device(self.dev):
+            if not self.use_graph:
+                for _ in range(n):
+                    if self.halo_fn is not None:
+                        self.halo.copy_(self.halo_fn(self.state["b"]))
+                    self._step()
+            else:
+                k = self.unroll
+                if n >= k:
+                    g = self._graph(k)
+                    for _ in range(n // k):
+                        g.replay()
+                    launch_count += (n // k) * k * self.kernels_per_iteration
+                if n % k:
+                    self._graph(n % k).replay()
+                    launch_count += (n % k) * self.kernels_per_iteration
+        self.done += n

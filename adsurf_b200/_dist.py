@@ -33,6 +33,13 @@ def shard_bounds(S, rank=None, world=None):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def min_shard_rows(S, world=None):
+    """rows of the smallest shard"""
+    if world is None:
+        world = rank_world()[1]
+    return S // world
+
+
 def all_gather_rows(local, S, dim=0):
     """Concatenate the per-rank blocks along `dim` into the full [.., S, ..] tensor on every rank.
 

@@ -88,11 +88,13 @@ class _cal_grad_base(torch.nn.Module):
             a = b * self.vp_vs_ratio
             rho = self.rho
         elif self.initial_method == "USArray":
-            # the reference's AK135 substitution for Vs > 4.6 writes into temporaries (no effect);
-            # what survives is: Brocher where Vs <= 4.6, the initial Vp / rho elsewhere
+            # the reference's AK135 substitution for Vs > 4.6 writes into temporaries (no effect); what survives
+            # is its masked in-place update (_model.py:440-446): Brocher where Vs <= 4.6, and entries above
+            # 4.6 km/s keep whatever Vp / rho they last had (self.a / self.rho persist between calls)
             low = b <= 4.6
             a = torch.where(low, brocher_vp(b), self.a)
             rho = torch.where(low, brocher_rho(a), self.rho)
+            self.a, self.rho = a.detach(), rho.detach()
         else:
             a, rho = self.a, self.rho
         return a, rho
@@ -267,58 +269,77 @@ class iter_inversion:
         vs_and_thick = inversion_method.lower() == "vs-and-thick"
         last = iteration
         prev = None
-        fused = os.environ.get("ADSURF_FUSED_OPT", "1") != "0" and dev.type == "cuda"
+        fused = os.environ.get("ADSURF_FUSED_OPT", "1") != "0" and _capi.fused_available(dev)
         if fused:
-            # device-resident iteration (one fused DMF evaluation + one optimiser-step launch, S = 1); the loss is
-            # read back every iteration because the reference's early stopping looks at it (_model.py:168-186)
+            # Device-resident loop (S = 1): a CUDA graph of whole iterations replayed in chunks; the reference's
+            # early stopping (:168-186) looks at every loss, so it is replayed on the host over each finished chunk —
+            # one synchronisation per `check_every` iterations instead of one per iteration.  Iterations that ran
+            # past the stopping point inside a chunk only wrote history rows, which are reset below.
             method = mp.initialize_method if mp.initialize_method in _capi.VP_MODE else ""
             with torch.no_grad():
                 a_now, r_now = calculator._velocities()
             c64 = lambda x: x.detach().to(torch.float64).reshape(1, -1).contiguous().clone()
             state = {"b": c64(calculator.b), "d": c64(calculator.d), "alpha": c64(a_now), "rho": c64(r_now)}
-            for key in ("mb", "vb", "md", "vd"):
-                state[key] = torch.zeros_like(state["b"])
             consts = {"b0": c64(calculator.b), "alpha0": c64(a), "rho0": c64(rho), "lower_b": c64(lower_b),
                       "upper_b": c64(upper_b), "mindepth": c64(layer_mindepth), "maxdepth": c64(layer_maxdepth)}
             mode = ops.COMPRESS[_compress_mode(ip.compress, ip.normalized, ip.compress_method)]
-            grads = tuple(torch.empty_like(state["b"]) for _ in range(4))
-            ws_step = torch.empty(3 * b.numel() * 8, dtype=torch.uint8, device=dev)
-            vl, tl = vlist.reshape(1, -1).contiguous(), tlist.reshape(1, -1).contiguous()
-            loss_buf = loss_list.reshape(-1, 1)
             # single-model loops: half-space rule only on the vs-and-thick branch, no NaN repair (:122-159)
-            proj = _capi.PROJ_LAST_LAYER if vs_and_thick else 0
-        for j in tqdm(range(iteration), disable=not getattr(ip, "progress", False)):
-            if fused:
-                lr_j = ip.lr * ip.gamma ** (j // ip.step_size)
-                _capi.dmf_step(state["d"], state["alpha"], state["b"], state["rho"], tl, vl, calculator.Clist, mode,
-                               with_grad=True, loss=loss_buf[j], grads=grads)
-                _capi.ensemble_adam_step(state, grads, loss_buf[j], consts, vp_mode=_capi.VP_MODE[method],
-                                         vp_vs_ratio=mp.vp_vs_ratio, invert_thick=vs_and_thick,
-                                         layering=_capi.LAYERING.get(mp.layering_method, 0),
-                                         damp_vertical=ip.damp_vertical, damp_horizontal=0.0, lr=lr_j, beta1=0.9,
-                                         beta2=0.999, eps=1e-8, step=j + 1, iter_b=iter_vs[j:j + 1],
-                                         iter_d=iter_thick[j:j + 1] if vs_and_thick else None, ws=ws_step,
-                                         proj_flags=proj)
-                cur = float(loss_list[j])
-            else:
-                loss = calculator(vlist, tlist)
-                optimizer.zero_grad()
-                loss.backward()
-                with torch.no_grad():
-                    pb = calculator.b
-                    pb.data = torch.minimum(torch.maximum(pb.data, lower_b), upper_b)
-                    if vs_and_thick:
-                        pb.data[-1] = torch.maximum(pb.data[-1], pb.data[-2])  # half-space >= layer above (:129)
-                        iter_vs[j] = pb.data
-                        pd = calculator.d
-                        pd.data = _clip_depths(pd.data, layer_mindepth, layer_maxdepth, mp.layering_method)
-                        iter_thick[j] = pd.data
-                    else:
-                        iter_vs[j] = pb.data
-                optimizer.step()
-                scheduler.step()
-                cur = float(loss.detach())  # the reference syncs every iteration for its progress bar (:164)
-                loss_list[j] = cur
+            loop = _capi.InversionLoop(
+                state, consts, tlist.reshape(1, -1).contiguous(), vlist.reshape(1, -1).contiguous(), calculator.Clist,
+                compress=mode, vp_mode=_capi.VP_MODE[method], vp_vs_ratio=mp.vp_vs_ratio, invert_thick=vs_and_thick,
+                layering=_capi.LAYERING.get(mp.layering_method, 0),
+                proj_flags=_capi.PROJ_LAST_LAYER if vs_and_thick else 0, damp_vertical=ip.damp_vertical,
+                damp_horizontal=0.0, lr=ip.lr, gamma=ip.gamma, step_size=ip.step_size, T=iteration)
+            check_every = int(os.environ.get("ADSURF_CHECK_EVERY", "64"))
+            stop, j0 = None, 0
+            while j0 < iteration and stop is None:
+                n = min(check_every, iteration - j0)
+                loop.run(n)
+                chunk = loop.loss_hist[j0:j0 + n, 0].cpu().numpy()  # synchronises
+                for j in range(j0, j0 + n):
+                    cur = float(chunk[j - j0])
+                    if j > 0:
+                        if cur > 0.6:
+                            trigger_times = 0
+                        if (cur > prev) or (abs(cur - prev) / abs(prev) < eps):
+                            trigger_times += 1
+                            if trigger_times >= patience:
+                                stop = j
+                        else:
+                            trigger_times = 0
+                    if stop is None and cur != cur:  # NaN: drop this iterate and stop (:180-186)
+                        last, stop = j, j
+                    if stop is not None:
+                        print("Early Stopping in Iteration:{}".format(j))
+                        break
+                    prev = cur
+                j0 += n
+            loss_list, iter_vs = loop.loss_hist[:, 0], loop.iter_b_hist[:, 0]
+            if vs_and_thick:
+                iter_thick = loop.iter_d_hist[:, 0]
+            if stop is not None and stop + 1 < iteration:  # rows written past the stopping point
+                loss_list[stop + 1:] = 10.0
+                iter_vs[stop + 1:] = 0.0
+                iter_thick[stop + 1:] = 0.0
+        for j in tqdm(range(0 if not fused else iteration, iteration), disable=not getattr(ip, "progress", False)):
+            loss = calculator(vlist, tlist)
+            optimizer.zero_grad()
+            loss.backward()
+            with torch.no_grad():
+                pb = calculator.b
+                pb.data = torch.minimum(torch.maximum(pb.data, lower_b), upper_b)
+                if vs_and_thick:
+                    pb.data[-1] = torch.maximum(pb.data[-1], pb.data[-2])  # half-space >= layer above (:129)
+                    iter_vs[j] = pb.data
+                    pd = calculator.d
+                    pd.data = _clip_depths(pd.data, layer_mindepth, layer_maxdepth, mp.layering_method)
+                    iter_thick[j] = pd.data
+                else:
+                    iter_vs[j] = pb.data
+            optimizer.step()
+            scheduler.step()
+            cur = float(loss.detach())  # the reference syncs every iteration for its progress bar (:164)
+            loss_list[j] = cur
             if j > 0:
                 if cur > 0.6:
                     trigger_times = 0
@@ -346,47 +367,66 @@ class iter_inversion:
         self.inv_process = {"iter_vs": iter_vs.tolist(), "iter_thick": iter_thick.tolist(), "loss": loss_np.tolist()}
 
 
+def _halo_rows(b, row0, S_all):
+    """Vs rows row0-2, row0-1, row0+S, row0+S+1 of a sharded ensemble (zeros outside [0, S_all)): every rank
+    contributes its first and last two rows to one small all-gather (reference coupling: _model.py:471-473)."""
+    import torch.distributed as dist
+    rank, world = _dist.rank_world()
+    edge = torch.cat((b[:2], b[-2:]), dim=0).contiguous()
+    got = [torch.empty_like(edge) for _ in range(world)]
+    dist.all_gather(got, edge)
+    out = torch.zeros_like(edge)
+    if rank > 0:
+        out[0:2] = got[rank - 1][2:4]
+    if rank < world - 1:
+        out[2:4] = got[rank + 1][0:2]
+    return out
+
+
 def _fused_ensemble_loop(self, calculator, vlist, tlist, Clist, a_init, rho_init, lower_b, upper_b, mindepth, maxdepth,
-                         iter_vs, iter_thick, loss_list, vs_and_thick):
-    """Iterations of multi_inversion with everything on the device: per iteration one fused
-    DMF evaluation with gradient (`adsurf_dmf_step`) and one optimiser step (`adsurf_ensemble_adam_step`:
-    velocity chain, Tikhonov terms, projection, Adam, next Vp/rho).  Same order of operations as the torch loop
-    below (loss -> gradient -> projection -> record -> Adam -> StepLR); tests compare the two trajectories."""
+                         vs_and_thick, shard=None):
+    """Iterations of multi_inversion with everything on the device: a CUDA graph of whole
+    iterations (`adsurf_inversion_step`: dense pass, pointwise forward + adjoint with the DMF seed, velocity chain,
+    Tikhonov terms, projection, Adam, StepLR, history) replayed `iteration` times with no host work in between.
+    Same order of operations as the torch loop below (loss -> gradient -> projection -> record -> Adam -> StepLR);
+    tests compare the two trajectories.  Sharded ensembles with horizontal damping exchange four Vs rows per
+    iteration (`_halo_rows`) and issue the iterations one by one.  Returns (loss [T,S], iter_vs, iter_thick)."""
     ip, mp = self.inv_param, self.model_param
     c64 = lambda x: x.detach().to(torch.float64).contiguous().clone()
     b, d = c64(calculator.b), c64(calculator.d)
-    S, L = b.shape
     method = mp.initialize_method if mp.initialize_method in _capi.VP_MODE else ""
-    vp_mode = _capi.VP_MODE[method]
-    a0, r0 = c64(a_init), c64(rho_init)
     with torch.no_grad():  # Vp / rho of the first evaluation come from the velocity chain, like forward() does
         calculator_a, calculator_r = calculator._velocities()
     state = {"b": b, "d": d, "alpha": c64(calculator_a), "rho": c64(calculator_r)}
-    for key in ("mb", "vb", "md", "vd"):
-        state[key] = torch.zeros_like(b)
     full = lambda x: (torch.ones_like(b) * x).contiguous()
-    consts = {"b0": c64(calculator.b), "alpha0": a0, "rho0": r0, "lower_b": full(lower_b), "upper_b": full(upper_b),
-              "mindepth": full(mindepth), "maxdepth": full(maxdepth)}
+    consts = {"b0": c64(calculator.b), "alpha0": c64(a_init), "rho0": c64(rho_init), "lower_b": full(lower_b),
+              "upper_b": full(upper_b), "mindepth": full(mindepth), "maxdepth": full(maxdepth)}
     mode = ops.COMPRESS[_compress_mode(ip.compress, ip.normalized, ip.compress_method)]
-    layering = _capi.LAYERING.get(mp.layering_method, 0)
-    grads = tuple(torch.empty_like(b) for _ in range(4))
-    ws_step = torch.empty(3 * S * L * 8, dtype=torch.uint8, device=b.device)
-    ws_dmf = None
-    vlist, tlist, Clist = (x.contiguous() for x in (vlist, tlist, Clist))
-    for j in range(ip.iteration):
-        lr = ip.lr * ip.gamma ** (j // ip.step_size)  # StepLR: scheduler.step() follows optimizer.step()
-        loss = loss_list[j]
-        out = _capi.dmf_step(state["d"], state["alpha"], state["b"], state["rho"], tlist, vlist, Clist, mode,
-                             with_grad=True, loss=loss, grads=grads, ws=ws_dmf)
-        _capi.ensemble_adam_step(state, grads, loss, consts, vp_mode=vp_mode, vp_vs_ratio=mp.vp_vs_ratio,
-                                 invert_thick=vs_and_thick, layering=layering, damp_vertical=ip.damp_vertical,
-                                 damp_horizontal=ip.damp_horizontal, lr=lr, beta1=0.9, beta2=0.999, eps=1e-8,
-                                 step=j + 1, iter_b=iter_vs[j], iter_d=iter_thick[j] if vs_and_thick else None,
-                                 ws=ws_step)
+    row0, S_all, halo_fn = 0, b.shape[0], None
+    if shard is not None:
+        row0, _, S_all = shard
+        if ip.damp_horizontal > 0:
+            halo_fn = lambda bb: _halo_rows(bb, row0, S_all)
+    loop = _capi.InversionLoop(
+        state, consts, tlist.contiguous(), vlist.contiguous(), Clist.contiguous(), compress=mode,
+        vp_mode=_capi.VP_MODE[method], vp_vs_ratio=mp.vp_vs_ratio, invert_thick=vs_and_thick,
+        layering=_capi.LAYERING.get(mp.layering_method, 0),
+        proj_flags=_capi.PROJ_LAST_LAYER | (0 if vs_and_thick else _capi.PROJ_NAN_REPAIR),
+        damp_vertical=ip.damp_vertical, damp_horizontal=ip.damp_horizontal, lr=ip.lr, gamma=ip.gamma,
+        step_size=ip.step_size, T=ip.iteration, row0=row0, S_all=S_all, halo_fn=halo_fn)
+    import time
+    loop.prepare(ip.iteration)  # graph capture: set-up, not iterations
+    if b.is_cuda:
+        torch.cuda.synchronize(b.device)
+    self._t_loop = time.perf_counter()
+    loop.run(ip.iteration)
     with torch.no_grad():
         calculator.b.data.copy_(state["b"])
         if vs_and_thick:
             calculator.d.data.copy_(state["d"])
+    self.loop = loop
+    iter_thick = loop.iter_d_hist if vs_and_thick else torch.zeros_like(loop.iter_b_hist)
+    return loop.loss_hist, loop.iter_b_hist, iter_thick
 
 
 def _final_model(model_param, thick, vs, AK135_data):
@@ -464,9 +504,6 @@ class multi_inversion:
         optimizer = torch.optim.Adam(calculator.parameters(), lr=ip.lr)
         scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=ip.step_size, gamma=ip.gamma)
         iteration = ip.iteration
-        iter_vs = torch.zeros((iteration, S, L), dtype=torch.float64, device=dev)
-        iter_thick = torch.zeros((iteration, S, L), dtype=torch.float64, device=dev)
-        loss_list = torch.full((iteration, S), 10.0, dtype=torch.float64, device=dev)
         if self.vsrange_sign == "mul":
             lower_b, upper_b = self.vsrange[0] * b, self.vsrange[1] * b
         else:  # the reference offsets the FIRST model's Vs for every model (_model.py:577-578)
@@ -475,16 +512,23 @@ class multi_inversion:
         vs_and_thick = inversion_method.lower() == "vs-and-thick"
         b0 = b.clone()
         ones = torch.ones(S, dtype=torch.float64, device=dev)
-        fused = (os.environ.get("ADSURF_FUSED_OPT", "1") != "0" and dev.type == "cuda"
-                 and not (sharded and ip.damp_horizontal > 0))
+        # device-resident loop; a sharded ensemble with horizontal damping needs two rows per side from its neighbours
+        fused = (os.environ.get("ADSURF_FUSED_OPT", "1") != "0" and _capi.fused_available(dev)
+                 and not (sharded and ip.damp_horizontal > 0 and _dist.min_shard_rows(S_all) < 2))
+        if not fused:
+            iter_vs = torch.zeros((iteration, S, L), dtype=torch.float64, device=dev)
+            iter_thick = torch.zeros((iteration, S, L), dtype=torch.float64, device=dev)
+            loss_list = torch.full((iteration, S), 10.0, dtype=torch.float64, device=dev)
         import time
         if dev.type == "cuda":
             torch.cuda.synchronize(dev)
-        t_loop = time.perf_counter()
+        t_setup = t_loop = time.perf_counter()
         if fused:
-            # whole iteration on the device: adsurf_dmf_step + adsurf_ensemble_adam_step, no torch autograd
-            self._fused_loop(calculator, vlist, tlist, Clist, a, rho, lower_b, upper_b, layer_mindepth, layer_maxdepth,
-                             iter_vs, iter_thick, loss_list, vs_and_thick)
+            # whole iterations on the device (adsurf_inversion_step in a CUDA graph), no torch autograd
+            loss_list, iter_vs, iter_thick = self._fused_loop(
+                calculator, vlist, tlist, Clist, a, rho, lower_b, upper_b, layer_mindepth, layer_maxdepth,
+                vs_and_thick, shard=(lo, hi, S_all) if sharded else None)
+            t_loop = self._t_loop
         for j in tqdm(range(0 if not fused else iteration, iteration), disable=not getattr(ip, "progress", False)):
             loss = calculator(vlist, tlist)
             optimizer.zero_grad()
@@ -508,14 +552,23 @@ class multi_inversion:
             loss_list[j] = loss.detach()
         if dev.type == "cuda":
             torch.cuda.synchronize(dev)
-        # seconds spent in the optimisation loop proper (what the reference's tqdm bar times)
-        self.timing = {"loop_s": time.perf_counter() - t_loop, "iterations": iteration, "fused": bool(fused)}
+        # seconds spent in the optimisation loop proper (what the reference's tqdm bar times); setup_s = building the
+        # device-resident loop (buffers, CUDA-graph capture) before the first iteration
+        t_end = time.perf_counter()
+        self.timing = {"loop_s": t_end - t_loop, "setup_s": t_loop - t_setup, "iterations": iteration,
+                       "fused": bool(fused), "gather_s": 0.0}
         loss_list = torch.where(torch.isnan(loss_list), torch.full_like(loss_list, 10.0), loss_list)
-        if sharded:  # the only exchange of the run: per-model losses and iterates of every rank
+        if sharded:  # the exchange that ends the run: per-model losses and iterates of every rank
             loss_list = _dist.all_gather_rows(loss_list, S_all, dim=1)
             iter_vs = _dist.all_gather_rows(iter_vs, S_all, dim=1)
-            iter_thick = _dist.all_gather_rows(iter_thick, S_all, dim=1)
+            if vs_and_thick:
+                iter_thick = _dist.all_gather_rows(iter_thick, S_all, dim=1)
+            else:
+                iter_thick = torch.zeros_like(iter_vs)
             S = S_all
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            self.timing["gather_s"] = time.perf_counter() - t_end
         loss_np = loss_list.cpu().numpy()
         iter_vs = iter_vs.cpu().numpy()
         iter_thick = iter_thick.cpu().numpy()

@@ -209,7 +209,7 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
     for (int cc = 0; cc < n; ++cc) {
       const int k = kb + cc;
       const Sample z = make_sample_dense(omega0, ics[cc], iw0);
-      const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab, nullptr, nullptr, hk};
+      const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab, hk};
       const double v = sample_forward(src, z);
       if (det && active) det[((size_t)s * K + k) * NF + f] = v;
       vmax = fmax(vmax, v);
@@ -247,12 +247,9 @@ __global__ void k_minmax_reduce(const double* __restrict__ pmax, const double* _
   if (cmin) cmin[i] = vmin;
 }
 
-// E-store in global memory (L2-resident working set): cache-global loads/stores, lane-interleaved
-// ADSURF_SLAB_HINT=1 (compile-time): tag slab accesses with an L2 evict_last policy so the write-back
-// cache keeps them resident while det streams through with evict-first stores.
-#ifndef ADSURF_SLAB_HINT
-#define ADSURF_SLAB_HINT 1
-#endif
+// E-store in global memory (L2-resident working set), lane-interleaved.  Slab accesses carry an L2 evict_last
+// policy so the write-back cache keeps them resident (inside the persisting carve-out that adsurf_init reserves)
+// while det streams through with evict-first stores.
 __device__ __forceinline__ unsigned long long l2_evict_last_policy() {
   unsigned long long pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -267,51 +264,38 @@ struct GlobalStore {
   unsigned long long pol;
   __device__ __forceinline__ Slot slot(int m) const { return Slot{p + (size_t)m * (kSlot * kWarp), pol}; }
   __device__ __forceinline__ static double ld(Slot s, int j) {
-#if ADSURF_SLAB_HINT
     double v;
     asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(s.q + j * kWarp), "l"(s.pol));
     return v;
-#else
-    return __ldcg(s.q + j * kWarp);
-#endif
   }
   __device__ __forceinline__ static void st(Slot s, int j, double v) {
-#if ADSURF_SLAB_HINT
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(s.q + j * kWarp), "d"(v), "l"(s.pol) : "memory");
-#else
-    __stcg(s.q + j * kWarp, v);
-#endif
   }
 };
 
 // Dense grid, fused forward + adjoint with per-model gradient reduction.  Persistent: each block
-// walks the virtual blocks vb = blockIdx.x, blockIdx.x + gridDim.x, ... (vb -> model, chunk of units).
-// kGlobal = false: the per-layer row vectors E_{m+1} live in shared memory (40 B per thread per
-//   layer, which caps residency at 8 warps per SM for 20 layers);
-// kGlobal = true: they live in a per-resident-warp slab of global memory that stays in L2
-//   (148 SMs x 12..16 warps x 24 KB = 43..58 MB of the 126 MB L2), so residency is bounded by
-//   registers only and the FP64 pipe sees 3-4 warps per scheduler instead of 2.
-template <bool kGlobal, int kThreads, int kMaxRegs>
+// walks the virtual blocks vb = blockIdx.x, blockIdx.x + gridDim.x, ... (vb -> model, velocity chunk, period
+// group).  The per-layer row vectors E_{m+1} and transcendental results live in a per-resident-warp slab of
+// global memory that stays in L2 (148 SMs x 12 warps x 43.8 KB = 78 MB of the 126 MB L2 at 20 layers), so
+// residency is bounded by registers only.
+template <int kThreads, int kMaxRegs>
 __global__ void __maxnreg__(kMaxRegs)
 k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const double* __restrict__ beta,
            const double* __restrict__ rho, const double* __restrict__ t, const double* __restrict__ c,
            const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp, int total_vblocks,
            double* __restrict__ det, double* __restrict__ part, double* __restrict__ estore) {
   extern __shared__ double smem[];
-  constexpr int kAccPer = kGlobal ? 64 : 4;             // accumulator doubles per (warp, layer)
+  constexpr int kAccPer = 64;                           // accumulator doubles per (warp, layer): [4][16]
   constexpr int kTab = kTabAdj;
   double* par = smem + kSmemHead;                       // staged layer constants (after the exp table)
-  double* accs = par + par_doubles(L);                  // [wpb][L][4][16] (global slabs) or [wpb][4][L]
+  double* accs = par + par_doubles(L);                  // [wpb][L][4][16]
   double* tab = accs + (size_t)gp.wpb * kAccPer * L;    // [tc][L-1][kTab]
   double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
   double* hks = ics + ((gp.tc + 1) & ~1);               // [wpb*32][2]: omega/alpha_hs, omega/beta_hs per lane
-  double* ests = hks + 2 * kThreads;                    // [wpb][L-1][kSlot][32] (shared variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
-  const unsigned long long slab_policy = kGlobal ? l2_evict_last_policy() : 0ull;
+  const GlobalStore st{estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + lane, l2_evict_last_policy()};
   double* acc = accs + (size_t)warp * kAccPer * L;
-  double* estp = kGlobal ? estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + lane
-                         : ests + (size_t)warp * slab + lane;
   for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
     const BlockCoord bc = block_coord(vb, gp);
     const int s = bc.s;
@@ -338,95 +322,8 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
       for (int cc = 0; cc < n; ++cc) {
         const int k = kb + cc;
         const Sample z = make_sample_dense(omega0, ics[cc], iw0);
-        const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab, nullptr, nullptr, hk};
+        const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab, hk};
         const size_t idx = ((size_t)s * K + k) * NF + fc;
-        // inactive lanes (period tile overhang) replay a valid sample with a zero seed
-        const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
-        double v;
-        if (kGlobal) {
-          const GlobalStore st{estp, slab_policy};
-          FoldSink sink{acc, lane};
-          v = sample_forward_store(src, z, st);
-          if (det && active) __stcs(det + idx, v);  // streaming store: keep the store slabs in L2
-          sample_adjoint(src, z, seed, v, st, sink);
-        } else {
-          const PlainStore<kWarp> st{estp};
-          ReduceSink sink{acc, L, lane};
-          v = sample_forward_store(src, z, st);
-          if (det && active) __stcs(det + idx, v);
-          sample_adjoint(src, z, seed, v, st, sink);
-        }
-      }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
-      double v = 0.0;
-      if (kGlobal) {
-        const int which = i / L, m = i - which * L;  // output order [4][L]
-        for (int w = 0; w < gp.wpb; ++w) {
-          const double* q = accs + (size_t)w * kAccPer * L + ((m * 4 + which) << 4);
-#pragma unroll
-          for (int l = 0; l < 16; ++l) v += q[l];
-        }
-      } else {
-        for (int w = 0; w < gp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
-      }
-      part[((size_t)s * gp.bpm + bc.blk) * 4 * L + i] = v;
-    }
-  }
-}
-
-// The same fused sweep with a free warp <-> work assignment: a block = (model, velocity chunk); per table fill
-// (tc trial velocities) its warps share the tc x nft (velocity, period tile) tasks round-robin, so the block size
-// is not tied to the number of period tiles of a model (ADSURF_GRID_BWD=f8: 2 blocks x 8 warps per SM at 128
-// registers, one table fill serves 8 warps).  omega and 1/omega per period are staged once per block.
-template <int kThreads, int kMaxRegs>
-__global__ void __maxnreg__(kMaxRegs)
-k_grid_bwd_flex(const double* __restrict__ d, const double* __restrict__ alpha, const double* __restrict__ beta,
-                const double* __restrict__ rho, const double* __restrict__ t, const double* __restrict__ c,
-                const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp, int total_vblocks,
-                double* __restrict__ det, double* __restrict__ part, double* __restrict__ estore) {
-  extern __shared__ double smem[];
-  constexpr int kW = kThreads / kWarp;
-  constexpr int kTab = kTabAdj;
-  double* par = smem + kSmemHead;                       // staged layer constants (after the exp table)
-  double* accs = par + par_doubles(L);                  // [kW][L][4][16]
-  double* tab = accs + (size_t)kW * 64 * L;             // [tc][L-1][kTab]
-  double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
-  double* omg = ics + ((gp.tc + 1) & ~1);               // [nft*32][4]: omega, 1/max(omega, 1e-4), omega/alpha_hs, omega/beta_hs
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
-  const GlobalStore st{estore + ((size_t)blockIdx.x * kW + warp) * slab + lane, l2_evict_last_policy()};
-  double* acc = accs + (size_t)warp * 64 * L;
-  const int nft = gp.nft;
-  for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
-    const int s = vb / gp.bpm, ch = vb - s * gp.bpm;
-    __syncthreads();  // previous virtual block has flushed its accumulators
-    stage_params(par, d, alpha, beta, rho, s, L);
-    for (int i = threadIdx.x; i < kW * 64 * L; i += blockDim.x) accs[i] = 0.0;
-    __syncthreads();  // staged parameters visible
-    for (int i = threadIdx.x; i < nft * kWarp; i += blockDim.x) {
-      const double om = omega_of_period(t[(size_t)s * NF + min(i, NF - 1)]);
-      omg[4 * i] = om;
-      omg[4 * i + 1] = 1.0 / fmax(om, 1.0e-4);
-      stage_half_k(omg + 4 * i + 2, par, L, om);
-    }
-    const int k0 = ch * gp.chunk, k1 = min(K, k0 + gp.chunk);
-    for (int kb = k0; kb < k1; kb += gp.tc) {
-      const int n = min(gp.tc, k1 - kb);
-      __syncthreads();
-      fill_table<kTab>(tab, ics, par, L, c + (size_t)s * K + kb, n);
-      __syncthreads();
-      const int ntask = n * nft;
-      for (int task = warp; task < ntask; task += kW) {
-        const int cc = task / nft, tile = task - cc * nft;
-        const int f = tile * kWarp + lane;
-        const bool active = f < NF;
-        const Dbl2 om = ld2(omg + 4 * f);
-        const Sample z = make_sample_dense(om.x, ics[cc], om.y);
-        const TableSource<kTab, true> src{par, L, tab + (size_t)cc * (L - 1) * kTab, omg + 4 * f, ics + cc,
-                                          omg + 4 * f + 2};
-        const size_t idx = ((size_t)s * K + (kb + cc)) * NF + (active ? f : NF - 1);
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
         FoldSink sink{acc, lane};
@@ -439,12 +336,12 @@ k_grid_bwd_flex(const double* __restrict__ d, const double* __restrict__ alpha, 
     for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
       const int which = i / L, m = i - which * L;  // output order [4][L]
       double v = 0.0;
-      for (int w = 0; w < kW; ++w) {
-        const double* q = accs + (size_t)w * 64 * L + ((m * 4 + which) << 4);
+      for (int w = 0; w < gp.wpb; ++w) {
+        const double* q = accs + (size_t)w * kAccPer * L + ((m * 4 + which) << 4);
 #pragma unroll
         for (int l = 0; l < 16; ++l) v += q[l];
       }
-      part[((size_t)s * gp.bpm + ch) * 4 * L + i] = v;
+      part[((size_t)s * gp.bpm + bc.blk) * 4 * L + i] = v;
     }
   }
 }
@@ -668,120 +565,202 @@ __device__ __forceinline__ double lap(double xm, double x0, double xp, int i, in
   return 2.0 * x0 - xm - xp;
 }
 
-// phase 1 (reads the CURRENT, not yet projected, b — the point where the misfit was evaluated): gradient of
-// the data term w.r.t. b through the velocity chain, sign fields of the two Tikhonov terms, total loss
-__global__ void k_ens_prepare(const double* __restrict__ b, const double* __restrict__ alpha,
-                              const double* __restrict__ ga, const double* __restrict__ gb,
-                              const double* __restrict__ gr, int S, int L, int vp_mode, double ratio, double dv,
-                              double dh, double* __restrict__ gt, double* __restrict__ sv, double* __restrict__ sh,
-                              double* __restrict__ loss) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
-  double add = 0.0;
-  for (int l = 0; l < L; ++l) {
-    const size_t i = (size_t)s * L + l;
-    const double x0 = b[i];
-    double g = gb[i];
-    if (vp_mode == 1 || (vp_mode == 3 && x0 <= 4.6)) {
-      g += (ga[i] + gr[i] * brocher_drho(alpha[i])) * brocher_dvp(x0);
-    } else if (vp_mode == 2) {
-      g += ga[i] * ratio;
-    }
-    gt[i] = g;
-    if (dv > 0.0) {
-      const double mv = dv * lap(l > 0 ? b[i - 1] : 0.0, x0, l < L - 1 ? b[i + 1] : 0.0, l, L) / L;
-      add += fabs(mv);
-      sv[i] = sgn(mv);
-    }
-    if (dh > 0.0) {
-      const double mh = dh * lap(s > 0 ? b[i - L] : 0.0, x0, s < S - 1 ? b[i + L] : 0.0, s, S) / L;
-      add += fabs(mh);
-      sh[i] = sgn(mh);
-    }
-  }
-  loss[s] += add;
-}
-
+// One optimiser step of the inversion loop = two launches with one thread per (model, layer):
+//   k_ens_prepare  reads the CURRENT (not yet projected) b — the point where the misfit was evaluated — and forms the
+//                  gradient of the data term w.r.t. b through the velocity chain (summing the adjoint kernel's block
+//                  partials on the way when they are handed over unreduced), the sign fields of the two Tikhonov terms
+//                  and their contribution to the misfit; snapshots b and d so that phase 2 can update in place;
+//   k_ens_adam     projection (Vs clip, half-space rule, depth clip: the serial recurrences over the layers are a few
+//                  cheap operations per layer and are simply recomputed by every thread up to its own layer),
+//                  iterate / misfit history, Tikhonov subgradients, Adam, next Vp / rho, iteration counter.
+// The iteration index, learning-rate schedule and Adam bias corrections come either from the host (lr, bc1, bc2s) or
+// from a device counter, which makes the launch sequence of one iteration a replayable CUDA graph.
 struct EnsArgs {
-  double *b, *d, *alpha, *rho, *mb, *vb, *md, *vd, *iter_b, *iter_d;
-  const double *gd, *gt, *b0, *a0, *r0, *lob, *upb, *mind, *maxd, *sv, *sh;
+  double *b, *d, *alpha, *rho, *mb, *vb, *md, *vd;
+  const double *gd, *ga, *gb, *gr;  // reduced gradients [S,L] ...
+  const double *part, *loss_part;   // ... or the adjoint kernel's block partials [S][bpm][4][L], [S][bpm]
+  int bpm, npicks;
+  double* loss;                     // [S]: data misfit in (reduced-gradient form) / total misfit out
+  const double *b0, *a0, *r0, *lob, *upb, *mind, *maxd;
+  double *gt, *gdr, *sv, *sh, *tik, *bo, *dold, *shh;  // scratch: 7 x [S,L] + [2,L]
+  const double* halo;               // [4,L]: Vs rows row0-2, row0-1, row0+S, row0+S+1 of a sharded ensemble (or NULL)
+  int row0, S_all;                  // global index of local row 0 and global ensemble size (horizontal damping)
   int S, L, vp_mode, invert_thick, layering, proj_flags;
-  double ratio, dv, dh, lr, beta1, beta2, eps, bc1, bc2s;
+  double ratio, dv, dh, lr, gamma, beta1, beta2, eps, bc1, bc2s;
+  int step_size;
+  int* counter;                     // device: [0] iteration index j (0-based), [1] block ticket; NULL: host scalars
+  int T;                            // history slots (counter form)
+  double *loss_hist, *iter_b, *iter_d;  // counter form: bases of [T,S], [T,S,L]; host form: this iteration's slot
 };
 
-__device__ __forceinline__ double adam(double p, double g, double& m, double& v, const EnsArgs& A) {
-  m = m + (1.0 - A.beta1) * (g - m);                // exp_avg.lerp_(grad, 1 - beta1)
-  v = A.beta2 * v + (1.0 - A.beta2) * g * g;        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-  const double denom = sqrt(v) / A.bc2s + A.eps;    // bias_correction2_sqrt
-  return p - (A.lr / A.bc1) * (m / denom);
-}
-
-// phase 2: one thread per model
-__global__ void k_ens_adam(EnsArgs A) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= A.S) return;
+__global__ void k_ens_prepare(EnsArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int L = A.L, S = A.S;
-  const size_t o = (size_t)s * L;
-  // --- projection of Vs (before the optimiser step, as the reference orders it); torch.clamp keeps NaN
-  double prev = 0.0;
-  for (int l = 0; l < L; ++l) {
-    double x = A.b[o + l];
-    if (x != x && (A.proj_flags & 2)) x = A.b0[o + l];              // NaN repair of the ensemble vs-only loop (:624-626)
-    if (x == x) x = fmin(fmax(x, A.lob[o + l]), A.upb[o + l]);       // clip_(min, max): max wins when min > max
-    if ((A.proj_flags & 1) && l == L - 1 && L > 1 && x == x && prev == prev) x = fmax(x, prev);  // (:129/:599/:631)
-    prev = x;
-    A.b[o + l] = x;
-    if (A.iter_b) A.iter_b[o + l] = x;
+  if (i >= S * L) return;
+  const int s = i / L, l = i - s * L;
+  const double x0 = A.b[i];
+  double gd, ga, gb, gr;
+  if (A.part) {
+    gd = ga = gb = gr = 0.0;
+    for (int k = 0; k < A.bpm; ++k) {
+      const double* q = A.part + ((size_t)s * A.bpm + k) * 4 * L + l;
+      gd += q[0];
+      ga += q[L];
+      gb += q[2 * L];
+      gr += q[3 * L];
+    }
+  } else {
+    gd = A.gd ? A.gd[i] : 0.0;
+    ga = A.ga[i];
+    gb = A.gb[i];
+    gr = A.gr[i];
   }
-  // --- projection of the depths
-  if (A.invert_thick) {
-    const double floor_t = A.mind[0];
-    double depth = 0.0, pdepth = 0.0;  // running cumulative depth (raw) and previous projected depth
-    for (int l = 0; l < L; ++l) {
-      depth += A.d[o + l];
-      double z = depth;
-      if (A.layering == 1) {
-        z = fmin(fmax(z, A.mind[o + l]), A.maxd[o + l]);
-      } else if (A.layering == 2) {
-        const double lo = l == 0 ? A.mind[o + l] : pdepth + A.mind[o + l];
-        z = fmin(fmax(z, lo), A.maxd[o + l]);
-      }
-      const double th = fmax(z - pdepth, floor_t);
-      pdepth = z;
-      A.d[o + l] = th;
-      if (A.iter_d) A.iter_d[o + l] = th;
+  double g = gb;
+  if (A.vp_mode == 1 || (A.vp_mode == 3 && x0 <= 4.6)) {
+    g += (ga + gr * brocher_drho(A.alpha[i])) * brocher_dvp(x0);
+  } else if (A.vp_mode == 2) {
+    g += ga * A.ratio;
+  }
+  A.gt[i] = g;
+  A.gdr[i] = gd;
+  double tik = 0.0;
+  if (A.dv > 0.0) {
+    const double mv = A.dv * lap(l > 0 ? A.b[i - 1] : 0.0, x0, l < L - 1 ? A.b[i + 1] : 0.0, l, L) / L;
+    tik += fabs(mv);
+    A.sv[i] = sgn(mv);
+  }
+  if (A.dh > 0.0) {
+    const int r = A.row0 + s, Sa = A.S_all;
+    const double* h = A.halo;
+    const double xm = s > 0 ? A.b[i - L] : (h ? h[L + l] : 0.0);
+    const double xp = s < S - 1 ? A.b[i + L] : (h ? h[2 * L + l] : 0.0);
+    const double mh = A.dh * lap(xm, x0, xp, r, Sa) / L;
+    tik += fabs(mh);
+    A.sh[i] = sgn(mh);
+    if (h) {  // sign field of the two rows next to the shard (owned by the neighbouring ranks)
+      if (s == 0 && r > 0) A.shh[l] = sgn(A.dh * lap(h[l], h[L + l], x0, r - 1, Sa) / L);
+      if (s == S - 1 && r + 1 < Sa) A.shh[L + l] = sgn(A.dh * lap(x0, h[2 * L + l], h[3 * L + l], r + 1, Sa) / L);
     }
   }
-  // --- Tikhonov subgradients on top of the chain gradient of phase 1, Adam, next alpha / rho
-  for (int l = 0; l < L; ++l) {
-    const double x = A.b[o + l];
-    double g = A.gt[o + l];
+  A.tik[i] = tik;
+  A.bo[i] = x0;
+  A.dold[i] = A.d[i];
+}
+
+__device__ __forceinline__ double adam(double p, double g, double& m, double& v, const EnsArgs& A, double lr, double bc1,
+                                       double bc2s) {
+  m = m + (1.0 - A.beta1) * (g - m);              // exp_avg.lerp_(grad, 1 - beta1)
+  v = A.beta2 * v + (1.0 - A.beta2) * g * g;      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const double denom = sqrt(v) / bc2s + A.eps;    // bias_correction2_sqrt
+  return p - (lr / bc1) * (m / denom);
+}
+
+__global__ void k_ens_adam(EnsArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int L = A.L, S = A.S;
+  int j = 0;
+  double lr = A.lr, bc1 = A.bc1, bc2s = A.bc2s;
+  if (A.counter) {
+    j = A.counter[0];
+    // StepLR as torch chains it (lr <- lr * gamma every step_size steps); Adam bias corrections of step j + 1
+    for (int n = A.step_size > 0 ? j / A.step_size : 0; n > 0; --n) lr *= A.gamma;
+    bc1 = 1.0 - pow(A.beta1, (double)(j + 1));
+    bc2s = sqrt(1.0 - pow(A.beta2, (double)(j + 1)));
+  }
+  if (i < S * L) {
+    const int s = i / L, l = i - s * L;
+    const size_t o = (size_t)s * L;
+    const bool rec = !A.counter || j < A.T;
+    const size_t ho = A.counter ? (size_t)j * S * L : 0;
+    // --- projection of Vs (before the optimiser step, as the reference orders it); torch.clamp keeps NaN
+    auto proj_b = [&](int ll) {
+      double x = A.bo[o + ll];
+      if (x != x && (A.proj_flags & 2)) x = A.b0[o + ll];            // NaN repair of the ensemble vs-only loop (:624-626)
+      if (x == x) x = fmin(fmax(x, A.lob[o + ll]), A.upb[o + ll]);   // clip_(min, max): max wins when min > max
+      return x;
+    };
+    double x = proj_b(l);
+    if ((A.proj_flags & 1) && l == L - 1 && L > 1) {                 // half-space >= layer above (:129/:599/:631)
+      const double prev = proj_b(L - 2);
+      if (x == x && prev == prev) x = fmax(x, prev);
+    }
+    if (A.iter_b && rec) A.iter_b[ho + i] = x;
+    // --- projection of the depths: cumulative depth clipped per layer (LR) or against the previous projected
+    // depth (LN), back to thicknesses >= min thickness (:133-147, :603-620)
+    double th = A.dold[i];
+    if (A.invert_thick) {
+      const double floor_t = A.mind[0];
+      double depth = 0.0, pdepth = 0.0, z = 0.0;
+      for (int ll = 0; ll <= l; ++ll) {
+        pdepth = z;
+        depth += A.dold[o + ll];
+        z = depth;
+        if (A.layering == 1) {
+          z = fmin(fmax(z, A.mind[o + ll]), A.maxd[o + ll]);
+        } else if (A.layering == 2) {
+          const double lo = ll == 0 ? A.mind[o + ll] : pdepth + A.mind[o + ll];
+          z = fmin(fmax(z, lo), A.maxd[o + ll]);
+        }
+      }
+      th = fmax(z - pdepth, floor_t);
+      if (A.iter_d && rec) A.iter_d[ho + i] = th;
+    }
+    // --- Tikhonov subgradients on top of the chain gradient of phase 1, Adam, next alpha / rho
+    double g = A.gt[i];
     if (A.dv > 0.0) {
-      const double c = lap(l > 0 ? A.sv[o + l - 1] : 0.0, A.sv[o + l], l < L - 1 ? A.sv[o + l + 1] : 0.0, l, L);
+      const double c = lap(l > 0 ? A.sv[i - 1] : 0.0, A.sv[i], l < L - 1 ? A.sv[i + 1] : 0.0, l, L);
       g += A.dv / L * c;
     }
     if (A.dh > 0.0) {
-      const double c = lap(s > 0 ? A.sh[o - L + l] : 0.0, A.sh[o + l], s < S - 1 ? A.sh[o + L + l] : 0.0, s, S);
-      g += A.dh / L * c;
+      const int r = A.row0 + s, Sa = A.S_all;
+      const double sm = s > 0 ? A.sh[i - L] : (A.halo && r > 0 ? A.shh[l] : 0.0);
+      const double sp = s < S - 1 ? A.sh[i + L] : (A.halo && r + 1 < Sa ? A.shh[L + l] : 0.0);
+      g += A.dh / L * lap(sm, A.sh[i], sp, r, Sa);
     }
-    double m = A.mb[o + l], v = A.vb[o + l];
-    const double xn = adam(x, g, m, v, A);
-    A.mb[o + l] = m;
-    A.vb[o + l] = v;
-    A.b[o + l] = xn;
-    if (A.vp_mode == 1 || A.vp_mode == 3) {
-      const bool low = A.vp_mode == 1 || xn <= 4.6;
-      const double an = low ? brocher_vp(xn) : A.a0[o + l];
-      A.alpha[o + l] = an;
-      A.rho[o + l] = low ? brocher_rho(an) : A.r0[o + l];
+    double m = A.mb[i], v = A.vb[i];
+    const double xn = adam(x, g, m, v, A, lr, bc1, bc2s);
+    A.mb[i] = m;
+    A.vb[i] = v;
+    A.b[i] = xn;
+    if (A.vp_mode == 1 || (A.vp_mode == 3 && xn <= 4.6)) {
+      // USArray (3): entries above 4.6 km/s keep their current Vp / rho, as the reference's masked in-place
+      // update leaves them (_model.py:440-446; its AK135 loop writes into temporaries)
+      const double an = brocher_vp(xn);
+      A.alpha[i] = an;
+      A.rho[i] = brocher_rho(an);
     } else if (A.vp_mode == 2) {
-      A.alpha[o + l] = xn * A.ratio;
+      A.alpha[i] = xn * A.ratio;
     }
     if (A.invert_thick) {
-      double m2 = A.md[o + l], v2 = A.vd[o + l];
-      A.d[o + l] = adam(A.d[o + l], A.gd[o + l], m2, v2, A);
-      A.md[o + l] = m2;
-      A.vd[o + l] = v2;
+      double m2 = A.md[i], v2 = A.vd[i];
+      A.d[i] = adam(th, A.gdr[i], m2, v2, A, lr, bc1, bc2s);
+      A.md[i] = m2;
+      A.vd[i] = v2;
+    }
+    if (l == 0) {  // total misfit of model s
+      double tot;
+      if (A.loss_part) {
+        tot = 0.0;
+        for (int k = 0; k < A.bpm; ++k) tot += A.loss_part[(size_t)s * A.bpm + k];
+        tot /= (double)A.npicks;
+      } else {
+        tot = A.loss[s];
+      }
+      double add = 0.0;
+      for (int ll = 0; ll < L; ++ll) add += A.tik[o + ll];
+      tot += add;
+      A.loss[s] = tot;
+      if (A.loss_hist && rec) A.loss_hist[(A.counter ? (size_t)j * S : 0) + s] = tot;
+    }
+  }
+  if (A.counter) {  // the last block to finish advances the iteration index (every block has read it by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&A.counter[1], 1) == (int)gridDim.x - 1) {
+        A.counter[1] = 0;
+        A.counter[0] = j + 1;
+      }
     }
   }
 }
@@ -800,15 +779,25 @@ __global__ void k_math_probe(const double* __restrict__ x, int n, double* __rest
 // ------------------------------------------------------------------------------------------
 // Host-side planning
 // ------------------------------------------------------------------------------------------
-constexpr int kNumSM = 148;
 constexpr size_t kSmemBudget = 100 * 1024;   // per block, so that two blocks fit an SM
 constexpr size_t kSmemMax = 227 * 1024;
+
+// SM count of the current device (grids, slab sizing and work splitting follow it; nothing assumes 148)
+inline int sm_count() {
+  int dev = 0, nsm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      nsm <= 0) {
+    cudaGetLastError();
+    nsm = 148;
+  }
+  return nsm;
+}
 
 inline size_t par_bytes(int L) { return (size_t)(kSmemHead + par_doubles(L)) * sizeof(double); }
 
 inline size_t est_bytes_per_warp(int L) { return (size_t)(L > 1 ? L - 1 : 0) * kSlot * kWarp * sizeof(double); }
 
-// warps per block for the adjoint kernels; 0 if even one warp does not fit
+// warps per block for the pointwise adjoint with the slabs in shared memory; 0 if even one warp does not fit
 inline int adj_wpb(int L) {
   const size_t fixed = par_bytes(L) + 64;
   const size_t per_warp = est_bytes_per_warp(L) + (size_t)4 * L * sizeof(double) + sizeof(double);
@@ -824,93 +813,109 @@ inline size_t adj_smem(int L, int wpb) {
          (size_t)wpb * est_bytes_per_warp(L);
 }
 
-// Where the dense adjoint keeps its per-layer row vectors and how many warps it runs.
-// Overridable for experiments with ADSURF_GRID_BWD (read once):
-//   g3   (default) slabs in the L2-resident global slab, 3 blocks x 4 warps per SM at <= 168 registers.  The
-//        register file is split per scheduler (16384 registers each), so residency goes in steps of one warp
-//        per scheduler: 3 warps up to 170 registers per thread, 4 only at <= 128 — variants with 14 or 15 warps
-//        per SM (2 x 7 at 144, 3 x 5 at 136) do not become resident and were measured 25 % slower;
-//   f8   free warp <-> task assignment, 2 blocks x 8 warps at 128 registers (4 warps per scheduler; the tighter
-//        register budget costs about what the extra warp brings: 2.31 G vs 2.35 G samples/s when measured);
-//   smem slabs in shared memory (2 blocks x 4 warps at 20 layers).
-enum { kBwdSmem = 0, kBwdG3 = 1, kBwdF8 = 2 };
-inline int bwd_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("ADSURF_GRID_BWD");
-    mode = kBwdG3;
-    if (e && !strcmp(e, "smem")) mode = kBwdSmem;
-    if (e && !strcmp(e, "f8")) mode = kBwdF8;
-  }
-  return mode;
-}
-inline int bwd_flex_warps() { return bwd_mode() == kBwdF8 ? 8 : 0; }  // 0 = period-tile kernel
-constexpr int kMaxResidentWarps = 160 * 16;  // upper bound on co-resident adjoint warps (global store slabs)
-
-inline int bwd_wpb_global() { return bwd_flex_warps() ? bwd_flex_warps() : 4; }
-
-inline size_t bwd_estore_bytes(int L) {
-  return bwd_mode() == kBwdSmem ? 0 : (size_t)kMaxResidentWarps * est_bytes_per_warp(L);
-}
+// The adjoint kernels with global (L2-resident) slabs run 3 blocks x 4 warps per SM at <= 168 registers: the
+// register file is split per scheduler (16384 registers each), so residency goes in steps of one warp per
+// scheduler — 3 warps up to 170 registers per thread, 4 only at <= 128.
+constexpr int kBwdWarps = 4, kBwdBlocksPerSM = 3, kFwdWarpsPerSM = 16;
+inline int max_resident_adj_warps(int nsm) { return nsm * kBwdBlocksPerSM * kBwdWarps; }
+inline size_t slab_bytes(int L, int nsm) { return (size_t)max_resident_adj_warps(nsm) * est_bytes_per_warp(L); }
 
 inline size_t table_bytes(int L, int tc, bool adjoint) {
   const size_t per = (size_t)(L > 1 ? L - 1 : 0);
   return (size_t)tc * per * (adjoint ? kTabAdj : kTabFwd) * sizeof(double) + (size_t)((tc + 1) & ~1) * sizeof(double);
 }
 
-inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint) {
-  GridPlan gp;
-  gp.nft = (NF + kWarp - 1) / kWarp;
-  int want = 8;
-  if (adjoint) {
-    want = bwd_wpb_global();
-    if (bwd_mode() == kBwdSmem) {  // slabs in shared memory: as many warps as fit beside the table
-      want = 0;
-      for (int w = 4; w >= 1 && !want; w >>= 1)
-        if (adj_smem(L, w) + table_bytes(L, 8, true) + (size_t)w * kWarp * 2 * sizeof(double) <=
-            (w > 1 ? kSmemBudget : kSmemMax))
-          want = w;
-    }
-  }
-  const int flex = adjoint ? bwd_flex_warps() : 0;
-  gp.wpb = flex ? flex : (want < gp.nft ? want : gp.nft);
-  if (gp.wpb < 1) gp.wpb = adjoint && want <= 0 ? 0 : 1;
-  gp.nfg = flex ? 1 : (gp.wpb > 0 ? (gp.nft + gp.wpb - 1) / gp.wpb : 0);
-  // table fills of up to 8 velocities, fewer for very deep models (keeps the table under ~24 KB)
-  gp.tc = 8;
-  while (gp.tc > 1 && table_bytes(L, gp.tc, adjoint) > 24 * 1024) gp.tc >>= 1;
-  if (flex) {
-    // free assignment: tc * nft tasks per fill should be a multiple of the warps per block
-    int best = gp.tc, waste = 1 << 30;
-    for (int tc = gp.tc; tc >= 1 && tc > gp.tc / 2; --tc) {
-      const int tasks = tc * gp.nft, w = ((tasks + flex - 1) / flex) * flex - tasks;
-      if (w * best < waste * tc) {  // compare idle slots per task: w / tasks
-        best = tc;
-        waste = w;
-      }
-    }
-    gp.tc = best;
-  }
-  // enough blocks for ~16 waves of a full machine, chunks not shorter than 2 table fills
-  const long long target = (long long)kNumSM * 4 * 16;
-  const long long base = (long long)S * (gp.nfg > 0 ? gp.nfg : 1);
-  long long nchunk = (target + base - 1) / base;
-  const long long maxchunks = K >= 2 * gp.tc ? K / (2 * gp.tc) : 1;
-  if (nchunk > maxchunks) nchunk = maxchunks;
-  if (nchunk < 1) nchunk = 1;
-  gp.chunk = (K + (int)nchunk - 1) / (int)nchunk;
-  gp.chunk = ((gp.chunk + gp.tc - 1) / gp.tc) * gp.tc;  // whole table fills
-  gp.nchunk = (K + gp.chunk - 1) / gp.chunk;
-  gp.bpm = gp.nchunk * gp.nfg;
-  return gp;
+inline size_t grid_fwd_smem(int L, int tc, int wpb) {
+  return par_bytes(L) + table_bytes(L, tc, false) + (size_t)wpb * kWarp * 2 * sizeof(double);
+}
+inline size_t grid_bwd_smem(int L, int tc, int wpb) {
+  return par_bytes(L) + (size_t)wpb * 64 * L * sizeof(double) + table_bytes(L, tc, true) +
+         (size_t)wpb * kWarp * 2 * sizeof(double);
 }
 
-inline PointsPlan plan_points(int S, int L, int N, bool allow_global) {
+// Split of the dense grid into blocks = (model, velocity chunk, period group of wpb tiles).
+// A thread walks its chunk's velocities one after the other, so the run time is
+//   (waves of resident blocks) x (chunk + table fills),
+// which for small problems (one model x a few hundred periods: BASELINE configs 1-3) is dominated by how the
+// block count rounds against the machine: the planner enumerates (warps per block, chunks per model) and keeps
+// the cheapest; for large problems every split costs the same and the tie-break is ~16 waves.
+inline GridPlan plan_grid_search(int S, int L, int NF, int K, bool adjoint, int nsm) {
+  GridPlan best;
+  best.nft = (NF + kWarp - 1) / kWarp;
+  best.wpb = 0;
+  double best_cost = 1e300;
+  const int nft = best.nft;
+  const int wmax = adjoint ? kBwdWarps : 8;
+  const int per = L > 1 ? L - 1 : 1;
+  int tcmax = 8;  // table fills of up to 8 velocities, fewer for very deep models (keeps the table under ~24 KB)
+  while (tcmax > 1 && table_bytes(L, tcmax, adjoint) > 24 * 1024) tcmax >>= 1;
+  for (int w = wmax < nft ? wmax : nft; w >= 1; w = (w > 4 ? 4 : w - 1)) {
+    if (adjoint && w != (wmax < nft ? wmax : nft)) break;  // the adjoint kernel is compiled for 4-warp blocks
+    const int nfg = (nft + w - 1) / w;
+    int bps = adjoint ? kBwdBlocksPerSM : kFwdWarpsPerSM / w;
+    const size_t smem = adjoint ? grid_bwd_smem(L, tcmax, w) : grid_fwd_smem(L, tcmax, w);
+    const int bsm = (int)(kSmemMax / (smem + 1024));
+    if (bsm < bps) bps = bsm;
+    if (bps < 1) bps = 1;
+    if (bps > 32) bps = 32;
+    const double R = (double)bps * nsm;  // resident blocks
+    const double live = (double)nft / ((double)nfg * w);  // fraction of a block's warps that own a period tile
+    int prev_chunk = 0;
+    for (int nchunk = 1; nchunk <= K; nchunk += (nchunk < 64 ? 1 : nchunk / 16)) {
+      const int chunk = (K + nchunk - 1) / nchunk;
+      if (chunk == prev_chunk) continue;
+      prev_chunk = chunk;
+      const int nch = (K + chunk - 1) / chunk;
+      const int tc = chunk < tcmax ? chunk : tcmax;
+      const double B = (double)S * nfg * nch;
+      const double full = floor(B / R), rem = B - full * R;
+      // a last wave that does not fill the machine: blocks are dealt round-robin to the SMs, so the busiest SM holds
+      // ceil(rem / nsm) of them; a warp then runs faster (less contention for the FP64 pipe) but not faster than
+      // its own dependent-issue latency allows (~0.55 of the time it takes at full residency)
+      const double cap = adjoint ? (double)(kBwdBlocksPerSM * kBwdWarps) : (double)kFwdWarpsPerSM;
+      const double waves = full + (rem > 0 ? fmin(1.0, fmax(0.55, ceil(rem / nsm) * w / cap)) : 0.0);
+      const int fills = (chunk + tc - 1) / tc;
+      // costs in units of one sample: a table entry ~ 0.04, per-block staging ~ 0.3, a fill's two barriers ~ 0.05
+      const double fill_cost = 0.05 + 0.04 * ceil((double)tc * per / (w * kWarp));
+      double cost = waves * (chunk + fills * fill_cost + 0.3);
+      cost *= 1.0 + 0.02 * (1.0 - live);                        // dead warps only help with the fills
+      cost *= 1.0 + 1e-3 * fabs(log2((B / R + 1e-9) / 16.0));  // tie-break: about 16 waves
+      if (cost < best_cost) {
+        best_cost = cost;
+        best.wpb = w;
+        best.nfg = nfg;
+        best.tc = tc;
+        best.chunk = chunk;
+        best.nchunk = nch;
+        best.bpm = nch * nfg;
+      }
+    }
+  }
+  return best;
+}
+
+// the search costs tens of microseconds and an inversion loop asks for the same plan every iteration
+inline GridPlan plan_grid(int S, int L, int NF, int K, bool adjoint, int nsm) {
+  struct Key {
+    int S, L, NF, K, adjoint, nsm;
+  };
+  thread_local Key key[2] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+  thread_local GridPlan plan[2];
+  const int slot = adjoint ? 1 : 0;
+  const Key k{S, L, NF, K, slot, nsm};
+  if (memcmp(&k, &key[slot], sizeof(Key)) != 0) {
+    plan[slot] = plan_grid_search(S, L, NF, K, adjoint, nsm);
+    key[slot] = k;
+  }
+  return plan[slot];
+}
+
+inline PointsPlan plan_points(int S, int L, int N, bool allow_global, int nsm) {
   PointsPlan pp;
   pp.units = (N + kWarp - 1) / kWarp;
   // large ensembles: 12 resident warps per SM with the slabs in L2; small problems: slabs in shared memory
-  pp.global = allow_global && (long long)S * pp.units >= (long long)kNumSM * 8;
-  pp.wpb = pp.global ? 4 : adj_wpb(L);
+  pp.global = allow_global && (long long)S * pp.units >= (long long)nsm * 8;
+  pp.wpb = pp.global ? kBwdWarps : adj_wpb(L);
   if (pp.wpb > pp.units) {
     int w = 1;
     while (w < pp.units) w <<= 1;
@@ -920,28 +925,10 @@ inline PointsPlan plan_points(int S, int L, int N, bool allow_global) {
   return pp;
 }
 
-inline size_t points_estore_bytes(const PointsPlan& pp, int L) {
-  return pp.global ? (size_t)kMaxResidentWarps * est_bytes_per_warp(L) : 0;
-}
+inline size_t points_estore_bytes(const PointsPlan& pp, int L, int nsm) { return pp.global ? slab_bytes(L, nsm) : 0; }
 
 inline size_t points_smem(const PointsPlan& pp, int L) {
   return pp.global ? par_bytes(L) + (size_t)pp.wpb * (64 * L + 1) * sizeof(double) : adj_smem(L, pp.wpb);
-}
-
-// The slabs are tagged evict_last; L2 honours that only inside its persisting carve-out, which is 0 bytes by
-// default.  Ask once per device for the largest carve-out the part allows (a context-wide limit, like a
-// shared-memory carve-out preference: it changes nothing for code that does not use persisting accesses).
-// ADSURF_PERSIST_L2=0 disables the request.
-inline void reserve_persisting_l2(int dev) {
-  static int done[64] = {0};
-  if (dev < 0 || dev >= 64 || done[dev]) return;
-  done[dev] = 1;
-  const char* e = getenv("ADSURF_PERSIST_L2");
-  if (e && !strcmp(e, "0")) return;
-  int maxb = 0;
-  if (cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && maxb > 0)
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxb);
-  cudaGetLastError();
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -968,7 +955,7 @@ inline int launch_points_bwd(const PointsPlan& pp, int S, int L, int N, const do
                              const double* beta, const double* rho, const double* t, const double* c,
                              const double* gF, double* F, double* gc, double* part, double* estore, double* Jd,
                              double* Ja, double* Jb, double* Jrho, const double* pmax, const double* pmin, int nchunk,
-                             int compress, int with_grad, double* norm, double* loss_part, cudaStream_t st) {
+                             int compress, int with_grad, double* norm, double* loss_part, int nsm, cudaStream_t st) {
   const size_t smem = points_smem(pp, L);
   const long long total_vb = (long long)S * pp.bpm;
   if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;
@@ -976,15 +963,13 @@ inline int launch_points_bwd(const PointsPlan& pp, int S, int L, int N, const do
   if (pp.global) {
     auto kern = k_points_bwd<kKind, true>;
     if (set_smem(kern, smem)) return ADSURF_E_CUDA;
-    int dev = 0, nsm = kNumSM, occ = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
       cudaGetLastError();
       return ADSURF_E_CUDA;
     }
+    if (occ > kBwdBlocksPerSM) occ = kBwdBlocksPerSM;  // the slab is sized for 3 x 4 warps per SM
     long long grid = (long long)occ * nsm;
-    if (grid * pp.wpb > kMaxResidentWarps) grid = kMaxResidentWarps / pp.wpb;
     if (grid > total_vb) grid = total_vb;
     kern<<<(unsigned)grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F, gc, part,
                                                 estore, Jd, Ja, Jb, Jrho, pmax, pmin, nchunk, compress, with_grad,
@@ -1006,7 +991,7 @@ inline int launch_points_bwd(const PointsPlan& pp, int S, int L, int N, const do
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
-const char* adsurf_version(void) { return "adsurf_b200 0.1 (sm_100a, fp64)"; }
+const char* adsurf_version(void) { return "adsurf_b200 0.2 (sm_100a, fp64)"; }
 
 const char* adsurf_error_string(int code) {
   switch (code) {
@@ -1021,39 +1006,85 @@ const char* adsurf_error_string(int code) {
   }
 }
 
+int adsurf_init(int device, unsigned flags) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return ADSURF_E_ARG;
+  }
+  if (flags & ~(unsigned)ADSURF_INIT_PERSIST_L2) return ADSURF_E_ARG;
+  if (flags & ADSURF_INIT_PERSIST_L2) {
+    int cur = 0, maxb = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return ADSURF_E_CUDA;
+    if (cur != device && cudaSetDevice(device) != cudaSuccess) return ADSURF_E_CUDA;
+    cudaError_t e = cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, device);
+    if (e == cudaSuccess && maxb > 0) e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxb);
+    if (cur != device) cudaSetDevice(cur);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return ADSURF_E_CUDA;
+    }
+  }
+  return ADSURF_OK;
+}
+
 size_t adsurf_workspace_bytes(int op, int S, int L, int n, int K) {
   if (S <= 0 || L <= 0 || n <= 0) return 0;
+  const int nsm = sm_count();
   switch (op) {
     case ADSURF_OP_POINTS_FWD:
     case ADSURF_OP_POINTS_JAC:
       return 0;
     case ADSURF_OP_POINTS_BWD: {
-      const PointsPlan pp = plan_points(S, L, n, true);
-      return align256((size_t)S * pp.bpm * 4 * L * sizeof(double)) + align256(points_estore_bytes(pp, L));
+      const PointsPlan pp = plan_points(S, L, n, true, nsm);
+      return align256((size_t)S * pp.bpm * 4 * L * sizeof(double)) + align256(points_estore_bytes(pp, L, nsm));
     }
     case ADSURF_OP_GRID_FWD: {
       if (K <= 0) return 0;
-      const GridPlan gp = plan_grid(S, L, n, K, false);
+      const GridPlan gp = plan_grid(S, L, n, K, false, nsm);
       return 2 * align256((size_t)S * gp.nchunk * n * sizeof(double));
     }
     case ADSURF_OP_GRID_BWD: {
       if (K <= 0) return 0;
-      const GridPlan gp = plan_grid(S, L, n, K, true);
-      return align256((size_t)S * gp.bpm * 4 * L * sizeof(double)) + align256(bwd_estore_bytes(L));
+      const GridPlan gp = plan_grid(S, L, n, K, true, nsm);
+      return align256((size_t)S * gp.bpm * 4 * L * sizeof(double)) + align256(slab_bytes(L, nsm));
     }
     case ADSURF_OP_DMF_STEP: {
-      const PointsPlan pp = plan_points(S, L, n, true);
+      const PointsPlan pp = plan_points(S, L, n, true, nsm);
       size_t b = align256((size_t)S * pp.bpm * 4 * L * sizeof(double)) + align256((size_t)S * pp.bpm * sizeof(double)) +
-                 align256(points_estore_bytes(pp, L));
+                 align256(points_estore_bytes(pp, L, nsm));
       if (K > 0) {
-        const GridPlan gp = plan_grid(S, L, n, K, false);
+        const GridPlan gp = plan_grid(S, L, n, K, false, nsm);
         b += 2 * align256((size_t)S * gp.nchunk * n * sizeof(double));
       }
       return b;
     }
+    case ADSURF_OP_ENSEMBLE_STEP:
+      return align256((size_t)(7 * (size_t)S * L + 2 * (size_t)L) * sizeof(double));
     default:
       return 0;
   }
+}
+
+int adsurf_plan_describe(int op, int S, int L, int n, int K, int* out) {
+  if (!out) return ADSURF_E_NULL;
+  if (S <= 0 || L <= 0 || n <= 0) return ADSURF_E_SHAPE;
+  const int nsm = sm_count();
+  memset(out, 0, 8 * sizeof(int));
+  out[7] = nsm;
+  if (op == ADSURF_OP_GRID_FWD || op == ADSURF_OP_GRID_BWD) {
+    if (K <= 0) return ADSURF_E_SHAPE;
+    const GridPlan gp = plan_grid(S, L, n, K, op == ADSURF_OP_GRID_BWD, nsm);
+    out[0] = gp.wpb; out[1] = gp.nfg; out[2] = gp.nchunk; out[3] = gp.chunk; out[4] = gp.tc; out[5] = gp.bpm;
+    out[6] = gp.nft;
+    return ADSURF_OK;
+  }
+  if (op == ADSURF_OP_POINTS_BWD || op == ADSURF_OP_DMF_STEP || op == ADSURF_OP_POINTS_JAC) {
+    const PointsPlan pp = plan_points(S, L, n, op != ADSURF_OP_POINTS_JAC, nsm);
+    out[0] = pp.wpb; out[1] = pp.units; out[5] = pp.bpm; out[6] = pp.global;
+    return ADSURF_OK;
+  }
+  return ADSURF_E_ARG;
 }
 
 int adsurf_det_points_fwd(const double* d, const double* alpha, const double* beta, const double* rho,
@@ -1064,6 +1095,7 @@ int adsurf_det_points_fwd(const double* d, const double* alpha, const double* be
   pp.units = (N + kWarp - 1) / kWarp;
   pp.wpb = 4;
   pp.bpm = (N + 127) / 128;
+  pp.global = 0;
   const size_t smem = par_bytes(L);
   if (set_smem(k_points_fwd, smem)) return ADSURF_E_CUDA;
   k_points_fwd<<<(unsigned)((size_t)S * pp.bpm), 128, smem, (cudaStream_t)stream>>>(d, alpha, beta, rho, t, c, L, N,
@@ -1079,21 +1111,22 @@ static int points_adjoint_common(int kind, const double* d, const double* alpha,
   if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
   if (S <= 0 || L <= 0 || N <= 0) return ADSURF_E_SHAPE;
   if (L - 1 > ADSURF_MAX_ADJ_LAYERS) return ADSURF_E_LAYERS;
-  const PointsPlan pp = plan_points(S, L, N, kind == 0);  // the Jacobian entry has no workspace: shared slabs
+  const int nsm = sm_count();
+  const PointsPlan pp = plan_points(S, L, N, kind == 0, nsm);  // the Jacobian entry has no workspace: shared slabs
   if (pp.wpb <= 0) return ADSURF_E_LAYERS;
   if (kind == 0) {
     const size_t part_bytes = align256((size_t)S * pp.bpm * 4 * L * sizeof(double));
-    if (!ws || ws_bytes < part_bytes + align256(points_estore_bytes(pp, L))) return ADSURF_E_WORKSPACE;
+    if (!ws || ws_bytes < part_bytes + align256(points_estore_bytes(pp, L, nsm))) return ADSURF_E_WORKSPACE;
     double* part = (double*)ws;
     double* estore = pp.global ? (double*)((char*)ws + part_bytes) : nullptr;
     const int rc = launch_points_bwd<0>(pp, S, L, N, d, alpha, beta, rho, t, c, gF, F, gc, part, estore, nullptr,
-                                        nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, nullptr, nullptr, st);
+                                        nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1, nullptr, nullptr, nsm, st);
     if (rc) return rc;
     k_grad_reduce<<<S, 128, 0, st>>>(part, L, pp.bpm, gd, ga, gb, grho);
     return check_launch();
   }
   return launch_points_bwd<1>(pp, S, L, N, d, alpha, beta, rho, t, c, nullptr, F, gc, nullptr, nullptr, Jd, Ja, Jb,
-                              Jrho, nullptr, nullptr, 0, 0, 1, nullptr, nullptr, st);
+                              Jrho, nullptr, nullptr, 0, 0, 1, nullptr, nullptr, nsm, st);
 }
 
 int adsurf_det_points_bwd(const double* d, const double* alpha, const double* beta, const double* rho,
@@ -1115,23 +1148,11 @@ int adsurf_det_points_jac(const double* d, const double* alpha, const double* be
 static int grid_fwd_launch(const double* d, const double* alpha, const double* beta, const double* rho,
                            const double* t, const double* c, int S, int L, int NF, int K, double* det, double* pmax,
                            double* pmin, uint32_t* signbits, const GridPlan& gp, cudaStream_t st) {
-  const size_t smem = par_bytes(L) + table_bytes(L, gp.tc, false) + (size_t)gp.wpb * kWarp * 2 * sizeof(double);
-  // register cap: 128 leaves the compiler free (it uses ~108: 4 warps per scheduler); ADSURF_GRID_FWD=r96 trades
-  // registers for a fifth warp per scheduler (experiments)
-  static int cap = -1;
-  if (cap < 0) {
-    const char* e = getenv("ADSURF_GRID_FWD");
-    cap = (e && !strcmp(e, "r96")) ? 96 : 128;
-  }
-  if (cap == 96) {
-    if (set_smem(k_grid_fwd<96>, smem)) return ADSURF_E_CUDA;
-    k_grid_fwd<96><<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K,
-                                                                                  gp, det, pmax, pmin, signbits);
-  } else {
-    if (set_smem(k_grid_fwd<128>, smem)) return ADSURF_E_CUDA;
-    k_grid_fwd<128><<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K,
-                                                                                   gp, det, pmax, pmin, signbits);
-  }
+  const size_t smem = grid_fwd_smem(L, gp.tc, gp.wpb);
+  if (smem > kSmemMax) return ADSURF_E_SHAPE;
+  if (set_smem(k_grid_fwd<128>, smem)) return ADSURF_E_CUDA;
+  k_grid_fwd<128><<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K,
+                                                                                 gp, det, pmax, pmin, signbits);
   return check_launch();
 }
 
@@ -1140,9 +1161,9 @@ int adsurf_det_grid_fwd(const double* d, const double* alpha, const double* beta
                         double* cmin, uint32_t* signbits, void* ws, size_t ws_bytes, void* stream) {
   if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
   if (S <= 0 || L <= 0 || NF <= 0 || K <= 0 || L > ADSURF_MAX_LAYERS) return ADSURF_E_SHAPE;
-  if ((size_t)S * (size_t)((NF + 31) / 32) * 4 > 0x7fffffffull) return ADSURF_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  const GridPlan gp = plan_grid(S, L, NF, K, false);
+  const GridPlan gp = plan_grid(S, L, NF, K, false, sm_count());
+  if ((size_t)S * (size_t)gp.bpm > 0x7fffffffull) return ADSURF_E_SHAPE;
   double *pmax = nullptr, *pmin = nullptr;
   if (cmax || cmin) {
     const size_t one = align256((size_t)S * gp.nchunk * NF * sizeof(double));
@@ -1167,61 +1188,54 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
   if (S <= 0 || L <= 0 || NF <= 0 || K <= 0) return ADSURF_E_SHAPE;
   if (L - 1 > ADSURF_MAX_ADJ_LAYERS) return ADSURF_E_LAYERS;
-  const GridPlan gp = plan_grid(S, L, NF, K, true);
+  const int nsm = sm_count();
+  const GridPlan gp = plan_grid(S, L, NF, K, true, nsm);
   if (gp.wpb <= 0) return ADSURF_E_LAYERS;
   const size_t part_bytes = align256((size_t)S * gp.bpm * 4 * L * sizeof(double));
-  const size_t need = part_bytes + align256(bwd_estore_bytes(L));
+  const size_t need = part_bytes + align256(slab_bytes(L, nsm));
   if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  const int mode = bwd_mode();
-  const size_t smem = par_bytes(L) +
-                      (size_t)gp.wpb * (mode == kBwdSmem ? 4 : 64) * L * sizeof(double) + table_bytes(L, gp.tc, true) +
-                      (mode == kBwdSmem ? (size_t)gp.wpb * est_bytes_per_warp(L) : 0) +
-                      (bwd_flex_warps() ? (size_t)gp.nft * kWarp * 4 * sizeof(double) : (size_t)gp.wpb * kWarp * 2 * sizeof(double));
-  double* estore = mode == kBwdSmem ? nullptr : (double*)((char*)ws + part_bytes);
+  const size_t smem = grid_bwd_smem(L, gp.tc, gp.wpb);
+  if (smem > kSmemMax) return ADSURF_E_LAYERS;
+  double* estore = (double*)((char*)ws + part_bytes);
   const long long total_vb = (long long)S * gp.bpm;
   if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;
-  int dev = 0, nsm = kNumSM, occ = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  reserve_persisting_l2(dev);
   const int threads = gp.wpb * kWarp;
-#define ADSURF_LAUNCH_BWD(KERN)                                                                                  \
-  do {                                                                                                           \
-    if (set_smem(KERN, smem)) return ADSURF_E_CUDA;                                                              \
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, threads, smem) != cudaSuccess || occ < 1) {    \
-      cudaGetLastError();                                                                                        \
-      return ADSURF_E_CUDA;                                                                                      \
-    }                                                                                                            \
-    long long grid = (long long)occ * nsm;                                                                       \
-    if (grid * gp.wpb > kMaxResidentWarps) grid = kMaxResidentWarps / gp.wpb;                                    \
-    if (grid > total_vb) grid = total_vb;                                                                        \
-    KERN<<<(unsigned)grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gdet, L, NF, K, gp, (int)total_vb,    \
-                                                det, (double*)ws, estore);                                       \
-  } while (0)
-  if (mode == kBwdG3) ADSURF_LAUNCH_BWD((k_grid_bwd<true, 128, 168>));        // 3 x 4 = 12 warps / SM
-  else if (mode == kBwdF8) ADSURF_LAUNCH_BWD((k_grid_bwd_flex<256, 128>));    // 2 x 8 = 16
-  else ADSURF_LAUNCH_BWD((k_grid_bwd<false, 128, 232>));
-#undef ADSURF_LAUNCH_BWD
+  auto kern = k_grid_bwd<kBwdWarps * kWarp, 168>;  // 3 x 4 = 12 warps / SM
+  if (set_smem(kern, smem)) return ADSURF_E_CUDA;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    return ADSURF_E_CUDA;
+  }
+  if (occ > kBwdBlocksPerSM) occ = kBwdBlocksPerSM;  // the slab is sized for 3 x 4 warps per SM
+  long long grid = (long long)occ * nsm;
+  if (grid > total_vb) grid = total_vb;
+  kern<<<(unsigned)grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gdet, L, NF, K, gp, (int)total_vb, det,
+                                              (double*)ws, estore);
   if (check_launch()) return ADSURF_E_CUDA;
   k_grad_reduce<<<S, 128, 0, st>>>((const double*)ws, L, gp.bpm, gd, galpha, gbeta, grho);
   return check_launch();
 }
 
-int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
-                    const double* c, const double* C, int S, int L, int N, int K, int compress, int with_grad,
-                    double* loss, double* F, double* norm, double* gd, double* galpha, double* gbeta, double* grho,
-                    void* ws, size_t ws_bytes, void* stream) {
-  if (!d || !alpha || !beta || !rho || !t || !c || !loss) return ADSURF_E_NULL;
+// dense pass (normalised modes) + pointwise forward/adjoint with the DMF seed; leaves the block partials in ws
+struct DmfLaunch {
+  PointsPlan pp;
+  double *part, *loss_part;
+};
+static int dmf_launch(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
+                      const double* c, const double* C, int S, int L, int N, int K, int compress, int with_grad,
+                      double* F, double* norm, void* ws, size_t ws_bytes, cudaStream_t st, DmfLaunch& out) {
+  if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
   if (compress < ADSURF_COMPRESS_NONE || compress > ADSURF_COMPRESS_NORM) return ADSURF_E_ARG;
   const bool normalised =
       (compress == ADSURF_COMPRESS_EXP || compress == ADSURF_COMPRESS_LOG || compress == ADSURF_COMPRESS_NORM);
   if (normalised && !C) return ADSURF_E_NULL;
   if (S <= 0 || L <= 0 || N <= 0 || (normalised && K <= 0)) return ADSURF_E_SHAPE;
   if (L - 1 > ADSURF_MAX_ADJ_LAYERS) return ADSURF_E_LAYERS;
-  const PointsPlan pp = plan_points(S, L, N, true);
+  const int nsm = sm_count();
+  const PointsPlan pp = plan_points(S, L, N, true, nsm);
   if (pp.wpb <= 0) return ADSURF_E_LAYERS;
-  cudaStream_t st = (cudaStream_t)stream;
   const size_t need = adsurf_workspace_bytes(ADSURF_OP_DMF_STEP, S, L, N, normalised ? K : 0);
   if (!ws || ws_bytes < need) return ADSURF_E_WORKSPACE;
   char* w = (char*)ws;
@@ -1230,12 +1244,13 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
   double* loss_part = (double*)w;
   w += align256((size_t)S * pp.bpm * sizeof(double));
   double* estore = pp.global ? (double*)w : nullptr;
-  w += align256(points_estore_bytes(pp, L));
+  w += align256(points_estore_bytes(pp, L, nsm));
   double *pmax = nullptr, *pmin = nullptr;
   int nchunk = 0;
   if (normalised) {
     // dense pass: max/min over the trial velocities at every observed period (constant for autograd)
-    const GridPlan gp = plan_grid(S, L, N, K, false);
+    const GridPlan gp = plan_grid(S, L, N, K, false, nsm);
+    if ((size_t)S * (size_t)gp.bpm > 0x7fffffffull) return ADSURF_E_SHAPE;
     const size_t one = align256((size_t)S * gp.nchunk * N * sizeof(double));
     pmax = (double*)w;
     pmin = (double*)(w + one);
@@ -1243,17 +1258,50 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
     const int rc = grid_fwd_launch(d, alpha, beta, rho, t, C, S, L, N, K, nullptr, pmax, pmin, nullptr, gp, st);
     if (rc) return rc;
   }
-  const int rc2 = launch_points_bwd<2>(pp, S, L, N, d, alpha, beta, rho, t, c, nullptr, F, nullptr, part, estore,
-                                       nullptr, nullptr, nullptr, nullptr, pmax, pmin, nchunk, compress, with_grad,
-                                       norm, loss_part, st);
-  if (rc2) return rc2;
-  k_loss_reduce<<<(S + 127) / 128, 128, 0, st>>>(loss_part, pp.bpm, N, loss, S);
+  out.pp = pp;
+  out.part = part;
+  out.loss_part = loss_part;
+  return launch_points_bwd<2>(pp, S, L, N, d, alpha, beta, rho, t, c, nullptr, F, nullptr, part, estore, nullptr,
+                              nullptr, nullptr, nullptr, pmax, pmin, nchunk, compress, with_grad, norm, loss_part,
+                              nsm, st);
+}
+
+int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
+                    const double* c, const double* C, int S, int L, int N, int K, int compress, int with_grad,
+                    double* loss, double* F, double* norm, double* gd, double* galpha, double* gbeta, double* grho,
+                    void* ws, size_t ws_bytes, void* stream) {
+  if (!loss) return ADSURF_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  DmfLaunch dl;
+  const int rc = dmf_launch(d, alpha, beta, rho, t, c, C, S, L, N, K, compress, with_grad, F, norm, ws, ws_bytes, st, dl);
+  if (rc) return rc;
+  k_loss_reduce<<<(S + 127) / 128, 128, 0, st>>>(dl.loss_part, dl.pp.bpm, N, loss, S);
   if (check_launch()) return ADSURF_E_CUDA;
   if (with_grad) {
-    k_grad_reduce<<<S, 128, 0, st>>>(part, L, pp.bpm, gd, galpha, gbeta, grho);
+    k_grad_reduce<<<S, 128, 0, st>>>(dl.part, L, dl.pp.bpm, gd, galpha, gbeta, grho);
     return check_launch();
   }
   return ADSURF_OK;
+}
+
+static int ens_launch(EnsArgs& A, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t SL = (size_t)A.S * A.L;
+  if (SL > 0x7fffffffull) return ADSURF_E_SHAPE;
+  if (!ws || ws_bytes < adsurf_workspace_bytes(ADSURF_OP_ENSEMBLE_STEP, A.S, A.L, 1, 0)) return ADSURF_E_WORKSPACE;
+  double* w = (double*)ws;
+  A.gt = w;
+  A.gdr = w + SL;
+  A.sv = w + 2 * SL;
+  A.sh = w + 3 * SL;
+  A.tik = w + 4 * SL;
+  A.bo = w + 5 * SL;
+  A.dold = w + 6 * SL;
+  A.shh = w + 7 * SL;
+  const int threads = 128, blocks = (int)((SL + threads - 1) / threads);
+  k_ens_prepare<<<blocks, threads, 0, st>>>(A);
+  if (check_launch()) return ADSURF_E_CUDA;
+  k_ens_adam<<<blocks, threads, 0, st>>>(A);
+  return check_launch();
 }
 
 int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho, const double* gd,
@@ -1270,28 +1318,60 @@ int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho, 
   if (invert_thick && (!gd || !md || !vd || !layer_mindepth || !layer_maxdepth)) return ADSURF_E_NULL;
   if (S <= 0 || L <= 0 || step < 1) return ADSURF_E_SHAPE;
   if (vp_mode < 0 || vp_mode > 3 || layering < 0 || layering > 2) return ADSURF_E_ARG;
-  if (!ws || ws_bytes < (size_t)3 * S * L * sizeof(double)) return ADSURF_E_WORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  double* gt = (double*)ws;
-  double* sv = gt + (size_t)S * L;
-  double* sh = sv + (size_t)S * L;
-  const int threads = 128, blocks = (S + threads - 1) / threads;
-  k_ens_prepare<<<blocks, threads, 0, st>>>(b, alpha, galpha, gbeta, grho, S, L, vp_mode, vp_vs_ratio, damp_vertical,
-                                            damp_horizontal, gt, sv, sh, loss);
-  if (check_launch()) return ADSURF_E_CUDA;
   EnsArgs A;
+  memset(&A, 0, sizeof(A));
   A.b = b; A.d = d; A.alpha = alpha; A.rho = rho; A.mb = mb; A.vb = vb; A.md = md; A.vd = vd;
-  A.iter_b = iter_b; A.iter_d = iter_d;
-  A.gd = gd; A.gt = gt; A.b0 = b0; A.a0 = alpha0; A.r0 = rho0;
-  A.lob = lower_b; A.upb = upper_b; A.mind = layer_mindepth; A.maxd = layer_maxdepth; A.sv = sv; A.sh = sh;
-  A.S = S; A.L = L; A.vp_mode = vp_mode; A.invert_thick = invert_thick; A.layering = layering;
-  A.proj_flags = proj_flags;
+  A.gd = gd; A.ga = galpha; A.gb = gbeta; A.gr = grho; A.loss = loss;
+  A.b0 = b0; A.a0 = alpha0; A.r0 = rho0; A.lob = lower_b; A.upb = upper_b; A.mind = layer_mindepth; A.maxd = layer_maxdepth;
+  A.row0 = 0; A.S_all = S;
+  A.S = S; A.L = L; A.vp_mode = vp_mode; A.invert_thick = invert_thick; A.layering = layering; A.proj_flags = proj_flags;
   A.ratio = vp_vs_ratio; A.dv = damp_vertical; A.dh = damp_horizontal; A.lr = lr; A.beta1 = beta1; A.beta2 = beta2;
   A.eps = eps;
   A.bc1 = 1.0 - pow(beta1, (double)step);
   A.bc2s = sqrt(1.0 - pow(beta2, (double)step));
-  k_ens_adam<<<blocks, threads, 0, st>>>(A);
-  return check_launch();
+  A.iter_b = iter_b; A.iter_d = iter_d;
+  return ens_launch(A, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t adsurf_inversion_workspace_bytes(const adsurf_inversion* p) {
+  if (!p || p->S <= 0 || p->L <= 0 || p->N <= 0) return 0;
+  const bool normalised = (p->compress == ADSURF_COMPRESS_EXP || p->compress == ADSURF_COMPRESS_LOG ||
+                           p->compress == ADSURF_COMPRESS_NORM);
+  return align256(adsurf_workspace_bytes(ADSURF_OP_DMF_STEP, p->S, p->L, p->N, normalised ? p->K : 0)) +
+         adsurf_workspace_bytes(ADSURF_OP_ENSEMBLE_STEP, p->S, p->L, 1, 0);
+}
+
+int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, void* stream) {
+  if (!p) return ADSURF_E_NULL;
+  if (!p->b || !p->d || !p->alpha || !p->rho || !p->mb || !p->vb || !p->b0 || !p->alpha0 || !p->rho0 || !p->lower_b ||
+      !p->upper_b || !p->counter || !p->loss)
+    return ADSURF_E_NULL;
+  if (p->invert_thick && (!p->md || !p->vd || !p->layer_mindepth || !p->layer_maxdepth)) return ADSURF_E_NULL;
+  if (p->vp_mode < 0 || p->vp_mode > 3 || p->layering < 0 || p->layering > 2 || p->T < 0) return ADSURF_E_ARG;
+  if (p->S_all < p->S || p->row0 < 0 || p->row0 + p->S > p->S_all) return ADSURF_E_ARG;
+  if (p->damp_horizontal > 0.0 && p->S_all > p->S && (!p->halo || p->S < 2)) return ADSURF_E_ARG;
+  const size_t need = adsurf_inversion_workspace_bytes(p);
+  if (!ws || ws_bytes < need || need == 0) return ADSURF_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ens_bytes = adsurf_workspace_bytes(ADSURF_OP_ENSEMBLE_STEP, p->S, p->L, 1, 0);
+  const size_t dmf_bytes = need - ens_bytes;
+  DmfLaunch dl;
+  const int rc = dmf_launch(p->d, p->alpha, p->b, p->rho, p->t, p->c, p->C, p->S, p->L, p->N, p->K, p->compress, 1,
+                            nullptr, nullptr, ws, dmf_bytes, st, dl);
+  if (rc) return rc;
+  EnsArgs A;
+  memset(&A, 0, sizeof(A));
+  A.b = p->b; A.d = p->d; A.alpha = p->alpha; A.rho = p->rho; A.mb = p->mb; A.vb = p->vb; A.md = p->md; A.vd = p->vd;
+  A.part = dl.part; A.loss_part = dl.loss_part; A.bpm = dl.pp.bpm; A.npicks = p->N; A.loss = p->loss;
+  A.b0 = p->b0; A.a0 = p->alpha0; A.r0 = p->rho0; A.lob = p->lower_b; A.upb = p->upper_b;
+  A.mind = p->layer_mindepth; A.maxd = p->layer_maxdepth;
+  A.halo = p->S_all > p->S ? p->halo : nullptr; A.row0 = p->row0; A.S_all = p->S_all;
+  A.S = p->S; A.L = p->L; A.vp_mode = p->vp_mode; A.invert_thick = p->invert_thick; A.layering = p->layering;
+  A.proj_flags = p->proj_flags;
+  A.ratio = p->vp_vs_ratio; A.dv = p->damp_vertical; A.dh = p->damp_horizontal; A.lr = p->lr; A.gamma = p->gamma;
+  A.beta1 = p->beta1; A.beta2 = p->beta2; A.eps = p->eps; A.step_size = p->step_size;
+  A.counter = p->counter; A.T = p->T; A.loss_hist = p->loss_hist; A.iter_b = p->iter_b_hist; A.iter_d = p->iter_d_hist;
+  return ens_launch(A, (char*)ws + dmf_bytes, ens_bytes, st);
 }
 
 int adsurf_math_probe(const double* x, int n, double* out_rsqrt, double* out_expneg, double* out_sin,
@@ -1311,7 +1391,7 @@ int adsurf_fp64_peak_probe(int iters, int repeats, double* tflops, double* ms, v
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const int blocks = kNumSM * 8, threads = 256;
+  const int blocks = sm_count() * 8, threads = 256;
   k_dfma_probe<<<blocks, threads, 0, st>>>(iters, out, 0.999999, 1e-9);  // warm-up
   float best = 1e30f;
   for (int r = 0; r < repeats; ++r) {

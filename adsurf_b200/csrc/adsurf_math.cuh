@@ -18,20 +18,6 @@
 #define ADSURF_HD inline
 #endif
 
-// experiment switches for the adjoint sweep's layer loop (see sample_adjoint)
-#ifndef ADSURF_ADJ_MODE
-#define ADSURF_ADJ_MODE 1
-#endif
-#ifndef ADSURF_FETCH_CLAMP
-#define ADSURF_FETCH_CLAMP 1
-#endif
-#ifndef ADSURF_E_FETCH_SELF
-#define ADSURF_E_FETCH_SELF 0
-#endif
-#ifndef ADSURF_SINK_DEFER
-#define ADSURF_SINK_DEFER 1
-#endif
-
 namespace adsurf {
 
 constexpr double kTwoPi = 6.283185307179586;  // 2.0 * np.pi
@@ -694,7 +680,6 @@ struct DirectSource {
   ADSURF_HD int flags(int) const { return -1; }
   ADSURF_HD const double* half_k() const { return nullptr; }
   ADSURF_HD bool small_phases(const Sample&) const { return false; }
-  ADSURF_HD Sample again(const Sample& z) const { return z; }
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     alignas(16) double tab[kTabAdj];
     table_entry<kTabAdj, true>(tab, par, m, z.ic);
@@ -705,26 +690,15 @@ struct DirectSource {
   ADSURF_HD void prep(Layer& y, int m, const Sample& z, const Dbl2&) const { prep(y, m, z); }
 };
 
-template <int kN, bool kRemake = false>
+template <int kN>
 struct TableSource {
   static constexpr bool kUniformFlags = true;   // flags come from the shared (velocity, layer) table
   static constexpr bool kWantIc = false;
   const double* __restrict__ par;
   int L;
   const double* __restrict__ tab;  // [L-1][kN] for the current trial velocity (16-byte aligned)
-  // kRemake: where the sample's (omega, 1/omega) pair and 1/c are staged, so that the half-space quantities
-  // (k, k^2, 1/omega, 1/omega^2) need not stay in registers across the layer loop of the adjoint sweep
-  const double* omq = nullptr;
-  const double* icq = nullptr;
-  const double* hkq = nullptr;  // this lane's staged (omega/alpha_hs, omega/beta_hs), see load_half
+  const double* hkq;               // this lane's staged (omega/alpha_hs, omega/beta_hs), see load_half
   ADSURF_HD const double* half_k() const { return hkq; }
-  ADSURF_HD Sample again(const Sample& z) const {
-    if (kRemake) {
-      const Dbl2 om = ld2(omq);
-      return make_sample(om.x, *icq, om.y);
-    }
-    return z;
-  }
   ADSURF_HD int flags(int m) const { return (int)dbl_bits(tab[m * kN + T_FL]); }
   // every phase of the sample below 1e5 (the inline sincos's range): p = omega n d, n <= max(1/c, 1/beta)
   ADSURF_HD bool small_phases(const Sample& z) const {
@@ -911,13 +885,11 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   double gic = 0.0;
   // The stored values of layer m+1 are fetched while layer m is being worked on (the slab lives in L2: a few
   // hundred cycles away) — the transcendental results as soon as eig_finish has consumed layer m's, the row
-  // vector once the contractions are under way.  Two register buffers alternate so that a load never targets
-  // registers that are still live: a single buffer makes the compiler load into temporaries and copy all nine
-  // doubles at the end of every layer.
+  // vector once the contractions are under way.
   struct Buf {
     double e[5], cv[4];
   };
-  Buf A{}, B{};
+  Buf A{};
   auto fetch_c = [&](Buf& b, int m, int flm) {  // flm: regime flags of layer m (-1: unknown, read everything)
     const typename Store::Slot q = est.slot(m);
     b.cv[0] = Store::ld(q, 5);
@@ -938,89 +910,38 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
   LayerGrad pend;
   pend.d = pend.a = pend.b = pend.rho = 0.0;
   int fl = -1;  // flags of layer m (read one layer ahead; -1: pointwise sources, generic path)
-  auto layer = [&](int m, auto tag, Buf& cur, Buf& nxt) {
+  auto layer = [&](int m, auto tag) {
     constexpr int kFl = decltype(tag)::value;
     const int fln = Source::kUniformFlags ? (m < L - 2 ? src.flags(m + 1) : 0) : -1;  // 0: no layer
-#if ADSURF_E_FETCH_SELF
-    fetch_e(cur, m);  // needed after the restore, the column-side contractions and the deferred sink
-#endif
     Layer y;
-    y.P.c0 = cur.cv[0]; y.P.c1 = cur.cv[1]; y.S.c0 = cur.cv[2]; y.S.c1 = cur.cv[3];
+    y.P.c0 = A.cv[0]; y.P.c1 = A.cv[1]; y.S.c0 = A.cv[2]; y.S.c1 = A.cv[3];
     src.prep(y, m, z);
     layer_set_flags(y, kFl >= 0 ? kFl : y.fl);
     layer_eig_restore(y, z.omega);
-#if ADSURF_SINK_DEFER
     sink(m > 0 ? m - 1 : 0, pend.d, pend.a, pend.b, pend.rho);  // layer m-1 (zeros before layer 0)
-#endif
-#if ADSURF_FETCH_CLAMP
     const int mn = m + 1 <= L - 2 ? m + 1 : m;  // the last layer re-reads its own slot: no predicated loads
-    fetch_c(nxt, mn, fln);
-    const LayerGrad g = layer_adjoint<Source::kWantIc>(y, cur.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
-#if !ADSURF_E_FETCH_SELF
-    fetch_e(nxt, mn);
-#endif
-#else
-    if (m + 1 <= L - 2) fetch_c(nxt, m + 1, fln);
-    const LayerGrad g = layer_adjoint<Source::kWantIc>(y, cur.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
-    if (m + 1 <= L - 2) fetch_e(nxt, m + 1);
-#endif
+    fetch_c(A, mn, fln);
+    const LayerGrad g = layer_adjoint<Source::kWantIc>(y, A.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
+    fetch_e(A, mn);
     gic += g.ic;
-#if ADSURF_SINK_DEFER
     pend = g;
-#else
-    sink(m, g.d, g.a, g.b, g.rho);
-#endif
     fl = fln;
   };
   if (L > 1) {
     if (Source::kUniformFlags) fl = src.flags(0);
     fetch_c(A, 0, fl);
-#if !ADSURF_E_FETCH_SELF
     fetch_e(A, 0);
-#endif
   }
-  // Regime specialisation (dense kernels: the flags are warp-uniform table entries).
+  // Regime specialisation (dense kernels: the flags are warp-uniform table entries).  Consecutive layers in the
+  // same regime (the usual case: oscillatory S near the surface, evanescent below) run in a loop of their own.
   const int last = L - 2;
   int m = 0;
-#if ADSURF_ADJ_MODE == 0
-  // one dispatch per layer
-  for (; m <= last; ++m) {
-    if (fl == kEO) layer(m, std::integral_constant<int, kEO>{}, A, A);
-    else if (fl == kEE) layer(m, std::integral_constant<int, kEE>{}, A, A);
-    else layer(m, std::integral_constant<int, -1>{}, A, A);
-  }
-#else
-  // Consecutive layers in the same regime (the usual case: oscillatory S near the surface, evanescent below)
-  // run in a loop of their own.
   auto run = [&](auto tag) {
     constexpr int kFl = decltype(tag)::value;
-#if ADSURF_ADJ_MODE == 1
     do {
-      layer(m, tag, A, A);
+      layer(m, tag);
       ++m;
     } while (fl == kFl);
-#else
-    for (;;) {  // two layers per trip (buffers A -> B -> A)
-      layer(m, tag, A, B);
-      ++m;
-      if (fl != kFl) {
-#if ADSURF_ADJ_MODE == 3
-        if (m <= last) {  // odd run length: re-read the next layer's values into A instead of copying B
-          fetch_c(A, m, fl);
-#if !ADSURF_E_FETCH_SELF
-          fetch_e(A, m);
-#endif
-        }
-#else
-        A = B;
-#endif
-        break;
-      }
-      layer(m, tag, B, A);
-      ++m;
-      if (fl != kFl) break;
-    }
-#endif
   };
   while (m <= last) {
     if (fl == kEO) {
@@ -1028,17 +949,14 @@ ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed,
     } else if (fl == kEE) {
       run(std::integral_constant<int, kEE>{});
     } else {
-      layer(m, std::integral_constant<int, -1>{}, A, A);
+      layer(m, std::integral_constant<int, -1>{});
       ++m;
     }
   }
-#endif
-#if ADSURF_SINK_DEFER
   if (L > 1) sink(last, pend.d, pend.a, pend.b, pend.rho);
-#endif
   double e[5];
   // half-space: dDelta/dE_hs = D^-1 s~_{L-1}, in the reference's variables
-  const Sample zh = src.again(z);
+  const Sample& zh = z;
   Half h;
   load_half(h, par, L, zh, src.half_k());
   half_space(h, zh.k, zh.k2, e);

@@ -4,22 +4,29 @@
     python bench.py --gpus N --steps K --warmup W            (ours; torchrun launches N ranks for N > 1)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-One "step" = one fused forward+adjoint sweep of the Rayleigh secular function over the dense grid
-(4096 Monte-Carlo models x 128 periods x 1024 trial velocities, 20 layers = 536 870 912 samples)
-PER GPU (weak scaling: every rank sweeps its own 4096-model ensemble, seed = rank; no data-path
-collective — the path has no exchange step).  Prints ONE JSON line (rank 0).
+One "step" = one fused forward+adjoint sweep of the Rayleigh secular function over the dense grid of config 5
+(4096 Monte-Carlo models x 128 periods x 1024 trial velocities, 20 layers = 536 870 912 samples).  The problem
+is FIXED: with N ranks the model axis is sharded (4096/N models per GPU, `adsurf_b200._dist.shard_bounds`) and every
+step ends with the exchange the design calls for — one NCCL all-gather of the per-model gradients
+[4, 4096/N, 20] -> [4, 4096, 20] — inside the timed region ("scaling": "strong").  Prints ONE JSON line (rank 0).
 
-  value     samples/s over all ranks, inputs resident in HBM, CUDA events on the launching stream.
-  e2e       the same sweep through the C-ABI call with the inputs in pinned HOST memory: every step
-            copies the models / periods / velocities host->device and reads the per-model
-            gradients back device->host inside the timed region.
-  roofline  FP64-pipe roofline of the fused forward+adjoint kernel: achieved = samples/s x
-            3*(168*(L-1)+31) algorithmic FLOP per sample / kernel time measured live
-            with CUDA events; peak = a register-resident DFMA loop measured in this same process
-            (MEASURED_PEAKS.json has no FP64 entry), nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
-            = 37.2 TFLOP/s reported beside it.
-  cpu_baseline  the float64 oracle port of the reference's torch path (oracle/dltar_oracle.py)
-            timed on this box's host cores on a bounded chunk of the same workload.
+  value     samples/s of the whole job, inputs resident in HBM, CUDA events on the launching stream, max over ranks.
+  e2e       the same step through the C-ABI call with the inputs in pinned HOST memory: every step copies the models /
+            periods / velocities host->device and reads the gathered gradients back device->host inside the timed
+            region.  `e2e.api` (N = 1): the path a user of the reference takes — the `_cps` shim
+            `dltar_matrix(...)` -> `.backward(gdet)` with host tensors in and gradients out, on a 512-model slice.
+  roofline  FP64-pipe roofline of the fused forward+adjoint kernel.  achieved = samples/s x 3*(168*(L-1)+31)
+            algorithmic FLOP per sample (SURVEY.md §8d) over the kernel time measured live with CUDA events;
+            peak = NOMINAL 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s (MEASURED_PEAKS.json has no FP64 entry);
+            the in-process DFMA probe is reported beside it, and so are the counters that do not depend on the FLOP
+            contract: executed FP64 instructions per sample and FP64-pipe active % from the committed ncu capture
+            (profiles/r2_roofline_inputs.json), and the DRAM bytes of one launch from the same capture.
+  inversion the north-star loop: `multi_inversion` of a 4096-model FRIUL7W ensemble (config-4 shape: 20 layers,
+            300 picks, Vs only) sharded over the N ranks, iterations/s of the device-resident loop including the
+            all-gather of losses and iterates that ends the run.
+  configs   (N = 1) iterations/s of BASELINE configs 2-4 through `inversion(...)`.
+  cpu_baseline (N = 1) the float64 oracle port of the reference's torch path timed on this box's host cores on a
+            bounded chunk of the same workload.
 """
 from __future__ import annotations
 
@@ -42,6 +49,8 @@ import torch  # noqa: E402
 L_LAYERS, NF, K_TRIAL, S_MODELS = 20, 128, 1024, 4096
 METRIC = "DMF det samples/s fwd+bwd (model x freq x c)"
 UNIT = "samples/s"
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
+ROOFLINE_INPUTS = os.path.join(ROOT, "profiles", "r2_roofline_inputs.json")
 
 
 def flop_per_sample(L):
@@ -136,16 +145,18 @@ def time_cpu(budget_s=15.0, models=4, kc=128):
             break
     return {"value": samples / el, "unit": UNIT, "cores": cores, "threads": torch.get_num_threads(), "kind": "port",
             "sample": f"{n} x fwd+bwd of oracle/dltar_oracle.py (float64 torch-CPU port of the reference's "
-                      f"dltar_matrix) on {models} models x {NF} f x {kc} c x {L_LAYERS} layers of config 5, {el:.1f} s"}
+                      f"dltar_matrix) on {models} models x {NF} f x {kc} c x {L_LAYERS} layers of config 5, {el:.1f} s",
+            "reference_code_here": "profiles/r2_reference_cpu_timing.json: the reference's own dltar_matrix + backward "
+                                   "timed in the build container (it cannot travel to the GPU box)"}
 
 
 def run_reference(args):
-    """--impl reference: the oracle port on the host cores; each step = one bounded chunk."""
+    """--impl reference: the oracle port on the host cores (rank 0 only); each step = one bounded chunk."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: use every host core explicitly
     models, kc = 4, 128
     chunk = cpu_chunk(models, kc)
     for _ in range(args.warmup):
@@ -160,7 +171,7 @@ def run_reference(args):
               f"{models} models x {NF} f x {kc} c x {L_LAYERS} layers of config 5")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "config5: 20-layer FRIUL7W Monte-Carlo ensemble, 128 f x 1024 c dense sweep fwd+bwd "
                                "(bounded chunk per step)", "layers": L_LAYERS},
@@ -170,15 +181,26 @@ def run_reference(args):
     }))
 
 
-# ----------------------------------------------------------------------------- GPU leg
+def roofline_inputs():
+    """counters of the dominant kernel taken from the committed ncu capture of this round"""
+    try:
+        with open(ROOFLINE_INPUTS) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------- GPU legs
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--models", type=int, default=S_MODELS, help="models per GPU (config 5: 4096)")
+    ap.add_argument("--models", type=int, default=S_MODELS, help="models of the whole job (config 5: 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline legs only (profiling runs)")
+    ap.add_argument("--inversion-iters", type=int, default=300)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -196,29 +218,41 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    from adsurf_b200 import _capi
-    from adsurf_b200.workload import config5
-    _capi.lib()
-
-    S, L = args.models, L_LAYERS
-    host = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in config5(S, NF, K_TRIAL, L, seed=rank)]
-    d, a, b, rho, t, c = (x.to(dev) for x in host)
-    n_samples = S * NF * K_TRIAL
-    det = torch.empty((S, K_TRIAL, NF), dtype=torch.float64, device=dev)   # 4.3 GB per GPU: inputs+outputs >> L2
-    grads = tuple(torch.empty((S, L), dtype=torch.float64, device=dev) for _ in range(4))
-    ws = torch.empty(max(_capi.lib().adsurf_workspace_bytes(_capi.OP_GRID_BWD, S, L, NF, K_TRIAL), 8),
-                     dtype=torch.uint8, device=dev)
-    lib = _capi.lib()
     import ctypes
+    from adsurf_b200 import _capi, _dist
+    from adsurf_b200.workload import config5
+    lib = _capi.lib()
+    _capi.init(dev)  # persisting-L2 carve-out for the adjoint slabs (explicit, see include/adsurf_b200.h)
+
+    S_all, L = args.models, L_LAYERS
+    lo, hi = _dist.shard_bounds(S_all, rank, world)
+    S = hi - lo
+    if S_all % world:
+        raise SystemExit("bench.py: the model count must divide by the number of ranks")
+    full = config5(S_all, NF, K_TRIAL, L, seed=0)  # the same ensemble on every rank; each keeps its shard
+    host = [torch.from_numpy(np.ascontiguousarray(x[lo:hi])).pin_memory() for x in full]
+    del full
+    d, a, b, rho, t, c = (x.to(dev) for x in host)
+    n_local = S * NF * K_TRIAL
+    n_total = S_all * NF * K_TRIAL
+    det = torch.empty((S, K_TRIAL, NF), dtype=torch.float64, device=dev)   # 4.3 GB at N = 1: >> L2
+    gloc = torch.empty((4, S, L), dtype=torch.float64, device=dev)         # gd, ga, gb, grho of this shard
+    gall = torch.empty((world, 4, S, L), dtype=torch.float64, device=dev)  # gathered: rank-major
+    ws = torch.empty(max(lib.adsurf_workspace_bytes(_capi.OP_GRID_BWD, S, L, NF, K_TRIAL), 8), dtype=torch.uint8,
+                     device=dev)
     P = lambda x: ctypes.c_void_p(x.data_ptr())
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
 
-    def step(dd, aa, bb, rr, tt, cc):
+    def sweep(dd, aa, bb, rr, tt, cc):
         rc = lib.adsurf_det_grid_bwd(P(dd), P(aa), P(bb), P(rr), P(tt), P(cc), None, S, L, NF, K_TRIAL, P(det),
-                                     P(grads[0]), P(grads[1]), P(grads[2]), P(grads[3]), P(ws), ws.numel(), sp)
+                                     P(gloc[0]), P(gloc[1]), P(gloc[2]), P(gloc[3]), P(ws), ws.numel(), sp)
         if rc != 0:
             raise RuntimeError(f"adsurf_det_grid_bwd failed: {rc}")
+
+    def exchange():
+        if dist is not None:
+            dist.all_gather_into_tensor(gall, gloc)
 
     def barrier():
         if dist is not None:
@@ -232,33 +266,36 @@ def main():
         dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
         return float(tt_[0])
 
-    # FP64 peak on this GPU, this process (burst; the sweep itself runs for seconds -> also see clocks)
-    peak_tf, _ = _capi.fp64_peak_probe(iters=4096, repeats=5, device=dev)
+    peak_probe, _ = _capi.fp64_peak_probe(iters=4096, repeats=5, device=dev)
 
     # ---------------- device-resident leg
     for _ in range(args.warmup):
-        step(d, a, b, rho, t, c)
+        sweep(d, a, b, rho, t, c)
+        exchange()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    E = lambda: torch.cuda.Event(enable_timing=True)
+    e0, e1 = E(), E()
+    ka, kb = [E() for _ in range(args.steps)], [E() for _ in range(args.steps)]
     barrier()
     w0 = time.time()
     e0.record(stream)
-    for _ in range(args.steps):
-        step(d, a, b, rho, t, c)
+    for i in range(args.steps):
+        ka[i].record(stream)
+        sweep(d, a, b, rho, t, c)
+        kb[i].record(stream)
+        exchange()
     e1.record(stream)
     barrier()
     w1 = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1))
+    kernel_ms = max_over_ranks(sum(x.elapsed_time(y) for x, y in zip(ka, kb)) / args.steps)
     clocks = sampler.stop(w0, w1) if rank == 0 else None
-    value = world * n_samples * args.steps / (ms * 1e-3)
-    kernel_ms = ms / args.steps  # the adjoint kernel is >99.9% of the step (second-stage reduce ~ microseconds)
-
-    # sustained FP64 peak right after the sweep (clocks settled under load)
-    peak_tf_after, _ = _capi.fp64_peak_probe(iters=4096, repeats=3, device=dev)
+    value = n_total * args.steps / (ms * 1e-3)
+    peak_after, _ = _capi.fp64_peak_probe(iters=4096, repeats=3, device=dev)
 
     # ---------------- secondary: forward-only dense sweep with fused max/min (what every DMF iteration runs
     # K times more often than the pointwise adjoint), same grid, det not materialised
@@ -282,18 +319,21 @@ def main():
     e1.record(stream)
     barrier()
     ms_fwd = max_over_ranks(e0.elapsed_time(e1))
-    fwd_value = world * n_samples * args.steps / (ms_fwd * 1e-3)
+    fwd_value = n_total * args.steps / (ms_fwd * 1e-3)
 
     # ---------------- end-to-end leg: host buffers -> C ABI -> host results
-    hgr = [torch.empty((S, L), dtype=torch.float64).pin_memory() for _ in range(4)]
+    hgr = torch.empty((world, 4, S, L), dtype=torch.float64).pin_memory()
     dbuf = [torch.empty_like(x, device=dev) for x in host]
 
     def e2e_step():
         for src, dst in zip(host, dbuf):
             dst.copy_(src, non_blocking=True)
-        step(*dbuf)
-        for src, dst in zip(grads, hgr):
-            dst.copy_(src, non_blocking=True)
+        sweep(*dbuf)
+        if dist is not None:
+            exchange()
+            hgr.copy_(gall, non_blocking=True)
+        else:
+            hgr[0].copy_(gloc, non_blocking=True)
         stream.synchronize()  # the caller reads the gradients on the host
 
     for _ in range(2):
@@ -305,36 +345,76 @@ def main():
     e1.record(stream)
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = world * n_samples * args.steps / (ms_e2e * 1e-3)
+    e2e_value = n_total * args.steps / (ms_e2e * 1e-3)
     h2d = sum(x.numel() * 8 for x in host)
-    d2h = sum(x.numel() * 8 for x in hgr)
+    d2h = hgr.numel() * 8
+    del det, dbuf, ws_f
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras:
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        import configs_e2e as CE
+        # ---------------- e2e through the package API (the reference's call): shim -> autograd -> host gradients
+        if world == 1:
+            extras["e2e_api"] = CE.api_dense_e2e(models=min(512, S_all), steps=3)
+        # ---------------- north-star loop: sharded multi_inversion (config-4 shape at 4096 models)
+        CE.config4(5, S=S_all)  # warm-up: library load, allocator, NCCL buffers
+        barrier()
+        rec = CE.config4(args.inversion_iters, S=S_all)
+        loop_s = max_over_ranks(rec["loop_seconds"] + rec["gather_seconds"])
+        total_s = max_over_ranks(rec["loop_seconds"] + rec["gather_seconds"] + rec["setup_seconds"])
+        extras["inversion"] = {
+            "what": f"multi_inversion (device-resident loop, CUDA graph of whole iterations) of {S_all} models x 300 "
+                    f"picks x 20 layers, Vs only, sharded over {world} rank(s), + final all-gather of losses / iterates",
+            "iterations": args.inversion_iters, "it_per_s": args.inversion_iters / loop_s,
+            "it_per_s_incl_setup": args.inversion_iters / total_s, "loop_plus_gather_s": loop_s,
+            "pointwise_samples_per_s": args.inversion_iters * S_all * 300 / loop_s,
+            "median_first_loss": rec["median_first_loss"], "median_last_loss": rec["median_last_loss"],
+            "kernels_per_iteration": 3}
+        if world == 1:
+            CE.config2(5), CE.config3(5)
+            c2, c3, c4 = CE.config2(600), CE.config3(400), CE.config4(300, S=1024)
+            keep = ("what", "iterations_run", "it_per_s", "best_loss", "reference")
+            extras["configs"] = {f"config{r['config']}": {k: r[k] for k in keep if k in r} for r in (c2, c3, c4)}
 
     if rank == 0:
-        achieved_tf = (n_samples / (kernel_ms * 1e-3)) * flop_per_sample(L) / 1e12
-        nominal = 148 * 64 * 2 * 1.965e9 / 1e12
+        achieved_tf = (n_local / (kernel_ms * 1e-3)) * flop_per_sample(L) / 1e12
+        ri = roofline_inputs() or {}
+        bytes_per_sample = ri.get("dram_bytes_per_sample")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config5: 4096 models x 128 f x 1024 c per GPU, 20-layer FRIUL7W Monte-Carlo ensemble "
-                                   "(reference generator, seed=rank), fused fwd+adjoint, gdet=1, det written",
-                       "models_per_gpu": S, "layers": L, "periods": NF, "trial_velocities": K_TRIAL,
-                       "samples_per_step_per_gpu": n_samples,
-                       "l2": "outputs 4.3 GB/step per GPU (> 126 MB L2); compute-bound, no reuse across steps"},
+            "config": {"workload": f"config5: {S_all} models x 128 f x 1024 c (fixed problem), 20-layer FRIUL7W "
+                                   "Monte-Carlo ensemble (reference generator, seed 0), fused fwd+adjoint, gdet=1, det "
+                                   f"written; model axis sharded over {world} rank(s), gradients all-gathered every step",
+                       "models": S_all, "models_per_gpu": S, "layers": L, "periods": NF, "trial_velocities": K_TRIAL,
+                       "samples_per_step": n_total,
+                       "collective": "none (1 rank)" if world == 1 else
+                                     f"NCCL all_gather_into_tensor [4,{S},{L}] f64 per rank per step",
+                       "l2": f"outputs {n_local * 8 / 1e9:.1f} GB/step per GPU (> 126 MB L2); compute-bound, no reuse "
+                             "across steps"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
-                    "call": "adsurf_det_grid_bwd (C ABI) with pinned host inputs copied H2D and gradients read D2H every step"},
+                    "call": "adsurf_det_grid_bwd (C ABI) with pinned host inputs copied H2D, gradients gathered and "
+                            "read D2H every step"},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf,
-                         # DRAM bytes per launch of the dominant kernel, scaled from the ncu --set full capture
-                         # in profiles/r1_ncu_full_final.txt (9.4 MB read + 536.0 MB written for 67 108 864
-                         # samples = 8.13 B/sample: the det output; the slabs stay in the persisting L2 carve-out)
-                         "traffic": 8.13 * n_samples, "traffic_source": "profiles/r1_ncu_full_final.txt",
-                         "peak_source": "measured in-process: register-resident DFMA loop (adsurf_fp64_peak_probe), burst",
-                         "peak_after_sweep": peak_tf_after, "peak_nominal": nominal,
-                         "frac_of_nominal": achieved_tf / nominal,
-                         "flop_per_sample": flop_per_sample(L), "kernel": "k_grid_bwd", "kernel_ms": kernel_ms,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved_tf / NOMINAL_FP64_TFLOPS,
+                         "peak_source": "nominal: 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP64 "
+                                        "entry and the profiling guide states no FP64 fallback)",
+                         "peak_probe": peak_probe, "peak_probe_after_sweep": peak_after,
+                         "frac_of_probe": achieved_tf / peak_probe,
+                         "peak_probe_source": "in-process register-resident DFMA loop (adsurf_fp64_peak_probe), burst",
+                         "flop_per_sample": flop_per_sample(L),
+                         "flop_source": "SURVEY.md §8d contract: 3 x (168 (L-1) + 31), entry-form count",
+                         "executed_fp64_inst_per_sample": ri.get("fp64_inst_per_sample"),
+                         "executed_flop_per_sample": ri.get("executed_flop_per_sample"),
+                         "pipe_fp64_active": ri.get("pipe_fp64_active"),
+                         "traffic": bytes_per_sample * n_local if bytes_per_sample else None,
+                         "traffic_source": ri.get("source"),
+                         "kernel": "k_grid_bwd", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * args.steps / ms,
                          "hbm_bytes_per_sample_algorithmic": 8,
                          "note": "FP64-pipe bound (~600 FLOP/B); HBM and tensor rooflines do not bind this path"},
             "clocks": clocks,
@@ -342,12 +422,14 @@ def main():
                              "call": "adsurf_det_grid_fwd with fused max/min over c (det not materialised)",
                              "flop_per_sample": flop_per_sample(L) // 3,
                              "achieved_tflops": fwd_value / world * (flop_per_sample(L) // 3) / 1e12,
-                             "frac_of_measured_fp64_peak": fwd_value / world * (flop_per_sample(L) // 3) / 1e12 / peak_tf},
+                             "frac_of_nominal_fp64_peak": fwd_value / world * (flop_per_sample(L) // 3) / 1e12
+                                                          / NOMINAL_FP64_TFLOPS},
         }
-        if not args.no_cpu_baseline and world == 1:
+        out.update(extras)
+        if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = time_cpu()
-        elif not args.no_cpu_baseline:
-            out["cpu_baseline"] = time_cpu(budget_s=8.0)
+        elif world > 1:
+            out["cpu_baseline"] = None  # N = 1 only (the task's contract); `--impl reference` times the CPU arm
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()

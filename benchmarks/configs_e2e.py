@@ -94,10 +94,37 @@ def config4(iters, S=1024):
     loss = np.asarray(inv.inv_process["loss"])
     return {"config": 4, "what": f"{S} models, 20-layer FRIUL7W, N=300 picks, compress=False, vs only",
             "iterations_run": iters, "it_per_s": iters / inv.timing["loop_s"], "loop_seconds": inv.timing["loop_s"],
+            "gather_seconds": inv.timing["gather_s"], "setup_seconds": inv.timing["setup_s"],
             "total_seconds_incl_result_lists": dt, "best_loss": float(loss.min()),
             "median_first_loss": float(np.median(loss[0])), "median_last_loss": float(np.median(loss[-1])),
             "reference": {"it_per_s": 2.60, "models": 100, "device": "cuda:0 (author's)", "best_loss": 2.1835e-4,
                           "iterations": 4000}}
+
+
+def api_dense_e2e(models=512, steps=3):
+    """Config-5 slice through the call a user of the reference makes: the `_cps` shim
+    `dltar_matrix(vlist, tlist, d, a, b, rho, 2, -1, device="cuda")` on HOST tensors, `.backward(gdet)`, gradients
+    read back to the host.  (The autograd contract costs a forward launch that writes det and a fused
+    forward+adjoint launch in backward; inputs go host->device and gradients device->host every step.)"""
+    from adsurf_b200._cps import _surf96_matrixAll_gpu as shim
+    from adsurf_b200.workload import config5
+    d, a, b, rho, t, c = (torch.from_numpy(np.ascontiguousarray(x)) for x in config5(models, 128, 1024, 20, seed=0))
+    gdet = torch.ones((models, 1024, 128), dtype=torch.float64, device="cuda")
+
+    def step():
+        leaves = [x.clone().requires_grad_(True) for x in (d, a, b, rho)]
+        det = shim.dltar_matrix(c, t, *leaves, 2, -1, device="cuda")
+        det.backward(gdet)
+        return [x.grad.cpu() for x in leaves]
+
+    step()
+    _, dt = timed(lambda: [step() for _ in range(steps)])
+    n = models * 128 * 1024
+    return {"value": n * steps / dt, "unit": "samples/s", "models": models, "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "call": "adsurf_b200._cps._surf96_matrixAll_gpu.dltar_matrix(host tensors, device='cuda').backward(gdet); "
+                    "gradients .cpu()",
+            "h2d_bytes_per_step": int(sum(x.numel() for x in (d, a, b, rho, t, c)) * 8),
+            "d2h_bytes_per_step": int(4 * d.numel() * 8)}
 
 
 def main():

@@ -15,7 +15,11 @@
  *     only combination the reference's torch path can execute;
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync;
  *   - `ws` is scratch of at least adsurf_workspace_bytes(...) bytes (may be NULL when that is 0);
- *   - outputs are overwritten, never accumulated; no global state, re-entrant;
+ *   - outputs are overwritten, never accumulated; the library keeps no state between calls and is re-entrant
+ *     (calls on distinct streams may run from distinct host threads).  The ONLY device-wide effect is opt-in:
+ *     adsurf_init(device, ADSURF_INIT_PERSIST_L2), see below;
+ *   - grids, slab sizes and work splits follow the SM count of the CURRENT device at call time (query and
+ *     launch on the same device);
  *   - return value: ADSURF_OK (0) or a negative ADSURF_E_* code; never throws, NaN/Inf inputs
  *     propagate to the outputs (the reference's host loop repairs them, _model.py:624-626).
  */
@@ -47,7 +51,8 @@ enum adsurf_op {
   ADSURF_OP_POINTS_JAC = 2,
   ADSURF_OP_GRID_FWD = 3,
   ADSURF_OP_GRID_BWD = 4,
-  ADSURF_OP_DMF_STEP = 5
+  ADSURF_OP_DMF_STEP = 5,
+  ADSURF_OP_ENSEMBLE_STEP = 6 /* adsurf_ensemble_adam_step: n, K ignored */
 };
 
 /* DMF compression (reference _model.py:450-462) */
@@ -62,9 +67,26 @@ enum adsurf_compress {
 const char* adsurf_version(void);
 const char* adsurf_error_string(int code);
 
+/* Optional, explicit per-device set-up.  flags:
+ *   ADSURF_INIT_PERSIST_L2  raise cudaLimitPersistingL2CacheSize of `device` to the maximum the part allows.  The
+ *     adjoint kernels keep their per-warp layer slabs (43.8 KB per resident warp at 20 layers, 78 MB per GPU) in L2
+ *     with evict_last accesses; L2 honours that policy only inside the persisting carve-out, which is 0 bytes by
+ *     default.  The limit is CONTEXT-WIDE (it is shared with every other library in the process, though it changes
+ *     nothing for code that issues no persisting accesses), hence opt-in: without it everything still works, the
+ *     slabs are merely written back to HBM (measured: 10x the DRAM traffic of adsurf_det_grid_bwd, ~15 % slower).
+ * Nothing else in this library touches device-wide state.  No reference counterpart. */
+#define ADSURF_INIT_PERSIST_L2 1u
+int adsurf_init(int device, unsigned flags);
+
 /* Scratch bytes needed by an operation.  n = N (points ops) or NF (grid ops); K ignored by points ops
  * except DMF_STEP. */
 size_t adsurf_workspace_bytes(int op, int S, int L, int n, int K);
+
+/* How an operation would be split over the current device (diagnostics, tests, documentation): out[8] =
+ * grid ops:   {warps per block, period groups, velocity chunks, velocities per chunk, velocities per table fill,
+ *              blocks per model, period tiles, SM count};
+ * points ops: {warps per block, warp units per model, 0, 0, 0, blocks per model, slabs in L2 (1) or shared (0), SMs}. */
+int adsurf_plan_describe(int op, int S, int L, int n, int K, int* out);
 
 /* F[s,i] = Delta_R(model s; t[s,i], c[s,i]).
  * Replaces dltar_vector / dltar4_vector: _cps/_surf96_vectorAll_gpu.py:194,303-399 (batched),
@@ -143,8 +165,10 @@ int adsurf_fp64_peak_probe(int iters, int repeats, double* tflops, double* ms, v
  *      `step` (1-based) on b, and on d when invert_thick
  *   5. alpha, rho for the next iteration from the updated b.
  * b, d, alpha, rho and the Adam moments mb, vb, md, vd [S,L] are updated in place; b0, alpha0, rho0 are the
- * initial model (NaN repair / fixed values); ws >= 3*S*L doubles.  Replaces the torch autograd chain,
- * torch.optim.Adam and the numpy clipping round trip of multi_inversion (_model.py:589-636). */
+ * initial model (NaN repair / fixed values); ws >= adsurf_workspace_bytes(ADSURF_OP_ENSEMBLE_STEP, S, L, 1, 0).
+ * vp_mode 3 (USArray): entries whose updated Vs exceeds 4.6 km/s keep their current Vp / rho (the reference's
+ * masked in-place update, _model.py:440-446).  Replaces the torch autograd chain, torch.optim.Adam and the numpy
+ * clipping round trip of multi_inversion (_model.py:589-636). */
 int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho,
                               const double* gd, const double* galpha, const double* gbeta, const double* grho,
                               double* loss, double* mb, double* vb, double* md, double* vd,
@@ -155,6 +179,34 @@ int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho,
                               int proj_flags, double damp_vertical, double damp_horizontal,
                               double lr, double beta1, double beta2, double eps, int step,
                               double* iter_b, double* iter_d, void* ws, size_t ws_bytes, void* stream);
+
+/* One WHOLE inversion iteration, replayable: adsurf_dmf_step (without its two reduction launches) followed by the
+ * optimiser step above, with the iteration index j read from DEVICE memory — so the launch sequence (3-4 kernels)
+ * can be captured once in a CUDA graph and replayed `T` times with no host work in between.
+ *   counter[0] (device int) = j, the 0-based index of the iteration about to run; the last kernel increments it.
+ *               counter[1] is scratch (must be 0 at the first call).
+ *   learning rate of iteration j: lr * gamma^(j / step_size) (torch StepLR stepped after every optimiser step);
+ *   Adam bias corrections use step j + 1;
+ *   loss[S] receives the total misfit of iteration j; loss_hist [T,S], iter_b_hist / iter_d_hist [T,S,L] (each may
+ *   be NULL) receive row j while j < T (what the reference appends to its Python lists, _model.py:597-636);
+ *   sharded ensembles (one process per GPU, this rank owns global rows row0 .. row0+S-1 of S_all): with
+ *   damp_horizontal > 0 `halo` [4,L] holds the CURRENT Vs rows row0-2, row0-1, row0+S, row0+S+1 (rows outside
+ *   [0, S_all) are ignored) — the only data a rank needs from its neighbours (reference :471-473); S >= 2 then.
+ * Replaces one trip of the loops at _model.py:118-186 (iter_inversion, S = 1) and :589-636 (multi_inversion). */
+typedef struct adsurf_inversion {
+  int S, L, N, K, T;
+  const double *t, *c, *C;                           /* picks [S,N] (period, velocity), trial velocities [S,K] */
+  double *b, *d, *alpha, *rho, *mb, *vb, *md, *vd;   /* state [S,L], updated in place */
+  const double *b0, *alpha0, *rho0, *lower_b, *upper_b, *layer_mindepth, *layer_maxdepth; /* [S,L] */
+  double *loss, *loss_hist, *iter_b_hist, *iter_d_hist;
+  int* counter;
+  const double* halo;
+  int row0, S_all;
+  int compress, vp_mode, invert_thick, layering, proj_flags, step_size;
+  double vp_vs_ratio, damp_vertical, damp_horizontal, lr, gamma, beta1, beta2, eps;
+} adsurf_inversion;
+size_t adsurf_inversion_workspace_bytes(const adsurf_inversion* p);
+int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, void* stream);
 
 /* Validation hook: evaluates the kernels' inline elementary functions on the device,
  * out_rsqrt[i] = 1/sqrt(x[i]), out_expneg[i] = exp(-x[i]), out_sin/out_cos[i] = sin/cos(x[i]).

@@ -48,6 +48,26 @@ def test_workspace_sizes_are_host_side(lib):
     assert lib.adsurf_workspace_bytes(_capi.OP_GRID_BWD, 0, 20, 128, 1024) == 0
 
 
+def test_grid_planner_covers_the_grid_and_fills_the_machine(lib):
+    """host-side work split (no GPU: the planner then assumes 148 SMs)"""
+    from adsurf_b200 import _capi
+    for adj in (False, True):
+        op = _capi.OP_GRID_BWD if adj else _capi.OP_GRID_FWD
+        for S, L, NF, K in ((1, 6, 500, 1201), (100, 3, 174, 200), (4096, 20, 128, 1024), (512, 20, 128, 1024),
+                            (1, 2, 1, 1), (3, 2, 33, 7), (2, 45, 70, 40), (1, 90, 31, 9), (7, 20, 300, 450)):
+            p = _capi.plan_describe(op, S, L, NF, K)
+            assert p["nft"] == (NF + 31) // 32 and 1 <= p["wpb"] <= (4 if adj else 8)
+            assert p["wpb"] * p["nfg"] >= p["nft"] > p["wpb"] * (p["nfg"] - 1)
+            assert p["nchunk"] * p["chunk"] >= K > (p["nchunk"] - 1) * p["chunk"]
+            assert 1 <= p["tc"] <= min(8, p["chunk"]) and p["bpm"] == p["nchunk"] * p["nfg"]
+    # config 2's dense pass (one model): about one wave of blocks instead of 24 serial velocities per thread
+    p = _capi.plan_describe(_capi.OP_GRID_FWD, 1, 6, 500, 1201)
+    assert p["chunk"] <= 12 and p["bpm"] * p["wpb"] <= 2 * p["sms"] * 16
+    # the headline sweep keeps whole table fills and many waves
+    p = _capi.plan_describe(_capi.OP_GRID_BWD, 4096, 20, 128, 1024)
+    assert p["wpb"] == 4 and p["tc"] == 8 and p["chunk"] >= 64
+
+
 def test_argument_validation_without_gpu(lib):
     """NULL pointers and bad shapes are rejected before any CUDA call"""
     assert lib.adsurf_det_points_fwd(None, None, None, None, None, None, 1, 1, 1, None, None) == -1

@@ -1,7 +1,8 @@
 """N > 1 path on the CPU: world_size-2 gloo, ensemble sharded over the model axis.
 
 The sharded `multi_inversion` (rows split across ranks, horizontal-damping halo, final all-gather)
-must reproduce the single-process run exactly.  C-ABI calls are served by the oracle (fake backend);
+must reproduce the single-process run exactly — both the device-resident loop (`InversionLoop`, which exchanges
+four Vs rows per iteration) and the torch-autograd loop; the two loops must agree with each other.  C-ABI calls are served by the oracle (fake backend);
 this tests the host-side sharding logic, not the kernels."""
 import os
 import socket
@@ -46,10 +47,12 @@ def _problem():
     return mp_, ip, init, obs
 
 
-def _run():
+def _run(fused=True):
     from adsurf_b200._model import multi_inversion
     mp_, ip, init, obs = _problem()
+    os.environ["ADSURF_FUSED_OPT"] = "1" if fused else "0"
     inv = multi_inversion(mp_, ip, init, obs, vsrange_sign="add", vsrange=[-0.5, 0.5], device="cpu")
+    assert inv.timing["fused"] == fused
     return (np.asarray(inv.inv_process["loss"]), np.asarray(inv.inv_process["iter_vs"]),
             np.asarray(inv.inv_process["iter_thick"]), np.asarray(inv.inv_model["vs"]))
 
@@ -58,13 +61,19 @@ def _worker(rank, world, port, out_dir):
     torch.set_num_threads(1)
     from tests import fake_backend
     fake_backend.install(_MP())
-    ref = _run()  # single-process result, before the process group exists
+    ref = _run()  # single-process result (device-resident loop), before the process group exists
+    ref_torch = _run(fused=False)  # torch-autograd loop
+    for x, y in zip(ref, ref_torch):
+        np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-12)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         from adsurf_b200 import _dist
         assert _dist.is_sharded() and _dist.shard_bounds(5) == ((0, 3) if rank == 0 else (3, 5))
-        got = _run()
+        got = _run()  # sharded, device-resident loop with the four-row halo exchange (horizontal damping > 0)
         for x, y in zip(got, ref):
+            np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-14)
+        got_torch = _run(fused=False)  # sharded torch-autograd loop (full all-gather of Vs per iteration)
+        for x, y in zip(got_torch, ref_torch):
             np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-14)
         # uneven all-gather helper
         lo, hi = _dist.shard_bounds(5)

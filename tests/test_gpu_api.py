@@ -226,3 +226,159 @@ def test_fused_single_model_loop_matches_torch_loop(api, inv_method, monkeypatch
                       np.asarray(inv.inv_process["iter_thick"]), np.asarray(inv.inv_model["vs"]))
     for x, y in zip(runs["1"], runs["0"]):
         np.testing.assert_allclose(x, y, rtol=1e-7, atol=1e-10)
+
+
+def _single_model_problem(iters, lr):
+    import types
+    from adsurf_b200._utils import depth_ln
+    s = load("shipped_fixtures")
+    obs = s["disper_00"][::5]
+    lo, hi = depth_ln(0.2, 16.0, 6, 3.8)
+    mp_ = types.SimpleNamespace(clist=np.arange(2, 3.2, 0.004), layering_method="LN", initialize_method="Brocher",
+                                vp_vs_ratio=2.45, rho=2)
+    ip = types.SimpleNamespace(damp_vertical=0.002, damp_horizontal=0, compress=True, normalized=True,
+                               compress_method="exp", inversion_method="vs-and-thick", lr=lr, iteration=iters,
+                               step_size=10, gamma=0.75, optimizer="Adam")
+    init = types.SimpleNamespace(init_model={"vs": s["c2_init_vs"], "vp": s["c2_init_vp"], "rho": s["c2_init_rho"],
+                                             "thick": s["c2_init_thick"], "layer_mindepth": lo, "layer_maxdepth": hi})
+    return mp_, ip, init, obs
+
+
+def test_early_stopping_of_the_device_resident_loop(api, monkeypatch, capsys):
+    """The reference's early stopping (patience 50 on a non-improving loss, _model.py:168-186) evaluated on the host
+    over chunks of device-resident iterations stops at the same iteration and returns the same records as the
+    per-iteration torch loop (rows past the stopping point stay at their initial values)."""
+    from adsurf_b200._model import iter_inversion
+    mp_, ip, init, obs = _single_model_problem(iters=90, lr=1e-9)  # the loss barely moves: |dl|/l < 1e-4 every step
+    runs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ADSURF_FUSED_OPT", flag)
+        monkeypatch.setenv("ADSURF_CHECK_EVERY", "7")
+        inv = iter_inversion(mp_, ip, init, obs, vsrange_sign="mul", vsrange=[0.1, 2], device="cuda")
+        runs[flag] = (np.asarray(inv.inv_process["loss"]), np.asarray(inv.inv_process["iter_vs"]),
+                      np.asarray(inv.inv_process["iter_thick"]))
+        assert "Early Stopping in Iteration:50" in capsys.readouterr().out
+    for x, y in zip(runs["1"], runs["0"]):
+        assert x.shape == y.shape
+        np.testing.assert_allclose(x, y, rtol=1e-7, atol=1e-10)
+    assert np.all(runs["1"][0][51:] == 10.0) and np.all(runs["1"][1][51:] == 0.0)
+
+
+def test_graph_replay_equals_direct_launches(api):
+    """InversionLoop: replaying the captured CUDA graph (unroll 3, 7 iterations = 2 replays + 1 remainder graph)
+    gives bit-identical state and history to issuing adsurf_inversion_step call by call; the device iteration
+    counter ends at 7; iterating past T leaves the history alone."""
+    from adsurf_b200 import _capi
+    from tests.golden_models import brocher_np
+    rng = np.random.default_rng(11)
+    g = load("dmf_exp_m6")
+    S, T = 40, 7
+    b = np.tile(g["b"][0], (S, 1)) * (1 + rng.normal(0, 0.03, (S, 6)))
+    a, rho = brocher_np(b)
+    d = np.tile(g["d"][0], (S, 1))
+    Gt = lambda x: torch.tensor(np.ascontiguousarray(x, dtype=np.float64), device="cuda")
+    t, c = Gt(np.tile(g["t"][0], (S, 1))), Gt(np.tile(g["c"][0], (S, 1)))
+    C = Gt(np.tile(np.arange(2, 3.2, 0.01), (S, 1)))
+    out = {}
+    for use_graph in (False, True):
+        state = {"b": Gt(b), "d": Gt(d), "alpha": Gt(a), "rho": Gt(rho)}
+        consts = {"b0": Gt(b), "alpha0": Gt(a), "rho0": Gt(rho), "lower_b": Gt(0.7 * b), "upper_b": Gt(1.3 * b),
+                  "mindepth": Gt(np.cumsum(d, 1) * 0.8), "maxdepth": Gt(np.cumsum(d, 1) * 1.2)}
+        loop = _capi.InversionLoop(state, consts, t, c, C, compress=_capi.COMPRESS_EXP, vp_mode=1, vp_vs_ratio=0.0,
+                                   invert_thick=True, layering=1, proj_flags=_capi.PROJ_LAST_LAYER, damp_vertical=0.002,
+                                   damp_horizontal=0.001, lr=0.005, gamma=0.5, step_size=3, T=T, unroll=3,
+                                   use_graph=use_graph)
+        loop.run(T)
+        torch.cuda.synchronize()
+        assert loop.counter.tolist() == [T, 0]
+        hist = (loop.loss_hist.clone(), loop.iter_b_hist.clone(), loop.iter_d_hist.clone())
+        loop.run(2)  # past T: state advances, history rows are not written out of bounds
+        torch.cuda.synchronize()
+        assert loop.counter.tolist() == [T + 2, 0]
+        assert all(torch.equal(x, y) for x, y in zip(hist, (loop.loss_hist, loop.iter_b_hist, loop.iter_d_hist)))
+        out[use_graph] = hist + (state["b"].clone(), state["d"].clone(), state["alpha"].clone(), state["mb"].clone())
+    for x, y in zip(out[True], out[False]):
+        assert torch.equal(x, y)
+    assert torch.isfinite(out[True][0]).all() and (out[True][0] < 10.0).all()
+
+
+def test_config4_device_loop_matches_torch_loop_at_1024_models(api, monkeypatch):
+    """1024-model FRIUL7W ensemble (N=300 picks, 20 layers, compress=False): every loss, iterate and final model of
+    the device-resident loop against the torch-autograd loop over 4 iterations."""
+    from adsurf_b200.workload import config5_ensemble
+    s = load("shipped_fixtures")
+    obs = s["disper_02"]
+    d, a, b, rho = config5_ensemble(1024, 20, seed=0)
+    mp = api.Model_param(dc=0.01, vmin=0.5, vmax=5.0, tmin=1 / 20, tmax=5, layering_method="None",
+                         initialize_method="Brocher", layering_ratio=1.2, depth_factor=2, layer_number=6,
+                         vp_vs_ratio=2.45, rho=2)
+    ip = api.inv_param(inversion_method="vs", compress=False, compress_method="exp", normalized=True, lr=0.03,
+                       damp_vertical=0.0, damp_horizontal=0.0, iteration=4, step_size=2, gamma=0.75)
+    init = api.Init_model(model_param=mp, pvs_obs=obs, vp=a[0], vs=b[0], rho=rho[0], thick=d[0])
+    for key, val in (("vs", b), ("vp", a), ("thick", d), ("rho", rho)):
+        init.init_model[key] = val
+    pvs = np.ones((1024, obs.shape[0], 2)) * obs[:, :2]
+    runs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ADSURF_FUSED_OPT", flag)
+        inv = api.inversion(model_param=mp, inv_param=ip, init_model=init, pvs_obs=pvs, vsrange_sign="mul",
+                            vsrange=[0.1, 2.5], device="cuda:0")
+        assert inv.timing["fused"] == (flag == "1")
+        runs[flag] = (np.asarray(inv.inv_process["loss"]), np.asarray(inv.inv_process["iter_vs"]),
+                      np.asarray(inv.inv_model["vs"]), np.asarray(inv.inv_model["vp"]))
+    for x, y in zip(runs["1"], runs["0"]):
+        np.testing.assert_allclose(x, y, rtol=1e-7, atol=1e-10)
+
+
+def test_nan_propagates_through_dense_and_dmf_kernels(api):
+    """NaN inputs never trap: the affected model's outputs are NaN, its neighbours' are untouched (the reference's
+    host loop repairs NaN models, _model.py:624-626,638-639)."""
+    from adsurf_b200 import _capi
+    g = load("grid_m6")
+    Gt = lambda x: torch.tensor(np.ascontiguousarray(x, dtype=np.float64), device="cuda")
+    d, a, b, rho, t, c = (Gt(g[k]) for k in ("d", "a", "b", "rho", "tlist", "vlist"))
+    bad = b.clone()
+    bad[1, 2] = float("nan")
+    det, cmax, cmin, _ = _capi.grid_fwd(d, a, bad, rho, t, c, want_minmax=True)
+    ref = _capi.grid_fwd(d, a, b, rho, t, c)[0]
+    assert torch.isnan(det[1]).all() and torch.isnan(cmax[1]).all() and torch.isnan(cmin[1]).all()
+    assert torch.equal(det[0], ref[0]) and torch.equal(det[2:], ref[2:])
+    out = _capi.grid_bwd(d, a, bad, rho, t, c, None)[1:]
+    good = _capi.grid_bwd(d, a, b, rho, t, c, None)[1:]
+    for x, y in zip(out, good):
+        assert torch.isnan(x[1]).any() and torch.equal(x[0], y[0]) and torch.equal(x[2:], y[2:])
+    p = load("dmf_exp_m6")
+    pd, pa, pb, pr, pt, pc, pC = (Gt(p[k]) for k in ("d", "a", "b", "rho", "t", "c", "C"))
+    pbad = pb.clone()
+    pbad[0, 1] = float("nan")
+    res = _capi.dmf_step(pd, pa, pbad, pr, pt, pc, pC, _capi.COMPRESS_EXP)
+    ok = _capi.dmf_step(pd, pa, pb, pr, pt, pc, pC, _capi.COMPRESS_EXP)
+    assert torch.isnan(res[0][0]) and torch.equal(res[0][1:], ok[0][1:])
+    for x, y in zip(res[3:], ok[3:]):
+        assert torch.equal(x[1:], y[1:])
+
+
+def test_all_sensitivity_kernels(api):
+    """dc/d(vs, vp, thickness, rho) of the 30-layer model from the per-sample Jacobian kernel against autograd on
+    the oracle (implicit-function formula of notebook 02_2 cell 12)."""
+    from adsurf_b200 import ops
+    g = load("points_m30")
+    out = ops.sensitivity(g["c"][0], g["t"][0], g["d"][0], g["a"][0], g["b"][0], g["rho"][0])
+    Jc = np.diag(g["Jc"]).reshape(-1, 1)
+    for key, J in (("dc_dvs", "Jb"), ("dc_dvp", "Ja"), ("dc_dthick", "Jd"), ("dc_drho", "Jrho")):
+        ref = -g[J] / Jc
+        got = out[key].cpu().numpy()
+        scale = np.max(np.abs(ref), axis=1, keepdims=True)
+        assert np.max(np.abs(got - ref) / np.maximum(scale, 1e-300)) < 1e-8, key
+
+
+def test_explicit_init_and_planner_follow_the_device(api):
+    from adsurf_b200 import _capi
+    lib = _capi.lib()
+    assert lib.adsurf_init(0, 0) == 0 and lib.adsurf_init(0, _capi.INIT_PERSIST_L2) == 0
+    assert lib.adsurf_init(99, 0) == -6 and lib.adsurf_init(0, 8) == -6
+    nsm = torch.cuda.get_device_properties(0).multi_processor_count
+    L = 20
+    slab = nsm * 12 * (L - 1) * 9 * 32 * 8   # 3 blocks x 4 warps per SM, [L-1][9][32] doubles each
+    assert lib.adsurf_workspace_bytes(_capi.OP_GRID_BWD, 4096, L, 128, 1024) >= slab
+    assert lib.adsurf_workspace_bytes(_capi.OP_GRID_BWD, 4096, L, 128, 1024) < slab + (64 << 20)
