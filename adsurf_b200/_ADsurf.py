@@ -104,15 +104,25 @@ def cal_determinant(vel_model, model_param, sampling_method="log-wavelength", sa
     return tlist, vlist, F.to(want)
 
 
-def cal_dispersion_curve(vel_model, model_param, sampling_method="log-wavelength", sampling_num=100, dispOrder=[0]):
-    """Modal dispersion curves [period, c, mode] by root search (_ADsurf.py:232-310 -> _surf96.surf96)."""
+def cal_dispersion_curve(vel_model, model_param, sampling_method="log-wavelength", sampling_num=100, dispOrder=[0],
+                         device=None):
+    """Modal dispersion curves [period, c, mode] by root search (_ADsurf.py:232-310 -> _surf96.surf96).
+
+    device=None / "cpu": the sequential host solver (`_surf96.surf96`, as in the reference);
+    device="cuda" (any capitalisation, or a torch.device): the same search run by the CUDA kernel
+    (`dispersion.dispersion_curves`) — all requested modes in one launch, same mode bookkeeping, same roots."""
     from ._surf96 import surf96
     b, a, rho, d = (np.asarray(list2numpy(vel_model[k]), dtype=np.float64) for k in ("vs", "vp", "rho", "thick"))
     t = _periods(model_param, sampling_method, sampling_num)
     ifunc = ifunc_list["dunkin"]["rayleigh"]
     parts = []
+    on_gpu = device is not None and torch.device(str(device).lower()).type == "cuda"
+    if on_gpu:
+        from .dispersion import dispersion_curves
+        wanted = sorted(set(dispOrder))
+        curves = dispersion_curves(t, d, a, b, rho, modes=wanted, dc=model_param.dc, device=device)
     for mode in sorted(set(dispOrder)):
-        c = np.asarray(surf96(t, d, a, b, rho, mode, 0, ifunc, model_param.dc))
+        c = curves[wanted.index(mode)] if on_gpu else np.asarray(surf96(t, d, a, b, rho, mode, 0, ifunc, model_param.dc))
         ok = c > 0
         if mode > 0 and not ok.any():
             break  # the reference stops stacking at the first absent overtone
@@ -139,8 +149,8 @@ class True_model:
         self.tlist, self.vlist, F = cal_determinant(self.vel_model, self.model_param, sampling_method, sampling_num)
         return F
 
-    def _cal_dispersion_curve(self, sampling_method="log-wavelength", sampling_num=100, dispOrder=[0]):
-        return cal_dispersion_curve(self.vel_model, self.model_param, sampling_method, sampling_num, dispOrder)
+    def _cal_dispersion_curve(self, sampling_method="log-wavelength", sampling_num=100, dispOrder=[0], device=None):
+        return cal_dispersion_curve(self.vel_model, self.model_param, sampling_method, sampling_num, dispOrder, device)
 
 
 class Init_model:
@@ -214,15 +224,18 @@ class Init_model:
         self.tlist, self.vlist, F = cal_determinant(self.init_model, self.model_param, sampling_method, sampling_num)
         return F
 
-    def _cal_dispersion_curve(self, sampling_method="log-wavelength", sampling_num=100, dispOrder=[0]):
-        return cal_dispersion_curve(self.init_model, self.model_param, sampling_method, sampling_num, dispOrder)
+    def _cal_dispersion_curve(self, sampling_method="log-wavelength", sampling_num=100, dispOrder=[0], device=None):
+        return cal_dispersion_curve(self.init_model, self.model_param, sampling_method, sampling_num, dispOrder, device)
 
 
 class init_model_MonteCarlo:
     """Ensemble of initial models around `init_model` (reference _ADsurf.py:541-646)."""
 
     def __init__(self, model_param, init_model, sampling_num=200, sampling_method="normal", vsrange_sign="mul",
-                 vsrange=[-0.2, 0.2], sigma_vs=10, sigma_thick=0, AK135_data=[], forward=True):
+                 vsrange=[-0.2, 0.2], sigma_vs=10, sigma_thick=0, AK135_data=[], forward=True, generator="numpy",
+                 seed=0, device=None):
+        # generator="device": the ensemble is drawn and pre-screened on the GPU and stays there (CUDA tensors)
+        self.generator, self.seed, self.device = generator, seed, device
         self.model_param = model_param
         self.init_model = init_model
         self.sampling_num = sampling_num
@@ -244,7 +257,8 @@ class init_model_MonteCarlo:
             depth_down_boundary=list2numpy(im["layer_mindepth"]), depth_up_boundary=list2numpy(im["layer_maxdepth"]),
             vsrange_sign=self.vsrange_sign, vsrange=self.vsrange, sampling_num=self.sampling_num,
             sampling_method=self.sampling_method, gen_velMethod=mp.initialize_method, vp_vs_ratio=mp.vp_vs_ratio,
-            sigma_vs=self.sigma_vs, sigma_thick=self.sigma_thick, AK135_data=self.AK135_data, forward=self.forward)
+            sigma_vs=self.sigma_vs, sigma_thick=self.sigma_thick, AK135_data=self.AK135_data, forward=self.forward,
+            generator=self.generator, seed=self.seed, device=self.device)
         for key in ("vs", "vp", "rho", "thick"):
             self.MonteCarlo_model[key] = res["model"][key]
         self.MonteCarlo_model["loss"] = res["loss"]
@@ -256,7 +270,8 @@ def inversion(model_param, inv_param, init_model, pvs_obs, vsrange_sign="mul", v
 
     `device` accepts what the reference accepts plus any capitalisation ("Cuda", "cuda:0", "cpu",
     torch.device); the arithmetic always runs on the GPU."""
-    ndim = np.asarray(list2numpy(init_model.init_model["vs"])).ndim
+    vs0 = init_model.init_model["vs"]
+    ndim = vs0.dim() if torch.is_tensor(vs0) else np.asarray(list2numpy(vs0)).ndim
     if ndim == 1:
         return iter_inversion(model_param, inv_param, init_model, pvs_obs, vsrange_sign, vsrange, AK135_data, device)
     if ndim == 2:

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # ADSURF_LIB: load another build of the library (kernel experiments); the default is the in-tree build
 LIB_PATH = os.environ.get("ADSURF_LIB") or os.path.join(_HERE, "_lib", "libadsurf_b200.so")
 
-OP_POINTS_FWD, OP_POINTS_BWD, OP_POINTS_JAC, OP_GRID_FWD, OP_GRID_BWD, OP_DMF_STEP, OP_ENSEMBLE_STEP = range(7)
+OP_POINTS_FWD, OP_POINTS_BWD, OP_POINTS_JAC, OP_GRID_FWD, OP_GRID_BWD, OP_DMF_STEP, OP_ENSEMBLE_STEP, OP_DISPERSION = range(8)
 INIT_PERSIST_L2 = 1
 COMPRESS_NONE, COMPRESS_EXP, COMPRESS_LOG, COMPRESS_EXP_NONORM, COMPRESS_NORM = range(5)
 
@@ -36,6 +36,8 @@ EXPORTS = (
     "adsurf_ensemble_adam_step",
     "adsurf_inversion_workspace_bytes",
     "adsurf_inversion_step",
+    "adsurf_dispersion_curves",
+    "adsurf_mc_generate",
 )
 
 
@@ -93,6 +95,11 @@ def lib():
         L.adsurf_math_probe.restype = ci
         L.adsurf_plan_describe.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(ci)]
         L.adsurf_plan_describe.restype = ci
+        L.adsurf_dispersion_curves.argtypes = [vp] * 5 + [ci] * 4 + [ctypes.c_double, vp, vp, vp, sz, vp]
+        L.adsurf_dispersion_curves.restype = ci
+        L.adsurf_mc_generate.argtypes = ([vp] * 9 + [ci, ci, ci, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci,
+                                          ctypes.c_ulonglong] + [vp] * 5)
+        L.adsurf_mc_generate.restype = ci
         L.adsurf_init.argtypes = [ci, ctypes.c_uint]
         L.adsurf_init.restype = ci
         L.adsurf_inversion_workspace_bytes.argtypes = [ctypes.POINTER(InversionStruct)]
@@ -297,6 +304,41 @@ def dmf_step(d, a, b, rho, t, c, C, compress, with_grad=True, want_F=False, want
                                      _stream(d)))
     launch_count += (1 if normalised else 0) + 2 + (1 if with_grad else 0)
     return (loss, F, norm) + grads
+
+
+def dispersion_curves(d, a, b, rho, t, nmodes, dc):
+    """(c [S,nmodes,NF], status int32 [S]): modal phase velocities by the reference's root search, one thread per model"""
+    global launch_count
+    _req(d, a, b, rho, t)
+    S, L = d.shape
+    NF = t.shape[1]
+    dev = d.device
+    c = torch.empty((S, int(nmodes), NF), dtype=torch.float64, device=dev)
+    status = torch.empty((S,), dtype=torch.int32, device=dev)
+    ws, nbytes = _workspace(OP_DISPERSION, S, L, NF, 0, d)
+    with torch.cuda.device(dev):
+        _check(lib().adsurf_dispersion_curves(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), S, L, NF, int(nmodes),
+                                              float(dc), _ptr(c), _ptr(status), _ptr(ws), nbytes, _stream(d)))
+    launch_count += 1
+    return c, status
+
+
+def mc_generate(d, a, b, rho, vs_lo, vs_hi, S, *, vel_method, vp_vs_ratio=0.0, sigma_vs, sigma_thick=0.0, layering=0,
+                depth_lo=None, depth_hi=None, ak135=None, seed=0):
+    """(d, alpha, beta, rho) [S,L] CUDA tensors: Monte-Carlo ensemble generated on the device (adsurf_mc_generate)"""
+    global launch_count
+    _req(d, a, b, rho, vs_lo, vs_hi, depth_lo, depth_hi, ak135)
+    L = b.numel()
+    dev = b.device
+    out = [torch.empty((int(S), L), dtype=torch.float64, device=dev) for _ in range(4)]
+    with torch.cuda.device(dev):
+        _check(lib().adsurf_mc_generate(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(vs_lo), _ptr(vs_hi), _ptr(depth_lo),
+                                        _ptr(depth_hi), _ptr(ak135), 0 if ak135 is None else int(ak135.shape[0]), int(S),
+                                        L, int(vel_method), float(vp_vs_ratio or 0.0), float(sigma_vs),
+                                        float(sigma_thick), int(layering), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                        _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream(b)))
+    launch_count += 1
+    return tuple(out)
 
 
 def fp64_peak_probe(iters=2048, repeats=5, device=None):

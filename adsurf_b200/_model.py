@@ -24,7 +24,7 @@ import torch
 import os
 
 from . import _capi, _dist, ops
-from ._utils import gen_model, gen_model1, ifunc_list, list2numpy, numpy2tensor
+from ._utils import gen_model, gen_model1, ifunc_list, list2numpy, numpy2tensor, tensor2numpy
 
 try:  # progress bars are optional
     from tqdm import tqdm
@@ -359,7 +359,7 @@ class iter_inversion:
         iter_vs = iter_vs[:last].cpu().numpy()
         iter_thick = iter_thick[:last].cpu().numpy()
         best = int(np.argmin(loss_np))
-        inv_thick = iter_thick[best] if vs_and_thick else list2numpy(im["thick"])
+        inv_thick = iter_thick[best] if vs_and_thick else tensor2numpy(list2numpy(im["thick"]))
         inv_vs = iter_vs[best]
         inv_vp, inv_vs, inv_rho = _final_model(mp, inv_thick, inv_vs, self.AK135_data)
         self.inv_model = {"thick": np.asarray(inv_thick).tolist(), "vp": inv_vp.tolist(), "vs": inv_vs.tolist(),
@@ -573,7 +573,7 @@ class multi_inversion:
         iter_vs = iter_vs.cpu().numpy()
         iter_thick = iter_thick.cpu().numpy()
         best_num = np.argmin(loss_np, axis=0)
-        inv_thick = np.array(list2numpy(im["thick"]), dtype=np.float64, copy=True)
+        inv_thick = np.array(tensor2numpy(list2numpy(im["thick"])), dtype=np.float64, copy=True)
         if vs_and_thick:
             for i in range(S):
                 inv_thick[i] = iter_thick[best_num[i], i, :]

@@ -45,6 +45,7 @@
 
 #include "adsurf_b200.h"
 #include "adsurf_math.cuh"
+#include "adsurf_dispersion.cuh"
 
 namespace {
 
@@ -765,6 +766,106 @@ __global__ void k_ens_adam(EnsArgs A) {
   }
 }
 
+// modal dispersion curves (N1): the reference's sequential root search, one thread per model (adsurf_dispersion.cuh)
+__global__ void k_dispersion(const double* __restrict__ d, const double* __restrict__ a, const double* __restrict__ b,
+                             const double* __restrict__ rho, const double* __restrict__ t, int S, int L, int NF,
+                             int nmodes, double dc, double* __restrict__ cout, double* __restrict__ work,
+                             int* __restrict__ status) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const DispModel M{d + (size_t)s * L, a + (size_t)s * L, b + (size_t)s * L, rho + (size_t)s * L, L};
+  status[s] = disp_getc(M, t + (size_t)s * NF, NF, nmodes, dc, cout + (size_t)s * nmodes * NF, work + (size_t)s * NF);
+}
+
+// ---- Monte-Carlo ensemble generation on the device (N2) -------------------------------------------------
+// Philox4x32-10 counter-based generator (Salmon et al. 2011): counter = (model, layer, draw kind, 0), key = seed, so
+// every (model, layer) draw is independent of the launch geometry and reproducible from the seed alone.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// one standard normal per (model, layer, kind): Box-Muller on two 53-bit-spaced uniforms in (0, 1)
+__device__ __forceinline__ double philox_normal(unsigned long long seed, uint32_t s, uint32_t l, uint32_t kind) {
+  uint32_t r[4];
+  philox4x32_10(s, l, kind, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const double u1 = ((double)r[0] * 4294967296.0 + (double)r[1] + 0.5) * (1.0 / 18446744073709551616.0);
+  const double u2 = ((double)r[2] * 4294967296.0 + (double)r[3] + 0.5) * (1.0 / 18446744073709551616.0);
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  return sqrt(-2.0 * log(u1)) * cs;
+}
+
+struct McArgs {
+  const double *d, *a, *b, *rho;              // base model [L]
+  const double *vs_lo, *vs_hi;                // [L]
+  const double *dep_lo, *dep_hi;              // [L] depth bounds (leading zero already dropped) or NULL
+  const double* ak135;                        // [nak,3] (USArray) or NULL
+  double *od, *oa, *ob, *orho;                // [S,L]
+  int S, L, vel_method, layering, nak;        // vel_method 1 Brocher, 2 Constant, 3 USArray
+  double ratio, sigma_vs, sigma_thick;
+  unsigned long long seed;
+};
+
+// one thread per model: Vs ~ N(vs_l, ((hi-lo)/sigma_vs)^2) clipped to [lo, hi]; optional depth perturbation (LR: depth
+// clipped per layer; LN: against the previous perturbed depth), thickness >= dep_lo[1], last = second to last; then
+// Vp / rho from the velocity rule.  Row 0 is the unperturbed model (reference _MonteCarlo.py:81-169).
+__global__ void k_mc_generate(McArgs A) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= A.S) return;
+  const int L = A.L;
+  const size_t o = (size_t)s * L;
+  double pdepth = 0.0, depth0 = 0.0;
+  for (int l = 0; l < L; ++l) {
+    double vs = A.b[l], th = A.d[l];
+    if (s > 0) {
+      const double z = philox_normal(A.seed, (uint32_t)s, (uint32_t)l, 0u);
+      vs = fmin(fmax(vs + (A.vs_hi[l] - A.vs_lo[l]) / A.sigma_vs * z, A.vs_lo[l]), A.vs_hi[l]);
+    }
+    depth0 += A.d[l];
+    if (A.dep_lo && A.layering && A.sigma_thick > 0.0 && s > 0) {
+      const double z = philox_normal(A.seed, (uint32_t)s, (uint32_t)l, 1u);
+      double dep = depth0 + (A.dep_hi[l] - A.dep_lo[l]) / A.sigma_thick * z;
+      const double lo = (A.layering == 2 && l > 0) ? pdepth + A.dep_lo[l] : A.dep_lo[l];
+      dep = fmin(fmax(dep, lo), A.dep_hi[l]);  // np.clip: the upper bound wins when lo > hi
+      th = fmax(dep - pdepth, A.dep_lo[1 < L ? 1 : 0]);
+      pdepth = dep;
+    }
+    A.ob[o + l] = vs;
+    A.od[o + l] = th;
+    double vp = A.a[l], rr = A.rho[l];
+    if (s > 0) {
+      if (A.vel_method == 1 || A.vel_method == 3) {
+        vp = brocher_vp(vs);
+        rr = brocher_rho(vp);
+        if (A.vel_method == 3 && vs > 4.6 && A.ak135) {  // nearest AK135 entry (columns: depth, rho, vp)
+          double bv = INFINITY, br = INFINITY, nvp = vp, nrr = rr;
+          for (int j = 0; j < A.nak; ++j) {
+            const double dv = fabs(A.ak135[3 * j + 2] - vp), dr = fabs(A.ak135[3 * j + 1] - rr);
+            if (dv < bv) { bv = dv; nvp = A.ak135[3 * j + 2]; }
+            if (dr < br) { br = dr; nrr = A.ak135[3 * j + 1]; }
+          }
+          vp = nvp;
+          rr = nrr;
+        }
+      } else if (A.vel_method == 2) {
+        vp = vs * A.ratio;
+      }
+    }
+    A.oa[o + l] = vp;
+    A.orho[o + l] = rr;
+  }
+  if (A.dep_lo && A.layering && A.sigma_thick > 0.0 && L > 1) A.od[o + L - 1] = A.od[o + L - 2];  // row 0 too (:119-123)
+}
+
 __global__ void k_math_probe(const double* __restrict__ x, int n, double* __restrict__ rs, double* __restrict__ ex,
                              double* __restrict__ sn, double* __restrict__ cs) {
   stage_exp_table();
@@ -1061,6 +1162,8 @@ size_t adsurf_workspace_bytes(int op, int S, int L, int n, int K) {
     }
     case ADSURF_OP_ENSEMBLE_STEP:
       return align256((size_t)(7 * (size_t)S * L + 2 * (size_t)L) * sizeof(double));
+    case ADSURF_OP_DISPERSION:
+      return align256((size_t)S * n * sizeof(double));
     default:
       return 0;
   }
@@ -1372,6 +1475,39 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
   A.beta1 = p->beta1; A.beta2 = p->beta2; A.eps = p->eps; A.step_size = p->step_size;
   A.counter = p->counter; A.T = p->T; A.loss_hist = p->loss_hist; A.iter_b = p->iter_b_hist; A.iter_d = p->iter_d_hist;
   return ens_launch(A, (char*)ws + dmf_bytes, ens_bytes, st);
+}
+
+int adsurf_dispersion_curves(const double* d, const double* alpha, const double* beta, const double* rho,
+                             const double* t, int S, int L, int NF, int nmodes, double dc, double* c, int* status,
+                             void* ws, size_t ws_bytes, void* stream) {
+  if (!d || !alpha || !beta || !rho || !t || !c || !status) return ADSURF_E_NULL;
+  if (S <= 0 || L <= 0 || NF <= 0 || nmodes <= 0) return ADSURF_E_SHAPE;
+  if (!(dc > 0.0)) return ADSURF_E_ARG;
+  if (!ws || ws_bytes < (size_t)S * NF * sizeof(double)) return ADSURF_E_WORKSPACE;
+  const int threads = 32;  // one model per thread: spread the ensemble over as many SMs as possible
+  k_dispersion<<<(S + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(d, alpha, beta, rho, t, S, L, NF, nmodes,
+                                                                                  dc, c, (double*)ws, status);
+  return check_launch();
+}
+
+int adsurf_mc_generate(const double* d, const double* alpha, const double* beta, const double* rho, const double* vs_lower,
+                       const double* vs_upper, const double* depth_lower, const double* depth_upper,
+                       const double* ak135, int n_ak135, int S, int L, int vel_method, double vp_vs_ratio,
+                       double sigma_vs, double sigma_thick, int layering, unsigned long long seed, double* out_d,
+                       double* out_alpha, double* out_beta, double* out_rho, void* stream) {
+  if (!d || !alpha || !beta || !rho || !vs_lower || !vs_upper || !out_d || !out_alpha || !out_beta || !out_rho)
+    return ADSURF_E_NULL;
+  if (S <= 0 || L <= 0) return ADSURF_E_SHAPE;
+  if (vel_method < 1 || vel_method > 3 || layering < 0 || layering > 2 || !(sigma_vs > 0.0)) return ADSURF_E_ARG;
+  if ((depth_lower == nullptr) != (depth_upper == nullptr)) return ADSURF_E_NULL;
+  McArgs A;
+  A.d = d; A.a = alpha; A.b = beta; A.rho = rho; A.vs_lo = vs_lower; A.vs_hi = vs_upper;
+  A.dep_lo = depth_lower; A.dep_hi = depth_upper; A.ak135 = ak135; A.nak = ak135 ? n_ak135 : 0;
+  A.od = out_d; A.oa = out_alpha; A.ob = out_beta; A.orho = out_rho;
+  A.S = S; A.L = L; A.vel_method = vel_method; A.layering = layering;
+  A.ratio = vp_vs_ratio; A.sigma_vs = sigma_vs; A.sigma_thick = sigma_thick; A.seed = seed;
+  k_mc_generate<<<(S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(A);
+  return check_launch();
 }
 
 int adsurf_math_probe(const double* x, int n, double* out_rsqrt, double* out_expneg, double* out_sin,

@@ -1,35 +1,59 @@
-"""All-modes-at-once dispersion-curve extraction on the GPU.
+"""Modal dispersion curves on the GPU — two extractors.
 
-The reference extracts a curve with ~13 *sequential* scalar determinant evaluations per period and
-per mode (`_surf96.getc`: ladder bracketing + Neville refinement, period k starts from the root of
-period k-1).  Here the same roots come out of two batched steps built on the dense kernels:
+`dispersion_curves` — the reference's own root search (`_surf96.getc/getsol/nevill`: ladder bracketing from the
+previous period's root, Neville refinement to 1e-6 relative, mode bookkeeping with `clow`, `one = 1e-2`,
+`onea = 1.5`, zeros for absent modes) run by the CUDA kernel `k_dispersion`, one thread per model (C ABI
+`adsurf_dispersion_curves`).  Same brackets, same iterates: mode indices are the reference's and roots agree with
+`_surf96.surf96` within 1e-6 km/s.  The search is sequential within a model, so the parallel axis is the ensemble:
+the curves of 4096 models cost what one costs.  `cal_dispersion_curve(..., device="cuda")` calls it.
 
-  1. one dense sweep `det[K, NF]` over the trial-velocity ladder c_k = c_low + k*dc (the reference's
-     step `dc`, starting like `getc` 10 % below the slowest layer's half-space Rayleigh velocity and
-     ending at max(Vs)): every sign change along c brackets a root, the n-th sign change at a period is
-     mode n (the fundamental is the slowest root, overtones follow in increasing c);
-  2. all brackets of all periods and modes are refined together by safeguarded regula falsi
-     (Illinois), one pointwise-kernel launch per iteration, to a relative width of `rtol`.
-
-Modes that do not exist at a period (no n-th sign change below max(Vs)) return 0, like the reference.
-Differences from `surf96` by construction: brackets come from a fixed ladder instead of a ladder
-that follows the previous period's root, so two roots closer than `dc` are missed by both but not
-necessarily at the same periods; roots are converged to `rtol` (default 1e-12) whereas the reference
-stops at 1e-6 relative, so values agree to the reference's own tolerance (~3e-6 km/s), not to 1e-6.
-`adsurf_b200._surf96.surf96` remains the bit-for-bit-compatible path.
+`dispersion_curves_dense` — a different algorithm for the same roots: one dense sweep `det[K, NF]` over a fixed
+trial-velocity ladder (every sign change along c brackets a root; the n-th sign change at a period is mode n), then
+all brackets of all periods and modes refined together by safeguarded regula falsi (Illinois), one pointwise-kernel
+launch per iteration, to a relative width of `rtol` (default 1e-12).  Converged roots, i.e. zeros of the secular
+function to rounding — they agree with the reference to ITS tolerance (1e-6 relative, ~3e-6 km/s), and brackets
+come from a fixed ladder instead of one that follows the previous root, so two roots closer than `dc` may be
+resolved at different periods than `getc` does.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 
-from . import ops
-from ._surf96 import gtsolh
+from . import _capi, ops
+from ._surf96 import DispersionError, gtsolh
 
 
 @torch.no_grad()
-def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, rtol=1e-12, max_iter=60, device=None):
-    """Phase velocities c[len(modes), len(t)] of the requested Rayleigh modes of ONE layered model.
+def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, device=None):
+    """Phase velocities of the requested Rayleigh modes by the reference's root search on the GPU.
+
+    t: periods [NF] (or [S,NF]); d, a, b, rho: thickness, Vp, Vs, density [L] (one model) or [S,L] (an ensemble).
+    Returns c[len(modes), NF] (one model) or c[S, len(modes), NF]; 0 where a mode does not exist.
+    Raises DispersionError if the fundamental mode of any model cannot be bracketed (as `_surf96.getc` does)."""
+    dev = ops._device_of(device=device)
+    D, A_, B_, R = (torch.as_tensor(np.asarray(x, dtype=np.float64), device=dev) for x in (d, a, b, rho))
+    single = D.dim() == 1
+    if single:
+        D, A_, B_, R = (x.reshape(1, -1) for x in (D, A_, B_, R))
+    S = D.shape[0]
+    T = torch.as_tensor(np.asarray(t, dtype=np.float64), device=dev)
+    T = T.reshape(1, -1).expand(S, -1) if T.dim() == 1 else T
+    if bool((B_[:, 0] <= 0).any()):
+        raise NotImplementedError("adsurf_b200: water layer not supported")
+    modes = [int(m) for m in modes]
+    c, status = _capi.dispersion_curves(D.contiguous(), A_.contiguous(), B_.contiguous(), R.contiguous(),
+                                        T.contiguous(), max(modes) + 1, float(dc))
+    if bool(status.any()):
+        raise DispersionError("failed to find root for fundamental mode")
+    out = c[:, modes, :].cpu().numpy()
+    return out[0] if single else out
+
+
+@torch.no_grad()
+def dispersion_curves_dense(t, d, a, b, rho, modes=(0,), dc=0.005, rtol=1e-12, max_iter=60, device=None):
+    """Converged roots c[len(modes), len(t)] of the requested Rayleigh modes of ONE layered model (dense-grid
+    bracketing + batched Illinois refinement; see the module docstring).
 
     t: periods (s); d, a, b, rho: thickness, Vp, Vs, density per layer (last = half-space)."""
     t_np = np.asarray(t, dtype=np.float64).reshape(-1)
@@ -45,7 +69,9 @@ def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, rtol=1e-12, max_ite
     D, A_, B_, R = (torch.as_tensor(x, device=dev) for x in (d_np, a_np, b_np, r_np))
     det = ops.det_grid(C, T, D, A_, B_, R)                      # [K, NF]
     sg = torch.sign(det)
-    change = sg[:-1] != sg[1:]                                    # [K-1, NF] bracket k = (c_k, c_{k+1})
+    # a bracket needs finite values of opposite sign at both ends (NaN or an exact zero at a ladder point is not a
+    # sign change: it would shift the mode index of every higher root at that period)
+    change = (sg[:-1] * sg[1:]) < 0                               # [K-1, NF] bracket k = (c_k, c_{k+1})
     order = torch.cumsum(change.to(torch.int32), dim=0)          # running count of sign changes along c
     NF = T.numel()
     modes = list(modes)
@@ -85,6 +111,13 @@ def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, rtol=1e-12, max_ite
         f_hi = torch.where(left, f_hi, fx)
         if bool(torch.all((hi_f - lo_f) <= rtol * hi_f)):
             break
-    root = (0.5 * (lo_f + hi_f)).reshape(M, NF)
+    # whichever end has the smaller |F| (an Illinois end can be stale when the iteration cap is hit)
+    f_lo_true, f_hi_true = F(lo_f), F(hi_f)
+    root = torch.where(f_lo_true.abs() <= f_hi_true.abs(), lo_f, hi_f)
+    wide = ((hi_f - lo_f) > 1e3 * rtol * hi_f) & ok.reshape(1, -1)
+    if bool(wide.any()):
+        import warnings
+        warnings.warn(f"dispersion_curves_dense: {int(wide.sum())} bracket(s) did not converge in {max_iter} iterations")
+    root = root.reshape(M, NF)
     root = torch.where(ok & (root <= betmx), root, torch.zeros_like(root))
     return root.cpu().numpy()

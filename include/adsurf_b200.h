@@ -52,7 +52,8 @@ enum adsurf_op {
   ADSURF_OP_GRID_FWD = 3,
   ADSURF_OP_GRID_BWD = 4,
   ADSURF_OP_DMF_STEP = 5,
-  ADSURF_OP_ENSEMBLE_STEP = 6 /* adsurf_ensemble_adam_step: n, K ignored */
+  ADSURF_OP_ENSEMBLE_STEP = 6, /* adsurf_ensemble_adam_step: n, K ignored */
+  ADSURF_OP_DISPERSION = 7     /* adsurf_dispersion_curves: n = NF */
 };
 
 /* DMF compression (reference _model.py:450-462) */
@@ -207,6 +208,40 @@ typedef struct adsurf_inversion {
 } adsurf_inversion;
 size_t adsurf_inversion_workspace_bytes(const adsurf_inversion* p);
 int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, void* stream);
+
+/* Modal Rayleigh phase-velocity curves by the classical root search, for S models at once:
+ * c[s,n,k] = phase velocity of mode n (0 = fundamental .. nmodes-1) of model s at period t[s,k], 0 where the mode does
+ * not exist.  One thread per model runs the reference's own sequential algorithm — start 10 % below the slowest
+ * layer's half-space Rayleigh velocity, walk a `dc` ladder from the previous period's root (and above the previous
+ * mode's root) to the first sign change of the normalised secular function, refine by Neville interpolation with
+ * bisection safeguards to 1e-6 relative — with identical bookkeeping (clow, one = 1e-2, onea = 1.5), so mode indices
+ * and the zeros for absent modes are the reference's and the roots agree with it to its own iterates (1e-6 km/s).
+ * Periods are searched in the order given (the reference passes them ascending).  status[s] = 1 when the fundamental
+ * mode cannot be bracketed (the reference raises DispersionError), else 0.  ws >= S*NF doubles.
+ * Replaces _surf96.surf96 / getc / getsol / nevill / gtsolh (_surf96.py:452-760) behind cal_dispersion_curve
+ * (_ADsurf.py:232-310), phase velocity (itype = 0); group velocity is two calls at t/(1 +- dt) on the host. */
+int adsurf_dispersion_curves(const double* d, const double* alpha, const double* beta, const double* rho,
+                             const double* t, int S, int L, int NF, int nmodes, double dc,
+                             double* c, int* status, void* ws, size_t ws_bytes, void* stream);
+
+/* Monte-Carlo ensemble of initial models, generated on the device: row 0 = the base model
+ * (d, alpha, beta, rho [L]); rows 1..S-1: Vs_l ~ Normal(beta_l, ((vs_upper_l - vs_lower_l) / sigma_vs)^2) clipped to
+ * [vs_lower_l, vs_upper_l]; with depth bounds (depth_lower/upper [L], leading zero already dropped as the reference
+ * does) and sigma_thick > 0 the cumulative depths are perturbed the same way and clipped (layering 1 = LR: per layer;
+ * 2 = LN: at least depth_lower_l below the previous perturbed depth), thickness >= depth_lower[1], last = second to
+ * last; Vp / rho by vel_method (1 Brocher, 2 Constant ratio with rho kept, 3 USArray: Brocher, nearest AK135 entry
+ * [n_ak135,3] = (depth, rho, vp) above 4.6 km/s).  Random numbers: Philox4x32-10 keyed by `seed`, counter = (model,
+ * layer, draw kind) — reproducible and independent of the launch geometry, but NOT the numpy Mersenne-Twister stream
+ * of the reference: ensembles agree with the reference's in distribution, not draw by draw (the host generator
+ * `ADsurf_MonteCarlo(..., device=None)` keeps numpy's stream for seeded parity).
+ * Replaces the generation half of ADsurf_MonteCarlo (_MonteCarlo.py:81-169). */
+int adsurf_mc_generate(const double* d, const double* alpha, const double* beta, const double* rho,
+                       const double* vs_lower, const double* vs_upper,
+                       const double* depth_lower, const double* depth_upper,
+                       const double* ak135, int n_ak135,
+                       int S, int L, int vel_method, double vp_vs_ratio, double sigma_vs, double sigma_thick,
+                       int layering, unsigned long long seed,
+                       double* out_d, double* out_alpha, double* out_beta, double* out_rho, void* stream);
 
 /* Validation hook: evaluates the kernels' inline elementary functions on the device,
  * out_rsqrt[i] = 1/sqrt(x[i]), out_expneg[i] = exp(-x[i]), out_sin/out_cos[i] = sin/cos(x[i]).

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "adsurf_math.cuh"
+#include "adsurf_dispersion.cuh"
 
 using namespace adsurf;
 
@@ -20,6 +21,16 @@ struct HostSink {
 }  // namespace
 
 extern "C" {
+
+// modal dispersion curves of S models by the kernel's root search (adsurf_dispersion.cuh), run on the host
+void host_dispersion(const double* d, const double* a, const double* b, const double* rho, const double* t, int S, int L,
+                     int NF, int nmodes, double dc, double* c, int* status) {
+  std::vector<double> work(NF);
+  for (int s = 0; s < S; ++s) {
+    const DispModel M{d + (size_t)s * L, a + (size_t)s * L, b + (size_t)s * L, rho + (size_t)s * L, L};
+    status[s] = disp_getc(M, t + (size_t)s * NF, NF, nmodes, dc, c + (size_t)s * nmodes * NF, work.data());
+  }
+}
 
 // elementary functions of the kernel header, for accuracy tests against libm
 void host_elementary(const double* x, int n, double* rs, double* ex, double* sn, double* cs) {

@@ -134,23 +134,79 @@ def test_config4_friul_ensemble_step_and_sensitivity(api):
     assert np.max(np.abs(got - kern) / scale) < 1e-6   # roots are float32-accurate: dF/dc is well away from 0
 
 
-@pytest.mark.parametrize("tag,modes,dc", [("m6", (0,), 0.001), ("m3", (0, 1, 2), 0.001), ("m20", (0,), 0.01)])
-def test_gpu_dispersion_curves_match_reference_solver(api, tag, modes, dc):
-    """all modes at once from the dense kernel + batched refinement vs the reference's sequential solver"""
+@pytest.mark.parametrize("tag,modes", [("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,))])
+def test_gpu_dispersion_curves_match_reference_solver(api, tag, modes):
+    """k_dispersion (the reference's root search with its mode bookkeeping, one thread per model) against the
+    reference's sequential solver in float64: every period, every mode, 1e-6 km/s; identical zeros for absent modes."""
     from adsurf_b200.dispersion import dispersion_curves
     g = load("surf96_roots")
     t, d, a, b, rho = (g[f"{tag}_{k}"] for k in ("t", "d", "a", "b", "rho"))
-    c = dispersion_curves(t, d, a, b, rho, modes=modes, dc=dc)
+    c = dispersion_curves(t, d, a, b, rho, modes=modes, dc=float(g[f"{tag}_dc"]))
+    assert c.shape == (len(modes), len(t))
     for i, mode in enumerate(modes):
         ref = g[f"{tag}_mode{mode}_c"]
-        both = (c[i] > 0) & (ref > 0)
-        assert both.sum() >= 0.9 * (ref > 0).sum()
-        assert np.max(np.abs(c[i][both] - ref[both])) < 5e-6
-    # converged roots are zeros of the secular function to rounding
+        assert np.array_equal(c[i] > 0, ref > 0)           # mode indices / absent modes: exact
+        assert np.max(np.abs(c[i] - ref)) <= 1e-6          # km/s, 100 % of the points
+
+
+def test_gpu_dispersion_ensemble_equals_single_models(api):
+    """the parallel axis is the ensemble: 96 perturbed 6-layer models in one launch == 96 single-model launches"""
+    from adsurf_b200.dispersion import dispersion_curves
+    from tests.golden_models import brocher_np
+    g = load("surf96_roots")
+    rng = np.random.default_rng(4)
+    S = 96
+    b = g["m6_b"] * (1 + rng.normal(0, 0.02, (S, 6)))
+    a, rho = brocher_np(b)
+    d = np.tile(g["m6_d"], (S, 1))
+    c = dispersion_curves(g["m6_t"], d, a, b, rho, modes=(0, 1), dc=0.005)
+    assert c.shape == (S, 2, len(g["m6_t"])) and np.all(c[:, 0] > 0)
+    for s in (0, 17, 95):
+        one = dispersion_curves(g["m6_t"], d[s], a[s], b[s], rho[s], modes=(0, 1), dc=0.005)
+        assert np.array_equal(one, c[s])
+
+
+@pytest.mark.parametrize("name,tol", [("disper_00", 3e-6), ("disper_01", 3e-6), ("disper_02", 6e-6)])
+def test_cal_dispersion_curve_on_gpu_reproduces_shipped_fixtures(api, name, tol):
+    """`cal_dispersion_curve(..., device="cuda")` against the reference's shipped disper*.txt (outputs of its own
+    `cal_dispersion_curve`, examples 00_0 / 01_0 / 02_0): same rows, same mode labels, c within the float32 accuracy
+    the files were generated with (up to 2.6e-6 km/s on config 1; FRIUL7W reaches 4 km/s: 1.2e-6 relative)."""
+    from adsurf_b200._utils import gen_model
+    from adsurf_b200.workload import friul7w
+    fx = load("shipped_fixtures")[name]
+    if name == "disper_00":
+        mp = api.Model_param(dc=0.001, vmin=2, vmax=3.2, tmin=1 / 10, tmax=5)
+        model, num, order = gen_model(np.array([0.4, 0.5, 0.5, 0.5, 0.5, 0.5]),
+                                      np.array([2.39, 2.54, 2.7, 2.82, 2.93, 3.04]), area=True), 500, [0]
+    elif name == "disper_01":
+        mp = api.Model_param(dc=0.001, vmin=0.2, vmax=0.4, tmin=1 / 100, tmax=1 / 5)
+        model, num, order = gen_model(np.array([0.005] * 3), np.array([0.3, 0.22, 0.4]), area=True), 500, [0, 1, 2]
+    else:
+        mp = api.Model_param(dc=0.01, vmin=0.5, vmax=5.0, tmin=1 / 20, tmax=5)
+        model, num, order = friul7w(20), 300, [0]
+    th, vp, vs, rho = model
+    vel = {"thick": th, "vp": vp, "vs": vs, "rho": rho}
+    got = api.cal_dispersion_curve(vel, mp, "log-wavelength", num, order, device="Cuda")
+    assert got.shape == fx.shape and np.array_equal(got[:, 2], fx[:, 2])
+    np.testing.assert_allclose(got[:, 0], fx[:, 0], rtol=1e-6)
+    assert np.max(np.abs(got[:, 1] - fx[:, 1])) <= tol
+    host = api.cal_dispersion_curve(vel, mp, "log-wavelength", num if name != "disper_01" else 40, order)
+    if name != "disper_01":  # the sequential host solver walks the same iterates
+        assert np.max(np.abs(host[:, 1] - got[:, 1])) <= 1e-9
+
+
+def test_dense_grid_extractor_converges_to_roots(api):
+    """the other extractor (dense sweep + batched Illinois): zeros of the secular function to rounding, within the
+    reference solver's own stopping tolerance (1e-6 relative) of its roots"""
     from adsurf_b200 import ops
-    has = c[0] > 0
-    F = ops.det_points(c[0][has], t[has], d, a, b, rho).cpu().numpy()
-    cmax, cmin = ops.det_grid_minmax(np.linspace(c[0][has].min() * 0.9, b.max(), 200), t[has], d, a, b, rho)
+    from adsurf_b200.dispersion import dispersion_curves_dense
+    g = load("surf96_roots")
+    t, d, a, b, rho = (g[f"m6_{k}"] for k in ("t", "d", "a", "b", "rho"))
+    c = dispersion_curves_dense(t, d, a, b, rho, modes=(0,), dc=0.001)
+    ref = g["m6_mode0_c"]
+    assert np.all(c[0] > 0) and np.max(np.abs(c[0] - ref) / ref) < 2e-6
+    F = ops.det_points(c[0], t, d, a, b, rho).cpu().numpy()
+    cmax, cmin = ops.det_grid_minmax(np.linspace(c[0].min() * 0.9, b.max(), 200), t, d, a, b, rho)
     assert np.max(np.abs(F) / (cmax - cmin).cpu().numpy()) < 1e-9
 
 
@@ -382,3 +438,70 @@ def test_explicit_init_and_planner_follow_the_device(api):
     slab = nsm * 12 * (L - 1) * 9 * 32 * 8   # 3 blocks x 4 warps per SM, [L-1][9][32] doubles each
     assert lib.adsurf_workspace_bytes(_capi.OP_GRID_BWD, 4096, L, 128, 1024) >= slab
     assert lib.adsurf_workspace_bytes(_capi.OP_GRID_BWD, 4096, L, 128, 1024) < slab + (64 << 20)
+
+
+def test_device_side_monte_carlo_ensemble(api):
+    """adsurf_mc_generate behind ADsurf_MonteCarlo(generator="device"): same distribution as the reference's numpy
+    generator (not the same stream), row 0 = base model, bounds respected, depth rules (LR / LN), deterministic in
+    the seed, pre-screen misfit equal to the host-generated path on the same models, and the CUDA-tensor ensemble
+    feeds `inversion(...)` without touching the host."""
+    from adsurf_b200._MonteCarlo import ADsurf_MonteCarlo
+    from adsurf_b200.workload import friul7w
+    s = load("shipped_fixtures")
+    obs = s["disper_02"]
+    th, vp, vs, rho = friul7w(20)
+    clist = np.arange(0.5, 5.0, 0.01)
+    S = 4096
+    kw = dict(layering_method="None", vsrange_sign="add", vsrange=[-1, 1], sampling_num=S, sampling_method="normal",
+              gen_velMethod="Brocher", sigma_vs=30, sigma_thick=20)
+    res = ADsurf_MonteCarlo(obs, clist, th, vp, vs, rho, forward=True, generator="device", seed=7, **kw)
+    M = res["model"]
+    assert all(torch.is_tensor(M[k]) and M[k].is_cuda and M[k].shape == (S, 20) for k in ("thick", "vs", "vp", "rho"))
+    assert res["loss"].is_cuda and res["loss"].shape == (S,) and torch.isfinite(res["loss"]).all()
+    b = M["vs"].cpu().numpy()
+    np.testing.assert_array_equal(b[0], vs)
+    np.testing.assert_array_equal(M["thick"].cpu().numpy(), np.tile(th, (S, 1)))     # thickness unchanged here
+    assert np.all(b >= vs - 1 - 1e-15) and np.all(b <= vs + 1 + 1e-15)
+    z = (b[1:] - vs) / (2.0 / 30)                                                      # ~N(0,1): 4095 x 20 draws
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    assert abs(np.mean(np.abs(z) < 1.0) - 0.6827) < 0.01 and abs(np.mean(z ** 3)) < 0.05
+    corr = np.corrcoef(z.T)                                                            # layers are independent
+    assert np.max(np.abs(corr - np.eye(20))) < 0.08
+    from tests.golden_models import brocher_np
+    a_ref, r_ref = brocher_np(b[1:])
+    np.testing.assert_allclose(M["vp"].cpu().numpy()[1:], a_ref, rtol=1e-13)
+    np.testing.assert_allclose(M["rho"].cpu().numpy()[1:], r_ref, rtol=1e-13)
+    again = ADsurf_MonteCarlo(obs, clist, th, vp, vs, rho, forward=False, generator="device", seed=7, **kw)
+    other = ADsurf_MonteCarlo(obs, clist, th, vp, vs, rho, forward=False, generator="device", seed=8, **kw)
+    assert torch.equal(again["model"]["vs"], M["vs"]) and not torch.equal(other["model"]["vs"], M["vs"])
+    # pre-screen on device-generated models == the host path's pre-screen of the same models (first 64)
+    from adsurf_b200 import ops
+    t = np.tile(obs[:, 0], (64, 1)); c = np.tile(obs[:, 1], (64, 1)); C = np.tile(clist, (64, 1))
+    ref = ops.dmf_data_misfit(c, t, C, *(M[k][:64].cpu().numpy() for k in ("thick", "vp", "vs", "rho")), compress="norm")
+    np.testing.assert_allclose(res["loss"][:64].cpu().numpy(), ref.cpu().numpy(), rtol=1e-12)
+    # depth perturbation: LN keeps every layer at least depth_lower below the previous one; LR clips per layer
+    L = 6
+    d6, b6 = np.full(L, 0.5), np.linspace(2.4, 3.0, L)
+    a6, r6 = brocher_np(b6)
+    lo, hi = np.full(L, 0.1), np.cumsum(d6) * 1.5
+    for method in ("LR", "LN"):
+        out = ADsurf_MonteCarlo(obs, clist, d6, a6, b6, r6, layering_method=method, depth_up_boundary=list(hi),
+                                depth_down_boundary=list(lo), vsrange_sign="mul", vsrange=[0.8, 1.2], sampling_num=512,
+                                sigma_vs=10, sigma_thick=5, forward=False, generator="device", seed=1)
+        thick = out["model"]["thick"].cpu().numpy()
+        np.testing.assert_array_equal(thick[0, :-1], d6[:-1])
+        assert np.all(thick >= lo[1] - 1e-15) and np.array_equal(thick[:, -1], thick[:, -2])
+        assert thick[1:, :-1].std() > 0.01
+    # the CUDA-tensor ensemble goes straight into inversion(...)
+    mp = api.Model_param(dc=0.01, vmin=0.5, vmax=5.0, tmin=1 / 20, tmax=5, layering_method="None",
+                         initialize_method="Brocher", layering_ratio=1.2, depth_factor=2, layer_number=6,
+                         vp_vs_ratio=2.45, rho=2)
+    ip = api.inv_param(inversion_method="vs", compress=False, lr=0.03, iteration=3, step_size=200, gamma=0.75)
+    init = api.Init_model(model_param=mp, pvs_obs=obs, vp=vp, vs=vs, rho=rho, thick=th)
+    mc = api.init_model_MonteCarlo(mp, init, sampling_num=256, vsrange_sign="add", vsrange=[-1, 1], sigma_vs=30,
+                                   sigma_thick=20, forward=False, generator="device", seed=3)
+    for key in ("vs", "vp", "thick", "rho"):
+        init.init_model[key] = mc.MonteCarlo_model[key]
+    pvs = np.ones((256, obs.shape[0], 2)) * obs[:, :2]
+    inv = api.inversion(mp, ip, init, pvs, vsrange_sign="mul", vsrange=[0.1, 2.5], device="cuda")
+    assert np.asarray(inv.inv_process["loss"]).shape == (3, 256) and np.isfinite(inv.inv_process["loss"]).all()
