@@ -83,24 +83,43 @@ struct ReduceSink {
   }
 };
 
-// Dense adjoint with the slabs in global memory (shared memory is free): fold the warp once
-// (lane l with lane l^16) and keep 16 per-lane partial sums per (layer, gradient) in shared memory:
-// acc[L][4][16].  2 exchanges + 2 read-modify-writes per layer, no dependent shuffle chain; the 16
-// lanes x warps are summed once per virtual block.
+// Adjoint with the slabs in global memory (shared memory is free): fold the warp once (lane l with lane l^16)
+// and keep 16 per-lane partial sums per (layer, gradient) in shared memory: acc[row][4][16], row = layer + 1 (row 0
+// takes the zeros a walking sweep deposits first).  2 exchanges + 2 read-modify-writes per layer, no dependent
+// shuffle chain; the 16 lanes x warps are summed once per virtual block.
+constexpr int kAccRow = 64;  // doubles per (warp, layer): [4][16]
 struct FoldSink {
-  double* acc;  // this warp's [L][4][16]
-  int lane;
-  __device__ __forceinline__ void operator()(int m, double gd, double ga, double gb, double gr) const {
-    const bool hi = lane & 16;
-    const double k0 = hi ? gb : gd, k1 = hi ? gr : ga;  // lower half owns (gd, ga), upper half (gb, grho)
+  double* p;  // this lane's cell of the current row: row + ((lane >> 4) << 5) + (lane & 15)
+  bool hi;    // upper half-warp: owns (gb, grho); the lower half owns (gd, ga)
+  __device__ __forceinline__ FoldSink(double* acc, int lane) : p(acc + ((lane >> 4) << 5) + (lane & 15)), hi(lane & 16) {}
+  __device__ __forceinline__ void fold(double* q, double gd, double ga, double gb, double gr) const {
+    const double k0 = hi ? gb : gd, k1 = hi ? gr : ga;
     const double x0 = hi ? gd : gb, x1 = hi ? ga : gr;
     const double a0 = k0 + __shfl_xor_sync(0xffffffffu, x0, 16);
     const double a1 = k1 + __shfl_xor_sync(0xffffffffu, x1, 16);
-    double* q = acc + ((m * 4 + ((lane >> 4) << 1)) << 4) + (lane & 15);
     q[0] += a0;
     q[16] += a1;
   }
+  // walking form (dense sweep): rows in the order the sweep visits them
+  __device__ __forceinline__ void put(double gd, double ga, double gb, double gr) {
+    fold(p, gd, ga, gb, gr);
+    p += kAccRow;
+  }
+  // indexed form (pointwise sweep): layer m lives in row m + 1
+  __device__ __forceinline__ void operator()(int m, double gd, double ga, double gb, double gr) const {
+    fold(p + (m + 1) * kAccRow, gd, ga, gb, gr);
+  }
 };
+// sum of the 16 lane cells of (warp w, layer m, gradient which) in accs[wpb][L+1][4][16]
+__device__ __forceinline__ double fold_total(const double* __restrict__ accs, int wpb, int L, int m, int which) {
+  double v = 0.0;
+  for (int w = 0; w < wpb; ++w) {
+    const double* q = accs + ((size_t)w * (L + 1) + (m + 1)) * kAccRow + (which << 4);
+#pragma unroll
+    for (int l = 0; l < 16; ++l) v += q[l];
+  }
+  return v;
+}
 
 struct JacSink {  // write this sample's Jacobian rows
   double *jd, *ja, *jb, *jr;
@@ -154,19 +173,23 @@ __device__ __forceinline__ BlockCoord block_coord(int vb, const GridPlan& gp) {
   return bc;
 }
 
+// Table of n trial velocities: per velocity a sentinel entry followed by the L-1 layer entries, one more sentinel
+// at the end (TableSource in adsurf_math.cuh); ics[cc] = 1 / c.
 template <int kTab>
 __device__ __forceinline__ void fill_table(double* __restrict__ tab, double* __restrict__ ics,
                                            const double* __restrict__ par, int L, const double* __restrict__ cs,
                                            int n) {
-  const int per = L - 1;
-  for (int e = threadIdx.x; e < n * per; e += blockDim.x) {
-    const int cc = e / per, m = e - cc * per;
-    const double ic = 1.0 / cs[cc];
-    if (m == 0) ics[cc] = ic;
-    table_entry<kTab>(tab + (size_t)e * kTab, par, m, ic);
+  for (int e = threadIdx.x; e < n * L; e += blockDim.x) {
+    const int cc = e / L, j = e - cc * L;
+    double* __restrict__ q = tab + (size_t)e * kTab;
+    if (j == 0) {
+      ics[cc] = 1.0 / cs[cc];
+      table_sentinel(q, kTab);
+    } else {
+      table_entry<kTab>(q, par, j - 1, 1.0 / cs[cc]);
+    }
   }
-  if (per == 0)
-    for (int cc = threadIdx.x; cc < n; cc += blockDim.x) ics[cc] = 1.0 / cs[cc];
+  if (threadIdx.x == blockDim.x - 1) table_sentinel(tab + (size_t)n * L * kTab, kTab);
 }
 
 // Dense grid, forward only: det / fused max,min over k / sign bitmap.
@@ -180,8 +203,8 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
   extern __shared__ double smem[];
   double* par = smem + kSmemHead;
   constexpr int kTab = kTabFwd;
-  double* tab = par + par_doubles(L);                   // [tc][L-1][kTab]
-  double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
+  double* tab = par + par_doubles(L);                   // [tc][sentinel + L-1 layers][kTab] + sentinel
+  double* ics = tab + table_doubles(L, gp.tc, kTab);    // [tc]
   double* hks = ics + ((gp.tc + 1) & ~1);               // [wpb*32][2]: omega/alpha_hs, omega/beta_hs per lane
   const BlockCoord bc = block_coord(blockIdx.x, gp);
   const int s = bc.s;
@@ -210,7 +233,7 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
     for (int cc = 0; cc < n; ++cc) {
       const int k = kb + cc;
       const Sample z = make_sample_dense(omega0, ics[cc], iw0);
-      const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab, hk};
+      const TableSource<kTab> src{par, L, tab + (size_t)(cc * L + 1) * kTab, hk};
       const double v = sample_forward(src, z);
       if (det && active) det[((size_t)s * K + k) * NF + f] = v;
       vmax = fmax(vmax, v);
@@ -263,7 +286,8 @@ struct GlobalStore {
     unsigned long long pol;
   };
   unsigned long long pol;
-  __device__ __forceinline__ Slot slot(int m) const { return Slot{p + (size_t)m * (kSlot * kWarp), pol}; }
+  __device__ __forceinline__ Slot slot(int m) const { return Slot{p + (ptrdiff_t)m * (kSlot * kWarp), pol}; }
+  __device__ __forceinline__ static Slot step(Slot s, int n) { return Slot{s.q + n * (kSlot * kWarp), s.pol}; }
   __device__ __forceinline__ static double ld(Slot s, int j) {
     double v;
     asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(s.q + j * kWarp), "l"(s.pol));
@@ -286,23 +310,22 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
            const double* __restrict__ gdet, int L, int NF, int K, GridPlan gp, int total_vblocks,
            double* __restrict__ det, double* __restrict__ part, double* __restrict__ estore) {
   extern __shared__ double smem[];
-  constexpr int kAccPer = 64;                           // accumulator doubles per (warp, layer): [4][16]
   constexpr int kTab = kTabAdj;
   double* par = smem + kSmemHead;                       // staged layer constants (after the exp table)
-  double* accs = par + par_doubles(L);                  // [wpb][L][4][16]
-  double* tab = accs + (size_t)gp.wpb * kAccPer * L;    // [tc][L-1][kTab]
-  double* ics = tab + (size_t)gp.tc * (L - 1) * kTab;   // [tc]
+  double* accs = par + par_doubles(L);                  // [wpb][L+1][4][16]
+  double* tab = accs + (size_t)gp.wpb * kAccRow * (L + 1);  // [tc][sentinel + L-1 layers][kTab] + sentinel
+  double* ics = tab + table_doubles(L, gp.tc, kTab);    // [tc]
   double* hks = ics + ((gp.tc + 1) & ~1);               // [wpb*32][2]: omega/alpha_hs, omega/beta_hs per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
+  const size_t slab = (size_t)L * kSlot * kWarp;        // L-1 layers + the spare slot the read-ahead touches
   const GlobalStore st{estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + lane, l2_evict_last_policy()};
-  double* acc = accs + (size_t)warp * kAccPer * L;
+  double* acc = accs + (size_t)warp * kAccRow * (L + 1);
   for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
     const BlockCoord bc = block_coord(vb, gp);
     const int s = bc.s;
     __syncthreads();  // previous virtual block has flushed its accumulators
     stage_params(par, d, alpha, beta, rho, s, L);
-    for (int i = threadIdx.x; i < gp.wpb * kAccPer * L; i += blockDim.x) accs[i] = 0.0;
+    for (int i = threadIdx.x; i < gp.wpb * kAccRow * (L + 1); i += blockDim.x) accs[i] = 0.0;
     const int ft = bc.fg * gp.wpb + warp;
     const bool live = ft < gp.nft;
     const int f = ft * kWarp + lane;
@@ -323,7 +346,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
       for (int cc = 0; cc < n; ++cc) {
         const int k = kb + cc;
         const Sample z = make_sample_dense(omega0, ics[cc], iw0);
-        const TableSource<kTab> src{par, L, tab + (size_t)cc * (L - 1) * kTab, hk};
+        const TableSource<kTab> src{par, L, tab + (size_t)(cc * L + 1) * kTab, hk};
         const size_t idx = ((size_t)s * K + k) * NF + fc;
         // inactive lanes (period tile overhang) replay a valid sample with a zero seed
         const double seed = active ? (gdet ? gdet[idx] : 1.0) : 0.0;
@@ -336,13 +359,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
       const int which = i / L, m = i - which * L;  // output order [4][L]
-      double v = 0.0;
-      for (int w = 0; w < gp.wpb; ++w) {
-        const double* q = accs + (size_t)w * kAccPer * L + ((m * 4 + which) << 4);
-#pragma unroll
-        for (int l = 0; l < 16; ++l) v += q[l];
-      }
-      part[((size_t)s * gp.bpm + bc.blk) * 4 * L + i] = v;
+      part[((size_t)s * gp.bpm + bc.blk) * 4 * L + i] = fold_total(accs, gp.wpb, L, m, which);
     }
   }
 }
@@ -427,14 +444,14 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
   // kGlobal: persistent blocks, store slabs in the L2-resident global slab, per-lane fold accumulators (large
   // ensembles); otherwise one block per (model, 32*wpb picks) with the slabs in shared memory (small problems).
   extern __shared__ double smem[];
-  constexpr int kAccPer = kGlobal ? 64 : 4;
+  const int acc_per_warp = kGlobal ? kAccRow * (L + 1) : 4 * L;
   double* par = smem + kSmemHead;
-  double* accs = par + par_doubles(L);                  // [wpb][L][4][16] or [wpb][4][L]
-  double* lossw = accs + (size_t)pp.wpb * kAccPer * L;  // [wpb]
+  double* accs = par + par_doubles(L);                  // [wpb][L+1][4][16] or [wpb][4][L]
+  double* lossw = accs + (size_t)pp.wpb * acc_per_warp; // [wpb]
   double* ests = lossw + pp.wpb;                        // [wpb][L-1][kSlot][32] (shared variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
-  double* acc = accs + (size_t)warp * kAccPer * L;
+  const size_t slab = (size_t)L * kSlot * kWarp;
+  double* acc = accs + (size_t)warp * acc_per_warp;
   const unsigned long long slab_policy = kGlobal ? l2_evict_last_policy() : 0ull;
   double* estp = kGlobal ? estore + ((size_t)blockIdx.x * pp.wpb + warp) * slab + lane : ests + (size_t)warp * slab + lane;
   for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
@@ -442,7 +459,7 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
     const int blk = vb - s * pp.bpm;
     __syncthreads();
     stage_params(par, d, alpha, beta, rho, s, L);
-    for (int i = threadIdx.x; i < pp.wpb * kAccPer * L + pp.wpb; i += blockDim.x) accs[i] = 0.0;
+    for (int i = threadIdx.x; i < pp.wpb * acc_per_warp + pp.wpb; i += blockDim.x) accs[i] = 0.0;
     __syncthreads();
     const int unit = blk * pp.wpb + warp;
     if (unit < pp.units) {
@@ -501,12 +518,7 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
       for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
         double v = 0.0;
         if (kGlobal) {
-          const int which = i / L, m = i - which * L;
-          for (int w = 0; w < pp.wpb; ++w) {
-            const double* q = accs + (size_t)w * kAccPer * L + ((m * 4 + which) << 4);
-#pragma unroll
-            for (int l = 0; l < 16; ++l) v += q[l];
-          }
+          v = fold_total(accs, pp.wpb, L, i % L, i / L);
         } else {
           for (int w = 0; w < pp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
         }
@@ -896,7 +908,8 @@ inline int sm_count() {
 
 inline size_t par_bytes(int L) { return (size_t)(kSmemHead + par_doubles(L)) * sizeof(double); }
 
-inline size_t est_bytes_per_warp(int L) { return (size_t)(L > 1 ? L - 1 : 0) * kSlot * kWarp * sizeof(double); }
+// store slab of one warp: a slot per layer above the half-space plus the spare slot the dense read-ahead touches
+inline size_t est_bytes_per_warp(int L) { return (size_t)L * kSlot * kWarp * sizeof(double); }
 
 // warps per block for the pointwise adjoint with the slabs in shared memory; 0 if even one warp does not fit
 inline int adj_wpb(int L) {
@@ -922,15 +935,15 @@ inline int max_resident_adj_warps(int nsm) { return nsm * kBwdBlocksPerSM * kBwd
 inline size_t slab_bytes(int L, int nsm) { return (size_t)max_resident_adj_warps(nsm) * est_bytes_per_warp(L); }
 
 inline size_t table_bytes(int L, int tc, bool adjoint) {
-  const size_t per = (size_t)(L > 1 ? L - 1 : 0);
-  return (size_t)tc * per * (adjoint ? kTabAdj : kTabFwd) * sizeof(double) + (size_t)((tc + 1) & ~1) * sizeof(double);
+  return (size_t)table_doubles(L, tc, adjoint ? kTabAdj : kTabFwd) * sizeof(double) +
+         (size_t)((tc + 1) & ~1) * sizeof(double);
 }
 
 inline size_t grid_fwd_smem(int L, int tc, int wpb) {
   return par_bytes(L) + table_bytes(L, tc, false) + (size_t)wpb * kWarp * 2 * sizeof(double);
 }
 inline size_t grid_bwd_smem(int L, int tc, int wpb) {
-  return par_bytes(L) + (size_t)wpb * 64 * L * sizeof(double) + table_bytes(L, tc, true) +
+  return par_bytes(L) + (size_t)wpb * kAccRow * (L + 1) * sizeof(double) + table_bytes(L, tc, true) +
          (size_t)wpb * kWarp * 2 * sizeof(double);
 }
 
@@ -1029,7 +1042,7 @@ inline PointsPlan plan_points(int S, int L, int N, bool allow_global, int nsm) {
 inline size_t points_estore_bytes(const PointsPlan& pp, int L, int nsm) { return pp.global ? slab_bytes(L, nsm) : 0; }
 
 inline size_t points_smem(const PointsPlan& pp, int L) {
-  return pp.global ? par_bytes(L) + (size_t)pp.wpb * (64 * L + 1) * sizeof(double) : adj_smem(L, pp.wpb);
+  return pp.global ? par_bytes(L) + (size_t)pp.wpb * (kAccRow * (L + 1) + 1) * sizeof(double) : adj_smem(L, pp.wpb);
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }

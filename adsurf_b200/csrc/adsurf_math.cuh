@@ -263,7 +263,8 @@ ADSURF_HD void sincos_core(double q, double* sn, double* cs) {
 // the density gradient of a layer from the vectors on either side of it:
 //   rho dDelta/drho = (E'_0 s_0 - E_0 s'_0) - (E'_4 s_4 - E_4 s'_4),   E' = E.CA, s' = CA.s.
 // regime flags of a (velocity, layer) pair: oscillatory (k < kx) and regular (k != kx) for P and S
-enum { F_LTP = 1, F_POSP = 2, F_LTS = 4, F_POSS = 8, F_REGULAR = F_POSP | F_POSS };
+enum { F_LTP = 1, F_POSP = 2, F_LTS = 4, F_POSS = 8, F_REGULAR = F_POSP | F_POSS,
+       F_END = 16 };  // F_END: sentinel entry of the shared table (no layer), see TableSource
 
 struct Eig {
   double r, ir;     // n = sqrt(|1/c^2 - 1/v^2|) and its reciprocal (frequency-free)
@@ -630,7 +631,8 @@ ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ 
   tab[T_GK] = gk;
   tab[T_G1] = g1;
   const int fl = (ic < sa ? F_LTP : 0) | (da > 0.0 ? F_POSP : 0) | (ic < sb ? F_LTS : 0) | (db > 0.0 ? F_POSS : 0);
-  tab[T_FL] = bits_dbl((long long)fl);  // raw bits, read back with dbl_bits()
+  // raw bits, read back with dbl_bits(): regime flags in the low word, the layer index in the high word
+  tab[T_FL] = bits_dbl(((long long)m << 32) | (long long)fl);
   tab[T_TQA] = kFast ? (ic < sa ? -pr[P_IA3] : pr[P_IA3]) * (ina * ina) : pr[P_IA3] / ((ic + sa) * (ic - sa));
   if (kN > kTabFwd) {
     tab[T_TQB] = kFast ? (ic < sb ? -pr[P_IB3] : pr[P_IB3]) * (inb * inb) : pr[P_IB3] / ((ic + sb) * (ic - sb));
@@ -673,47 +675,47 @@ ADSURF_HD void layer_from_entry(Layer& y, const double* __restrict__ q, const do
 }
 
 struct DirectSource {
-  static constexpr bool kUniformFlags = false;  // per-sample (t, c): regimes may differ between lanes
   static constexpr bool kWantIc = true;         // the pointwise kernels return dF/dc
   const double* __restrict__ par;
   int L;
-  ADSURF_HD int flags(int) const { return -1; }
   ADSURF_HD const double* half_k() const { return nullptr; }
-  ADSURF_HD bool small_phases(const Sample&) const { return false; }
   ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
     alignas(16) double tab[kTabAdj];
     table_entry<kTabAdj, true>(tab, par, m, z.ic);
     layer_from_entry<kTabAdj>(y, tab, par + m * kNumPar, z.omega, Dbl2{tab[T_PDA], tab[T_PDB]});
     y.rho = par[m * kNumPar + P_RHO];
   }
-  ADSURF_HD Dbl2 phases(int) const { return Dbl2{0.0, 0.0}; }
-  ADSURF_HD void prep(Layer& y, int m, const Sample& z, const Dbl2&) const { prep(y, m, z); }
 };
 
+// Dense kernels: the entries of one trial velocity in the block's shared table.  Layout of the table (built by
+// the kernels' fill_table): per velocity one SENTINEL entry (flags = F_END, phases 0) followed by the L-1 layer
+// entries, and one more sentinel after the last velocity — so the entry before layer 0 and the entry after layer
+// L-2 are both sentinels.  The sweeps walk the entries with a running pointer and stop at a sentinel: no layer
+// index, no bounds tests, no predicated loads in the layer loops.
 template <int kN>
 struct TableSource {
-  static constexpr bool kUniformFlags = true;   // flags come from the shared (velocity, layer) table
   static constexpr bool kWantIc = false;
   const double* __restrict__ par;
   int L;
-  const double* __restrict__ tab;  // [L-1][kN] for the current trial velocity (16-byte aligned)
+  const double* __restrict__ tab;  // entry of layer 0 for the current trial velocity (16-byte aligned)
   const double* hkq;               // this lane's staged (omega/alpha_hs, omega/beta_hs), see load_half
   ADSURF_HD const double* half_k() const { return hkq; }
-  ADSURF_HD int flags(int m) const { return (int)dbl_bits(tab[m * kN + T_FL]); }
+  ADSURF_HD static int flags(const double* q) { return (int)dbl_bits(q[T_FL]); }
   // every phase of the sample below 1e5 (the inline sincos's range): p = omega n d, n <= max(1/c, 1/beta)
   ADSURF_HD bool small_phases(const Sample& z) const {
     return z.omega * fmax(z.ic, par[kNumPar * L + 2]) * par[kNumPar * L + 3] < 1.0e5;
   }
-  ADSURF_HD void prep(Layer& y, int m, const Sample& z) const {
-    layer_from_entry<kN>(y, tab + m * kN, par + m * kNumPar, z.omega, ld2(tab + m * kN + T_PDA));
-  }
-  // the phase pair (n d for P and S) of layer m, which the dense sweeps read one layer ahead: it heads the
-  // layer's longest dependent chain (phase -> exp / sincos -> ...)
-  ADSURF_HD Dbl2 phases(int m) const { return ld2(tab + m * kN + T_PDA); }
-  ADSURF_HD void prep(Layer& y, int m, const Sample& z, const Dbl2& ph) const {
-    layer_from_entry<kN>(y, tab + m * kN, par + m * kNumPar, z.omega, ph);
-  }
+  // the layer's staged record (read only where c coincides with a layer velocity): its index rides in the entry
+  ADSURF_HD const double* record(const double* q) const { return par + (int)(dbl_bits(q[T_FL]) >> 32) * kNumPar; }
 };
+// doubles of one velocity's entries in the table (sentinel + layers) and of a table of tc velocities
+ADSURF_HD int table_stride(int L, int kN) { return L * kN; }
+ADSURF_HD int table_doubles(int L, int tc, int kN) { return (tc * L + 1) * kN; }
+// sentinel entry
+ADSURF_HD void table_sentinel(double* __restrict__ tab, int kN) {
+  for (int i = 0; i < kN; ++i) tab[i] = 0.0;
+  tab[T_FL] = bits_dbl((long long)F_END);
+}
 
 // The half-space vector is linear in ra, rb = sqrt((k+kx)|k-kx|): at a trial velocity that coincides
 // with the half-space velocity the result depends on the last bit of kx, so kx is formed with the
@@ -764,12 +766,14 @@ struct PlainStore {
   double* p;
   typedef double* Slot;
   ADSURF_HD Slot slot(int m) const { return p + (size_t)m * (kSlot * kStride); }
+  ADSURF_HD static Slot step(Slot q, int n) { return q + n * (kSlot * kStride); }  // n slots further
   ADSURF_HD static double ld(Slot q, int j) { return q[j * kStride]; }
   ADSURF_HD static void st(Slot q, int j, double v) { q[j * kStride] = v; }
 };
 struct NoStore {
   typedef int Slot;
   ADSURF_HD Slot slot(int) const { return 0; }
+  ADSURF_HD static Slot step(Slot q, int) { return q; }
   ADSURF_HD static void st(Slot, int, double) {}
 };
 
@@ -778,83 +782,99 @@ constexpr int kEE = F_REGULAR;                  // both evanescent: c below both
 constexpr int kOO = F_REGULAR | F_LTP | F_LTS;  // both oscillatory: c above both
 constexpr int kOE = F_REGULAR | F_LTP;
 
+// one layer of the bottom-up sweep: eigenfunction terms of the regime kFl (>= 0: regular, |phase| < 1e5, branch-free
+// bodies; -1: huge phase, NaN, or c exactly on a layer velocity), optional store, E <- E . CA
+template <int kFl, bool kStore, typename Store>
+ADSURF_HD void forward_layer(Layer& y, double (&e)[5], double omega, typename Store::Slot q) {
+  if (kFl >= 0) {
+    layer_set_flags(y, kFl);
+    if (kFl & F_LTP) eig_osc(y.P); else eig_evan(y.P);
+    if (kFl & F_LTS) eig_osc(y.S); else eig_evan(y.S);
+    y.P.w = y.P.sn * y.P.ir;
+    y.S.w = y.S.sn * y.S.ir;
+  } else {
+    layer_set_flags(y, y.fl);
+    const double wd = omega * y.pr[P_D];
+    eig_forward(y.P, wd);
+    eig_forward(y.S, wd);
+  }
+  y.a0 = layer_a0(y.P, y.S);
+  if (kStore) {
+    // the second value (cos) exists only for an oscillatory term; the adjoint sweep loads it on the same rule
+    Store::st(q, 5, y.P.c0);
+    if (kFl >= 0 ? (kFl & F_LTP) != 0 : y.P.lt) Store::st(q, 6, y.P.c1);
+    Store::st(q, 7, y.S.c0);
+    if (kFl >= 0 ? (kFl & F_LTS) != 0 : y.S.lt) Store::st(q, 8, y.S.c1);
+  }
+  row_apply(e, y);
+}
+
 // Bottom-up sweep E <- E . CA_m, m = L-2 .. 0, from the half-space vector; kStore keeps E_{m+1} and the
-// transcendental results of every layer in slot m for the adjoint sweep.
-// Dense kernels (warp-uniform regime flags from the table): consecutive layers in the same regime run in a
-// straight-line loop of their own — no selects, the P and S polynomial chains (each a ~16-deep dependent FP64
-// sequence, 8 cycles per link) interleaved by the scheduler — and the next layer's flags are read one layer
-// ahead, so the branch that closes a run never waits for shared memory.
-template <bool kStore, typename Source, typename Store>
-ADSURF_HD double forward_sweep(const Source& src, const Sample& z, const Store& est) {
+// transcendental results of every layer in slot m for the adjoint sweep.  Pointwise sources (one table entry
+// computed per sample and layer, regimes differ between lanes): the generic layer body.
+template <bool kStore, typename Store>
+ADSURF_HD double forward_sweep(const DirectSource& src, const Sample& z, const Store& est) {
   const int L = src.L;
   double e[5];
-  half_start(src.par, L, z, src.half_k(), e);
-  Dbl2 ph{0.0, 0.0};  // phase pair of layer m (dense sweeps: read one layer ahead)
-  auto step = [&](int m, auto tag) {
-    constexpr int kFl = decltype(tag)::value;
-    Layer y;
-    if (Source::kUniformFlags) src.prep(y, m, z, ph); else src.prep(y, m, z);
-    if (kFl >= 0) {  // regular regime, |phase| < 1e5: branch-free bodies
-      layer_set_flags(y, kFl);
-      if (kFl & F_LTP) eig_osc(y.P); else eig_evan(y.P);
-      if (kFl & F_LTS) eig_osc(y.S); else eig_evan(y.S);
-      y.P.w = y.P.sn * y.P.ir;
-      y.S.w = y.S.sn * y.S.ir;
-    } else {         // huge phase, NaN, or c exactly on a layer velocity
-      layer_set_flags(y, y.fl);
-      const double wd = z.omega * y.pr[P_D];
-      eig_forward(y.P, wd);
-      eig_forward(y.S, wd);
-    }
-    y.a0 = layer_a0(y.P, y.S);
-    if (kStore) {
-      // the second value (cos) exists only for an oscillatory term; the adjoint sweep loads it on the same rule
-      const typename Store::Slot q = est.slot(m);
-      Store::st(q, 5, y.P.c0);
-      if (kFl >= 0 ? (kFl & F_LTP) != 0 : y.P.lt) Store::st(q, 6, y.P.c1);
-      Store::st(q, 7, y.S.c0);
-      if (kFl >= 0 ? (kFl & F_LTS) != 0 : y.S.lt) Store::st(q, 8, y.S.c1);
-    }
-    row_apply(e, y);
-    if (kStore && m > 0) {  // E_m multiplies CA_{m-1}: stored right after it is formed, a whole layer before
-      const typename Store::Slot q = est.slot(m - 1);  // its registers are overwritten (no store/overwrite hazard)
+  half_start(src.par, L, z, nullptr, e);
+  for (int m = L - 2; m >= 0; --m) {
+    const typename Store::Slot q = est.slot(m);
+    if (kStore) {  // E_{m+1} multiplies CA_m
 #pragma unroll
       for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
     }
-  };
-  if (kStore && L >= 2) {
-    const typename Store::Slot q = est.slot(L - 2);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) Store::st(q, i, e[i]);
+    Layer y;
+    src.prep(y, m, z);
+    forward_layer<-1, kStore, Store>(y, e, z.omega, q);
   }
-  int m = L - 2;
-  if (Source::kUniformFlags && src.small_phases(z)) {
-    int fl = m >= 0 ? src.flags(m) : -2;
-    if (m >= 0) ph = src.phases(m);
-    auto run = [&](auto tag) {
-      constexpr int kFl = decltype(tag)::value;
-      do {
-        const int mp = m > 0 ? m - 1 : 0;
-        const int fln = m > 0 ? src.flags(mp) : -2;
-        const Dbl2 phn = src.phases(mp);
-        step(m, tag);
-        --m;
-        fl = fln;
-        ph = phn;
-      } while (kFl >= 0 && fl == kFl);
-    };
-    while (m >= 0) {
-      if (fl == kEO) run(std::integral_constant<int, kEO>{});
-      else if (fl == kEE) run(std::integral_constant<int, kEE>{});
-      else if (fl == kOO) run(std::integral_constant<int, kOO>{});
-      else if (fl == kOE) run(std::integral_constant<int, kOE>{});
-      else run(std::integral_constant<int, -1>{});
-    }
-  } else {
-    for (; m >= 0; --m) {
-      ph = src.phases(m);
-      step(m, std::integral_constant<int, -1>{});
-    }
+  return e[0];
+}
+
+// Dense kernels (warp-uniform regime flags from the shared table): consecutive layers in the same regime run in a
+// straight-line loop of their own — no selects, the P and S polynomial chains (each a ~16-deep dependent FP64
+// sequence, 8 cycles per link) interleaved by the scheduler.  The table entries and the store slots are walked
+// with running pointers; the next layer's flags and phase pair (which heads the layer's longest dependent chain:
+// phase -> exp / sincos -> ...) are read one layer ahead, so the branch that closes a run never waits for shared
+// memory; a sentinel entry ends the sweep.
+template <bool kStore, int kN, typename Store>
+ADSURF_HD double forward_sweep(const TableSource<kN>& src, const Sample& z, const Store& est) {
+  const int L = src.L;
+  double e[5];
+  half_start(src.par, L, z, src.half_k(), e);
+  const double* __restrict__ q = src.tab + (L - 2) * kN;  // layer L-2 (the leading sentinel when there is no layer)
+  typename Store::Slot sq = est.slot(L - 2);
+  int fl = TableSource<kN>::flags(q);
+  Dbl2 ph = ld2(q + T_PDA);
+  if (kStore && !(fl & F_END)) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) Store::st(sq, i, e[i]);
+  }
+  const bool small = src.small_phases(z);
+  auto run = [&](auto tag) {
+    constexpr int kFl = decltype(tag)::value;
+    do {
+      const int fln = TableSource<kN>::flags(q - kN);
+      const Dbl2 phn = ld2(q - kN + T_PDA);
+      Layer y;
+      layer_from_entry<kN>(y, q, kFl < 0 ? src.record(q) : src.par, z.omega, ph);
+      forward_layer<kFl, kStore, Store>(y, e, z.omega, sq);
+      q -= kN;
+      sq = Store::step(sq, -1);
+      if (kStore && !(fln & F_END)) {  // E_m multiplies CA_{m-1}: stored right after it is formed, a whole layer
+#pragma unroll                          // before its registers are overwritten (no store/overwrite hazard)
+        for (int i = 0; i < 5; ++i) Store::st(sq, i, e[i]);
+      }
+      fl = fln;
+      ph = phn;
+    } while (kFl >= 0 && fl == kFl);
+  };
+  while (!(fl & F_END)) {
+    if (!small) run(std::integral_constant<int, -1>{});
+    else if (fl == kEO) run(std::integral_constant<int, kEO>{});
+    else if (fl == kEE) run(std::integral_constant<int, kEE>{});
+    else if (fl == kOO) run(std::integral_constant<int, kOO>{});
+    else if (fl == kOE) run(std::integral_constant<int, kOE>{});
+    else run(std::integral_constant<int, -1>{});
   }
   return e[0];
 }
@@ -868,109 +888,161 @@ ADSURF_HD double sample_forward_store(const Source& src, const Sample& z, const 
   return forward_sweep<true>(src, z, est);
 }
 
+// half-space end of the adjoint sweep: dDelta/dE_hs = D^-1 s~_{L-1}, in the reference's variables; returns
+// omega * dDelta/dk and the gradients of the half-space "layer" L-1
+ADSURF_HD double adjoint_half_space(const double* __restrict__ par, int L, const Sample& z, const double* hk,
+                                    const double (&s)[5], LayerGrad& g) {
+  double e[5];
+  Half h;
+  load_half(h, par, L, z, hk);
+  half_space(h, z.k, z.k2, e);
+  const double su[5] = {s[0], s[1] * z.iw, s[2], s[3] * z.iw, s[4] * z.iw2};
+  const HalfGrad hg = half_adjoint(h, e, su, z.k, z.k2);
+  const double* __restrict__ prh = par + (L - 1) * kNumPar;
+  const double w2 = z.omega * z.omega;
+  // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2:
+  //   d/dalpha = omega^2/alpha^3 hp,  d/dbeta = omega^2/beta^3 hs + 4 beta/omega^2 dDelta/dgammk
+  g.d = 0.0;
+  g.a = (w2 * prh[P_IA3]) * hg.hp;
+  g.b = (w2 * prh[P_IB3]) * hg.hs + (prh[P_CB] * z.iw2) * hg.gammk;
+  g.rho = hg.rho;
+  return z.omega * hg.k;  // k = omega * (k/omega)
+}
+
 // Top-down adjoint sweep.  s_0 = seed * e_0; for every layer m (and finally the half-space, m = L-1)
 // hands (m, dDelta/dd_m, /dalpha_m, /dbeta_m, /drho_m) * seed to `sink`.  det is the forward sweep's result.
-// Returns seed * dDelta/d(k/omega) (pointwise sources; 0 otherwise).
+// Returns seed * dDelta/d(k/omega).  Pointwise sources: generic layer body (regimes differ between lanes).
 // Software pipeline over the stored values: each group of registers is re-loaded for layer m+1 right
 // after its last use in layer m — the transcendental results once eig_finish has consumed them, the row
-// vector E once layer_adjoint is done — so the L2 latency of the slab hides behind the rest of the layer
+// vector E once layer_adjoint is done — so the latency of the slab hides behind the rest of the layer
 // without a second register buffer.
-template <typename Source, typename Store, typename Sink>
-ADSURF_HD double sample_adjoint(const Source& src, const Sample& z, double seed, double det, const Store& est,
+template <typename Store, typename Sink>
+ADSURF_HD double sample_adjoint(const DirectSource& src, const Sample& z, double seed, double det, const Store& est,
                                 Sink& sink) {
-  const double* __restrict__ par = src.par;
   const int L = src.L;
   double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
   double tq = seed * det;  // T_0
   double gic = 0.0;
-  // The stored values of layer m+1 are fetched while layer m is being worked on (the slab lives in L2: a few
-  // hundred cycles away) — the transcendental results as soon as eig_finish has consumed layer m's, the row
-  // vector once the contractions are under way.
-  struct Buf {
-    double e[5], cv[4];
-  };
-  Buf A{};
-  auto fetch_c = [&](Buf& b, int m, int flm) {  // flm: regime flags of layer m (-1: unknown, read everything)
-    const typename Store::Slot q = est.slot(m);
-    b.cv[0] = Store::ld(q, 5);
-    if (flm & F_LTP) b.cv[1] = Store::ld(q, 6);
-    b.cv[2] = Store::ld(q, 7);
-    if (flm & F_LTS) b.cv[3] = Store::ld(q, 8);
-  };
-  auto fetch_e = [&](Buf& b, int m) {
+  double e[5], cv[4];
+  auto fetch_c = [&](int m) {
     const typename Store::Slot q = est.slot(m);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) b.e[i] = Store::ld(q, i);
+    for (int i = 0; i < 4; ++i) cv[i] = Store::ld(q, 5 + i);
   };
-  // One layer; kFl >= 0 states the regime flags as a compile-time constant, which folds every "lt ? a : b" /
-  // "pos ? a : b" select of eig_finish / eig_adjoint away.
-  // The gradient of layer m goes to the sink while layer m+1 is being worked on: the sink's exchange and
-  // shared-memory round trips (short-scoreboard latencies in a dependent chain) then overlap FP64 work instead
-  // of stalling the warp at the end of every layer.
+  auto fetch_e = [&](int m) {
+    const typename Store::Slot q = est.slot(m);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) e[i] = Store::ld(q, i);
+  };
+  // the gradient of layer m goes to the sink while layer m+1 is being worked on (see the dense sweep)
   LayerGrad pend;
   pend.d = pend.a = pend.b = pend.rho = 0.0;
-  int fl = -1;  // flags of layer m (read one layer ahead; -1: pointwise sources, generic path)
-  auto layer = [&](int m, auto tag) {
-    constexpr int kFl = decltype(tag)::value;
-    const int fln = Source::kUniformFlags ? (m < L - 2 ? src.flags(m + 1) : 0) : -1;  // 0: no layer
+  const int last = L - 2;
+  if (L > 1) {
+    fetch_c(0);
+    fetch_e(0);
+  }
+  for (int m = 0; m <= last; ++m) {
     Layer y;
-    y.P.c0 = A.cv[0]; y.P.c1 = A.cv[1]; y.S.c0 = A.cv[2]; y.S.c1 = A.cv[3];
+    y.P.c0 = cv[0]; y.P.c1 = cv[1]; y.S.c0 = cv[2]; y.S.c1 = cv[3];
     src.prep(y, m, z);
-    layer_set_flags(y, kFl >= 0 ? kFl : y.fl);
+    layer_set_flags(y, y.fl);
     layer_eig_restore(y, z.omega);
     sink(m > 0 ? m - 1 : 0, pend.d, pend.a, pend.b, pend.rho);  // layer m-1 (zeros before layer 0)
-    const int mn = m + 1 <= L - 2 ? m + 1 : m;  // the last layer re-reads its own slot: no predicated loads
-    fetch_c(A, mn, fln);
-    const LayerGrad g = layer_adjoint<Source::kWantIc>(y, A.e, s, tq, z.omega, z.ic, z.ic2, z.t2);
-    fetch_e(A, mn);
+    const int mn = m + 1 <= last ? m + 1 : m;  // the last layer re-reads its own slot: no predicated loads
+    fetch_c(mn);
+    const LayerGrad g = layer_adjoint<true>(y, e, s, tq, z.omega, z.ic, z.ic2, z.t2);
+    fetch_e(mn);
     gic += g.ic;
     pend = g;
+  }
+  if (L > 1) sink(last, pend.d, pend.a, pend.b, pend.rho);
+  LayerGrad gh;
+  gic += adjoint_half_space(src.par, L, z, nullptr, s, gh);
+  sink(L - 1, gh.d, gh.a, gh.b, gh.rho);
+  return gic;
+}
+
+// Dense kernels.  The sink is a WALKING sink: put() deposits one layer's four gradients and moves on to the next
+// layer's accumulators; the sweep calls it L + 1 times — first with zeros (the gradient of layer m goes to the
+// sink while layer m+1 is being worked on: the sink's exchange and shared-memory round trips, short-scoreboard
+// latencies in a dependent chain, then overlap FP64 work instead of stalling the warp at the end of every
+// layer), then layers 0 .. L-2, then the half-space L-1.  Table entries, store slots and accumulators are walked
+// with running pointers; the store has one slot more than layers, so the read-ahead of the last layer needs no
+// bounds test; kFl >= 0 states the regime flags as a compile-time constant, which folds every "lt ? a : b" /
+// "pos ? a : b" select of eig_finish / eig_adjoint away; consecutive layers in the same regime (the usual case:
+// oscillatory S near the surface, evanescent below) run in a loop of their own.
+template <int kN, typename Store, typename Sink>
+ADSURF_HD void sample_adjoint(const TableSource<kN>& src, const Sample& z, double seed, double det, const Store& est,
+                              Sink& sink) {
+  const int L = src.L;
+  double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
+  double tq = seed * det;  // T_0
+  double e[5], cv[4] = {0.0, 0.0, 0.0, 0.0};
+  auto fetch_c = [&](typename Store::Slot q, int flm) {  // flm: regime flags of the layer in slot q
+    cv[0] = Store::ld(q, 5);
+    if (flm & F_LTP) cv[1] = Store::ld(q, 6);
+    cv[2] = Store::ld(q, 7);
+    if (flm & F_LTS) cv[3] = Store::ld(q, 8);
+  };
+  auto fetch_e = [&](typename Store::Slot q) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) e[i] = Store::ld(q, i);
+  };
+  LayerGrad pend;
+  pend.d = pend.a = pend.b = pend.rho = 0.0;
+  const double* __restrict__ q = src.tab;  // layer 0 (a sentinel when there is no layer)
+  typename Store::Slot sq = est.slot(0);
+  int fl = TableSource<kN>::flags(q);
+  if (!(fl & F_END)) {
+    fetch_c(sq, fl);
+    fetch_e(sq);
+  }
+  auto layer = [&](auto tag) {
+    constexpr int kFl = decltype(tag)::value;
+    const int fln = TableSource<kN>::flags(q + kN);
+    Layer y;
+    y.P.c0 = cv[0]; y.P.c1 = cv[1]; y.S.c0 = cv[2]; y.S.c1 = cv[3];
+    layer_from_entry<kN>(y, q, kFl < 0 ? src.record(q) : src.par, z.omega, ld2(q + T_PDA));
+    layer_set_flags(y, kFl >= 0 ? kFl : y.fl);
+    layer_eig_restore(y, z.omega);
+    sink.put(pend.d, pend.a, pend.b, pend.rho);
+    sq = Store::step(sq, 1);
+    fetch_c(sq, fln);  // after the last layer: the spare slot (values unused)
+    const LayerGrad g = layer_adjoint<false>(y, e, s, tq, z.omega, z.ic, z.ic2, z.t2);
+    fetch_e(sq);
+    pend = g;
+    q += kN;
     fl = fln;
   };
-  if (L > 1) {
-    if (Source::kUniformFlags) fl = src.flags(0);
-    fetch_c(A, 0, fl);
-    fetch_e(A, 0);
-  }
-  // Regime specialisation (dense kernels: the flags are warp-uniform table entries).  Consecutive layers in the
-  // same regime (the usual case: oscillatory S near the surface, evanescent below) run in a loop of their own.
-  const int last = L - 2;
-  int m = 0;
   auto run = [&](auto tag) {
     constexpr int kFl = decltype(tag)::value;
     do {
-      layer(m, tag);
-      ++m;
+      layer(tag);
     } while (fl == kFl);
   };
-  while (m <= last) {
-    if (fl == kEO) {
-      run(std::integral_constant<int, kEO>{});
-    } else if (fl == kEE) {
-      run(std::integral_constant<int, kEE>{});
-    } else {
-      layer(m, std::integral_constant<int, -1>{});
-      ++m;
-    }
+  while (!(fl & F_END)) {
+    if (fl == kEO) run(std::integral_constant<int, kEO>{});
+    else if (fl == kEE) run(std::integral_constant<int, kEE>{});
+    else layer(std::integral_constant<int, -1>{});
   }
-  if (L > 1) sink(last, pend.d, pend.a, pend.b, pend.rho);
-  double e[5];
-  // half-space: dDelta/dE_hs = D^-1 s~_{L-1}, in the reference's variables
-  const Sample& zh = z;
-  Half h;
-  load_half(h, par, L, zh, src.half_k());
-  half_space(h, zh.k, zh.k2, e);
-  const double su[5] = {s[0], s[1] * zh.iw, s[2], s[3] * zh.iw, s[4] * zh.iw2};
-  const HalfGrad g = half_adjoint(h, e, su, zh.k, zh.k2);
-  gic += zh.omega * g.k;  // k = omega * (k/omega)
-  const int mh = L - 1;
-  const double* __restrict__ prh = par + mh * kNumPar;
-  const double w2 = zh.omega * zh.omega;
-  // k_alpha = omega/alpha, k_beta = omega/beta, gammk = 2 beta^2 / omega^2:
-  //   d/dalpha = omega^2/alpha^3 hp,  d/dbeta = omega^2/beta^3 hs + 4 beta/omega^2 dDelta/dgammk
-  sink(mh, 0.0, (w2 * prh[P_IA3]) * g.hp, (w2 * prh[P_IB3]) * g.hs + (prh[P_CB] * zh.iw2) * g.gammk, g.rho);
-  return gic;
+  sink.put(pend.d, pend.a, pend.b, pend.rho);
+  LayerGrad gh;
+  adjoint_half_space(src.par, L, z, src.half_k(), s, gh);
+  sink.put(gh.d, gh.a, gh.b, gh.rho);
 }
+
+// adapter: a sink indexed by the layer number as a walking sink (host check, shared-memory reduce sink)
+template <typename Sink>
+struct WalkingSink {
+  Sink& sink;
+  int m;
+  ADSURF_HD explicit WalkingSink(Sink& s) : sink(s), m(-1) {}
+  ADSURF_HD void put(double gd, double ga, double gb, double gr) {
+    if (m >= 0) sink(m, gd, ga, gb, gr);
+    ++m;
+  }
+};
 
 // per-model layer constants staged for the kernels: par[L][kNumPar] (one 80-byte record per layer),
 // then the raw half-space velocities

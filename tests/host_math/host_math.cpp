@@ -79,27 +79,33 @@ int host_grid(const double* d, const double* alpha, const double* beta, const do
       stage_one(par.data(), L, m, d[s * L + m], alpha[s * L + m], beta[s * L + m], rho[s * L + m]);
     stage_bounds(par.data(), L, d + s * L, beta + s * L);
     for (int m = 0; m < L; ++m) gd[s * L + m] = ga[s * L + m] = gb[s * L + m] = grho[s * L + m] = 0.0;
-    // dense path: per-(velocity, layer) table + per-period lanes, as the dense kernels do
-    std::vector<double> tab((size_t)kTabAdj * (L > 1 ? L - 1 : 1) + 2);
+    // dense path: per-(velocity, layer) table (sentinel, layers, sentinel) + per-period lanes, as the dense kernels do
+    std::vector<double> tab((size_t)table_doubles(L, 1, kTabAdj) + 2), tabf((size_t)table_doubles(L, 1, kTabFwd) + 2);
     double* tb = tab.data() + (((size_t)tab.data() & 15) ? 1 : 0);  // 16-byte aligned like the shared table
+    double* tf = tabf.data() + (((size_t)tabf.data() & 15) ? 1 : 0);
+    std::vector<double> estd(kSlot * (size_t)L);  // one spare slot: the dense read-ahead touches it
     for (int k = 0; k < K; ++k) {
       const double ic = 1.0 / c[s * K + k];
-      for (int m = 0; m < L - 1; ++m) table_entry<kTabAdj>(tb + (size_t)m * kTabAdj, par.data(), m, ic);
-      const TableSource<kTabAdj> src{par.data(), L, tb};
-      // the forward-only kernel reads 16-double entries
-      std::vector<double> tabf((size_t)kTabFwd * (L > 1 ? L - 1 : 1) + 2);
-      double* tf = tabf.data() + (((size_t)tabf.data() & 15) ? 1 : 0);
-      for (int m = 0; m < L - 1; ++m) table_entry<kTabFwd>(tf + (size_t)m * kTabFwd, par.data(), m, ic);
-      const TableSource<kTabFwd> srcf{par.data(), L, tf};
+      table_sentinel(tb, kTabAdj);
+      table_sentinel(tf, kTabFwd);  // the forward-only kernel reads 16-double entries
+      for (int m = 0; m < L - 1; ++m) {
+        table_entry<kTabAdj>(tb + (size_t)(m + 1) * kTabAdj, par.data(), m, ic);
+        table_entry<kTabFwd>(tf + (size_t)(m + 1) * kTabFwd, par.data(), m, ic);
+      }
+      table_sentinel(tb + (size_t)L * kTabAdj, kTabAdj);
+      table_sentinel(tf + (size_t)L * kTabFwd, kTabFwd);
+      const TableSource<kTabAdj> src{par.data(), L, tb + kTabAdj, nullptr};
+      const TableSource<kTabFwd> srcf{par.data(), L, tf + kTabFwd, nullptr};
       for (int f = 0; f < NF; ++f) {
         const size_t idx = ((size_t)s * K + k) * NF + f;
         const double om0 = omega_of_period(t[s * NF + f]);
         const Sample z = make_sample_dense(om0, ic, 1.0 / fmax(om0, 1.0e-4));
-        det[idx] = sample_forward_store(src, z, PlainStore<1>{est.data()});
+        det[idx] = sample_forward_store(src, z, PlainStore<1>{estd.data()});
         const double v2 = sample_forward(srcf, z);
         if (det[idx] != v2 && !(det[idx] != det[idx] && v2 != v2)) return -1;
         HostSink sink{gd + s * L, ga + s * L, gb + s * L, grho + s * L, nullptr, nullptr, nullptr, nullptr};
-        sample_adjoint(src, z, gdet ? gdet[idx] : 1.0, det[idx], PlainStore<1>{est.data()}, sink);
+        WalkingSink<HostSink> walk(sink);
+        sample_adjoint(src, z, gdet ? gdet[idx] : 1.0, det[idx], PlainStore<1>{estd.data()}, walk);
       }
     }
   }
