@@ -961,8 +961,8 @@ inline GridPlan plan_grid_search(int S, int L, int NF, int K, bool adjoint, int 
   const int nft = best.nft;
   const int wmax = adjoint ? kBwdWarps : 8;
   const int per = L > 1 ? L - 1 : 1;
-  int tcmax = 8;  // table fills of up to 8 velocities, fewer for very deep models (keeps the table under ~24 KB)
-  while (tcmax > 1 && table_bytes(L, tcmax, adjoint) > 24 * 1024) tcmax >>= 1;
+  int tcmax = 8;  // table fills of up to 8 velocities, fewer for very deep models (keeps the table under 26 KB)
+  while (tcmax > 1 && table_bytes(L, tcmax, adjoint) > 26 * 1024) tcmax >>= 1;
   for (int w = wmax < nft ? wmax : nft; w >= 1; w = (w > 4 ? 4 : w - 1)) {
     if (adjoint && w != (wmax < nft ? wmax : nft)) break;  // the adjoint kernel is compiled for 4-warp blocks
     const int nfg = (nft + w - 1) / w;
