@@ -134,7 +134,7 @@ def test_config2_trajectory_head(ab):
 def test_gpu_dispersion_extraction_logic(ab):
     """dense-grid bracketing + batched regula falsi (adsurf_b200.dispersion) against the reference solver's
     roots; kernels served by the oracle here, the real kernels in tests/test_gpu_api.py."""
-    from adsurf_b200.dispersion import dispersion_curves
+    from adsurf_b200.dispersion import dispersion_curves_dense as dispersion_curves
     g = load("surf96_roots")
     t, d, a, b, rho = (g[f"m3_{k}"] for k in ("t", "d", "a", "b", "rho"))
     sel = slice(0, 60, 4)
