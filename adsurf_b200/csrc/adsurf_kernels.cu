@@ -43,6 +43,10 @@
 
 #include <type_traits>
 
+#ifndef ADSURF_BWD_REGS
+#define ADSURF_BWD_REGS 168
+#endif
+
 #include "adsurf_b200.h"
 #include "adsurf_math.cuh"
 #include "adsurf_dispersion.cuh"
@@ -288,6 +292,15 @@ struct GlobalStore {
   unsigned long long pol;
   __device__ __forceinline__ Slot slot(int m) const { return Slot{p + (ptrdiff_t)m * (kSlot * kWarp), pol}; }
   __device__ __forceinline__ static Slot step(Slot s, int n) { return Slot{s.q + n * (kSlot * kWarp), s.pol}; }
+  // pull the rows of a slot the adjoint sweep will load (flm: regime flags of that layer) towards L1
+  __device__ __forceinline__ static void prefetch(Slot s, int flm) {
+#pragma unroll
+    for (int j = 0; j < kSlot; ++j) {
+      if (j == 6 && !(flm & F_LTP)) continue;
+      if (j == 8 && !(flm & F_LTS)) continue;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(s.q + j * kWarp));
+    }
+  }
   __device__ __forceinline__ static double ld(Slot s, int j) {
     double v;
     asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(s.q + j * kWarp), "l"(s.pol));
@@ -317,7 +330,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
   double* ics = tab + table_doubles(L, gp.tc, kTab);    // [tc]
   double* hks = ics + ((gp.tc + 1) & ~1);               // [wpb*32][2]: omega/alpha_hs, omega/beta_hs per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t slab = (size_t)L * kSlot * kWarp;        // L-1 layers + the spare slot the read-ahead touches
+  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;  // (the read-ahead of the last layer touches the next slab)
   const GlobalStore st{estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + lane, l2_evict_last_policy()};
   double* acc = accs + (size_t)warp * kAccRow * (L + 1);
   for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
@@ -396,10 +409,12 @@ __global__ void __launch_bounds__(128) k_points_fwd(const double* __restrict__ d
   stage_params(par, d, alpha, beta, rho, s, L);
   __syncthreads();
   const int i = blk * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const double omega0 = omega_of_period(t[(size_t)s * N + i]);
-  const Sample z = make_sample(omega0, 1.0 / c[(size_t)s * N + i]);
-  F[(size_t)s * N + i] = sample_forward(DirectSource{par, L}, z);
+  if (blk * blockDim.x + (threadIdx.x & ~31) >= N) return;  // whole warps only: the sweep votes across the warp
+  const size_t idx = (size_t)s * N + (i < N ? i : N - 1);   // overhang lanes replay the last pick
+  const double omega0 = omega_of_period(t[idx]);
+  const Sample z = make_sample(omega0, 1.0 / c[idx]);
+  const double v = sample_forward(DirectSource{par, L}, z);
+  if (i < N) F[idx] = v;
 }
 
 // DMF compression: returns |G| and d|G|/dF (reference _model.py:455-464)
@@ -450,7 +465,7 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
   double* lossw = accs + (size_t)pp.wpb * acc_per_warp; // [wpb]
   double* ests = lossw + pp.wpb;                        // [wpb][L-1][kSlot][32] (shared variant only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t slab = (size_t)L * kSlot * kWarp;
+  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
   double* acc = accs + (size_t)warp * acc_per_warp;
   const unsigned long long slab_policy = kGlobal ? l2_evict_last_policy() : 0ull;
   double* estp = kGlobal ? estore + ((size_t)blockIdx.x * pp.wpb + warp) * slab + lane : ests + (size_t)warp * slab + lane;
@@ -469,7 +484,7 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
       const double cc = c[idx];
       const double ic = 1.0 / cc;
       const Sample z = make_sample(omega_of_period(t[idx]), ic);
-      const DirectSource src{par, L};
+      const DirectSourceT<kKind != 2> src{par, L};  // the DMF step does not return dF/dc
       typename std::conditional<kGlobal, GlobalStore, PlainStore<kWarp>>::type store;
       store.p = estp;
       if constexpr (kGlobal) store.pol = slab_policy;
@@ -606,11 +621,9 @@ struct EnsArgs {
   double *loss_hist, *iter_b, *iter_d;  // counter form: bases of [T,S], [T,S,L]; host form: this iteration's slot
 };
 
-__global__ void k_ens_prepare(EnsArgs A) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void ens_prepare_cell(const EnsArgs& A, int s, int l) {
   const int L = A.L, S = A.S;
-  if (i >= S * L) return;
-  const int s = i / L, l = i - s * L;
+  const int i = s * L + l;
   const double x0 = A.b[i];
   double gd, ga, gb, gr;
   if (A.part) {
@@ -660,6 +673,11 @@ __global__ void k_ens_prepare(EnsArgs A) {
   A.dold[i] = A.d[i];
 }
 
+__global__ void k_ens_prepare(EnsArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < A.S * A.L) ens_prepare_cell(A, i / A.L, i % A.L);
+}
+
 __device__ __forceinline__ double adam(double p, double g, double& m, double& v, const EnsArgs& A, double lr, double bc1,
                                        double bc2s) {
   m = m + (1.0 - A.beta1) * (g - m);              // exp_avg.lerp_(grad, 1 - beta1)
@@ -668,114 +686,143 @@ __device__ __forceinline__ double adam(double p, double g, double& m, double& v,
   return p - (lr / bc1) * (m / denom);
 }
 
+// iteration index, learning rate (StepLR as torch chains it: lr <- lr * gamma every step_size steps) and Adam bias
+// corrections of step j + 1, from the device counter or the host scalars
+struct EnsStep {
+  int j;
+  double lr, bc1, bc2s;
+};
+__device__ __forceinline__ EnsStep ens_step_of(const EnsArgs& A) {
+  EnsStep t{0, A.lr, A.bc1, A.bc2s};
+  if (A.counter) {
+    t.j = A.counter[0];
+    for (int n = A.step_size > 0 ? t.j / A.step_size : 0; n > 0; --n) t.lr *= A.gamma;
+    t.bc1 = 1.0 - pow(A.beta1, (double)(t.j + 1));
+    t.bc2s = sqrt(1.0 - pow(A.beta2, (double)(t.j + 1)));
+  }
+  return t;
+}
+
+__device__ __forceinline__ void ens_adam_cell(const EnsArgs& A, const EnsStep& T, int s, int l) {
+  const int L = A.L, S = A.S, j = T.j;
+  const int i = s * L + l;
+  const size_t o = (size_t)s * L;
+  const bool rec = !A.counter || j < A.T;
+  const size_t ho = A.counter ? (size_t)j * S * L : 0;
+  // --- projection of Vs (before the optimiser step, as the reference orders it); torch.clamp keeps NaN
+  auto proj_b = [&](int ll) {
+    double x = A.bo[o + ll];
+    if (x != x && (A.proj_flags & 2)) x = A.b0[o + ll];            // NaN repair of the ensemble vs-only loop (:624-626)
+    if (x == x) x = fmin(fmax(x, A.lob[o + ll]), A.upb[o + ll]);   // clip_(min, max): max wins when min > max
+    return x;
+  };
+  double x = proj_b(l);
+  if ((A.proj_flags & 1) && l == L - 1 && L > 1) {                 // half-space >= layer above (:129/:599/:631)
+    const double prev = proj_b(L - 2);
+    if (x == x && prev == prev) x = fmax(x, prev);
+  }
+  if (A.iter_b && rec) A.iter_b[ho + i] = x;
+  // --- projection of the depths: cumulative depth clipped per layer (LR) or against the previous projected
+  // depth (LN), back to thicknesses >= min thickness (:133-147, :603-620)
+  double th = A.dold[i];
+  if (A.invert_thick) {
+    const double floor_t = A.mind[0];
+    double depth = 0.0, pdepth = 0.0, z = 0.0;
+    for (int ll = 0; ll <= l; ++ll) {
+      pdepth = z;
+      depth += A.dold[o + ll];
+      z = depth;
+      if (A.layering == 1) {
+        z = fmin(fmax(z, A.mind[o + ll]), A.maxd[o + ll]);
+      } else if (A.layering == 2) {
+        const double lo = ll == 0 ? A.mind[o + ll] : pdepth + A.mind[o + ll];
+        z = fmin(fmax(z, lo), A.maxd[o + ll]);
+      }
+    }
+    th = fmax(z - pdepth, floor_t);
+    if (A.iter_d && rec) A.iter_d[ho + i] = th;
+  }
+  // --- Tikhonov subgradients on top of the chain gradient of phase 1, Adam, next alpha / rho
+  double g = A.gt[i];
+  if (A.dv > 0.0) {
+    const double c = lap(l > 0 ? A.sv[i - 1] : 0.0, A.sv[i], l < L - 1 ? A.sv[i + 1] : 0.0, l, L);
+    g += A.dv / L * c;
+  }
+  if (A.dh > 0.0) {
+    const int r = A.row0 + s, Sa = A.S_all;
+    const double sm = s > 0 ? A.sh[i - L] : (A.halo && r > 0 ? A.shh[l] : 0.0);
+    const double sp = s < S - 1 ? A.sh[i + L] : (A.halo && r + 1 < Sa ? A.shh[L + l] : 0.0);
+    g += A.dh / L * lap(sm, A.sh[i], sp, r, Sa);
+  }
+  double m = A.mb[i], v = A.vb[i];
+  const double xn = adam(x, g, m, v, A, T.lr, T.bc1, T.bc2s);
+  A.mb[i] = m;
+  A.vb[i] = v;
+  A.b[i] = xn;
+  if (A.vp_mode == 1 || (A.vp_mode == 3 && xn <= 4.6)) {
+    // USArray (3): entries above 4.6 km/s keep their current Vp / rho, as the reference's masked in-place
+    // update leaves them (_model.py:440-446; its AK135 loop writes into temporaries)
+    const double an = brocher_vp(xn);
+    A.alpha[i] = an;
+    A.rho[i] = brocher_rho(an);
+  } else if (A.vp_mode == 2) {
+    A.alpha[i] = xn * A.ratio;
+  }
+  if (A.invert_thick) {
+    double m2 = A.md[i], v2 = A.vd[i];
+    A.d[i] = adam(th, A.gdr[i], m2, v2, A, T.lr, T.bc1, T.bc2s);
+    A.md[i] = m2;
+    A.vd[i] = v2;
+  }
+  if (l == 0) {  // total misfit of model s
+    double tot;
+    if (A.loss_part) {
+      tot = 0.0;
+      for (int k = 0; k < A.bpm; ++k) tot += A.loss_part[(size_t)s * A.bpm + k];
+      tot /= (double)A.npicks;
+    } else {
+      tot = A.loss[s];
+    }
+    double add = 0.0;
+    for (int ll = 0; ll < L; ++ll) add += A.tik[o + ll];
+    tot += add;
+    A.loss[s] = tot;
+    if (A.loss_hist && rec) A.loss_hist[(A.counter ? (size_t)j * S : 0) + s] = tot;
+  }
+}
+
+// the last block to finish advances the iteration index (every block has read it by then)
+__device__ __forceinline__ void ens_advance(const EnsArgs& A, int j) {
+  if (!A.counter) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&A.counter[1], 1) == (int)gridDim.x - 1) {
+      A.counter[1] = 0;
+      A.counter[0] = j + 1;
+    }
+  }
+}
+
 __global__ void k_ens_adam(EnsArgs A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int L = A.L, S = A.S;
-  int j = 0;
-  double lr = A.lr, bc1 = A.bc1, bc2s = A.bc2s;
-  if (A.counter) {
-    j = A.counter[0];
-    // StepLR as torch chains it (lr <- lr * gamma every step_size steps); Adam bias corrections of step j + 1
-    for (int n = A.step_size > 0 ? j / A.step_size : 0; n > 0; --n) lr *= A.gamma;
-    bc1 = 1.0 - pow(A.beta1, (double)(j + 1));
-    bc2s = sqrt(1.0 - pow(A.beta2, (double)(j + 1)));
-  }
-  if (i < S * L) {
-    const int s = i / L, l = i - s * L;
-    const size_t o = (size_t)s * L;
-    const bool rec = !A.counter || j < A.T;
-    const size_t ho = A.counter ? (size_t)j * S * L : 0;
-    // --- projection of Vs (before the optimiser step, as the reference orders it); torch.clamp keeps NaN
-    auto proj_b = [&](int ll) {
-      double x = A.bo[o + ll];
-      if (x != x && (A.proj_flags & 2)) x = A.b0[o + ll];            // NaN repair of the ensemble vs-only loop (:624-626)
-      if (x == x) x = fmin(fmax(x, A.lob[o + ll]), A.upb[o + ll]);   // clip_(min, max): max wins when min > max
-      return x;
-    };
-    double x = proj_b(l);
-    if ((A.proj_flags & 1) && l == L - 1 && L > 1) {                 // half-space >= layer above (:129/:599/:631)
-      const double prev = proj_b(L - 2);
-      if (x == x && prev == prev) x = fmax(x, prev);
-    }
-    if (A.iter_b && rec) A.iter_b[ho + i] = x;
-    // --- projection of the depths: cumulative depth clipped per layer (LR) or against the previous projected
-    // depth (LN), back to thicknesses >= min thickness (:133-147, :603-620)
-    double th = A.dold[i];
-    if (A.invert_thick) {
-      const double floor_t = A.mind[0];
-      double depth = 0.0, pdepth = 0.0, z = 0.0;
-      for (int ll = 0; ll <= l; ++ll) {
-        pdepth = z;
-        depth += A.dold[o + ll];
-        z = depth;
-        if (A.layering == 1) {
-          z = fmin(fmax(z, A.mind[o + ll]), A.maxd[o + ll]);
-        } else if (A.layering == 2) {
-          const double lo = ll == 0 ? A.mind[o + ll] : pdepth + A.mind[o + ll];
-          z = fmin(fmax(z, lo), A.maxd[o + ll]);
-        }
-      }
-      th = fmax(z - pdepth, floor_t);
-      if (A.iter_d && rec) A.iter_d[ho + i] = th;
-    }
-    // --- Tikhonov subgradients on top of the chain gradient of phase 1, Adam, next alpha / rho
-    double g = A.gt[i];
-    if (A.dv > 0.0) {
-      const double c = lap(l > 0 ? A.sv[i - 1] : 0.0, A.sv[i], l < L - 1 ? A.sv[i + 1] : 0.0, l, L);
-      g += A.dv / L * c;
-    }
-    if (A.dh > 0.0) {
-      const int r = A.row0 + s, Sa = A.S_all;
-      const double sm = s > 0 ? A.sh[i - L] : (A.halo && r > 0 ? A.shh[l] : 0.0);
-      const double sp = s < S - 1 ? A.sh[i + L] : (A.halo && r + 1 < Sa ? A.shh[L + l] : 0.0);
-      g += A.dh / L * lap(sm, A.sh[i], sp, r, Sa);
-    }
-    double m = A.mb[i], v = A.vb[i];
-    const double xn = adam(x, g, m, v, A, lr, bc1, bc2s);
-    A.mb[i] = m;
-    A.vb[i] = v;
-    A.b[i] = xn;
-    if (A.vp_mode == 1 || (A.vp_mode == 3 && xn <= 4.6)) {
-      // USArray (3): entries above 4.6 km/s keep their current Vp / rho, as the reference's masked in-place
-      // update leaves them (_model.py:440-446; its AK135 loop writes into temporaries)
-      const double an = brocher_vp(xn);
-      A.alpha[i] = an;
-      A.rho[i] = brocher_rho(an);
-    } else if (A.vp_mode == 2) {
-      A.alpha[i] = xn * A.ratio;
-    }
-    if (A.invert_thick) {
-      double m2 = A.md[i], v2 = A.vd[i];
-      A.d[i] = adam(th, A.gdr[i], m2, v2, A, lr, bc1, bc2s);
-      A.md[i] = m2;
-      A.vd[i] = v2;
-    }
-    if (l == 0) {  // total misfit of model s
-      double tot;
-      if (A.loss_part) {
-        tot = 0.0;
-        for (int k = 0; k < A.bpm; ++k) tot += A.loss_part[(size_t)s * A.bpm + k];
-        tot /= (double)A.npicks;
-      } else {
-        tot = A.loss[s];
-      }
-      double add = 0.0;
-      for (int ll = 0; ll < L; ++ll) add += A.tik[o + ll];
-      tot += add;
-      A.loss[s] = tot;
-      if (A.loss_hist && rec) A.loss_hist[(A.counter ? (size_t)j * S : 0) + s] = tot;
-    }
-  }
-  if (A.counter) {  // the last block to finish advances the iteration index (every block has read it by then)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(&A.counter[1], 1) == (int)gridDim.x - 1) {
-        A.counter[1] = 0;
-        A.counter[0] = j + 1;
-      }
-    }
-  }
+  const EnsStep T = ens_step_of(A);
+  if (i < A.S * A.L) ens_adam_cell(A, T, i / A.L, i % A.L);
+  ens_advance(A, T.j);
+}
+
+// both phases in one launch when no model needs another block's data (damp_horizontal == 0): a block owns
+// blockDim / L whole models, a barrier separates the phases
+__global__ void k_ens_fused(EnsArgs A) {
+  const int L = A.L, mpb = blockDim.x / L;
+  const int local = threadIdx.x / L, l = threadIdx.x - local * L;
+  const int s = blockIdx.x * mpb + local;
+  const bool mine = local < mpb && s < A.S;
+  const EnsStep T = ens_step_of(A);
+  if (mine) ens_prepare_cell(A, s, l);
+  __syncthreads();
+  if (mine) ens_adam_cell(A, T, s, l);
+  ens_advance(A, T.j);
 }
 
 // modal dispersion curves (N1): the reference's sequential root search, one thread per model (adsurf_dispersion.cuh)
@@ -908,8 +955,11 @@ inline int sm_count() {
 
 inline size_t par_bytes(int L) { return (size_t)(kSmemHead + par_doubles(L)) * sizeof(double); }
 
-// store slab of one warp: a slot per layer above the half-space plus the spare slot the dense read-ahead touches
-inline size_t est_bytes_per_warp(int L) { return (size_t)L * kSlot * kWarp * sizeof(double); }
+// store slab of one warp: a slot per layer above the half-space.  The dense sweep's read-ahead of the last layer
+// touches the slot after it — the next warp's first slot (values unused) — so the whole store ends with one spare
+// slot (slab_bytes); a spare slot per warp would push the live slabs past the persisting-L2 capacity.
+inline size_t slot_bytes() { return (size_t)kSlot * kWarp * sizeof(double); }
+inline size_t est_bytes_per_warp(int L) { return (size_t)(L > 1 ? L - 1 : 0) * slot_bytes(); }
 
 // warps per block for the pointwise adjoint with the slabs in shared memory; 0 if even one warp does not fit
 inline int adj_wpb(int L) {
@@ -932,7 +982,9 @@ inline size_t adj_smem(int L, int wpb) {
 // scheduler — 3 warps up to 170 registers per thread, 4 only at <= 128.
 constexpr int kBwdWarps = 4, kBwdBlocksPerSM = 3, kFwdWarpsPerSM = 16;
 inline int max_resident_adj_warps(int nsm) { return nsm * kBwdBlocksPerSM * kBwdWarps; }
-inline size_t slab_bytes(int L, int nsm) { return (size_t)max_resident_adj_warps(nsm) * est_bytes_per_warp(L); }
+inline size_t slab_bytes(int L, int nsm) {
+  return (size_t)max_resident_adj_warps(nsm) * est_bytes_per_warp(L) + slot_bytes();
+}
 
 inline size_t table_bytes(int L, int tc, bool adjoint) {
   return (size_t)table_doubles(L, tc, adjoint ? kTabAdj : kTabFwd) * sizeof(double) +
@@ -1030,6 +1082,18 @@ inline PointsPlan plan_points(int S, int L, int N, bool allow_global, int nsm) {
   // large ensembles: 12 resident warps per SM with the slabs in L2; small problems: slabs in shared memory
   pp.global = allow_global && (long long)S * pp.units >= (long long)nsm * 8;
   pp.wpb = pp.global ? kBwdWarps : adj_wpb(L);
+  if (pp.global) {
+    // a block owns one model: pick the warps per block (4, 3 or 2; always 12 resident warps per SM) that leaves the
+    // fewest idle warps in a model's last block (300 picks = 10 warp units: 2 warps per block, not 4 + 4 + 2)
+    int best_pad = 1 << 30;
+    for (int w = kBwdWarps; w >= 2; --w) {
+      const int pad = (pp.units + w - 1) / w * w - pp.units;
+      if (pad < best_pad) {
+        best_pad = pad;
+        pp.wpb = w;
+      }
+    }
+  }
   if (pp.wpb > pp.units) {
     int w = 1;
     while (w < pp.units) w <<= 1;
@@ -1082,7 +1146,8 @@ inline int launch_points_bwd(const PointsPlan& pp, int S, int L, int N, const do
       cudaGetLastError();
       return ADSURF_E_CUDA;
     }
-    if (occ > kBwdBlocksPerSM) occ = kBwdBlocksPerSM;  // the slab is sized for 3 x 4 warps per SM
+    const int cap = kBwdBlocksPerSM * kBwdWarps / pp.wpb;  // the slab is sized for 12 warps per SM
+    if (occ > cap) occ = cap;
     long long grid = (long long)occ * nsm;
     if (grid > total_vb) grid = total_vb;
     kern<<<(unsigned)grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F, gc, part,
@@ -1317,7 +1382,7 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   const long long total_vb = (long long)S * gp.bpm;
   if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;
   const int threads = gp.wpb * kWarp;
-  auto kern = k_grid_bwd<kBwdWarps * kWarp, 168>;  // 3 x 4 = 12 warps / SM
+  auto kern = k_grid_bwd<kBwdWarps * kWarp, ADSURF_BWD_REGS>;  // 3 x 4 = 12 warps / SM
   if (set_smem(kern, smem)) return ADSURF_E_CUDA;
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
@@ -1413,7 +1478,13 @@ static int ens_launch(EnsArgs& A, void* ws, size_t ws_bytes, cudaStream_t st) {
   A.bo = w + 5 * SL;
   A.dold = w + 6 * SL;
   A.shh = w + 7 * SL;
-  const int threads = 128, blocks = (int)((SL + threads - 1) / threads);
+  const int threads = 128;
+  if (!(A.dh > 0.0) && A.L <= threads) {
+    const int mpb = threads / A.L;
+    k_ens_fused<<<(A.S + mpb - 1) / mpb, threads, 0, st>>>(A);
+    return check_launch();
+  }
+  const int blocks = (int)((SL + threads - 1) / threads);
   k_ens_prepare<<<blocks, threads, 0, st>>>(A);
   if (check_launch()) return ADSURF_E_CUDA;
   k_ens_adam<<<blocks, threads, 0, st>>>(A);

@@ -18,6 +18,17 @@
 #define ADSURF_HD inline
 #endif
 
+// experiment switches of the dense adjoint sweep (benchmarks/variants.sh builds them side by side)
+#ifndef ADSURF_VARIANT_PREFETCH
+#define ADSURF_VARIANT_PREFETCH 0
+#endif
+#ifndef ADSURF_VARIANT_SINK_LATE
+#define ADSURF_VARIANT_SINK_LATE 0
+#endif
+#ifndef ADSURF_VARIANT_FETCH_E_EARLY
+#define ADSURF_VARIANT_FETCH_E_EARLY 0
+#endif
+
 namespace adsurf {
 
 constexpr double kTwoPi = 6.283185307179586;  // 2.0 * np.pi
@@ -674,8 +685,9 @@ ADSURF_HD void layer_from_entry(Layer& y, const double* __restrict__ q, const do
   }
 }
 
-struct DirectSource {
-  static constexpr bool kWantIc = true;         // the pointwise kernels return dF/dc
+template <bool kIc>
+struct DirectSourceT {
+  static constexpr bool kWantIc = kIc;          // dF/dc wanted (gradient and Jacobian entries; not the DMF step)
   const double* __restrict__ par;
   int L;
   ADSURF_HD const double* half_k() const { return nullptr; }
@@ -686,6 +698,7 @@ struct DirectSource {
     y.rho = par[m * kNumPar + P_RHO];
   }
 };
+typedef DirectSourceT<true> DirectSource;
 
 // Dense kernels: the entries of one trial velocity in the block's shared table.  Layout of the table (built by
 // the kernels' fill_table): per velocity one SENTINEL entry (flags = F_END, phases 0) followed by the L-1 layer
@@ -767,6 +780,7 @@ struct PlainStore {
   typedef double* Slot;
   ADSURF_HD Slot slot(int m) const { return p + (size_t)m * (kSlot * kStride); }
   ADSURF_HD static Slot step(Slot q, int n) { return q + n * (kSlot * kStride); }  // n slots further
+  ADSURF_HD static void prefetch(Slot, int) {}
   ADSURF_HD static double ld(Slot q, int j) { return q[j * kStride]; }
   ADSURF_HD static void st(Slot q, int j, double v) { q[j * kStride] = v; }
 };
@@ -781,6 +795,21 @@ constexpr int kEO = F_REGULAR | F_LTS;          // P evanescent, S oscillatory: 
 constexpr int kEE = F_REGULAR;                  // both evanescent: c below both
 constexpr int kOO = F_REGULAR | F_LTP | F_LTS;  // both oscillatory: c above both
 constexpr int kOE = F_REGULAR | F_LTP;
+
+// Pointwise sweeps: lanes of a warp are different (period, velocity) picks, so regimes may differ between lanes —
+// but neighbouring picks mostly share them.  Returns the regime flags if every lane of the warp is in the same
+// regular regime with phases inside the inline sincos's range (then the branch-free specialised layer bodies
+// apply), else -1.  All 32 lanes must be converged here.
+ADSURF_HD int uniform_regime(const Layer& y) {
+  const bool ok = (y.fl & F_REGULAR) == F_REGULAR && (!(y.fl & F_LTP) || below1e5(fabs(y.P.p))) &&
+                  (!(y.fl & F_LTS) || below1e5(fabs(y.S.p)));
+#if defined(__CUDA_ARCH__)
+  const int fl0 = __shfl_sync(0xffffffffu, y.fl, 0);
+  return __all_sync(0xffffffffu, ok && y.fl == fl0) ? fl0 : -1;
+#else
+  return ok ? y.fl : -1;
+#endif
+}
 
 // one layer of the bottom-up sweep: eigenfunction terms of the regime kFl (>= 0: regular, |phase| < 1e5, branch-free
 // bodies; -1: huge phase, NaN, or c exactly on a layer velocity), optional store, E <- E . CA
@@ -812,8 +841,8 @@ ADSURF_HD void forward_layer(Layer& y, double (&e)[5], double omega, typename St
 // Bottom-up sweep E <- E . CA_m, m = L-2 .. 0, from the half-space vector; kStore keeps E_{m+1} and the
 // transcendental results of every layer in slot m for the adjoint sweep.  Pointwise sources (one table entry
 // computed per sample and layer, regimes differ between lanes): the generic layer body.
-template <bool kStore, typename Store>
-ADSURF_HD double forward_sweep(const DirectSource& src, const Sample& z, const Store& est) {
+template <bool kStore, bool kIc, typename Store>
+ADSURF_HD double forward_sweep(const DirectSourceT<kIc>& src, const Sample& z, const Store& est) {
   const int L = src.L;
   double e[5];
   half_start(src.par, L, z, nullptr, e);
@@ -825,7 +854,10 @@ ADSURF_HD double forward_sweep(const DirectSource& src, const Sample& z, const S
     }
     Layer y;
     src.prep(y, m, z);
-    forward_layer<-1, kStore, Store>(y, e, z.omega, q);
+    const int ur = uniform_regime(y);
+    if (ur == kEO) forward_layer<kEO, kStore, Store>(y, e, z.omega, q);
+    else if (ur == kEE) forward_layer<kEE, kStore, Store>(y, e, z.omega, q);
+    else forward_layer<-1, kStore, Store>(y, e, z.omega, q);
   }
   return e[0];
 }
@@ -916,9 +948,9 @@ ADSURF_HD double adjoint_half_space(const double* __restrict__ par, int L, const
 // after its last use in layer m — the transcendental results once eig_finish has consumed them, the row
 // vector E once layer_adjoint is done — so the latency of the slab hides behind the rest of the layer
 // without a second register buffer.
-template <typename Store, typename Sink>
-ADSURF_HD double sample_adjoint(const DirectSource& src, const Sample& z, double seed, double det, const Store& est,
-                                Sink& sink) {
+template <bool kIc, typename Store, typename Sink>
+ADSURF_HD double sample_adjoint(const DirectSourceT<kIc>& src, const Sample& z, double seed, double det,
+                                const Store& est, Sink& sink) {
   const int L = src.L;
   double s[5] = {seed, 0.0, 0.0, 0.0, 0.0};
   double tq = seed * det;  // T_0
@@ -946,15 +978,22 @@ ADSURF_HD double sample_adjoint(const DirectSource& src, const Sample& z, double
     Layer y;
     y.P.c0 = cv[0]; y.P.c1 = cv[1]; y.S.c0 = cv[2]; y.S.c1 = cv[3];
     src.prep(y, m, z);
-    layer_set_flags(y, y.fl);
-    layer_eig_restore(y, z.omega);
-    sink(m > 0 ? m - 1 : 0, pend.d, pend.a, pend.b, pend.rho);  // layer m-1 (zeros before layer 0)
     const int mn = m + 1 <= last ? m + 1 : m;  // the last layer re-reads its own slot: no predicated loads
-    fetch_c(mn);
-    const LayerGrad g = layer_adjoint<true>(y, e, s, tq, z.omega, z.ic, z.ic2, z.t2);
-    fetch_e(mn);
-    gic += g.ic;
-    pend = g;
+    auto body = [&](auto tag) {
+      constexpr int kFl = decltype(tag)::value;
+      layer_set_flags(y, kFl >= 0 ? kFl : y.fl);
+      layer_eig_restore(y, z.omega);
+      sink(m > 0 ? m - 1 : 0, pend.d, pend.a, pend.b, pend.rho);  // layer m-1 (zeros before layer 0)
+      fetch_c(mn);
+      const LayerGrad g = layer_adjoint<kIc>(y, e, s, tq, z.omega, z.ic, z.ic2, z.t2);
+      fetch_e(mn);
+      gic += g.ic;
+      pend = g;
+    };
+    const int ur = uniform_regime(y);
+    if (ur == kEO) body(std::integral_constant<int, kEO>{});
+    else if (ur == kEE) body(std::integral_constant<int, kEE>{});
+    else body(std::integral_constant<int, -1>{});
   }
   if (L > 1) sink(last, pend.d, pend.a, pend.b, pend.rho);
   LayerGrad gh;
@@ -1005,12 +1044,29 @@ ADSURF_HD void sample_adjoint(const TableSource<kN>& src, const Sample& z, doubl
     y.P.c0 = cv[0]; y.P.c1 = cv[1]; y.S.c0 = cv[2]; y.S.c1 = cv[3];
     layer_from_entry<kN>(y, q, kFl < 0 ? src.record(q) : src.par, z.omega, ld2(q + T_PDA));
     layer_set_flags(y, kFl >= 0 ? kFl : y.fl);
-    layer_eig_restore(y, z.omega);
-    sink.put(pend.d, pend.a, pend.b, pend.rho);
     sq = Store::step(sq, 1);
-    fetch_c(sq, fln);  // after the last layer: the spare slot (values unused)
+#if ADSURF_VARIANT_PREFETCH
+    Store::prefetch(sq, fln);  // pull the next layer's slot towards L1 a whole layer before it is loaded
+#endif
+    layer_eig_restore(y, z.omega);
+#if !ADSURF_VARIANT_SINK_LATE
+    sink.put(pend.d, pend.a, pend.b, pend.rho);
+#endif
+    fetch_c(sq, fln);  // after the last layer: the slot behind it (values unused)
+#if ADSURF_VARIANT_FETCH_E_EARLY
+    double en[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) en[i] = Store::ld(sq, i);
+    const LayerGrad g = layer_adjoint<false>(y, e, s, tq, z.omega, z.ic, z.ic2, z.t2);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) e[i] = en[i];
+#else
     const LayerGrad g = layer_adjoint<false>(y, e, s, tq, z.omega, z.ic, z.ic2, z.t2);
     fetch_e(sq);
+#endif
+#if ADSURF_VARIANT_SINK_LATE
+    sink.put(pend.d, pend.a, pend.b, pend.rho);
+#endif
     pend = g;
     q += kN;
     fl = fln;

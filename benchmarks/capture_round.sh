@@ -22,5 +22,22 @@ launches_bench)
   timeout 600 python bench.py --models 512 --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_512.log 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench512.csv \
       python bench.py --models 512 --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_launch_bench.log 2>&1 ;;
+quick)
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err ;;
+ncu_bwd)
+  timeout 600 python bench.py --models 512 --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_512.log 2>&1 && \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_grid_(bwd|fwd)' -s 4 -c 2 -f -o gpurun_out/prof_r2_grid \
+      python bench.py --models 512 --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_grid.log 2>&1 ;;
+ncu_points)
+  timeout 600 python benchmarks/configs_e2e.py --iters2 24 --iters3 24 --iters4 16 > gpurun_out/configs_short.log 2>&1 && \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_points_bwd|k_ens_|k_grid_fwd' -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-12} -f -o gpurun_out/prof_r2_points \
+      python benchmarks/configs_e2e.py --iters2 24 --iters3 24 --iters4 16 > gpurun_out/ncu_points.log 2>&1 ;;
+variants)
+  bash benchmarks/run_variants.sh > gpurun_out/run_variants.out 2>&1 ;;
+multi)
+  N=${NGPU:-2}
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "rc=$?" >> gpurun_out/bench_n$N.err ;;
 esac
 done
