@@ -464,7 +464,7 @@ class InversionLoop:
             nbytes = lib().adsurf_inversion_workspace_bytes(ctypes.byref(P))
         if nbytes == 0:
             raise AdsurfError("adsurf_inversion_workspace_bytes: bad problem description")
-        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)  # zero-filled once (C ABI contract)
         self.unroll = max(1, int(unroll))
         self.use_graph = bool(use_graph) and halo_fn is None and os.environ.get("ADSURF_GRAPH", "1") != "0"
         self._graphs = {}
@@ -491,7 +491,7 @@ class InversionLoop:
         Q.loss, Q.counter = scratch_loss.data_ptr(), scratch_cnt.data_ptr()
         Q.loss_hist = Q.iter_b_hist = Q.iter_d_hist = None
         Q.T = 0
-        self._step(Q, torch.empty_like(self.ws))
+        self._step(Q, torch.zeros_like(self.ws))
         torch.cuda.synchronize(self.dev)
 
     def _graph(self, n):

@@ -196,13 +196,26 @@ __device__ __forceinline__ void fill_table(double* __restrict__ tab, double* __r
   if (threadIdx.x == blockDim.x - 1) table_sentinel(tab + (size_t)n * L * kTab, kTab);
 }
 
+// Order-preserving map double -> uint64 (monotonic for non-NaN values; NaN maps to the largest key) so that a
+// maximum over blocks is one native 64-bit atomicMax per lane instead of a partials array and a reduction loop;
+// key 0 is below every value: a zeroed buffer is the identity.  The minimum travels as the maximum of -v.
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  if (v != v) return ~0ull;
+  const long long b = __double_as_longlong(v);
+  return b < 0 ? ~(unsigned long long)b : (unsigned long long)b | 0x8000000000000000ull;
+}
+__device__ __forceinline__ double order_value(unsigned long long k) {
+  if (k == ~0ull) return NAN;
+  return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
 // Dense grid, forward only: det / fused max,min over k / sign bitmap.
 template <int kMaxRegs>
 __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, const double* __restrict__ alpha,
                                                   const double* __restrict__ beta, const double* __restrict__ rho,
                                                   const double* __restrict__ t, const double* __restrict__ c, int L,
                                                   int NF, int K, GridPlan gp, double* __restrict__ det,
-                                                  double* __restrict__ pmax, double* __restrict__ pmin,
+                                                  double* __restrict__ pmax, double* __restrict__ pmin, int keyed,
                                                   uint32_t* __restrict__ signbits) {
   extern __shared__ double smem[];
   double* par = smem + kSmemHead;
@@ -252,8 +265,13 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
   if (pmax && active) {
     // torch.max/min propagate NaN; fmax/fmin do not
     if (anynan) { vmax = NAN; vmin = NAN; }
-    pmax[((size_t)s * gp.nchunk + bc.ch) * NF + f] = vmax;
-    pmin[((size_t)s * gp.nchunk + bc.ch) * NF + f] = vmin;
+    if (keyed) {  // [S,NF] ordered keys, combined across the velocity chunks with atomicMax
+      atomicMax(reinterpret_cast<unsigned long long*>(pmax) + (size_t)s * NF + f, order_key(vmax));
+      atomicMax(reinterpret_cast<unsigned long long*>(pmin) + (size_t)s * NF + f, order_key(-vmin));
+    } else {      // [S,nchunk,NF] partials for k_minmax_reduce
+      pmax[((size_t)s * gp.nchunk + bc.ch) * NF + f] = vmax;
+      pmin[((size_t)s * gp.nchunk + bc.ch) * NF + f] = vmin;
+    }
   }
 }
 
@@ -454,7 +472,7 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
              // Jacobian outputs
              double* __restrict__ Jd, double* __restrict__ Ja, double* __restrict__ Jb, double* __restrict__ Jrho,
              // DMF
-             const double* __restrict__ pmax, const double* __restrict__ pmin, int nchunk, int compress, int with_grad,
+             double* __restrict__ pmax, double* __restrict__ pmin, int nchunk, int compress, int with_grad,
              double* __restrict__ norm, double* __restrict__ loss_part) {
   // kGlobal: persistent blocks, store slabs in the L2-resident global slab, per-lane fold accumulators (large
   // ensembles); otherwise one block per (model, 32*wpb picks) with the slabs in shared memory (small problems).
@@ -485,6 +503,21 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
       const double ic = 1.0 / cc;
       const Sample z = make_sample(omega_of_period(t[idx]), ic);
       const DirectSourceT<kKind != 2> src{par, L};  // the DMF step does not return dF/dc
+      // max / min over the trial velocities from the dense pass: ordered keys [S,N], read once per pick (before the
+      // sweep: their latency hides behind it) and reset to the identity for the next evaluation
+      const bool normalised = kKind == 2 && (compress == ADSURF_COMPRESS_EXP || compress == ADSURF_COMPRESS_LOG ||
+                                             compress == ADSURF_COMPRESS_NORM);
+      unsigned long long key_max = 0ull, key_min = 0ull;
+      if (normalised) {
+        unsigned long long* kmax = reinterpret_cast<unsigned long long*>(pmax) + idx;
+        unsigned long long* kmin = reinterpret_cast<unsigned long long*>(pmin) + idx;
+        key_max = *kmax;
+        key_min = *kmin;
+        if (active) {
+          *kmax = 0ull;
+          *kmin = 0ull;
+        }
+      }
       typename std::conditional<kGlobal, GlobalStore, PlainStore<kWarp>>::type store;
       store.p = estp;
       if constexpr (kGlobal) store.pol = slab_policy;
@@ -494,17 +527,8 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
       if (kKind == 0) seed = gF[idx];
       if (kKind == 2) {
         double n = 1.0;
-        if (compress == ADSURF_COMPRESS_EXP || compress == ADSURF_COMPRESS_LOG || compress == ADSURF_COMPRESS_NORM) {
-          double vmax = -INFINITY, vmin = INFINITY;
-          bool anynan = false;
-          const int ii = active ? i : N - 1;
-          for (int ch = 0; ch < nchunk; ++ch) {
-            const double a = pmax[((size_t)s * nchunk + ch) * N + ii], b = pmin[((size_t)s * nchunk + ch) * N + ii];
-            anynan |= (a != a) | (b != b);
-            vmax = fmax(vmax, a);
-            vmin = fmin(vmin, b);
-          }
-          n = anynan ? NAN : (vmax - vmin);
+        if (normalised) {
+          n = order_value(key_max) + order_value(key_min);  // max - min (the minimum travels negated)
           if (norm && active) norm[idx] = n;
         }
         double absG;
@@ -1132,7 +1156,7 @@ template <int kKind>
 inline int launch_points_bwd(const PointsPlan& pp, int S, int L, int N, const double* d, const double* alpha,
                              const double* beta, const double* rho, const double* t, const double* c,
                              const double* gF, double* F, double* gc, double* part, double* estore, double* Jd,
-                             double* Ja, double* Jb, double* Jrho, const double* pmax, const double* pmin, int nchunk,
+                             double* Ja, double* Jb, double* Jrho, double* pmax, double* pmin, int nchunk,
                              int compress, int with_grad, double* norm, double* loss_part, int nsm, cudaStream_t st) {
   const size_t smem = points_smem(pp, L);
   const long long total_vb = (long long)S * pp.bpm;
@@ -1232,10 +1256,7 @@ size_t adsurf_workspace_bytes(int op, int S, int L, int n, int K) {
       const PointsPlan pp = plan_points(S, L, n, true, nsm);
       size_t b = align256((size_t)S * pp.bpm * 4 * L * sizeof(double)) + align256((size_t)S * pp.bpm * sizeof(double)) +
                  align256(points_estore_bytes(pp, L, nsm));
-      if (K > 0) {
-        const GridPlan gp = plan_grid(S, L, n, K, false, nsm);
-        b += 2 * align256((size_t)S * gp.nchunk * n * sizeof(double));
-      }
+      if (K > 0) b += 2 * align256((size_t)S * n * sizeof(double));  // ordered max / min keys of the dense pass
       return b;
     }
     case ADSURF_OP_ENSEMBLE_STEP:
@@ -1328,12 +1349,12 @@ int adsurf_det_points_jac(const double* d, const double* alpha, const double* be
 
 static int grid_fwd_launch(const double* d, const double* alpha, const double* beta, const double* rho,
                            const double* t, const double* c, int S, int L, int NF, int K, double* det, double* pmax,
-                           double* pmin, uint32_t* signbits, const GridPlan& gp, cudaStream_t st) {
+                           double* pmin, int keyed, uint32_t* signbits, const GridPlan& gp, cudaStream_t st) {
   const size_t smem = grid_fwd_smem(L, gp.tc, gp.wpb);
   if (smem > kSmemMax) return ADSURF_E_SHAPE;
   if (set_smem(k_grid_fwd<128>, smem)) return ADSURF_E_CUDA;
   k_grid_fwd<128><<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K,
-                                                                                 gp, det, pmax, pmin, signbits);
+                                                                                 gp, det, pmax, pmin, keyed, signbits);
   return check_launch();
 }
 
@@ -1352,7 +1373,7 @@ int adsurf_det_grid_fwd(const double* d, const double* alpha, const double* beta
     pmax = (double*)ws;
     pmin = (double*)((char*)ws + one);
   }
-  const int rc = grid_fwd_launch(d, alpha, beta, rho, t, c, S, L, NF, K, det, pmax, pmin, signbits, gp, st);
+  const int rc = grid_fwd_launch(d, alpha, beta, rho, t, c, S, L, NF, K, det, pmax, pmin, 0, signbits, gp, st);
   if (rc) return rc;
   if (pmax) {
     const size_t total = (size_t)S * NF;
@@ -1406,7 +1427,8 @@ struct DmfLaunch {
 };
 static int dmf_launch(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
                       const double* c, const double* C, int S, int L, int N, int K, int compress, int with_grad,
-                      double* F, double* norm, void* ws, size_t ws_bytes, cudaStream_t st, DmfLaunch& out) {
+                      double* F, double* norm, void* ws, size_t ws_bytes, bool zero_keys, cudaStream_t st,
+                      DmfLaunch& out) {
   if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
   if (compress < ADSURF_COMPRESS_NONE || compress > ADSURF_COMPRESS_NORM) return ADSURF_E_ARG;
   const bool normalised =
@@ -1427,23 +1449,26 @@ static int dmf_launch(const double* d, const double* alpha, const double* beta, 
   double* estore = pp.global ? (double*)w : nullptr;
   w += align256(points_estore_bytes(pp, L, nsm));
   double *pmax = nullptr, *pmin = nullptr;
-  int nchunk = 0;
   if (normalised) {
-    // dense pass: max/min over the trial velocities at every observed period (constant for autograd)
+    // dense pass: max/min over the trial velocities at every observed period (constant for autograd), combined
+    // across blocks as ordered keys [S,N] x 2; the pointwise kernel reads each key once and resets it to the identity
     const GridPlan gp = plan_grid(S, L, N, K, false, nsm);
     if ((size_t)S * (size_t)gp.bpm > 0x7fffffffull) return ADSURF_E_SHAPE;
-    const size_t one = align256((size_t)S * gp.nchunk * N * sizeof(double));
+    const size_t one = align256((size_t)S * N * sizeof(double));
     pmax = (double*)w;
     pmin = (double*)(w + one);
-    nchunk = gp.nchunk;
-    const int rc = grid_fwd_launch(d, alpha, beta, rho, t, C, S, L, N, K, nullptr, pmax, pmin, nullptr, gp, st);
+    if (zero_keys && cudaMemsetAsync(w, 0, 2 * one, st) != cudaSuccess) {
+      cudaGetLastError();
+      return ADSURF_E_CUDA;
+    }
+    const int rc = grid_fwd_launch(d, alpha, beta, rho, t, C, S, L, N, K, nullptr, pmax, pmin, 1, nullptr, gp, st);
     if (rc) return rc;
   }
   out.pp = pp;
   out.part = part;
   out.loss_part = loss_part;
   return launch_points_bwd<2>(pp, S, L, N, d, alpha, beta, rho, t, c, nullptr, F, nullptr, part, estore, nullptr,
-                              nullptr, nullptr, nullptr, pmax, pmin, nchunk, compress, with_grad, norm, loss_part,
+                              nullptr, nullptr, nullptr, pmax, pmin, 0, compress, with_grad, norm, loss_part,
                               nsm, st);
 }
 
@@ -1454,7 +1479,8 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
   if (!loss) return ADSURF_E_NULL;
   cudaStream_t st = (cudaStream_t)stream;
   DmfLaunch dl;
-  const int rc = dmf_launch(d, alpha, beta, rho, t, c, C, S, L, N, K, compress, with_grad, F, norm, ws, ws_bytes, st, dl);
+  const int rc = dmf_launch(d, alpha, beta, rho, t, c, C, S, L, N, K, compress, with_grad, F, norm, ws, ws_bytes, true, st,
+                            dl);
   if (rc) return rc;
   k_loss_reduce<<<(S + 127) / 128, 128, 0, st>>>(dl.loss_part, dl.pp.bpm, N, loss, S);
   if (check_launch()) return ADSURF_E_CUDA;
@@ -1543,8 +1569,9 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
   const size_t ens_bytes = adsurf_workspace_bytes(ADSURF_OP_ENSEMBLE_STEP, p->S, p->L, 1, 0);
   const size_t dmf_bytes = need - ens_bytes;
   DmfLaunch dl;
+  // (the order keys of the dense pass are reset by their reader: ws zero-filled before the first call of a loop)
   const int rc = dmf_launch(p->d, p->alpha, p->b, p->rho, p->t, p->c, p->C, p->S, p->L, p->N, p->K, p->compress, 1,
-                            nullptr, nullptr, ws, dmf_bytes, st, dl);
+                            nullptr, nullptr, ws, dmf_bytes, false, st, dl);
   if (rc) return rc;
   EnsArgs A;
   memset(&A, 0, sizeof(A));

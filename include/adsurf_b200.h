@@ -193,6 +193,8 @@ int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho,
  *   sharded ensembles (one process per GPU, this rank owns global rows row0 .. row0+S-1 of S_all): with
  *   damp_horizontal > 0 `halo` [4,L] holds the CURRENT Vs rows row0-2, row0-1, row0+S, row0+S+1 (rows outside
  *   [0, S_all) are ignored) — the only data a rank needs from its neighbours (reference :471-473); S >= 2 then.
+ *   ws (adsurf_inversion_workspace_bytes) must be ZERO-FILLED before the first call of a loop and left alone
+ *   between calls: the dense pass combines its per-block max / min in it with atomics and each call leaves it reset.
  * Replaces one trip of the loops at _model.py:118-186 (iter_inversion, S = 1) and :589-636 (multi_inversion). */
 typedef struct adsurf_inversion {
   int S, L, N, K, T;
