@@ -90,7 +90,7 @@ def config4(iters, S=1024):
     for key, val in (("vs", b), ("vp", a), ("thick", d), ("rho", rho)):
         init.init_model[key] = val
     pvs = np.ones((S, obs.shape[0], 2)) * obs[:, :2]
-    inv, dt = timed(lambda: A.inversion(mp, ip, init, pvs, vsrange_sign="mul", vsrange=[0.1, 2.5], device="cuda:0"))
+    inv, dt = timed(lambda: A.inversion(mp, ip, init, pvs, vsrange_sign="mul", vsrange=[0.1, 2.5], device="cuda"))
     loss = np.asarray(inv.inv_process["loss"])
     return {"config": 4, "what": f"{S} models, 20-layer FRIUL7W, N=300 picks, compress=False, vs only",
             "iterations_run": iters, "it_per_s": iters / inv.timing["loop_s"], "loop_seconds": inv.timing["loop_s"],
