@@ -33,6 +33,24 @@ ncu_points)
   timeout 600 python benchmarks/configs_e2e.py --iters2 24 --iters3 24 --iters4 16 > gpurun_out/configs_short.log 2>&1 && \
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_points_bwd|k_ens_|k_grid_fwd' -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-12} -f -o gpurun_out/prof_r2_points \
       python benchmarks/configs_e2e.py --iters2 24 --iters3 24 --iters4 16 > gpurun_out/ncu_points.log 2>&1 ;;
+ncu_c4)
+  # pointwise DMF kernel of config 4 (1024 and 4096 models): with --no-warm the launches are the InversionLoop's
+  # warm step (2 kernels) + iterations x 2; skip the first 6 matching kernels, capture 2 iterations
+  for M in 1024 4096; do
+    timeout 600 python benchmarks/configs_e2e.py --only 4 --models4 $M --iters4 8 --no-warm > gpurun_out/c4_$M.log 2>&1 && \
+    timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_points_bwd|k_ens_' -s 6 -c 4 -f \
+        -o gpurun_out/prof_r2_config4_$M python benchmarks/configs_e2e.py --only 4 --models4 $M --iters4 8 --no-warm \
+        > gpurun_out/ncu_c4_$M.log 2>&1
+  done ;;
+ncu_c3)
+  timeout 600 python benchmarks/configs_e2e.py --only 3 --iters3 8 --no-warm > gpurun_out/c3.log 2>&1 && \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_points_bwd|k_ens_|k_grid_fwd' -s 9 -c 6 -f \
+      -o gpurun_out/prof_r2_config3 python benchmarks/configs_e2e.py --only 3 --iters3 8 --no-warm > gpurun_out/ncu_c3.log 2>&1 ;;
+ncu_full)
+  # one full-size launch of the headline kernel (DRAM traffic of the launch the bench times)
+  timeout 600 python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/bench_1step.log 2>&1 && \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_grid_bwd' -s 3 -c 1 -f -o gpurun_out/prof_r2_full \
+      python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
 variants)
   bash benchmarks/run_variants.sh > gpurun_out/run_variants.out 2>&1 ;;
 multi)

@@ -132,11 +132,19 @@ def main():
     ap.add_argument("--iters2", type=int, default=2000)
     ap.add_argument("--iters3", type=int, default=1000)
     ap.add_argument("--iters4", type=int, default=400)
+    ap.add_argument("--only", type=int, default=0, help="run one config only (2, 3 or 4)")
+    ap.add_argument("--models4", type=int, default=1024, help="ensemble size of config 4")
+    ap.add_argument("--no-warm", action="store_true", help="skip the warm-up run (profiling: predictable launch counts)")
     args = ap.parse_args()
     A.cal_determinant  # noqa: B018 (import check)
     torch.zeros(1, device="cuda")
-    for fn, n in ((config2, args.iters2), (config3, args.iters3), (config4, args.iters4)):
-        fn(min(n, 5))  # warm-up (library load, allocator)
+    runs = ((2, config2, args.iters2), (3, config3, args.iters3),
+            (4, lambda n: config4(n, S=args.models4), args.iters4))
+    for k, fn, n in runs:
+        if args.only and k != args.only:
+            continue
+        if not args.no_warm:
+            fn(min(n, 5))  # warm-up (library load, allocator)
         print(json.dumps(fn(n)))
 
 
