@@ -46,6 +46,9 @@
 #ifndef ADSURF_BWD_REGS
 #define ADSURF_BWD_REGS 168
 #endif
+#ifndef ADSURF_VARIANT_NOCLOBBER
+#define ADSURF_VARIANT_NOCLOBBER 0
+#endif
 
 #include "adsurf_b200.h"
 #include "adsurf_math.cuh"
@@ -325,7 +328,11 @@ struct GlobalStore {
     return v;
   }
   __device__ __forceinline__ static void st(Slot s, int j, double v) {
+#if ADSURF_VARIANT_NOCLOBBER
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(s.q + j * kWarp), "d"(v), "l"(s.pol));
+#else
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(s.q + j * kWarp), "d"(v), "l"(s.pol) : "memory");
+#endif
   }
 };
 

@@ -13,10 +13,7 @@ build() {
   grep -A2 "k_grid_bwd" adsurf_b200/_lib/variants/build_$name.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name"
 }
 build base &
-build pf -DADSURF_VARIANT_PREFETCH=1 &
+build noclobber -DADSURF_VARIANT_NOCLOBBER=1 &
+build noearly -DADSURF_VARIANT_FETCH_E_EARLY=0 &
 build late -DADSURF_VARIANT_SINK_LATE=1 &
-build early -DADSURF_VARIANT_FETCH_E_EARLY=1 &
-wait
-build pf_late -DADSURF_VARIANT_PREFETCH=1 -DADSURF_VARIANT_SINK_LATE=1 &
-build early_late -DADSURF_VARIANT_FETCH_E_EARLY=1 -DADSURF_VARIANT_SINK_LATE=1 &
 wait
