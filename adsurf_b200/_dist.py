@@ -15,6 +15,11 @@ import torch.distributed as dist
 
 
 def is_sharded():
+    """True when the ensemble should be split over the ranks (ADSURF_NO_SHARD=1 keeps a rank's run whole, e.g. to
+    compare a sharded run with the unsharded one inside the same job)"""
+    import os
+    if os.environ.get("ADSURF_NO_SHARD") == "1":
+        return False
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 

@@ -43,13 +43,6 @@
 
 #include <type_traits>
 
-#ifndef ADSURF_BWD_REGS
-#define ADSURF_BWD_REGS 168
-#endif
-#ifndef ADSURF_VARIANT_NOCLOBBER
-#define ADSURF_VARIANT_NOCLOBBER 0
-#endif
-
 #include "adsurf_b200.h"
 #include "adsurf_math.cuh"
 #include "adsurf_dispersion.cuh"
@@ -313,26 +306,13 @@ struct GlobalStore {
   unsigned long long pol;
   __device__ __forceinline__ Slot slot(int m) const { return Slot{p + (ptrdiff_t)m * (kSlot * kWarp), pol}; }
   __device__ __forceinline__ static Slot step(Slot s, int n) { return Slot{s.q + n * (kSlot * kWarp), s.pol}; }
-  // pull the rows of a slot the adjoint sweep will load (flm: regime flags of that layer) towards L1
-  __device__ __forceinline__ static void prefetch(Slot s, int flm) {
-#pragma unroll
-    for (int j = 0; j < kSlot; ++j) {
-      if (j == 6 && !(flm & F_LTP)) continue;
-      if (j == 8 && !(flm & F_LTS)) continue;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(s.q + j * kWarp));
-    }
-  }
   __device__ __forceinline__ static double ld(Slot s, int j) {
     double v;
     asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(s.q + j * kWarp), "l"(s.pol));
     return v;
   }
   __device__ __forceinline__ static void st(Slot s, int j, double v) {
-#if ADSURF_VARIANT_NOCLOBBER
-    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(s.q + j * kWarp), "d"(v), "l"(s.pol));
-#else
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(s.q + j * kWarp), "d"(v), "l"(s.pol) : "memory");
-#endif
   }
 };
 
@@ -1410,7 +1390,7 @@ int adsurf_det_grid_bwd(const double* d, const double* alpha, const double* beta
   const long long total_vb = (long long)S * gp.bpm;
   if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;
   const int threads = gp.wpb * kWarp;
-  auto kern = k_grid_bwd<kBwdWarps * kWarp, ADSURF_BWD_REGS>;  // 3 x 4 = 12 warps / SM
+  auto kern = k_grid_bwd<kBwdWarps * kWarp, 168>;  // 3 x 4 = 12 warps / SM
   if (set_smem(kern, smem)) return ADSURF_E_CUDA;
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {

@@ -18,17 +18,6 @@
 #define ADSURF_HD inline
 #endif
 
-// experiment switches of the dense adjoint sweep (benchmarks/variants.sh builds them side by side)
-#ifndef ADSURF_VARIANT_PREFETCH
-#define ADSURF_VARIANT_PREFETCH 0
-#endif
-#ifndef ADSURF_VARIANT_SINK_LATE
-#define ADSURF_VARIANT_SINK_LATE 0
-#endif
-#ifndef ADSURF_VARIANT_FETCH_E_EARLY
-#define ADSURF_VARIANT_FETCH_E_EARLY 1  // measured on B200: 2.776 vs 2.711 G samples/s (profiles/r2_variants.txt)
-#endif
-
 namespace adsurf {
 
 constexpr double kTwoPi = 6.283185307179586;  // 2.0 * np.pi
@@ -780,7 +769,6 @@ struct PlainStore {
   typedef double* Slot;
   ADSURF_HD Slot slot(int m) const { return p + (size_t)m * (kSlot * kStride); }
   ADSURF_HD static Slot step(Slot q, int n) { return q + n * (kSlot * kStride); }  // n slots further
-  ADSURF_HD static void prefetch(Slot, int) {}
   ADSURF_HD static double ld(Slot q, int j) { return q[j * kStride]; }
   ADSURF_HD static void st(Slot q, int j, double v) { q[j * kStride] = v; }
 };
@@ -1045,30 +1033,18 @@ ADSURF_HD void sample_adjoint(const TableSource<kN>& src, const Sample& z, doubl
     layer_from_entry<kN>(y, q, kFl < 0 ? src.record(q) : src.par, z.omega, ld2(q + T_PDA));
     layer_set_flags(y, kFl >= 0 ? kFl : y.fl);
     sq = Store::step(sq, 1);
-#if ADSURF_VARIANT_PREFETCH
-    Store::prefetch(sq, fln);  // pull the next layer's slot towards L1 a whole layer before it is loaded
-#endif
     layer_eig_restore(y, z.omega);
-#if !ADSURF_VARIANT_SINK_LATE
     sink.put(pend.d, pend.a, pend.b, pend.rho);
-#endif
     fetch_c(sq, fln);  // after the last layer: the slot behind it (values unused)
-#if ADSURF_VARIANT_FETCH_E_EARLY
     // the next layer's row vector is requested a whole layer ahead, into registers of its own: issued only after
-    // the last use of e it arrives late and the top of the next layer waits for L2 (long-scoreboard stalls)
+    // the last use of e it arrives late and the top of the next layer waits for L2 (long-scoreboard stalls;
+    // measured 2.776 vs 2.711 G samples/s, profiles/r2_variants.txt)
     double en[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) en[i] = Store::ld(sq, i);
     const LayerGrad g = layer_adjoint<false>(y, e, s, tq, z.omega, z.ic, z.ic2, z.t2);
 #pragma unroll
     for (int i = 0; i < 5; ++i) e[i] = en[i];
-#else
-    const LayerGrad g = layer_adjoint<false>(y, e, s, tq, z.omega, z.ic, z.ic2, z.t2);
-    fetch_e(sq);
-#endif
-#if ADSURF_VARIANT_SINK_LATE
-    sink.put(pend.d, pend.a, pend.b, pend.rho);
-#endif
     pend = g;
     q += kN;
     fl = fln;

@@ -53,6 +53,10 @@ ncu_full)
       python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
 variants)
   bash benchmarks/run_variants.sh > gpurun_out/run_variants.out 2>&1 ;;
+sharded)
+  N=${NGPU:-2}
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+      benchmarks/check_sharded.py > gpurun_out/check_sharded_n$N.json 2> gpurun_out/check_sharded_n$N.err; echo "rc=$?" >> gpurun_out/check_sharded_n$N.err ;;
 multi)
   N=${NGPU:-2}
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \

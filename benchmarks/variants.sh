@@ -1,6 +1,6 @@
 #!/bin/bash
-# Build kernel variants side by side (compile-time switches of the dense adjoint sweep) — run here (nvcc, no GPU):
-#   benchmarks/variants.sh            -> adsurf_b200/_lib/variants/lib_<name>.so
+# Build kernel variants side by side (compile-time -D switches added for an experiment) — run here (nvcc, no GPU):
+#   benchmarks/variants.sh name:"-DFLAG=1" ...   -> adsurf_b200/_lib/variants/lib_<name>.so
 # and measure them on the GPU box with benchmarks/run_variants.sh (each is loaded through ADSURF_LIB).
 set -e
 cd "$(dirname "$0")/.."
@@ -12,8 +12,10 @@ build() {
        > adsurf_b200/_lib/variants/build_$name.log 2>&1
   grep -A2 "k_grid_bwd" adsurf_b200/_lib/variants/build_$name.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name"
 }
+# usage: benchmarks/variants.sh name1:"-DFLAG=1 ..." name2:"..."   (the current sources define no switches;
+# profiles/r2_variants.txt records what the round-2 switches measured before they were removed)
 build base &
-build noclobber -DADSURF_VARIANT_NOCLOBBER=1 &
-build noearly -DADSURF_VARIANT_FETCH_E_EARLY=0 &
-build late -DADSURF_VARIANT_SINK_LATE=1 &
+for spec in "$@"; do
+  build "${spec%%:*}" ${spec#*:} &
+done
 wait
