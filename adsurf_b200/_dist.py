@@ -55,6 +55,10 @@ def all_gather_rows(local, S, dim=0):
     sizes = [shard_bounds(S, r, world)[1] - shard_bounds(S, r, world)[0] for r in range(world)]
     big = max(sizes)
     x = local.movedim(dim, 0).contiguous()
+    if min(sizes) == big:  # equal shards: one collective straight into the result
+        full = torch.empty((world * big,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(full, x)
+        return full.movedim(0, dim)
     if x.shape[0] < big:
         pad = torch.zeros((big - x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         x = torch.cat((x, pad), dim=0)

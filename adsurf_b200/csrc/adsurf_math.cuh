@@ -1055,9 +1055,12 @@ ADSURF_HD void sample_adjoint(const TableSource<kN>& src, const Sample& z, doubl
       layer(tag);
     } while (fl == kFl);
   };
+  // (config 5: 55 % of the (velocity, layer) pairs are EE, 39 % EO, 6 % OO — trial velocities above a shallow
+  // layer's Vp —, OE never occurs: alpha > beta)
   while (!(fl & F_END)) {
     if (fl == kEO) run(std::integral_constant<int, kEO>{});
     else if (fl == kEE) run(std::integral_constant<int, kEE>{});
+    else if (fl == kOO) run(std::integral_constant<int, kOO>{});
     else layer(std::integral_constant<int, -1>{});
   }
   sink.put(pend.d, pend.a, pend.b, pend.rho);

@@ -79,6 +79,11 @@ def _worker(rank, world, port, out_dir):
         lo, hi = _dist.shard_bounds(5)
         full = _dist.all_gather_rows(torch.arange(lo, hi, dtype=torch.float64).reshape(-1, 1), 5)
         assert torch.equal(full.reshape(-1), torch.arange(5, dtype=torch.float64))
+        # equal shards take the single-collective path; gathered along a middle axis
+        lo, hi = _dist.shard_bounds(4)
+        part = torch.arange(lo, hi, dtype=torch.float64).reshape(1, -1, 1).expand(3, -1, 2).contiguous()
+        full = _dist.all_gather_rows(part, 4, dim=1)
+        assert full.shape == (3, 4, 2) and torch.equal(full[1, :, 0], torch.arange(4, dtype=torch.float64))
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
