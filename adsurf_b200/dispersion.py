@@ -25,12 +25,26 @@ from ._surf96 import DispersionError, gtsolh
 
 
 @torch.no_grad()
-def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, device=None):
-    """Phase velocities of the requested Rayleigh modes by the reference's root search on the GPU.
+def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, device=None, itype=0, dt=0.025):
+    """Phase (itype=0) or group (itype=1) velocities of the requested Rayleigh modes by the reference's root search
+    on the GPU.
 
     t: periods [NF] (or [S,NF]); d, a, b, rho: thickness, Vp, Vs, density [L] (one model) or [S,L] (an ensemble).
     Returns c[len(modes), NF] (one model) or c[S, len(modes), NF]; 0 where a mode does not exist.
+    Group velocity as the reference forms it (_surf96.py:735-758): two phase curves at t/(1+dt) and t/(1-dt),
+    U = (f1 - f2) / (f1/c1 - f2/c2), 0 where the second curve has no root.
     Raises DispersionError if the fundamental mode of any model cannot be bracketed (as `_surf96.getc` does)."""
+    if itype == 1:
+        t_np = np.asarray(t, dtype=np.float64)
+        t1, t2 = t_np / (1.0 + dt), t_np / (1.0 - dt)
+        c1 = dispersion_curves(t1, d, a, b, rho, modes, dc, device)
+        c2 = dispersion_curves(t2, d, a, b, rho, modes, dc, device)
+        f1 = np.broadcast_to((1.0 / t1) if t_np.ndim == 1 else (1.0 / t1)[:, None, :], c1.shape)
+        f2 = np.broadcast_to((1.0 / t2) if t_np.ndim == 1 else (1.0 / t2)[:, None, :], c1.shape)
+        out = np.zeros_like(c1)
+        ok = c2 > 0.0
+        out[ok] = (f1[ok] - f2[ok]) / (f1[ok] / c1[ok] - f2[ok] / c2[ok])
+        return out
     dev = ops._device_of(device=device)
     D, A_, B_, R = (torch.as_tensor(np.asarray(x, dtype=np.float64), device=dev) for x in (d, a, b, rho))
     single = D.dim() == 1

@@ -149,6 +149,18 @@ def test_gpu_dispersion_curves_match_reference_solver(api, tag, modes):
         assert np.max(np.abs(c[i] - ref)) <= 1e-6          # km/s, 100 % of the points
 
 
+def test_gpu_group_velocity_matches_host_solver(api):
+    """itype=1 (group velocity from two phase curves, _surf96.py:735-758) on the GPU against the host solver"""
+    from adsurf_b200._surf96 import surf96
+    from adsurf_b200.dispersion import dispersion_curves
+    g = load("surf96_roots")
+    t, d, a, b, rho = (g[f"m6_{k}"] for k in ("t", "d", "a", "b", "rho"))
+    u = dispersion_curves(t[::6], d, a, b, rho, modes=(0,), dc=0.005, itype=1)
+    ref = surf96(t[::6], d, a, b, rho, 0, 1, 2, 0.005)
+    assert u.shape == (1, len(t[::6])) and np.all(u > 0)
+    np.testing.assert_allclose(u[0], ref, rtol=0, atol=1e-6)
+
+
 def test_gpu_dispersion_ensemble_equals_single_models(api):
     """the parallel axis is the ensemble: 96 perturbed 6-layer models in one launch == 96 single-model launches"""
     from adsurf_b200.dispersion import dispersion_curves
