@@ -51,11 +51,6 @@ ncu_full)
   timeout 600 python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/bench_1step.log 2>&1 && \
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_grid_bwd' -s 3 -c 1 -f -o gpurun_out/prof_r2_full \
       python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
-memcheck)
-  # one sanitizer tool per call (B200_PROFILING.md); small cases only
-  timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py tests/test_gpu_api.py -q -x \
-      -k "golden or ragged or graph_replay or nan_propagates or dispersion_curves_match or monte_carlo" > gpurun_out/memcheck.log 2>&1
-  echo "memcheck rc=$?" >> gpurun_out/memcheck.log ;;
 variants)
   bash benchmarks/run_variants.sh > gpurun_out/run_variants.out 2>&1 ;;
 sharded)
