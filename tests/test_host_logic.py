@@ -144,3 +144,27 @@ def test_gpu_dispersion_extraction_logic(ab):
         both = (c[i] > 0) & (ref > 0)
         assert both.sum() >= 0.8 * (ref > 0).sum()
         assert np.max(np.abs(c[i][both] - ref[both])) < 5e-6  # the reference stops at 1e-6 relative
+
+
+def test_bench_reference_arm_runs_on_the_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the contract's
+    keys; under torchrun only rank 0 works (other ranks exit 0 silently)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["unit"] == "samples/s" and rec["value"] > 0 and rec["scaling"] == "strong"
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
+    assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["gpu_launches"] == 0
+    assert rec["metric"].startswith("DMF det samples/s fwd+bwd") and rec["dtype"] == "f64"
+    quiet = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                            "--warmup", "0"], capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"),
+                           timeout=600)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
