@@ -51,6 +51,9 @@ ncu_full)
   timeout 600 python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/bench_1step.log 2>&1 && \
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_grid_bwd' -s 3 -c 1 -f -o gpurun_out/prof_r2_full \
       python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
+persist)
+  python benchmarks/quick_line.py 1024 4 > gpurun_out/persist_l2.txt 2>&1
+  ADSURF_PERSIST_L2=0 python benchmarks/quick_line.py 1024 4 >> gpurun_out/persist_l2.txt 2>&1 ;;
 variants)
   bash benchmarks/run_variants.sh > gpurun_out/run_variants.out 2>&1 ;;
 sharded)
