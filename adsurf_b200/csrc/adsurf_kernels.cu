@@ -632,7 +632,11 @@ struct EnsArgs {
   double *loss_hist, *iter_b, *iter_d;  // counter form: bases of [T,S], [T,S,L]; host form: this iteration's slot
 };
 
-__device__ __forceinline__ void ens_prepare_cell(const EnsArgs& A, int s, int l) {
+// what phase 1 leaves for phase 2 of the SAME (model, layer) cell: kept in registers by the one-launch form
+struct EnsCell {
+  double gt, gdr, x0, d0;
+};
+__device__ __forceinline__ EnsCell ens_prepare_cell(const EnsArgs& A, int s, int l) {
   const int L = A.L, S = A.S;
   const int i = s * L + l;
   const double x0 = A.b[i];
@@ -679,9 +683,11 @@ __device__ __forceinline__ void ens_prepare_cell(const EnsArgs& A, int s, int l)
       if (s == S - 1 && r + 1 < Sa) A.shh[L + l] = sgn(A.dh * lap(x0, h[2 * L + l], h[3 * L + l], r + 1, Sa) / L);
     }
   }
+  const double d0 = A.d[i];
   A.tik[i] = tik;
   A.bo[i] = x0;
-  A.dold[i] = A.d[i];
+  A.dold[i] = d0;
+  return EnsCell{g, gd, x0, d0};
 }
 
 __global__ void k_ens_prepare(EnsArgs A) {
@@ -714,7 +720,8 @@ __device__ __forceinline__ EnsStep ens_step_of(const EnsArgs& A) {
   return t;
 }
 
-__device__ __forceinline__ void ens_adam_cell(const EnsArgs& A, const EnsStep& T, int s, int l) {
+template <bool kOwn>
+__device__ __forceinline__ void ens_adam_cell(const EnsArgs& A, const EnsStep& T, int s, int l, const EnsCell& own) {
   const int L = A.L, S = A.S, j = T.j;
   const int i = s * L + l;
   const size_t o = (size_t)s * L;
@@ -722,7 +729,7 @@ __device__ __forceinline__ void ens_adam_cell(const EnsArgs& A, const EnsStep& T
   const size_t ho = A.counter ? (size_t)j * S * L : 0;
   // --- projection of Vs (before the optimiser step, as the reference orders it); torch.clamp keeps NaN
   auto proj_b = [&](int ll) {
-    double x = A.bo[o + ll];
+    double x = (kOwn && ll == l) ? own.x0 : A.bo[o + ll];
     if (x != x && (A.proj_flags & 2)) x = A.b0[o + ll];            // NaN repair of the ensemble vs-only loop (:624-626)
     if (x == x) x = fmin(fmax(x, A.lob[o + ll]), A.upb[o + ll]);   // clip_(min, max): max wins when min > max
     return x;
@@ -735,7 +742,7 @@ __device__ __forceinline__ void ens_adam_cell(const EnsArgs& A, const EnsStep& T
   if (A.iter_b && rec) A.iter_b[ho + i] = x;
   // --- projection of the depths: cumulative depth clipped per layer (LR) or against the previous projected
   // depth (LN), back to thicknesses >= min thickness (:133-147, :603-620)
-  double th = A.dold[i];
+  double th = kOwn ? own.d0 : A.dold[i];
   if (A.invert_thick) {
     const double floor_t = A.mind[0];
     double depth = 0.0, pdepth = 0.0, z = 0.0;
@@ -754,7 +761,7 @@ __device__ __forceinline__ void ens_adam_cell(const EnsArgs& A, const EnsStep& T
     if (A.iter_d && rec) A.iter_d[ho + i] = th;
   }
   // --- Tikhonov subgradients on top of the chain gradient of phase 1, Adam, next alpha / rho
-  double g = A.gt[i];
+  double g = kOwn ? own.gt : A.gt[i];
   if (A.dv > 0.0) {
     const double c = lap(l > 0 ? A.sv[i - 1] : 0.0, A.sv[i], l < L - 1 ? A.sv[i + 1] : 0.0, l, L);
     g += A.dv / L * c;
@@ -781,7 +788,7 @@ __device__ __forceinline__ void ens_adam_cell(const EnsArgs& A, const EnsStep& T
   }
   if (A.invert_thick) {
     double m2 = A.md[i], v2 = A.vd[i];
-    A.d[i] = adam(th, A.gdr[i], m2, v2, A, T.lr, T.bc1, T.bc2s);
+    A.d[i] = adam(th, kOwn ? own.gdr : A.gdr[i], m2, v2, A, T.lr, T.bc1, T.bc2s);
     A.md[i] = m2;
     A.vd[i] = v2;
   }
@@ -818,7 +825,7 @@ __device__ __forceinline__ void ens_advance(const EnsArgs& A, int j) {
 __global__ void k_ens_adam(EnsArgs A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const EnsStep T = ens_step_of(A);
-  if (i < A.S * A.L) ens_adam_cell(A, T, i / A.L, i % A.L);
+  if (i < A.S * A.L) ens_adam_cell<false>(A, T, i / A.L, i % A.L, EnsCell{});
   ens_advance(A, T.j);
 }
 
@@ -830,9 +837,10 @@ __global__ void k_ens_fused(EnsArgs A) {
   const int s = blockIdx.x * mpb + local;
   const bool mine = local < mpb && s < A.S;
   const EnsStep T = ens_step_of(A);
-  if (mine) ens_prepare_cell(A, s, l);
+  EnsCell own{};
+  if (mine) own = ens_prepare_cell(A, s, l);
   __syncthreads();
-  if (mine) ens_adam_cell(A, T, s, l);
+  if (mine) ens_adam_cell<true>(A, T, s, l, own);
   ens_advance(A, T.j);
 }
 

@@ -53,7 +53,12 @@ ncu_full)
       python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
 persist)
   python benchmarks/quick_line.py 1024 4 > gpurun_out/persist_l2.txt 2>&1
-  ADSURF_PERSIST_L2=0 python benchmarks/quick_line.py 1024 4 >> gpurun_out/persist_l2.txt 2>&1 ;;
+  ADSURF_PERSIST_L2=0 python benchmarks/quick_line.py 1024 4 >> gpurun_out/persist_l2.txt 2>&1
+  python benchmarks/quick_line.py 1024 4 det >> gpurun_out/persist_l2.txt 2>&1
+  ADSURF_PERSIST_L2=0 python benchmarks/quick_line.py 1024 4 det >> gpurun_out/persist_l2.txt 2>&1 ;;
+configs_persist)
+  timeout 900 python benchmarks/configs_e2e.py --only 4 > gpurun_out/configs_c4_nopersist.jsonl 2>&1
+  ADSURF_PERSIST_L2=1 timeout 900 python benchmarks/configs_e2e.py --only 4 > gpurun_out/configs_c4_persist.jsonl 2>&1 ;;
 variants)
   bash benchmarks/run_variants.sh > gpurun_out/run_variants.out 2>&1 ;;
 sharded)

@@ -73,8 +73,9 @@ const char* adsurf_error_string(int code);
  *     adjoint kernels keep their per-warp layer slabs (43.8 KB per resident warp at 20 layers, 78 MB per GPU) in L2
  *     with evict_last accesses; L2 honours that policy only inside the persisting carve-out, which is 0 bytes by
  *     default.  The limit is CONTEXT-WIDE (it is shared with every other library in the process, though it changes
- *     nothing for code that issues no persisting accesses), hence opt-in: without it everything still works, the
- *     slabs are merely written back to HBM (measured: 10x the DRAM traffic of adsurf_det_grid_bwd, ~15 % slower).
+ *     nothing for code that issues no persisting accesses), hence opt-in: without it everything still works, part
+ *     of the slabs is merely written back to HBM (measured on B200: ~10x the DRAM traffic of adsurf_det_grid_bwd at
+ *     the same run time within 0.2 %: the path is FP64-bound, not bandwidth-bound).
  * Nothing else in this library touches device-wide state.  No reference counterpart. */
 #define ADSURF_INIT_PERSIST_L2 1u
 int adsurf_init(int device, unsigned flags);
