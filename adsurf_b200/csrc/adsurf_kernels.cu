@@ -395,193 +395,6 @@ __global__ void k_grad_reduce(const double* __restrict__ part, int L, int bpm, d
   }
 }
 
-struct PointsPlan {
-  int units;   // ceil(N/32) warp units per model
-  int wpb;
-  int bpm;
-  int global;  // 1: persistent blocks with the store slabs in the global (L2) slab
-};
-
-// Pointwise forward at the observed picks.
-__global__ void __launch_bounds__(128) k_points_fwd(const double* __restrict__ d, const double* __restrict__ alpha,
-                                                    const double* __restrict__ beta, const double* __restrict__ rho,
-                                                    const double* __restrict__ t, const double* __restrict__ c, int L,
-                                                    int N, PointsPlan pp, double* __restrict__ F) {
-  extern __shared__ double smem[];
-  double* par = smem + kSmemHead;
-  const int s = blockIdx.x / pp.bpm;
-  const int blk = blockIdx.x - s * pp.bpm;
-  stage_params(par, d, alpha, beta, rho, s, L);
-  __syncthreads();
-  const int i = blk * blockDim.x + threadIdx.x;
-  if (blk * blockDim.x + (threadIdx.x & ~31) >= N) return;  // whole warps only: the sweep votes across the warp
-  const size_t idx = (size_t)s * N + (i < N ? i : N - 1);   // overhang lanes replay the last pick
-  const double omega0 = omega_of_period(t[idx]);
-  const Sample z = make_sample(omega0, 1.0 / c[idx]);
-  const double v = sample_forward(DirectSource{par, L}, z);
-  if (i < N) F[idx] = v;
-}
-
-// DMF compression: returns |G| and d|G|/dF (reference _model.py:455-464)
-__device__ __forceinline__ void dmf_compress(int mode, double F, double n, double invN, double& absG, double& seed) {
-  if (mode == ADSURF_COMPRESS_NONE) {
-    absG = fabs(F);
-    seed = (F > 0.0 ? 1.0 : (F < 0.0 ? -1.0 : (F == 0.0 ? 0.0 : NAN))) * invN;
-    return;
-  }
-  const bool norm = (mode == ADSURF_COMPRESS_EXP) || (mode == ADSURF_COMPRESS_LOG) || (mode == ADSURF_COMPRESS_NORM);
-  const double in = norm ? 1.0 / n : 1.0;
-  const double u = F * in;
-  const double au = fabs(u);
-  const double sg = (u > 0.0 ? 1.0 : (u < 0.0 ? -1.0 : (u == 0.0 ? 0.0 : NAN)));
-  if (mode == ADSURF_COMPRESS_NORM) {
-    absG = au;
-    seed = sg * in * invN;
-  } else if (mode == ADSURF_COMPRESS_LOG) {
-    absG = log(au + 1.0);
-    seed = sg / (au + 1.0) * in * invN;
-  } else {
-    const double pw = pow(0.1, au);
-    absG = 1.0 - pw;  // |0.1^|u| - 1|
-    // G = pw - 1 <= 0; d|G|/du = -dG/du = ln(10) pw sign(u); torch's abs'(0) = 0 when G == 0 (u == 0)
-    seed = kLn10 * pw * sg * in * invN;
-  }
-}
-
-// Pointwise forward + adjoint.  kind 0: upstream gF given; kind 1: Jacobian rows; kind 2: fused DMF
-// (normalisation read from the dense pass partials, loss partial written per block).
-template <int kKind, bool kGlobal>
-__global__ void __maxnreg__(kGlobal ? 168 : 232)
-k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const double* __restrict__ beta,
-             const double* __restrict__ rho, const double* __restrict__ t, const double* __restrict__ c,
-             const double* __restrict__ gF, int L, int N, PointsPlan pp, int total_vblocks, double* __restrict__ F,
-             double* __restrict__ gc, double* __restrict__ part, double* __restrict__ estore,
-             // Jacobian outputs
-             double* __restrict__ Jd, double* __restrict__ Ja, double* __restrict__ Jb, double* __restrict__ Jrho,
-             // DMF
-             double* __restrict__ pmax, double* __restrict__ pmin, int nchunk, int compress, int with_grad,
-             double* __restrict__ norm, double* __restrict__ loss_part) {
-  // kGlobal: persistent blocks, store slabs in the L2-resident global slab, per-lane fold accumulators (large
-  // ensembles); otherwise one block per (model, 32*wpb picks) with the slabs in shared memory (small problems).
-  extern __shared__ double smem[];
-  const int acc_per_warp = kGlobal ? kAccRow * (L + 1) : 4 * L;
-  double* par = smem + kSmemHead;
-  double* accs = par + par_doubles(L);                  // [wpb][L+1][4][16] or [wpb][4][L]
-  double* lossw = accs + (size_t)pp.wpb * acc_per_warp; // [wpb]
-  double* ests = lossw + pp.wpb;                        // [wpb][L-1][kSlot][32] (shared variant only)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
-  double* acc = accs + (size_t)warp * acc_per_warp;
-  const unsigned long long slab_policy = kGlobal ? l2_evict_last_policy() : 0ull;
-  double* estp = kGlobal ? estore + ((size_t)blockIdx.x * pp.wpb + warp) * slab + lane : ests + (size_t)warp * slab + lane;
-  for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
-    const int s = vb / pp.bpm;
-    const int blk = vb - s * pp.bpm;
-    __syncthreads();
-    stage_params(par, d, alpha, beta, rho, s, L);
-    for (int i = threadIdx.x; i < pp.wpb * acc_per_warp + pp.wpb; i += blockDim.x) accs[i] = 0.0;
-    __syncthreads();
-    const int unit = blk * pp.wpb + warp;
-    if (unit < pp.units) {
-      const int i = unit * kWarp + lane;
-      const bool active = i < N;
-      const size_t idx = (size_t)s * N + (active ? i : N - 1);
-      const double cc = c[idx];
-      const double ic = 1.0 / cc;
-      const Sample z = make_sample(omega_of_period(t[idx]), ic);
-      const DirectSourceT<kKind != 2> src{par, L};  // the DMF step does not return dF/dc
-      // max / min over the trial velocities from the dense pass: ordered keys [S,N], read once per pick (before the
-      // sweep: their latency hides behind it) and reset to the identity for the next evaluation
-      const bool normalised = kKind == 2 && (compress == ADSURF_COMPRESS_EXP || compress == ADSURF_COMPRESS_LOG ||
-                                             compress == ADSURF_COMPRESS_NORM);
-      unsigned long long key_max = 0ull, key_min = 0ull;
-      if (normalised) {
-        unsigned long long* kmax = reinterpret_cast<unsigned long long*>(pmax) + idx;
-        unsigned long long* kmin = reinterpret_cast<unsigned long long*>(pmin) + idx;
-        key_max = *kmax;
-        key_min = *kmin;
-        if (active) {
-          *kmax = 0ull;
-          *kmin = 0ull;
-        }
-      }
-      typename std::conditional<kGlobal, GlobalStore, PlainStore<kWarp>>::type store;
-      store.p = estp;
-      if constexpr (kGlobal) store.pol = slab_policy;
-      const double v = sample_forward_store(src, z, store);
-      if (F && active) F[idx] = v;
-      double seed = 1.0;
-      if (kKind == 0) seed = gF[idx];
-      if (kKind == 2) {
-        double n = 1.0;
-        if (normalised) {
-          n = order_value(key_max) + order_value(key_min);  // max - min (the minimum travels negated)
-          if (norm && active) norm[idx] = n;
-        }
-        double absG;
-        dmf_compress(compress, v, n, 1.0 / (double)N, absG, seed);
-        double lsum = warp_sum(active ? absG : 0.0);
-        if (lane == 0) lossw[warp] = lsum;
-      }
-      if (kKind != 2 || with_grad) {
-        double gk;
-        if (kKind == 1) {
-          JacSink sink{Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
-                       Jrho ? Jrho + idx * L : nullptr, active};
-          gk = sample_adjoint(src, z, seed, v, store, sink);
-        } else if (kGlobal) {
-          FoldSink sink{acc, lane};
-          gk = sample_adjoint(src, z, active ? seed : 0.0, v, store, sink);  // overhang lanes: zero seed
-        } else {
-          ReduceSink sink{acc, L, lane};
-          gk = sample_adjoint(src, z, active ? seed : 0.0, v, store, sink);
-        }
-        if (gc && active) gc[idx] = -ic * z.ic * gk;  // gk = dDelta/d(k/omega), k/omega = 1/c
-      }
-    }
-    __syncthreads();
-    if (kKind != 1) {
-      for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
-        double v = 0.0;
-        if (kGlobal) {
-          v = fold_total(accs, pp.wpb, L, i % L, i / L);
-        } else {
-          for (int w = 0; w < pp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
-        }
-        part[((size_t)s * pp.bpm + blk) * 4 * L + i] = v;
-      }
-      if (kKind == 2 && threadIdx.x == 0) {
-        double v = 0.0;
-        for (int w = 0; w < pp.wpb; ++w) v += lossw[w];
-        loss_part[(size_t)s * pp.bpm + blk] = v;
-      }
-    }
-  }
-}
-
-__global__ void k_loss_reduce(const double* __restrict__ loss_part, int bpm, int N, double* __restrict__ loss, int S) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
-  double v = 0.0;
-  for (int b = 0; b < bpm; ++b) v += loss_part[(size_t)s * bpm + b];
-  loss[s] = v / (double)N;
-}
-
-// FP64 peak probe: 8 independent DFMA chains per thread
-__global__ void __launch_bounds__(256) k_dfma_probe(int iters, double* __restrict__ out, double a, double b) {
-  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0,
-         x6 = x0 + 6.0, x7 = x0 + 7.0;
-  for (int i = 0; i < iters; ++i) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-    }
-  }
-  const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-  if (r == 12345.678) out[0] = r;  // never true; keeps the chains alive
-}
-
 // ---- ensemble optimiser step (N3) -----------------------------------------------------------------------
 __device__ __forceinline__ double sgn(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : (v == 0.0 ? 0.0 : NAN)); }
 __device__ __forceinline__ double brocher_vp(double b) {
@@ -842,6 +655,222 @@ __global__ void k_ens_fused(EnsArgs A) {
   __syncthreads();
   if (mine) ens_adam_cell<true>(A, T, s, l, own);
   ens_advance(A, T.j);
+}
+
+struct PointsPlan {
+  int units;   // ceil(N/32) warp units per model
+  int wpb;
+  int bpm;
+  int global;  // 1: persistent blocks with the store slabs in the global (L2) slab
+};
+
+// Pointwise forward at the observed picks.
+__global__ void __launch_bounds__(128) k_points_fwd(const double* __restrict__ d, const double* __restrict__ alpha,
+                                                    const double* __restrict__ beta, const double* __restrict__ rho,
+                                                    const double* __restrict__ t, const double* __restrict__ c, int L,
+                                                    int N, PointsPlan pp, double* __restrict__ F) {
+  extern __shared__ double smem[];
+  double* par = smem + kSmemHead;
+  const int s = blockIdx.x / pp.bpm;
+  const int blk = blockIdx.x - s * pp.bpm;
+  stage_params(par, d, alpha, beta, rho, s, L);
+  __syncthreads();
+  const int i = blk * blockDim.x + threadIdx.x;
+  if (blk * blockDim.x + (threadIdx.x & ~31) >= N) return;  // whole warps only: the sweep votes across the warp
+  const size_t idx = (size_t)s * N + (i < N ? i : N - 1);   // overhang lanes replay the last pick
+  const double omega0 = omega_of_period(t[idx]);
+  const Sample z = make_sample(omega0, 1.0 / c[idx]);
+  const double v = sample_forward(DirectSource{par, L}, z);
+  if (i < N) F[idx] = v;
+}
+
+// DMF compression: returns |G| and d|G|/dF (reference _model.py:455-464)
+__device__ __forceinline__ void dmf_compress(int mode, double F, double n, double invN, double& absG, double& seed) {
+  if (mode == ADSURF_COMPRESS_NONE) {
+    absG = fabs(F);
+    seed = (F > 0.0 ? 1.0 : (F < 0.0 ? -1.0 : (F == 0.0 ? 0.0 : NAN))) * invN;
+    return;
+  }
+  const bool norm = (mode == ADSURF_COMPRESS_EXP) || (mode == ADSURF_COMPRESS_LOG) || (mode == ADSURF_COMPRESS_NORM);
+  const double in = norm ? 1.0 / n : 1.0;
+  const double u = F * in;
+  const double au = fabs(u);
+  const double sg = (u > 0.0 ? 1.0 : (u < 0.0 ? -1.0 : (u == 0.0 ? 0.0 : NAN)));
+  if (mode == ADSURF_COMPRESS_NORM) {
+    absG = au;
+    seed = sg * in * invN;
+  } else if (mode == ADSURF_COMPRESS_LOG) {
+    absG = log(au + 1.0);
+    seed = sg / (au + 1.0) * in * invN;
+  } else {
+    const double pw = pow(0.1, au);
+    absG = 1.0 - pw;  // |0.1^|u| - 1|
+    // G = pw - 1 <= 0; d|G|/du = -dG/du = ln(10) pw sign(u); torch's abs'(0) = 0 when G == 0 (u == 0)
+    seed = kLn10 * pw * sg * in * invN;
+  }
+}
+
+// Pointwise forward + adjoint.  kind 0: upstream gF given; kind 1: Jacobian rows; kind 2: fused DMF
+// (normalisation read from the dense pass partials, loss partial written per block).
+template <int kKind, bool kGlobal>
+__global__ void __maxnreg__(kGlobal ? 168 : 232)
+k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const double* __restrict__ beta,
+             const double* __restrict__ rho, const double* __restrict__ t, const double* __restrict__ c,
+             const double* __restrict__ gF, int L, int N, PointsPlan pp, int total_vblocks, double* __restrict__ F,
+             double* __restrict__ gc, double* __restrict__ part, double* __restrict__ estore,
+             // Jacobian outputs
+             double* __restrict__ Jd, double* __restrict__ Ja, double* __restrict__ Jb, double* __restrict__ Jrho,
+             // DMF
+             double* __restrict__ pmax, double* __restrict__ pmin, int nchunk, int compress, int with_grad,
+             double* __restrict__ norm, double* __restrict__ loss_part,
+             // fused optimiser step (DMF kind, no horizontal damping): the block that completes a model's partials runs it
+             int* __restrict__ model_done, EnsArgs E) {
+  // kGlobal: persistent blocks, store slabs in the L2-resident global slab, per-lane fold accumulators (large
+  // ensembles); otherwise one block per (model, 32*wpb picks) with the slabs in shared memory (small problems).
+  extern __shared__ double smem[];
+  const int acc_per_warp = kGlobal ? kAccRow * (L + 1) : 4 * L;
+  double* par = smem + kSmemHead;
+  double* accs = par + par_doubles(L);                  // [wpb][L+1][4][16] or [wpb][4][L]
+  double* lossw = accs + (size_t)pp.wpb * acc_per_warp; // [wpb]
+  double* ests = lossw + pp.wpb;                        // [wpb][L-1][kSlot][32] (shared variant only)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;
+  double* acc = accs + (size_t)warp * acc_per_warp;
+  const unsigned long long slab_policy = kGlobal ? l2_evict_last_policy() : 0ull;
+  double* estp = kGlobal ? estore + ((size_t)blockIdx.x * pp.wpb + warp) * slab + lane : ests + (size_t)warp * slab + lane;
+  for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
+    const int s = vb / pp.bpm;
+    const int blk = vb - s * pp.bpm;
+    __syncthreads();
+    stage_params(par, d, alpha, beta, rho, s, L);
+    for (int i = threadIdx.x; i < pp.wpb * acc_per_warp + pp.wpb; i += blockDim.x) accs[i] = 0.0;
+    __syncthreads();
+    const int unit = blk * pp.wpb + warp;
+    if (unit < pp.units) {
+      const int i = unit * kWarp + lane;
+      const bool active = i < N;
+      const size_t idx = (size_t)s * N + (active ? i : N - 1);
+      const double cc = c[idx];
+      const double ic = 1.0 / cc;
+      const Sample z = make_sample(omega_of_period(t[idx]), ic);
+      const DirectSourceT<kKind != 2> src{par, L};  // the DMF step does not return dF/dc
+      // max / min over the trial velocities from the dense pass: ordered keys [S,N], read once per pick (before the
+      // sweep: their latency hides behind it) and reset to the identity for the next evaluation
+      const bool normalised = kKind == 2 && (compress == ADSURF_COMPRESS_EXP || compress == ADSURF_COMPRESS_LOG ||
+                                             compress == ADSURF_COMPRESS_NORM);
+      unsigned long long key_max = 0ull, key_min = 0ull;
+      if (normalised) {
+        unsigned long long* kmax = reinterpret_cast<unsigned long long*>(pmax) + idx;
+        unsigned long long* kmin = reinterpret_cast<unsigned long long*>(pmin) + idx;
+        key_max = *kmax;
+        key_min = *kmin;
+        if (active) {
+          *kmax = 0ull;
+          *kmin = 0ull;
+        }
+      }
+      typename std::conditional<kGlobal, GlobalStore, PlainStore<kWarp>>::type store;
+      store.p = estp;
+      if constexpr (kGlobal) store.pol = slab_policy;
+      const double v = sample_forward_store(src, z, store);
+      if (F && active) F[idx] = v;
+      double seed = 1.0;
+      if (kKind == 0) seed = gF[idx];
+      if (kKind == 2) {
+        double n = 1.0;
+        if (normalised) {
+          n = order_value(key_max) + order_value(key_min);  // max - min (the minimum travels negated)
+          if (norm && active) norm[idx] = n;
+        }
+        double absG;
+        dmf_compress(compress, v, n, 1.0 / (double)N, absG, seed);
+        double lsum = warp_sum(active ? absG : 0.0);
+        if (lane == 0) lossw[warp] = lsum;
+      }
+      if (kKind != 2 || with_grad) {
+        double gk;
+        if (kKind == 1) {
+          JacSink sink{Jd ? Jd + idx * L : nullptr, Ja ? Ja + idx * L : nullptr, Jb ? Jb + idx * L : nullptr,
+                       Jrho ? Jrho + idx * L : nullptr, active};
+          gk = sample_adjoint(src, z, seed, v, store, sink);
+        } else if (kGlobal) {
+          FoldSink sink{acc, lane};
+          gk = sample_adjoint(src, z, active ? seed : 0.0, v, store, sink);  // overhang lanes: zero seed
+        } else {
+          ReduceSink sink{acc, L, lane};
+          gk = sample_adjoint(src, z, active ? seed : 0.0, v, store, sink);
+        }
+        if (gc && active) gc[idx] = -ic * z.ic * gk;  // gk = dDelta/d(k/omega), k/omega = 1/c
+      }
+    }
+    __syncthreads();
+    if (kKind != 1) {
+      for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
+        double v = 0.0;
+        if (kGlobal) {
+          v = fold_total(accs, pp.wpb, L, i % L, i / L);
+        } else {
+          for (int w = 0; w < pp.wpb; ++w) v += accs[(size_t)w * 4 * L + i];
+        }
+        part[((size_t)s * pp.bpm + blk) * 4 * L + i] = v;
+      }
+      if (kKind == 2 && threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < pp.wpb; ++w) v += lossw[w];
+        loss_part[(size_t)s * pp.bpm + blk] = v;
+      }
+    }
+    if (kKind == 2 && model_done) {
+      // Optimiser step of model s by the block that delivers its last partials (threadFenceReduction pattern):
+      // every block publishes its partials, takes a ticket, and the holder of the last ticket sees them all.
+      __shared__ int last_block;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int ticket = atomicAdd(&model_done[s], 1);
+        last_block = ticket == pp.bpm - 1;
+        if (last_block) model_done[s] = 0;  // ready for the next iteration
+      }
+      __syncthreads();
+      if (last_block) {
+        __threadfence();
+        const EnsStep T = ens_step_of(E);
+        for (int l = threadIdx.x; l < L; l += blockDim.x) ens_prepare_cell(E, s, l);
+        __syncthreads();
+        for (int l = threadIdx.x; l < L; l += blockDim.x) ens_adam_cell<false>(E, T, s, l, EnsCell{});
+        if (threadIdx.x == 0) {  // the last MODEL to finish advances the iteration index
+          __threadfence();
+          if (atomicAdd(&E.counter[1], 1) == E.S - 1) {
+            E.counter[1] = 0;
+            E.counter[0] = T.j + 1;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void k_loss_reduce(const double* __restrict__ loss_part, int bpm, int N, double* __restrict__ loss, int S) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double v = 0.0;
+  for (int b = 0; b < bpm; ++b) v += loss_part[(size_t)s * bpm + b];
+  loss[s] = v / (double)N;
+}
+
+// FP64 peak probe: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) k_dfma_probe(int iters, double* __restrict__ out, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0,
+         x6 = x0 + 6.0, x7 = x0 + 7.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 12345.678) out[0] = r;  // never true; keeps the chains alive
 }
 
 // modal dispersion curves (N1): the reference's sequential root search, one thread per model (adsurf_dispersion.cuh)
@@ -1152,7 +1181,12 @@ inline int launch_points_bwd(const PointsPlan& pp, int S, int L, int N, const do
                              const double* beta, const double* rho, const double* t, const double* c,
                              const double* gF, double* F, double* gc, double* part, double* estore, double* Jd,
                              double* Ja, double* Jb, double* Jrho, double* pmax, double* pmin, int nchunk,
-                             int compress, int with_grad, double* norm, double* loss_part, int nsm, cudaStream_t st) {
+                             int compress, int with_grad, double* norm, double* loss_part, int nsm, cudaStream_t st,
+                             int* model_done = nullptr, const EnsArgs* fused = nullptr) {
+  EnsArgs E;
+  memset(&E, 0, sizeof(E));
+  if (fused) E = *fused;
+  if (!fused) model_done = nullptr;
   const size_t smem = points_smem(pp, L);
   const long long total_vb = (long long)S * pp.bpm;
   if (total_vb > 0x7fffffffLL) return ADSURF_E_SHAPE;
@@ -1171,13 +1205,13 @@ inline int launch_points_bwd(const PointsPlan& pp, int S, int L, int N, const do
     if (grid > total_vb) grid = total_vb;
     kern<<<(unsigned)grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F, gc, part,
                                                 estore, Jd, Ja, Jb, Jrho, pmax, pmin, nchunk, compress, with_grad,
-                                                norm, loss_part);
+                                                norm, loss_part, model_done, E);
   } else {
     auto kern = k_points_bwd<kKind, false>;
     if (set_smem(kern, smem)) return ADSURF_E_CUDA;
     kern<<<(unsigned)total_vb, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F, gc,
                                                     part, nullptr, Jd, Ja, Jb, Jrho, pmax, pmin, nchunk, compress,
-                                                    with_grad, norm, loss_part);
+                                                    with_grad, norm, loss_part, model_done, E);
   }
   return check_launch();
 }
@@ -1423,7 +1457,7 @@ struct DmfLaunch {
 static int dmf_launch(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
                       const double* c, const double* C, int S, int L, int N, int K, int compress, int with_grad,
                       double* F, double* norm, void* ws, size_t ws_bytes, bool zero_keys, cudaStream_t st,
-                      DmfLaunch& out) {
+                      DmfLaunch& out, int* model_done = nullptr, EnsArgs* fused = nullptr) {
   if (!d || !alpha || !beta || !rho || !t || !c) return ADSURF_E_NULL;
   if (compress < ADSURF_COMPRESS_NONE || compress > ADSURF_COMPRESS_NORM) return ADSURF_E_ARG;
   const bool normalised =
@@ -1462,9 +1496,14 @@ static int dmf_launch(const double* d, const double* alpha, const double* beta, 
   out.pp = pp;
   out.part = part;
   out.loss_part = loss_part;
+  if (fused) {  // the optimiser step reads the block partials of this launch
+    fused->part = part;
+    fused->loss_part = loss_part;
+    fused->bpm = pp.bpm;
+  }
   return launch_points_bwd<2>(pp, S, L, N, d, alpha, beta, rho, t, c, nullptr, F, nullptr, part, estore, nullptr,
                               nullptr, nullptr, nullptr, pmax, pmin, 0, compress, with_grad, norm, loss_part,
-                              nsm, st);
+                              nsm, st, model_done, fused);
 }
 
 int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, const double* rho, const double* t,
@@ -1486,7 +1525,7 @@ int adsurf_dmf_step(const double* d, const double* alpha, const double* beta, co
   return ADSURF_OK;
 }
 
-static int ens_launch(EnsArgs& A, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int ens_scratch(EnsArgs& A, void* ws, size_t ws_bytes) {
   const size_t SL = (size_t)A.S * A.L;
   if (SL > 0x7fffffffull) return ADSURF_E_SHAPE;
   if (!ws || ws_bytes < adsurf_workspace_bytes(ADSURF_OP_ENSEMBLE_STEP, A.S, A.L, 1, 0)) return ADSURF_E_WORKSPACE;
@@ -1499,6 +1538,13 @@ static int ens_launch(EnsArgs& A, void* ws, size_t ws_bytes, cudaStream_t st) {
   A.bo = w + 5 * SL;
   A.dold = w + 6 * SL;
   A.shh = w + 7 * SL;
+  return ADSURF_OK;
+}
+
+static int ens_launch(EnsArgs& A, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int rc = ens_scratch(A, ws, ws_bytes);
+  if (rc) return rc;
+  const size_t SL = (size_t)A.S * A.L;
   const int threads = 128;
   if (!(A.dh > 0.0) && A.L <= threads) {
     const int mpb = threads / A.L;
@@ -1546,7 +1592,7 @@ size_t adsurf_inversion_workspace_bytes(const adsurf_inversion* p) {
   const bool normalised = (p->compress == ADSURF_COMPRESS_EXP || p->compress == ADSURF_COMPRESS_LOG ||
                            p->compress == ADSURF_COMPRESS_NORM);
   return align256(adsurf_workspace_bytes(ADSURF_OP_DMF_STEP, p->S, p->L, p->N, normalised ? p->K : 0)) +
-         adsurf_workspace_bytes(ADSURF_OP_ENSEMBLE_STEP, p->S, p->L, 1, 0);
+         adsurf_workspace_bytes(ADSURF_OP_ENSEMBLE_STEP, p->S, p->L, 1, 0) + align256((size_t)p->S * sizeof(int));
 }
 
 int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, void* stream) {
@@ -1562,16 +1608,12 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
   if (!ws || ws_bytes < need || need == 0) return ADSURF_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t ens_bytes = adsurf_workspace_bytes(ADSURF_OP_ENSEMBLE_STEP, p->S, p->L, 1, 0);
-  const size_t dmf_bytes = need - ens_bytes;
-  DmfLaunch dl;
-  // (the order keys of the dense pass are reset by their reader: ws zero-filled before the first call of a loop)
-  const int rc = dmf_launch(p->d, p->alpha, p->b, p->rho, p->t, p->c, p->C, p->S, p->L, p->N, p->K, p->compress, 1,
-                            nullptr, nullptr, ws, dmf_bytes, false, st, dl);
-  if (rc) return rc;
+  const size_t done_bytes = align256((size_t)p->S * sizeof(int));
+  const size_t dmf_bytes = need - ens_bytes - done_bytes;
   EnsArgs A;
   memset(&A, 0, sizeof(A));
   A.b = p->b; A.d = p->d; A.alpha = p->alpha; A.rho = p->rho; A.mb = p->mb; A.vb = p->vb; A.md = p->md; A.vd = p->vd;
-  A.part = dl.part; A.loss_part = dl.loss_part; A.bpm = dl.pp.bpm; A.npicks = p->N; A.loss = p->loss;
+  A.npicks = p->N; A.loss = p->loss;
   A.b0 = p->b0; A.a0 = p->alpha0; A.r0 = p->rho0; A.lob = p->lower_b; A.upb = p->upper_b;
   A.mind = p->layer_mindepth; A.maxd = p->layer_maxdepth;
   A.halo = p->S_all > p->S ? p->halo : nullptr; A.row0 = p->row0; A.S_all = p->S_all;
@@ -1580,6 +1622,21 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
   A.ratio = p->vp_vs_ratio; A.dv = p->damp_vertical; A.dh = p->damp_horizontal; A.lr = p->lr; A.gamma = p->gamma;
   A.beta1 = p->beta1; A.beta2 = p->beta2; A.eps = p->eps; A.step_size = p->step_size;
   A.counter = p->counter; A.T = p->T; A.loss_hist = p->loss_hist; A.iter_b = p->iter_b_hist; A.iter_d = p->iter_d_hist;
+  const int rs = ens_scratch(A, (char*)ws + dmf_bytes, ens_bytes);
+  if (rs) return rs;
+  // Without horizontal damping no model needs another model's data: the block of the pointwise kernel that delivers
+  // a model's last partials runs that model's optimiser step in the same launch (ticket counters model_done[S],
+  // zero between calls).  With it, the sign field of the neighbouring models is a grid-wide dependency: two more
+  // launches.  (The order keys of the dense pass and the counters are reset by their readers: ws zero-filled before
+  // the first call of a loop.)
+  const bool in_kernel = !(p->damp_horizontal > 0.0);
+  int* model_done = (int*)((char*)ws + dmf_bytes + ens_bytes);
+  DmfLaunch dl;
+  const int rc = dmf_launch(p->d, p->alpha, p->b, p->rho, p->t, p->c, p->C, p->S, p->L, p->N, p->K, p->compress, 1,
+                            nullptr, nullptr, ws, dmf_bytes, false, st, dl, in_kernel ? model_done : nullptr,
+                            in_kernel ? &A : nullptr);
+  if (rc || in_kernel) return rc;
+  A.part = dl.part; A.loss_part = dl.loss_part; A.bpm = dl.pp.bpm;
   return ens_launch(A, (char*)ws + dmf_bytes, ens_bytes, st);
 }
 

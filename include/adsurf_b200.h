@@ -183,8 +183,11 @@ int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho,
                               double* iter_b, double* iter_d, void* ws, size_t ws_bytes, void* stream);
 
 /* One WHOLE inversion iteration, replayable: adsurf_dmf_step (without its two reduction launches) followed by the
- * optimiser step above, with the iteration index j read from DEVICE memory — so the launch sequence (3-4 kernels)
- * can be captured once in a CUDA graph and replayed `T` times with no host work in between.
+ * optimiser step above, with the iteration index j read from DEVICE memory — so the launch sequence can be captured
+ * once in a CUDA graph and replayed `T` times with no host work in between.  Launches per iteration: the dense pass
+ * (normalised modes only) + the pointwise forward/adjoint kernel, in which the block that delivers a model's last
+ * partial sums runs that model's optimiser step; with damp_horizontal > 0 the optimiser step is two further launches
+ * (the sign field of the neighbouring models is a grid-wide dependency).
  *   counter[0] (device int) = j, the 0-based index of the iteration about to run; the last kernel increments it.
  *               counter[1] is scratch (must be 0 at the first call).
  *   learning rate of iteration j: lr * gamma^(j / step_size) (torch StepLR stepped after every optimiser step);
