@@ -442,9 +442,10 @@ class InversionLoop:
         self.halo_fn = halo_fn
         self.halo = torch.zeros((4, L), **f64) if halo_fn is not None else None
         self.S_all = S if S_all is None else int(S_all)
-        # dense pass (normalised modes) + pointwise forward/adjoint, whose last block per model runs the optimiser step
-        # (two more launches with horizontal damping: the neighbours' sign field is a grid-wide dependency)
-        self.kernels_per_iteration = (1 if normalised else 0) + 1 + (2 if damp_horizontal > 0 else 0)
+        # dense pass (normalised modes) + pointwise forward/adjoint + optimiser step (its own launch for ensembles, two
+        # with horizontal damping; inside the pointwise kernel for single-model problems)
+        small = S * plan_describe(OP_DMF_STEP, S, L, c.shape[1])["bpm"] <= torch.cuda.get_device_properties(dev).multi_processor_count
+        self.kernels_per_iteration = (1 if normalised else 0) + 1 + (2 if damp_horizontal > 0 else (0 if small else 1))
         P = InversionStruct()
         P.S, P.L, P.N, P.K, P.T = S, L, c.shape[1], (C.shape[1] if self.C is not None else 0), self.T
         P.t, P.c, P.C = t.data_ptr(), c.data_ptr(), (self.C.data_ptr() if self.C is not None else None)

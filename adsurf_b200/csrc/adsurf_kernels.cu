@@ -1624,12 +1624,16 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
   A.counter = p->counter; A.T = p->T; A.loss_hist = p->loss_hist; A.iter_b = p->iter_b_hist; A.iter_d = p->iter_d_hist;
   const int rs = ens_scratch(A, (char*)ws + dmf_bytes, ens_bytes);
   if (rs) return rs;
-  // Without horizontal damping no model needs another model's data: the block of the pointwise kernel that delivers
-  // a model's last partials runs that model's optimiser step in the same launch (ticket counters model_done[S],
-  // zero between calls).  With it, the sign field of the neighbouring models is a grid-wide dependency: two more
-  // launches.  (The order keys of the dense pass and the counters are reset by their readers: ws zero-filled before
-  // the first call of a loop.)
-  const bool in_kernel = !(p->damp_horizontal > 0.0);
+  // Small problems (single-model inversions: fewer blocks than SMs) are latency-bound, and there a launch is worth
+  // saving: the block of the pointwise kernel that delivers a model's last partials runs that model's optimiser
+  // step in the same launch (ticket counters model_done[S], zero between calls).  For ensembles the optimiser step is
+  // a launch of its own, parallel over all (model, layer) cells — run inside the pointwise kernel it would
+  // serialise ~10 us of dependent loads per model behind that model's block (measured: 1024 models 3 870 instead of
+  // 4 560 it/s) — and with horizontal damping two launches (the neighbours' sign field is a grid-wide dependency).
+  // (The order keys of the dense pass and the counters are reset by their readers: ws zero-filled before the first
+  // call of a loop.)
+  const PointsPlan ppq = plan_points(p->S, p->L, p->N, true, sm_count());
+  const bool in_kernel = !(p->damp_horizontal > 0.0) && (long long)p->S * ppq.bpm <= sm_count();
   int* model_done = (int*)((char*)ws + dmf_bytes + ens_bytes);
   DmfLaunch dl;
   const int rc = dmf_launch(p->d, p->alpha, p->b, p->rho, p->t, p->c, p->C, p->S, p->L, p->N, p->K, p->compress, 1,

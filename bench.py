@@ -371,7 +371,7 @@ def main():
             "it_per_s_incl_setup": args.inversion_iters / total_s, "loop_plus_gather_s": loop_s,
             "pointwise_samples_per_s": args.inversion_iters * S_all * 300 / loop_s,
             "median_first_loss": rec["median_first_loss"], "median_last_loss": rec["median_last_loss"],
-            "kernels_per_iteration": 1}
+            "kernels_per_iteration": 2}
         if world == 1:
             CE.config2(5), CE.config3(5)
             c2, c3, c4 = CE.config2(600), CE.config3(400), CE.config4(300, S=1024)

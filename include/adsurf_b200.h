@@ -185,9 +185,9 @@ int adsurf_ensemble_adam_step(double* b, double* d, double* alpha, double* rho,
 /* One WHOLE inversion iteration, replayable: adsurf_dmf_step (without its two reduction launches) followed by the
  * optimiser step above, with the iteration index j read from DEVICE memory — so the launch sequence can be captured
  * once in a CUDA graph and replayed `T` times with no host work in between.  Launches per iteration: the dense pass
- * (normalised modes only) + the pointwise forward/adjoint kernel, in which the block that delivers a model's last
- * partial sums runs that model's optimiser step; with damp_horizontal > 0 the optimiser step is two further launches
- * (the sign field of the neighbouring models is a grid-wide dependency).
+ * (normalised modes only) + the pointwise forward/adjoint kernel + the optimiser step (one launch; two with
+ * damp_horizontal > 0: the sign field of the neighbouring models is a grid-wide dependency; none for problems with
+ * fewer blocks than SMs, where the block that delivers a model's last partial sums runs its optimiser step).
  *   counter[0] (device int) = j, the 0-based index of the iteration about to run; the last kernel increments it.
  *               counter[1] is scratch (must be 0 at the first call).
  *   learning rate of iteration j: lr * gamma^(j / step_size) (torch StepLR stepped after every optimiser step);
