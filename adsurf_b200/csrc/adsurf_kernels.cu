@@ -9,20 +9,23 @@
 //   * one thread per (model, period, trial velocity) sample; lanes of a warp run over PERIODS at a fixed trial
 //     velocity, so det[s,k,f] is written coalesced and the three-way branch "c <,==,> layer velocity" is
 //     warp-uniform (it does not depend on the period);
-//   * a block = (model, velocity chunk, group of <= 4 period tiles).  Per-model layer records (1/alpha, 1/beta,
+//   * a block = (model, velocity chunk, group of period tiles) chosen by a host-side planner that follows the
+//     device's SM count (plan_grid).  Per-model layer records (1/alpha, 1/beta,
 //     2 beta^2, rho, 1/rho, d, ...) are staged once per block in shared memory.  The layers are swept in
 //     frequency-free variables (CA(omega) = D^-1 CA~ D, D = diag(1, w, 1, w, w^2)): everything about a layer
 //     except its two phases depends on (velocity, layer) only — sqrt(|1/c^2 - 1/v^2|), its reciprocal, the
 //     phase per unit omega, the eight coefficient scalars, the regime flags, the adjoint's chain constants —
-//     and is computed once per 8 velocities into a shared table read by every lane as 16-byte broadcasts
-//     (TableSource); a lane spends two multiplies on a layer's set-up;
+//     and is computed once per <= 8 velocities into a shared table read by every lane as 16-byte broadcasts
+//     (TableSource); a lane spends two multiplies on a layer's set-up; sentinel entries bracket every velocity's
+//     layers, so the sweeps walk the table (and the store slots, and the accumulators) with running pointers;
 //   * the 5-component compound state lives in registers; the 5x5 Dunkin matrix is never formed: the layer
 //     product uses its rank structure (two rank-one couplings around the Kronecker product of the P and S
 //     blocks), 33 FMAs per product; elementary functions are inline (table-driven exp, Cody-Waite sincos);
 //   * the adjoint is a hand-derived reverse sweep: pass 1 (bottom-up) stores, per layer, the row vector
 //     E_{m+1} and the transcendental results (up to 9 doubles per thread) in a per-resident-warp slab of global
-//     memory that stays in the persisting part of L2; pass 2 (top-down) carries the column vector
-//     s_m = CA_{m-1}...CA_0 e_0, reloads the stored values one layer ahead, and contracts
+//     memory that stays in L2 (evict_last accesses; adsurf_init optionally reserves the persisting carve-out);
+//     pass 2 (top-down) carries the column vector s_m = CA_{m-1}...CA_0 e_0, requests the stored values a whole
+//     layer ahead into registers of their own, and contracts
 //     dDelta = E_{m+1} . dCA_m . s_m analytically into (d, alpha, beta, rho) while advancing s in the same
 //     expressions — no transcendental is evaluated twice; the kernel is persistent (3 blocks x 4 warps per SM:
 //     the register file allows 3 warps per scheduler up to 170 registers).  In both passes consecutive layers of
@@ -30,8 +33,13 @@
 //     stored transcendentals) read one layer ahead and the gradient sink deferred by one layer;
 //   * per-model gradient sums: one warp fold + per-lane shared accumulators -> one partial per block ->
 //     deterministic second-stage reduce (no atomics);
-//   * the dense forward pass fuses max/min over the trial velocities (what the DMF needs) and an optional
-//     sign bitmap, so det never has to be materialised.
+//   * the dense forward pass fuses max/min over the trial velocities (what the DMF needs: combined across blocks
+//     with ordered-key 64-bit atomics) and an optional sign bitmap, so det never has to be materialised;
+//   * one iteration of an inversion loop is a replayable launch sequence (adsurf_inversion_step): the iteration
+//     index, StepLR and the Adam bias corrections come from a device counter, the optimiser step (velocity chain,
+//     Tikhonov terms, projection, Adam, history) runs one thread per (model, layer);
+//   * dispersion curves: the reference's sequential root search, one thread per model (adsurf_dispersion.cuh);
+//     Monte-Carlo ensembles: Philox4x32-10 normals on the device.
 // No tensor cores (not a contraction), no library calls on the path.
 
 #include <cuda_runtime.h>

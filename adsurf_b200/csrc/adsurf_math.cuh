@@ -1,6 +1,6 @@
 // adsurf_math.cuh — per-sample arithmetic of the Rayleigh secular function and its hand-derived
 // adjoint.  Shared by the CUDA kernels (adsurf_kernels.cu) and by the host-side math check that
-// tests/ builds from this same header (tests/host_math/host_math.cu) — the check compiles these
+// tests/ builds from this same header (tests/host_math/host_math.cpp) — the check compiles these
 // functions for the CPU so the adjoint algebra can be verified against the oracle without a GPU.
 // The product library never runs this code on the host.
 //
