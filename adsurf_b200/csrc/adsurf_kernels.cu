@@ -141,7 +141,10 @@ struct JacSink {  // write this sample's Jacobian rows
   }
 };
 
-// stage the per-model layer constants
+// stage the per-model layer constants; kBounds: also the phase bounds the dense sweeps test once per sample
+// (TableSource::small_phases) — a serial loop over the layers on one thread, which the pointwise kernels (one
+// sample per thread and staging) skip
+template <bool kBounds>
 __device__ __forceinline__ void stage_params(double* __restrict__ par, const double* __restrict__ d,
                                              const double* __restrict__ alpha, const double* __restrict__ beta,
                                              const double* __restrict__ rho, int s, int L) {
@@ -150,7 +153,7 @@ __device__ __forceinline__ void stage_params(double* __restrict__ par, const dou
     stage_one(par, L, m, d[(size_t)s * L + m], alpha[(size_t)s * L + m], beta[(size_t)s * L + m],
               rho[(size_t)s * L + m]);
   }
-  if (threadIdx.x == blockDim.x - 1) stage_bounds(par, L, d + (size_t)s * L, beta + (size_t)s * L);
+  if (kBounds && threadIdx.x == blockDim.x - 1) stage_bounds(par, L, d + (size_t)s * L, beta + (size_t)s * L);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -229,7 +232,7 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
   double* hks = ics + ((gp.tc + 1) & ~1);               // [wpb*32][2]: omega/alpha_hs, omega/beta_hs per lane
   const BlockCoord bc = block_coord(blockIdx.x, gp);
   const int s = bc.s;
-  stage_params(par, d, alpha, beta, rho, s, L);
+  stage_params<true>(par, d, alpha, beta, rho, s, L);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ft = bc.fg * gp.wpb + warp;
   const bool live = ft < gp.nft;  // warps beyond the last period tile only help filling the table
@@ -350,7 +353,7 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
     const BlockCoord bc = block_coord(vb, gp);
     const int s = bc.s;
     __syncthreads();  // previous virtual block has flushed its accumulators
-    stage_params(par, d, alpha, beta, rho, s, L);
+    stage_params<true>(par, d, alpha, beta, rho, s, L);
     for (int i = threadIdx.x; i < gp.wpb * kAccRow * (L + 1); i += blockDim.x) accs[i] = 0.0;
     const int ft = bc.fg * gp.wpb + warp;
     const bool live = ft < gp.nft;
@@ -681,7 +684,7 @@ __global__ void __launch_bounds__(128) k_points_fwd(const double* __restrict__ d
   double* par = smem + kSmemHead;
   const int s = blockIdx.x / pp.bpm;
   const int blk = blockIdx.x - s * pp.bpm;
-  stage_params(par, d, alpha, beta, rho, s, L);
+  stage_params<false>(par, d, alpha, beta, rho, s, L);
   __syncthreads();
   const int i = blk * blockDim.x + threadIdx.x;
   if (blk * blockDim.x + (threadIdx.x & ~31) >= N) return;  // whole warps only: the sweep votes across the warp
@@ -750,7 +753,7 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
     const int s = vb / pp.bpm;
     const int blk = vb - s * pp.bpm;
     __syncthreads();
-    stage_params(par, d, alpha, beta, rho, s, L);
+    stage_params<false>(par, d, alpha, beta, rho, s, L);
     for (int i = threadIdx.x; i < pp.wpb * acc_per_warp + pp.wpb; i += blockDim.x) accs[i] = 0.0;
     __syncthreads();
     const int unit = blk * pp.wpb + warp;
