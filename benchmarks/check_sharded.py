@@ -46,9 +46,11 @@ def main():
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    S = 64 * world + 3  # uneven shards
-    out = {"world": world, "models": S, "backend": dist.get_backend()}
-    for name, dh in (("damp_h=0 (graph replay)", 0.0), ("damp_h=0.003 (halo exchange)", 0.003)):
+    out = {"world": world, "backend": dist.get_backend()}
+    # uneven shards (padded list all-gather) and even ones (single all_gather_into_tensor), with / without damping
+    for name, S, dh in (("131 models, damp_h=0 (graph replay)", 64 * world + 3, 0.0),
+                        ("131 models, damp_h=0.003 (halo exchange)", 64 * world + 3, 0.003),
+                        ("128 models, damp_h=0.003 (halo exchange, even shards)", 64 * world, 0.003)):
         got = run(S, dh)
         assert got[3]["fused"]
         dist.barrier()
