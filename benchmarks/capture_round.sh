@@ -59,6 +59,8 @@ persist)
 configs_persist)
   timeout 900 python benchmarks/configs_e2e.py --only 4 > gpurun_out/configs_c4_nopersist.jsonl 2>&1
   ADSURF_PERSIST_L2=1 timeout 900 python benchmarks/configs_e2e.py --only 4 > gpurun_out/configs_c4_persist.jsonl 2>&1 ;;
+dispersion)
+  timeout 900 python benchmarks/dispersion_bench.py > gpurun_out/dispersion_bench.json 2> gpurun_out/dispersion_bench.err ;;
 variants)
   bash benchmarks/run_variants.sh > gpurun_out/run_variants.out 2>&1 ;;
 sharded)
