@@ -309,7 +309,7 @@ def dmf_step(d, a, b, rho, t, c, C, compress, with_grad=True, want_F=False, want
 
 
 def dispersion_curves(d, a, b, rho, t, nmodes, dc):
-    """(c [S,nmodes,NF], status int32 [S]): modal phase velocities by the reference's root search, one thread per model"""
+    """(c [S,nmodes,NF], status int32 [S]): modal phase velocities by the reference's root search, one warp per model"""
     global launch_count
     _req(d, a, b, rho, t)
     S, L = d.shape

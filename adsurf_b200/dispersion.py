@@ -2,7 +2,7 @@
 
 `dispersion_curves` — the reference's own root search (`_surf96.getc/getsol/nevill`: ladder bracketing from the
 previous period's root, Neville refinement to 1e-6 relative, mode bookkeeping with `clow`, `one = 1e-2`,
-`onea = 1.5`, zeros for absent modes) run by the CUDA kernel `k_dispersion`, one thread per model (C ABI
+`onea = 1.5`, zeros for absent modes) run by the CUDA kernel `k_dispersion`, one warp per model (C ABI
 `adsurf_dispersion_curves`).  Same brackets, same iterates: mode indices are the reference's and roots agree with
 `_surf96.surf96` within 1e-6 km/s.  The search is sequential within a model, so the parallel axis is the ensemble:
 the curves of 4096 models cost what one costs.  `cal_dispersion_curve(..., device="cuda")` calls it.
