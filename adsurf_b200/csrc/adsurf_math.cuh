@@ -24,8 +24,8 @@ constexpr double kTwoPi = 6.283185307179586;  // 2.0 * np.pi
 constexpr double kLn10 = 2.302585092994046;
 constexpr int kWarp = 32;
 constexpr int kNumPar = 10;  // staged per-layer record (80 bytes: five 16-byte loads)
-// 1/alpha, 1/beta, 2 beta^2, rho, 1/rho, d | adjoint only: 1/alpha^3, 1/beta^3, 4 beta, (pad)
-enum { P_IA = 0, P_IB = 1, P_TB2 = 2, P_RHO = 3, P_IR = 4, P_D = 5, P_IA3 = 6, P_IB3 = 7, P_CB = 8 };
+// 1/alpha, 1/beta, 2 beta^2, rho, 1/rho, d | adjoint only: 1/alpha^3, 1/beta^3, 4 beta | 2 beta^2 rho
+enum { P_IA = 0, P_IB = 1, P_TB2 = 2, P_RHO = 3, P_IR = 4, P_D = 5, P_IA3 = 6, P_IB3 = 7, P_CB = 8, P_GKR = 9 };
 
 // ---- inline elementary functions -------------------------------------------------------------
 // Straight-line (call-free, branch-free on the common path) so that the P and S terms of a layer
@@ -600,6 +600,7 @@ template <int kN, bool kFast = false>
 ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ par, int m, double ic) {
   const double* __restrict__ pr = par + m * kNumPar;
   const double sa = pr[P_IA], sb = pr[P_IB], dm = pr[P_D], rho = pr[P_RHO], ir = pr[P_IR], gk = pr[P_TB2];
+  const double gkr = pr[P_GKR];  // gk rho, staged per (model, layer)
   const double da = (ic + sa) * fabs(ic - sa), db = (ic + sb) * fabs(ic - sb);
   double na, nb, ina, inb;
   if (kFast) {
@@ -623,11 +624,12 @@ ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ 
   tab[T_INA] = ina;
   tab[T_INB] = inb;
   tab[T_IR] = ir;
+  const double t1 = (-2.0 * ic2) * g1;  // (-2 ic2) does not depend on the layer: hoisted by the pointwise sweeps
   tab[T_TG] = -2.0 * gam;
-  tab[T_AR] = gam * gk * rho;
+  tab[T_AR] = gam * gkr;
   tab[T_KR] = ic2 * ir;
-  tab[T_T1] = -2.0 * ic2 * g1;
-  tab[T_BR] = g1 * g1 * rho;
+  tab[T_T1] = t1;
+  tab[T_BR] = g1 * (g1 * rho);
   tab[T_GK] = gk;
   tab[T_G1] = g1;
   const int fl = (ic < sa ? F_LTP : 0) | (da > 0.0 ? F_POSP : 0) | (ic < sb ? F_LTS : 0) | (db > 0.0 ? F_POSS : 0);
@@ -637,8 +639,8 @@ ADSURF_HD void table_entry(double* __restrict__ tab, const double* __restrict__ 
   if (kN > kTabFwd) {
     tab[T_TQB] = kFast ? (ic < sb ? -pr[P_IB3] : pr[P_IB3]) * (inb * inb) : pr[P_IB3] / ((ic + sb) * (ic - sb));
     tab[T_CB] = pr[P_CB];
-    tab[T_C1] = 2.0 * gam * rho;
-    tab[T_C3] = 2.0 * g1 * ic2 * rho;
+    tab[T_C1] = (2.0 * ic2) * gkr;  // 2 gam rho
+    tab[T_C3] = -(t1 * rho);        // 2 g1 ic2 rho
   }
 }
 
@@ -1093,7 +1095,7 @@ ADSURF_HD void stage_one(double* __restrict__ par, int L, int m, double dm, doub
   par[m * kNumPar + P_IA3] = 1.0 / (a * a * a);
   par[m * kNumPar + P_IB3] = 1.0 / (b * b * b);
   par[m * kNumPar + P_CB] = 4.0 * b;
-  par[m * kNumPar + 9] = 0.0;
+  par[m * kNumPar + P_GKR] = (2.0 * b * b) * r;
   if (m == L - 1) {
     par[kNumPar * L + 0] = a;
     par[kNumPar * L + 1] = b;
