@@ -1,11 +1,13 @@
 // adsurf_dispersion.cuh — modal dispersion curves by the classical CPS / disba root search.
-// Shared by the CUDA kernel k_dispersion (one thread per model) and by the host-side check that tests/ builds from
+// Shared by the CUDA kernel k_dispersion (one warp per model) and by the host-side check that tests/ builds from
 // this same header (tests/host_math/host_math.cpp); the product library never runs it on the host.
 //
 // Same control flow as the reference's scalar solver (/root/reference/ADsurf/_surf96.py: gtsolh :576-594, getc
 // :596-691, getsol :543-574, nevill :452-541, dltar4 :217-297 with its per-layer normalisation), so that the same
-// brackets and the same iterates come out: the search is strictly sequential within a model (period k starts from the
-// root of period k-1, mode n from mode n-1), so the parallel axis is the ensemble — 4096 curves cost what one costs.
+// brackets and the same iterates come out.  The search is strictly sequential within a model (period k starts from the
+// root of period k-1, mode n from mode n-1) and so is the layer product of one evaluation; what is parallel inside an
+// evaluation is the per-layer preparation (square roots, divisions, sincos, exp: most of its cost), which the lanes of
+// the model's warp share out; the ensemble spreads over the warps.
 #pragma once
 #include <math.h>
 
@@ -28,91 +30,190 @@ ADSURF_HD void disp_sincos(double x, double* sn, double* cs) {
 #endif
 }
 
-// Same control flow as the reference's scalar solver (_surf96.py: gtsolh :576-594, getc :596-691, getsol
-// :543-574, nevill :452-541, dltar4 :217-297 with its per-layer normalisation) so that the same brackets and the same
-// iterates come out: the search is strictly sequential within a model (period k starts from the root of period
-// k-1, mode n from mode n-1), so the parallel axis is the ensemble — 4096 curves cost what one costs.
 struct DispModel {
   const double *d, *a, *b, *rho;
   int L;
 };
 
-// normalised Rayleigh secular function at (period t, phase velocity c): dltar4 with llw = -1
-ADSURF_HDN double disp_delta(const DispModel& M, double t, double c) {
-  double omega = kTwoPi / t;
-  const double wvno = omega / c;
-  omega = fmax(omega, 1.0e-4);
-  const double k2 = wvno * wvno, t2 = -2.0 * k2;
-  const int L = M.L;
-  double xka = omega / M.a[L - 1], xkb = omega / M.b[L - 1];
-  double ra = sqrt((wvno + xka) * fabs(wvno - xka));
-  double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-  double tt = M.b[L - 1] / omega;
-  double gk = 2.0 * tt * tt, gam = gk * k2, g1 = gam - 1.0, r1 = M.rho[L - 1];
-  double e0 = r1 * r1 * (g1 * g1 - gam * gk * ra * rb);
-  double e1 = -r1 * ra;
-  double e2 = r1 * (g1 - gk * ra * rb);
-  double e3 = r1 * rb;
-  double e4 = k2 - ra * rb;
-  for (int m = L - 2; m >= 0; --m) {
-    xka = omega / M.a[m];
-    xkb = omega / M.b[m];
-    tt = M.b[m] / omega;
-    gk = 2.0 * tt * tt;
-    gam = gk * k2;
-    g1 = gam - 1.0;
-    ra = sqrt((wvno + xka) * fabs(wvno - xka));
-    rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-    const double dm = M.d[m];
-    r1 = M.rho[m];
-    // eigenfunction terms (var, :96-157)
-    double cp, w, x, pex, cq, y, z, sex;
-    {
-      const double p = ra * dm;
-      if (wvno < xka) { double sn, cs; disp_sincos(p, &sn, &cs); cp = cs; w = sn / ra; x = -ra * sn; pex = 0.0; }
-      else if (wvno == xka) { cp = 1.0; w = dm; x = 0.0; pex = 0.0; }
-      else { const double fac = p < 16.0 ? exp(-2.0 * p) : 0.0, sn = (1.0 - fac) * 0.5; cp = (1.0 + fac) * 0.5; w = sn / ra; x = ra * sn; pex = p; }
-      const double q = rb * dm;
-      if (wvno < xkb) { double sn, cs; disp_sincos(q, &sn, &cs); cq = cs; y = sn / rb; z = -rb * sn; sex = 0.0; }
-      else if (wvno == xkb) { cq = 1.0; y = dm; z = 0.0; sex = 0.0; }
-      else { const double fac = q < 16.0 ? exp(-2.0 * q) : 0.0, sn = (1.0 - fac) * 0.5; cq = (1.0 + fac) * 0.5; y = sn / rb; z = rb * sn; sex = q; }
-    }
-    const double exa = pex + sex;
-    const double a0 = exa < 60.0 ? exp(-exa) : 0.0;
-    // E <- E . CA in the rank-structured form (adsurf_math.cuh), then the reference's max-normalisation (:278)
-    const double ir = 1.0 / r1, ar = gam * gk * r1, br = g1 * g1 * r1, kr = k2 * ir;
-    const double sa = e0 * ir + e2 * (t2 * gk) + e4 * ar;
-    const double sb = e0 * kr + e2 * (t2 * g1) + e4 * br;
-    const double h1 = sb * y + e1 * cq, h2 = sa * cq + e3 * y;
-    const double h3 = sa * z + e3 * cq, h4 = sb * cq + e1 * z;
-    const double ca = cp * h4 - x * h3 - sb * a0;
-    const double cb = cp * h2 - w * h1 - sa * a0;
-    const double n0 = a0 * e0 + ar * ca + br * cb;
-    const double n1 = cp * h1 - x * h2;
-    const double n2 = a0 * e2 + gk * ca + g1 * cb;
-    const double n3 = cp * h3 - w * h4;
-    const double n4 = a0 * e4 + ir * ca + kr * cb;
-    double big = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
-    if (big < 1.0e-40) big = 1.0;
-    e0 = n0 / big; e1 = n1 / big; e2 = n2 / big; e3 = n3 / big; e4 = n4 / big;
-  }
-  return e0;
+// The normalised Rayleigh secular function (dltar4 with llw = -1, :217-297) in three pieces, so that the scalar
+// evaluator (host check) and the warp-cooperative one (k_dispersion) run the same arithmetic:
+//   per (period, layer):      k_alpha, k_beta, gammk                               (disp_period_consts)
+//   per (evaluation, layer):  the layer's eigenfunction terms and matrix constants (disp_layer_terms: every sqrt,
+//                             division, sincos and exp of the evaluation; no dependence between layers)
+//   bottom-up:                E <- E . CA_m / max|.|                                (disp_layer_apply: 33 FMAs, one
+//                             reciprocal; the only sequential part)
+constexpr int kDispTerms = 16;  // doubles per layer handed from disp_layer_terms to disp_layer_apply
+constexpr int kDispPer = 6;     // doubles per layer kept per period: k_alpha, k_beta, gammk | warp evaluator: d, rho
+enum { DT_CP = 0, DT_W, DT_X, DT_CQ, DT_Y, DT_Z, DT_A0, DT_GK, DT_G1, DT_AR, DT_BR, DT_KR, DT_IR, DT_TGK, DT_TG1 };
+
+ADSURF_HD void disp_period_consts(double* __restrict__ per, double a, double b, double omega) {
+  const double tt = b / omega;
+  per[0] = omega / a;
+  per[1] = omega / b;
+  per[2] = 2.0 * tt * tt;
 }
+
+// eigenfunction terms of one wave type (var, :96-157): cos-like, sin-like / r, r * sin-like, exponent
+ADSURF_HD void disp_eig(double wvno, double xk, double r, double dm, double& cs, double& w, double& x, double& ex) {
+  const double p = r * dm;
+  if (wvno < xk) {
+    double sn;
+    disp_sincos(p, &sn, &cs);
+    w = sn / r;
+    x = -r * sn;
+    ex = 0.0;
+  } else if (wvno == xk) {
+    cs = 1.0;
+    w = dm;
+    x = 0.0;
+    ex = 0.0;
+  } else {
+    const double fac = p < 16.0 ? exp(-2.0 * p) : 0.0, sn = (1.0 - fac) * 0.5;
+    cs = (1.0 + fac) * 0.5;
+    w = sn / r;
+    x = r * sn;
+    ex = p;
+  }
+}
+
+ADSURF_HD void disp_layer_terms(double* __restrict__ q, const double* __restrict__ per, double wvno, double k2, double t2,
+                                double dm, double r1) {
+  const double xka = per[0], xkb = per[1], gk = per[2];
+  const double gam = gk * k2, g1 = gam - 1.0;
+  const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+  const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  double pex, sex;
+  disp_eig(wvno, xka, ra, dm, q[DT_CP], q[DT_W], q[DT_X], pex);
+  disp_eig(wvno, xkb, rb, dm, q[DT_CQ], q[DT_Y], q[DT_Z], sex);
+  const double exa = pex + sex;
+  const double ir = 1.0 / r1;
+  q[DT_A0] = exa < 60.0 ? exp(-exa) : 0.0;
+  q[DT_GK] = gk;
+  q[DT_G1] = g1;
+  q[DT_AR] = gam * gk * r1;
+  q[DT_BR] = g1 * g1 * r1;
+  q[DT_KR] = k2 * ir;
+  q[DT_IR] = ir;
+  q[DT_TGK] = t2 * gk;
+  q[DT_TG1] = t2 * g1;
+}
+
+// half-space vector (:231-244)
+ADSURF_HD void disp_half_terms(double* __restrict__ q, const double* __restrict__ per, double wvno, double k2, double r1) {
+  const double xka = per[0], xkb = per[1], gk = per[2];
+  const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+  const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  const double gam = gk * k2, g1 = gam - 1.0;
+  q[0] = r1 * r1 * (g1 * g1 - gam * gk * ra * rb);
+  q[1] = -r1 * ra;
+  q[2] = r1 * (g1 - gk * ra * rb);
+  q[3] = r1 * rb;
+  q[4] = k2 - ra * rb;
+}
+
+// E <- E . CA in the rank-structured form (adsurf_math.cuh), then the reference's max-normalisation (:278)
+ADSURF_HD void disp_layer_apply(double& e0, double& e1, double& e2, double& e3, double& e4, const double* __restrict__ q) {
+  const double cp = q[DT_CP], w = q[DT_W], x = q[DT_X], cq = q[DT_CQ], y = q[DT_Y], z = q[DT_Z], a0 = q[DT_A0];
+  const double gk = q[DT_GK], g1 = q[DT_G1], ar = q[DT_AR], br = q[DT_BR], kr = q[DT_KR], ir = q[DT_IR];
+  const double sa = e0 * ir + e2 * q[DT_TGK] + e4 * ar;
+  const double sb = e0 * kr + e2 * q[DT_TG1] + e4 * br;
+  const double h1 = sb * y + e1 * cq, h2 = sa * cq + e3 * y;
+  const double h3 = sa * z + e3 * cq, h4 = sb * cq + e1 * z;
+  const double ca = cp * h4 - x * h3 - sb * a0;
+  const double cb = cp * h2 - w * h1 - sa * a0;
+  const double n0 = a0 * e0 + ar * ca + br * cb;
+  const double n1 = cp * h1 - x * h2;
+  const double n2 = a0 * e2 + gk * ca + g1 * cb;
+  const double n3 = cp * h3 - w * h4;
+  const double n4 = a0 * e4 + ir * ca + kr * cb;
+  double big = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
+  if (big < 1.0e-40) big = 1.0;
+  // one reciprocal instead of the reference's five divisions: the values move by an ulp, the signs and the
+  // interpolated roots (converged to 1e-6 c) do not
+  const double ib = 1.0 / big;
+  e0 = n0 * ib; e1 = n1 * ib; e2 = n2 * ib; e3 = n3 * ib; e4 = n4 * ib;
+}
+
+// One thread evaluates everything (host check; any number of layers).
+struct DispScalarEval {
+  DispModel M;
+  double t;
+  ADSURF_HD void set_period(double t_) { t = t_; }
+  ADSURF_HDN double operator()(double c) const {
+    double omega = kTwoPi / t;
+    const double wvno = omega / c;
+    omega = fmax(omega, 1.0e-4);
+    const double k2 = wvno * wvno, t2 = -2.0 * k2;
+    const int L = M.L;
+    double per[kDispPer], q[kDispTerms];
+    disp_period_consts(per, M.a[L - 1], M.b[L - 1], omega);
+    disp_half_terms(q, per, wvno, k2, M.rho[L - 1]);
+    double e0 = q[0], e1 = q[1], e2 = q[2], e3 = q[3], e4 = q[4];
+    for (int m = L - 2; m >= 0; --m) {
+      disp_period_consts(per, M.a[m], M.b[m], omega);
+      disp_layer_terms(q, per, wvno, k2, t2, M.d[m], M.rho[m]);
+      disp_layer_apply(e0, e1, e2, e3, e4, q);
+    }
+    return e0;
+  }
+};
+
+#if defined(__CUDACC__)
+// One warp evaluates: lane m prepares layer m (lanes stride over the layers when there are more than 32), then every
+// lane runs the same bottom-up product over the staged terms.  All lanes must call with the same arguments; all
+// return the same value.  per [L][kDispPer] and lay [L][kDispTerms] are the warp's shared-memory scratch.
+struct DispWarpEval {
+  DispModel M;
+  double* per;
+  double* lay;
+  int lane;
+  double t;
+  __device__ void set_period(double t_) {
+    t = t_;
+    const double omega = fmax(kTwoPi / t, 1.0e-4);
+    __syncwarp();
+    for (int m = lane; m < M.L; m += 32) {
+      double* pm = per + m * kDispPer;
+      disp_period_consts(pm, M.a[m], M.b[m], omega);
+      pm[3] = M.d[m];
+      pm[4] = M.rho[m];
+    }
+    __syncwarp();
+  }
+  __device__ __noinline__ double operator()(double c) const {
+    const double wvno = (kTwoPi / t) / c;
+    const double k2 = wvno * wvno, t2 = -2.0 * k2;
+    const int L = M.L;
+    for (int m = lane; m < L; m += 32) {
+      const double* pm = per + m * kDispPer;
+      if (m < L - 1) disp_layer_terms(lay + m * kDispTerms, pm, wvno, k2, t2, pm[3], pm[4]);
+      else disp_half_terms(lay + m * kDispTerms, pm, wvno, k2, pm[4]);
+    }
+    __syncwarp();
+    const double* q = lay + (L - 1) * kDispTerms;
+    double e0 = q[0], e1 = q[1], e2 = q[2], e3 = q[3], e4 = q[4];
+    for (int m = L - 2; m >= 0; --m) disp_layer_apply(e0, e1, e2, e3, e4, lay + m * kDispTerms);
+    __syncwarp();  // the next evaluation overwrites the staged terms
+    return e0;
+  }
+};
+#endif
 
 ADSURF_HD double np_sign(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : (v == 0.0 ? 0.0 : v)); }
 
 // refine a bracketed root: Neville rational interpolation with bisection safeguards (:452-541)
-ADSURF_HDN double disp_nevill(const DispModel& M, double t, double c1, double c2, double del1, double del2) {
+template <class Eval>
+ADSURF_HDN double disp_nevill(const Eval& ev, double c1, double c2, double del1, double del2) {
   double xs[20], ys[20];
   for (int i = 0; i < 20; ++i) xs[i] = ys[i] = 0.0;
   double c3 = 0.5 * (c1 + c2);
-  double del3 = disp_delta(M, t, c3);
+  double del3 = ev(c3);
   int nev = 1, m = 1;
   for (int it = 0; it < 98; ++it) {
     if (c3 < fmin(c1, c2) || c3 > fmax(c1, c2)) {  // estimate left the bracket: halve instead
       nev = 0;
       c3 = 0.5 * (c1 + c2);
-      del3 = disp_delta(M, t, c3);
+      del3 = ev(c3);
     }
     const double s13 = del1 - del3, s32 = del3 - del2;
     if (np_sign(del3) * np_sign(del1) < 0.0) { c2 = c3; del2 = del3; }
@@ -122,7 +223,7 @@ ADSURF_HDN double disp_nevill(const DispModel& M, double t, double c1, double c2
     const double ss1 = fabs(del1), ss2 = fabs(del2);
     if (0.01 * ss1 > ss2 || 0.01 * ss2 > ss1 || nev == 0) {  // values too unequal for a polynomial fit
       c3 = 0.5 * (c1 + c2);
-      del3 = disp_delta(M, t, c3);
+      del3 = ev(c3);
       nev = 1;
       m = 1;
       continue;
@@ -138,12 +239,12 @@ ADSURF_HDN double disp_nevill(const DispModel& M, double t, double c1, double c2
     }
     if (ok) {
       c3 = xs[0];
-      del3 = disp_delta(M, t, c3);
+      del3 = ev(c3);
       nev = 2;
       m = m + 1 < 10 ? m + 1 : 10;
     } else {
       c3 = 0.5 * (c1 + c2);
-      del3 = disp_delta(M, t, c3);
+      del3 = ev(c3);
       nev = 1;
       m = 1;
     }
@@ -152,9 +253,10 @@ ADSURF_HDN double disp_nevill(const DispModel& M, double t, double c1, double c2
 }
 
 // walk the dc ladder until the secular function changes sign, then refine (:543-574); returns iret
-ADSURF_HD bool disp_getsol(const DispModel& M, double t1, double& c1, double clow, double dc, double cm, double betmx,
-                            bool ifirst, double& del1st) {
-  double del1 = disp_delta(M, t1, c1);
+template <class Eval>
+ADSURF_HD bool disp_getsol(const Eval& ev, double& c1, double clow, double dc, double cm, double betmx, bool ifirst,
+                            double& del1st) {
+  double del1 = ev(c1);
   if (ifirst) del1st = del1;
   double idir = (!ifirst && np_sign(del1st) * np_sign(del1) < 0.0) ? -1.0 : 1.0;
   for (;;) {
@@ -164,9 +266,9 @@ ADSURF_HD bool disp_getsol(const DispModel& M, double t1, double& c1, double clo
       c1 = clow;
       continue;
     }
-    const double del2 = disp_delta(M, t1, c2);
+    const double del2 = ev(c2);
     if (np_sign(del1) != np_sign(del2)) {
-      c1 = disp_nevill(M, t1, c1, c2, del1, del2);
+      c1 = disp_nevill(ev, c1, c2, del1, del2);
       return c1 > betmx;
     }
     c1 = c2;
@@ -194,7 +296,10 @@ ADSURF_HD double disp_gtsolh(double a, double b) {
 
 // getc (:596-691) for modes 0 .. nmodes-1 of one model; cout [nmodes, NF]; c [NF] scratch (the previous mode's roots).
 // Returns 0, or 1 when the fundamental mode cannot be bracketed (the reference raises DispersionError).
-ADSURF_HD int disp_getc(const DispModel& M, const double* ts, int NF, int nmodes, double dc, double* cout, double* c) {
+// ev evaluates the secular function of model M at the period given to set_period().
+template <class Eval>
+ADSURF_HD int disp_getc(Eval& ev, const DispModel& M, const double* ts, int NF, int nmodes, double dc, double* cout,
+                         double* c) {
   const int L = M.L;
   double betmx = -1.0e20, betmn = 1.0e20;
   int jmn = 0;
@@ -218,7 +323,8 @@ ADSURF_HD int disp_getc(const DispModel& M, const double* ts, int NF, int nmodes
       else if (ifirst) { clow = c1; c1 = c[0] + one * dc; }
       else if (iq > 0) { clow = c[k] + one * dc; c1 = fmax(c[k - 1], clow); }
       else { clow = cm; c1 = c[k - 1] - onea * dc; }
-      const bool iret = disp_getsol(M, ts[k], c1, clow, dc, cm, betmx, ifirst, del1st);
+      ev.set_period(ts[k]);
+      const bool iret = disp_getsol(ev, c1, clow, dc, cm, betmx, ifirst, del1st);
       if (iret) {
         if (iq == 0) return 1;
         for (int kk = k; kk < NF; ++kk) cg[kk] = 0.0;

@@ -884,19 +884,26 @@ __global__ void __launch_bounds__(256) k_dfma_probe(int iters, double* __restric
   if (r == 12345.678) out[0] = r;  // never true; keeps the chains alive
 }
 
-// modal dispersion curves (N1): the reference's sequential root search (adsurf_dispersion.cuh), one model per WARP with
-// one working lane: the search is data-dependent control flow all the way down (ladder walk, Neville / bisection
-// choices), and 32 models sharing a warp serialise on their divergence — measured 24 x slower per warp than one model
-// alone (64 models in 2 warps: 1.41 s, one model: 0.058 s), so a warp carries one model and the ensemble spreads over
-// 16 warps per SM.
-__global__ void k_dispersion(const double* __restrict__ d, const double* __restrict__ a, const double* __restrict__ b,
-                             const double* __restrict__ rho, const double* __restrict__ t, int S, int L, int NF,
-                             int nmodes, double dc, double* __restrict__ cout, double* __restrict__ work,
-                             int* __restrict__ status) {
-  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (s >= S || (threadIdx.x & 31) != 0) return;
+// modal dispersion curves (N1): the reference's sequential root search (adsurf_dispersion.cuh), one model per WARP.
+// The search is data-dependent control flow all the way down (ladder walk, Neville / bisection choices): 32 models
+// sharing a warp serialise on their divergence (measured 24 x slower per warp than one model alone), so a warp carries
+// one model, runs the control flow redundantly in every lane, and shares out the per-layer preparation of each
+// secular-function evaluation over its lanes (DispWarpEval); the ensemble spreads over the warps.
+constexpr int kDispThreads = 128;
+__host__ __device__ inline size_t disp_warp_doubles(int L) { return (size_t)L * (kDispPer + kDispTerms); }
+__global__ void __launch_bounds__(kDispThreads)
+k_dispersion(const double* __restrict__ d, const double* __restrict__ a, const double* __restrict__ b,
+             const double* __restrict__ rho, const double* __restrict__ t, int S, int L, int NF, int nmodes, double dc,
+             double* __restrict__ cout, double* __restrict__ work, int* __restrict__ status) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (kDispThreads / kWarp) + warp;
+  if (s >= S) return;  // whole warps: the evaluator synchronises the warp only
+  double* scratch = smem + (size_t)warp * disp_warp_doubles(L);
   const DispModel M{d + (size_t)s * L, a + (size_t)s * L, b + (size_t)s * L, rho + (size_t)s * L, L};
-  status[s] = disp_getc(M, t + (size_t)s * NF, NF, nmodes, dc, cout + (size_t)s * nmodes * NF, work + (size_t)s * NF);
+  DispWarpEval ev{M, scratch, scratch + (size_t)L * kDispPer, lane, 0.0};
+  const int rc = disp_getc(ev, M, t + (size_t)s * NF, NF, nmodes, dc, cout + (size_t)s * nmodes * NF, work + (size_t)s * NF);
+  if (lane == 0) status[s] = rc;
 }
 
 // ---- Monte-Carlo ensemble generation on the device (N2) -------------------------------------------------
@@ -1666,11 +1673,14 @@ int adsurf_dispersion_curves(const double* d, const double* alpha, const double*
   if (S <= 0 || L <= 0 || NF <= 0 || nmodes <= 0) return ADSURF_E_SHAPE;
   if (!(dc > 0.0)) return ADSURF_E_ARG;
   if (!ws || ws_bytes < (size_t)S * NF * sizeof(double)) return ADSURF_E_WORKSPACE;
-  const int threads = 64;  // one model per warp (one working lane), two warps per block
-  const long long blocks = ((long long)S * kWarp + threads - 1) / threads;
+  const int wpb = kDispThreads / kWarp;  // one model per warp
+  const long long blocks = ((long long)S + wpb - 1) / wpb;
   if (blocks > 0x7fffffffLL) return ADSURF_E_SHAPE;
-  k_dispersion<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(d, alpha, beta, rho, t, S, L, NF, nmodes, dc, c,
-                                                                      (double*)ws, status);
+  const size_t smem = wpb * disp_warp_doubles(L) * sizeof(double);
+  if (smem > 227 * 1024) return ADSURF_E_SHAPE;  // more than 360 layers
+  if (const int rc = set_smem(k_dispersion, smem)) return rc;
+  k_dispersion<<<(unsigned)blocks, kDispThreads, smem, (cudaStream_t)stream>>>(d, alpha, beta, rho, t, S, L, NF, nmodes,
+                                                                              dc, c, (double*)ws, status);
   return check_launch();
 }
 

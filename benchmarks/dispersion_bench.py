@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Timing of the GPU dispersion-curve extraction: the reference's root search run by `k_dispersion`
-(one thread per model) for one model and for ensembles, next to the sequential host solver (`_surf96.surf96`, the
+(one warp per model, the lanes sharing each evaluation) for one model and for ensembles, next to the sequential host solver (`_surf96.surf96`, the
 Python port with the reference's control flow) on this box.
 
     python benchmarks/dispersion_bench.py

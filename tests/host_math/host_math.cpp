@@ -28,7 +28,8 @@ void host_dispersion(const double* d, const double* a, const double* b, const do
   std::vector<double> work(NF);
   for (int s = 0; s < S; ++s) {
     const DispModel M{d + (size_t)s * L, a + (size_t)s * L, b + (size_t)s * L, rho + (size_t)s * L, L};
-    status[s] = disp_getc(M, t + (size_t)s * NF, NF, nmodes, dc, c + (size_t)s * nmodes * NF, work.data());
+    DispScalarEval ev{M, 0.0};
+    status[s] = disp_getc(ev, M, t + (size_t)s * NF, NF, nmodes, dc, c + (size_t)s * nmodes * NF, work.data());
   }
 }
 

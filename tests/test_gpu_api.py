@@ -136,7 +136,7 @@ def test_config4_friul_ensemble_step_and_sensitivity(api):
 
 @pytest.mark.parametrize("tag,modes", [("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,))])
 def test_gpu_dispersion_curves_match_reference_solver(api, tag, modes):
-    """k_dispersion (the reference's root search with its mode bookkeeping, one thread per model) against the
+    """k_dispersion (the reference's root search with its mode bookkeeping, one warp per model) against the
     reference's sequential solver in float64: every period, every mode, 1e-6 km/s; identical zeros for absent modes."""
     from adsurf_b200.dispersion import dispersion_curves
     g = load("surf96_roots")
@@ -176,6 +176,23 @@ def test_gpu_dispersion_ensemble_equals_single_models(api):
     for s in (0, 17, 95):
         one = dispersion_curves(g["m6_t"], d[s], a[s], b[s], rho[s], modes=(0, 1), dc=0.005)
         assert np.array_equal(one, c[s])
+
+
+def test_gpu_dispersion_more_layers_than_lanes(api):
+    """45 layers: the lanes of the model's warp stride over the layers of an evaluation (k_dispersion / DispWarpEval);
+    same roots as the sequential host solver"""
+    from adsurf_b200._surf96 import surf96
+    from adsurf_b200._utils import gen_model
+    from adsurf_b200.dispersion import dispersion_curves
+    L = 45
+    vs = np.linspace(1.0, 4.2, L) + 0.15 * np.sin(np.arange(L))
+    th, vp, vs, rho = gen_model(np.full(L, 0.35), vs, area=True)
+    t = np.exp(np.linspace(np.log(0.2), np.log(12.0), 24))
+    c = dispersion_curves(t, th, vp, vs, rho, modes=(0, 1), dc=0.005)
+    for mode in (0, 1):
+        ref = surf96(t, th, vp, vs, rho, mode, 0, 2, 0.005)
+        assert np.array_equal(c[mode] > 0, ref > 0)
+        assert np.max(np.abs(c[mode] - ref)) <= 1e-8
 
 
 @pytest.mark.parametrize("name,tol", [("disper_00", 3e-6), ("disper_01", 3e-6), ("disper_02", 6e-6)])
