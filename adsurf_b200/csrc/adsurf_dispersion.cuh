@@ -21,15 +21,6 @@
 
 namespace adsurf {
 
-ADSURF_HD void disp_sincos(double x, double* sn, double* cs) {
-#if defined(__CUDA_ARCH__)
-  sincos(x, sn, cs);
-#else
-  *sn = sin(x);
-  *cs = cos(x);
-#endif
-}
-
 struct DispModel {
   const double *d, *a, *b, *rho;
   int L;
@@ -43,7 +34,7 @@ struct DispModel {
 //   bottom-up:                E <- E . CA_m / max|.|                                (disp_layer_apply: 33 FMAs, one
 //                             reciprocal; the only sequential part)
 constexpr int kDispTerms = 16;  // doubles per layer handed from disp_layer_terms to disp_layer_apply
-constexpr int kDispPer = 6;     // doubles per layer kept per period: k_alpha, k_beta, gammk | warp evaluator: d, rho
+constexpr int kDispPer = 6;     // doubles per layer kept per period: k_alpha, k_beta, gammk | warp evaluator: d, rho, 1/rho
 enum { DT_CP = 0, DT_W, DT_X, DT_CQ, DT_Y, DT_Z, DT_A0, DT_GK, DT_G1, DT_AR, DT_BR, DT_KR, DT_IR, DT_TGK, DT_TG1 };
 
 ADSURF_HD void disp_period_consts(double* __restrict__ per, double a, double b, double omega) {
@@ -53,13 +44,21 @@ ADSURF_HD void disp_period_consts(double* __restrict__ per, double a, double b, 
   per[2] = 2.0 * tt * tt;
 }
 
-// eigenfunction terms of one wave type (var, :96-157): cos-like, sin-like / r, r * sin-like, exponent
-ADSURF_HD void disp_eig(double wvno, double xk, double r, double dm, double& cs, double& w, double& x, double& ex) {
+// sqrt(u) and 1/sqrt(u) from the rsqrt sequence of the pointwise kernels (u >= 0; 0 -> (0, inf), NaN -> NaN)
+ADSURF_HD void disp_root(double u, double& r, double& ir) {
+  ir = rsqrt_hd(u);
+  r = u > 0.0 ? u * ir : u;
+}
+
+// eigenfunction terms of one wave type (var, :96-157): cos-like, sin-like / r, r * sin-like, exponent.
+// Elementary functions: the kernels' inline exp / sincos (adsurf_math.cuh, <= 2 ulp), one code path per regime.
+ADSURF_HD void disp_eig(double wvno, double xk, double r, double ir, double dm, double& cs, double& w, double& x,
+                        double& ex) {
   const double p = r * dm;
   if (wvno < xk) {
     double sn;
-    disp_sincos(p, &sn, &cs);
-    w = sn / r;
+    sincos_fast(p, &sn, &cs);
+    w = sn * ir;
     x = -r * sn;
     ex = 0.0;
   } else if (wvno == xk) {
@@ -68,26 +67,27 @@ ADSURF_HD void disp_eig(double wvno, double xk, double r, double dm, double& cs,
     x = 0.0;
     ex = 0.0;
   } else {
-    const double fac = p < 16.0 ? exp(-2.0 * p) : 0.0, sn = (1.0 - fac) * 0.5;
+    const double fac = p < 16.0 ? exp_neg(2.0 * p) : 0.0, sn = (1.0 - fac) * 0.5;
     cs = (1.0 + fac) * 0.5;
-    w = sn / r;
+    w = sn * ir;
     x = r * sn;
     ex = p;
   }
 }
 
+// ir = 1 / rho of the layer
 ADSURF_HD void disp_layer_terms(double* __restrict__ q, const double* __restrict__ per, double wvno, double k2, double t2,
-                                double dm, double r1) {
+                                double dm, double r1, double ir) {
   const double xka = per[0], xkb = per[1], gk = per[2];
   const double gam = gk * k2, g1 = gam - 1.0;
-  const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
-  const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  double ra, ira, rb, irb;
+  disp_root((wvno + xka) * fabs(wvno - xka), ra, ira);
+  disp_root((wvno + xkb) * fabs(wvno - xkb), rb, irb);
   double pex, sex;
-  disp_eig(wvno, xka, ra, dm, q[DT_CP], q[DT_W], q[DT_X], pex);
-  disp_eig(wvno, xkb, rb, dm, q[DT_CQ], q[DT_Y], q[DT_Z], sex);
+  disp_eig(wvno, xka, ra, ira, dm, q[DT_CP], q[DT_W], q[DT_X], pex);
+  disp_eig(wvno, xkb, rb, irb, dm, q[DT_CQ], q[DT_Y], q[DT_Z], sex);
   const double exa = pex + sex;
-  const double ir = 1.0 / r1;
-  q[DT_A0] = exa < 60.0 ? exp(-exa) : 0.0;
+  q[DT_A0] = exa < 60.0 ? exp_neg(exa) : 0.0;
   q[DT_GK] = gk;
   q[DT_G1] = g1;
   q[DT_AR] = gam * gk * r1;
@@ -101,8 +101,9 @@ ADSURF_HD void disp_layer_terms(double* __restrict__ q, const double* __restrict
 // half-space vector (:231-244)
 ADSURF_HD void disp_half_terms(double* __restrict__ q, const double* __restrict__ per, double wvno, double k2, double r1) {
   const double xka = per[0], xkb = per[1], gk = per[2];
-  const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
-  const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  double ra, rb, unused;
+  disp_root((wvno + xka) * fabs(wvno - xka), ra, unused);
+  disp_root((wvno + xkb) * fabs(wvno - xkb), rb, unused);
   const double gam = gk * k2, g1 = gam - 1.0;
   q[0] = r1 * r1 * (g1 * g1 - gam * gk * ra * rb);
   q[1] = -r1 * ra;
@@ -111,12 +112,41 @@ ADSURF_HD void disp_half_terms(double* __restrict__ q, const double* __restrict_
   q[4] = k2 - ra * rb;
 }
 
-// E <- E . CA in the rank-structured form (adsurf_math.cuh), then the reference's max-normalisation (:278)
-ADSURF_HD void disp_layer_apply(double& e0, double& e1, double& e2, double& e3, double& e4, const double* __restrict__ q) {
-  const double cp = q[DT_CP], w = q[DT_W], x = q[DT_X], cq = q[DT_CQ], y = q[DT_Y], z = q[DT_Z], a0 = q[DT_A0];
-  const double gk = q[DT_GK], g1 = q[DT_G1], ar = q[DT_AR], br = q[DT_BR], kr = q[DT_KR], ir = q[DT_IR];
-  const double sa = e0 * ir + e2 * q[DT_TGK] + e4 * ar;
-  const double sb = e0 * kr + e2 * q[DT_TG1] + e4 * br;
+// The reference divides E by max|E| after every layer (:278).  The layer step is linear, so in exact arithmetic the
+// scales telescope: the normalised vector after layer m is the unnormalised one divided by ITS largest magnitude,
+// whatever happened before.  Hence: an exact power-of-two rescale per layer (keeps the range, rounds nothing; integer
+// work on the exponent fields instead of a max / reciprocal chain on the sequential path), and the reference's
+// normalisation once, after layer 0 (disp_finish).  Values differ from the reference's by its own rounding noise.
+ADSURF_HD double disp_pow2_scale(double n0, double n1, double n2, double n3, double n4) {
+  auto hi = [](double v) { return (unsigned)((unsigned long long)dbl_bits(v) >> 32) & 0x7fffffffu; };
+  unsigned h = hi(n0);
+  h = h > hi(n1) ? h : hi(n1);
+  h = h > hi(n2) ? h : hi(n2);
+  h = h > hi(n3) ? h : hi(n3);
+  h = h > hi(n4) ? h : hi(n4);
+  const unsigned ex = h >> 20;                   // biased exponent of the largest magnitude
+  if (ex == 0u || ex >= 2046u) return 1.0;       // zero / subnormal / Inf / NaN: leave alone
+  return bits_dbl((long long)(2046u - ex) << 52);  // 2^(1023 - ex): the largest magnitude lands in [1, 2)
+}
+
+// one layer's terms as eight 16-byte pairs (the order of the DT_* enum)
+struct DispTermRegs {
+  Dbl2 v[kDispTerms / 2];
+};
+ADSURF_HD DispTermRegs disp_load_terms(const double* __restrict__ q) {  // q 16-byte aligned
+  DispTermRegs r;
+#pragma unroll
+  for (int i = 0; i < kDispTerms / 2; ++i) r.v[i] = ld2(q + 2 * i);
+  return r;
+}
+
+// E <- E . CA in the rank-structured form (adsurf_math.cuh), rescaled by a power of two
+ADSURF_HD void disp_layer_apply(double& e0, double& e1, double& e2, double& e3, double& e4, const DispTermRegs& r) {
+  const double cp = r.v[0].x, w = r.v[0].y, x = r.v[1].x, cq = r.v[1].y, y = r.v[2].x, z = r.v[2].y, a0 = r.v[3].x;
+  const double gk = r.v[3].y, g1 = r.v[4].x, ar = r.v[4].y, br = r.v[5].x, kr = r.v[5].y, ir = r.v[6].x;
+  const double tgk = r.v[6].y, tg1 = r.v[7].x;
+  const double sa = e0 * ir + e2 * tgk + e4 * ar;
+  const double sb = e0 * kr + e2 * tg1 + e4 * br;
   const double h1 = sb * y + e1 * cq, h2 = sa * cq + e3 * y;
   const double h3 = sa * z + e3 * cq, h4 = sb * cq + e1 * z;
   const double ca = cp * h4 - x * h3 - sb * a0;
@@ -126,12 +156,14 @@ ADSURF_HD void disp_layer_apply(double& e0, double& e1, double& e2, double& e3, 
   const double n2 = a0 * e2 + gk * ca + g1 * cb;
   const double n3 = cp * h3 - w * h4;
   const double n4 = a0 * e4 + ir * ca + kr * cb;
-  double big = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
-  if (big < 1.0e-40) big = 1.0;
-  // one reciprocal instead of the reference's five divisions: the values move by an ulp, the signs and the
-  // interpolated roots (converged to 1e-6 c) do not
-  const double ib = 1.0 / big;
-  e0 = n0 * ib; e1 = n1 * ib; e2 = n2 * ib; e3 = n3 * ib; e4 = n4 * ib;
+  const double sc = disp_pow2_scale(n0, n1, n2, n3, n4);
+  e0 = n0 * sc; e1 = n1 * sc; e2 = n2 * sc; e3 = n3 * sc; e4 = n4 * sc;
+}
+
+// the reference's normalised value after layer 0: E[0] / max|E| (an all-zero vector stays zero, :279)
+ADSURF_HD double disp_finish(double e0, double e1, double e2, double e3, double e4) {
+  const double big = fmax(fmax(fmax(fabs(e0), fabs(e1)), fmax(fabs(e2), fabs(e3))), fabs(e4));
+  return big > 0.0 ? e0 / big : e0;
 }
 
 // One thread evaluates everything (host check; any number of layers).
@@ -145,54 +177,71 @@ struct DispScalarEval {
     omega = fmax(omega, 1.0e-4);
     const double k2 = wvno * wvno, t2 = -2.0 * k2;
     const int L = M.L;
-    double per[kDispPer], q[kDispTerms];
+    alignas(16) double per[kDispPer], q[kDispTerms];
     disp_period_consts(per, M.a[L - 1], M.b[L - 1], omega);
     disp_half_terms(q, per, wvno, k2, M.rho[L - 1]);
     double e0 = q[0], e1 = q[1], e2 = q[2], e3 = q[3], e4 = q[4];
     for (int m = L - 2; m >= 0; --m) {
       disp_period_consts(per, M.a[m], M.b[m], omega);
-      disp_layer_terms(q, per, wvno, k2, t2, M.d[m], M.rho[m]);
-      disp_layer_apply(e0, e1, e2, e3, e4, q);
+      disp_layer_terms(q, per, wvno, k2, t2, M.d[m], M.rho[m], 1.0 / M.rho[m]);
+      disp_layer_apply(e0, e1, e2, e3, e4, disp_load_terms(q));
     }
-    return e0;
+    return L > 1 ? disp_finish(e0, e1, e2, e3, e4) : e0;
   }
 };
 
 #if defined(__CUDACC__)
 // One warp evaluates: lane m prepares layer m (lanes stride over the layers when there are more than 32), then every
-// lane runs the same bottom-up product over the staged terms.  All lanes must call with the same arguments; all
-// return the same value.  per [L][kDispPer] and lay [L][kDispTerms] are the warp's shared-memory scratch.
+// lane runs the same bottom-up product over the staged terms, the next layer's terms loaded while the current layer is
+// worked on.  All lanes must call with the same arguments; all return the same value.  The warp's scratch —
+// per [L][kDispPer], then lay [L][kDispTerms] — starts `off` doubles into the kernel's dynamic shared memory (named
+// here, not passed as a pointer, so that the accesses compile to shared-memory instructions inside the non-inlined
+// evaluator).
 struct DispWarpEval {
   DispModel M;
-  double* per;
-  double* lay;
+  int off;
   int lane;
-  double t;
+  double omega0;  // 2 pi / period, unclamped
+  __device__ double* scratch() const { return adsurf_smem_head + off; }  // off includes the exp table (kSmemHead)
   __device__ void set_period(double t_) {
-    t = t_;
-    const double omega = fmax(kTwoPi / t, 1.0e-4);
+    omega0 = kTwoPi / t_;
+    const double omega = fmax(omega0, 1.0e-4);
+    double* per = scratch();
     __syncwarp();
     for (int m = lane; m < M.L; m += 32) {
       double* pm = per + m * kDispPer;
       disp_period_consts(pm, M.a[m], M.b[m], omega);
       pm[3] = M.d[m];
       pm[4] = M.rho[m];
+      pm[5] = 1.0 / M.rho[m];
     }
     __syncwarp();
   }
   __device__ __noinline__ double operator()(double c) const {
-    const double wvno = (kTwoPi / t) / c;
+    const double wvno = omega0 / c;
     const double k2 = wvno * wvno, t2 = -2.0 * k2;
     const int L = M.L;
+    const double* per = scratch();
+    double* lay = scratch() + L * kDispPer;
     for (int m = lane; m < L; m += 32) {
       const double* pm = per + m * kDispPer;
-      if (m < L - 1) disp_layer_terms(lay + m * kDispTerms, pm, wvno, k2, t2, pm[3], pm[4]);
+      if (m < L - 1) disp_layer_terms(lay + m * kDispTerms, pm, wvno, k2, t2, pm[3], pm[4], pm[5]);
       else disp_half_terms(lay + m * kDispTerms, pm, wvno, k2, pm[4]);
     }
     __syncwarp();
     const double* q = lay + (L - 1) * kDispTerms;
     double e0 = q[0], e1 = q[1], e2 = q[2], e3 = q[3], e4 = q[4];
-    for (int m = L - 2; m >= 0; --m) disp_layer_apply(e0, e1, e2, e3, e4, lay + m * kDispTerms);
+    if (L > 1) {
+      q -= kDispTerms;
+      DispTermRegs cur = disp_load_terms(q);
+      for (int m = L - 2; m >= 0; --m) {
+        if (m > 0) q -= kDispTerms;  // layer 0 re-reads its own terms: no predicated loads
+        const DispTermRegs nxt = disp_load_terms(q);
+        disp_layer_apply(e0, e1, e2, e3, e4, cur);
+        cur = nxt;
+      }
+      e0 = disp_finish(e0, e1, e2, e3, e4);
+    }
     __syncwarp();  // the next evaluation overwrites the staged terms
     return e0;
   }

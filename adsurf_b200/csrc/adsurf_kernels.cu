@@ -895,13 +895,13 @@ __global__ void __launch_bounds__(kDispThreads)
 k_dispersion(const double* __restrict__ d, const double* __restrict__ a, const double* __restrict__ b,
              const double* __restrict__ rho, const double* __restrict__ t, int S, int L, int NF, int nmodes, double dc,
              double* __restrict__ cout, double* __restrict__ work, int* __restrict__ status) {
-  extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * (kDispThreads / kWarp) + warp;
+  stage_exp_table();
+  __syncthreads();
   if (s >= S) return;  // whole warps: the evaluator synchronises the warp only
-  double* scratch = smem + (size_t)warp * disp_warp_doubles(L);
   const DispModel M{d + (size_t)s * L, a + (size_t)s * L, b + (size_t)s * L, rho + (size_t)s * L, L};
-  DispWarpEval ev{M, scratch, scratch + (size_t)L * kDispPer, lane, 0.0};
+  DispWarpEval ev{M, kSmemHead + warp * (int)disp_warp_doubles(L), lane, 0.0};
   const int rc = disp_getc(ev, M, t + (size_t)s * NF, NF, nmodes, dc, cout + (size_t)s * nmodes * NF, work + (size_t)s * NF);
   if (lane == 0) status[s] = rc;
 }
@@ -1676,7 +1676,7 @@ int adsurf_dispersion_curves(const double* d, const double* alpha, const double*
   const int wpb = kDispThreads / kWarp;  // one model per warp
   const long long blocks = ((long long)S + wpb - 1) / wpb;
   if (blocks > 0x7fffffffLL) return ADSURF_E_SHAPE;
-  const size_t smem = wpb * disp_warp_doubles(L) * sizeof(double);
+  const size_t smem = (kSmemHead + wpb * disp_warp_doubles(L)) * sizeof(double);
   if (smem > 227 * 1024) return ADSURF_E_SHAPE;  // more than 360 layers
   if (const int rc = set_smem(k_dispersion, smem)) return rc;
   k_dispersion<<<(unsigned)blocks, kDispThreads, smem, (cudaStream_t)stream>>>(d, alpha, beta, rho, t, S, L, NF, nmodes,

@@ -61,6 +61,10 @@ configs_persist)
   ADSURF_PERSIST_L2=1 timeout 900 python benchmarks/configs_e2e.py --only 4 > gpurun_out/configs_c4_persist.jsonl 2>&1 ;;
 dispersion)
   timeout 900 python benchmarks/dispersion_bench.py > gpurun_out/dispersion_bench.json 2> gpurun_out/dispersion_bench.err ;;
+ncu_disp)
+  timeout 300 python benchmarks/dispersion_bench.py --profile ${DISP_MODELS:-592} > gpurun_out/disp_profile.log 2>&1 && \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_dispersion' -s 1 -c 1 -f -o gpurun_out/prof_r2_dispersion \
+      python benchmarks/dispersion_bench.py --profile ${DISP_MODELS:-592} > gpurun_out/ncu_disp.log 2>&1 ;;
 variants)
   bash benchmarks/run_variants.sh > gpurun_out/run_variants.out 2>&1 ;;
 sharded)

@@ -34,6 +34,12 @@ def timed(fn, reps=3):
 def main():
     d, a, b, rho = config5_ensemble(4096, 20, seed=0)
     t = config5_periods(128)
+    if len(sys.argv) > 2 and sys.argv[1] == "--profile":  # two launches of S models (for ncu)
+        S = int(sys.argv[2])
+        for _ in range(2):
+            dispersion_curves(t, d[:S], a[:S], b[:S], rho[:S], modes=(0,), dc=0.01)
+        torch.cuda.synchronize()
+        return
     rec = {"what": "20-layer FRIUL7W ensemble of config 5, 128 periods, fundamental mode, dc = 0.01"}
     t0 = time.perf_counter()
     host = surf96(t, d[0], a[0], b[0], rho[0], 0, 0, 2, 0.01)

@@ -217,8 +217,8 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
 
 /* Modal Rayleigh phase-velocity curves by the classical root search, for S models at once:
  * c[s,n,k] = phase velocity of mode n (0 = fundamental .. nmodes-1) of model s at period t[s,k], 0 where the mode does
- * not exist.  One warp per model (one working lane: the search is divergent control flow throughout) runs the
- * reference's own sequential algorithm — start 10 % below the slowest
+ * not exist.  One warp per model (the search is divergent control flow throughout; the lanes share the per-layer
+ * work of every secular-function evaluation) runs the reference's own sequential algorithm — start 10 % below the slowest
  * layer's half-space Rayleigh velocity, walk a `dc` ladder from the previous period's root (and above the previous
  * mode's root) to the first sign change of the normalised secular function, refine by Neville interpolation with
  * bisection safeguards to 1e-6 relative — with identical bookkeeping (clow, one = 1e-2, onea = 1.5), so mode indices
