@@ -206,12 +206,15 @@ def test_config5_subset_against_oracle(ab):
         assert_grad_close(N(new), ref.numpy(), what=key + "(ones)")
 
 
-@pytest.mark.parametrize("S,L,N_,K", [(1, 2, 1, 1), (3, 2, 33, 7), (2, 45, 70, 40), (5, 6, 500, 130), (1, 90, 31, 9)])
+@pytest.mark.parametrize("S,L,N_,K", [(1, 2, 1, 1), (3, 2, 33, 7), (2, 45, 70, 40), (5, 6, 500, 130), (1, 90, 31, 9),
+                                      (40, 3, 174, 200), (17, 12, 65, 96), (150, 4, 40, 33), (2, 20, 128, 257),
+                                      (9, 31, 97, 50), (64, 7, 20, 12), (1, 20, 300, 450), (300, 5, 31, 3)])
 def test_ragged_shapes_against_oracle(ab, S, L, N_, K):
-    """odd sizes: one sample, non-multiples of 32, a single finite layer, deep stacks (1 warp per block)."""
+    """odd sizes: one sample, non-multiples of 32, a single finite layer, deep stacks (1 warp per block); shapes that
+    land in the planner's other regimes (more models than SMs, shallow models, many / few trial velocities)."""
     from adsurf_b200 import _capi
     from oracle import dltar_oracle as O
-    rng = np.random.default_rng(100 + L)
+    rng = np.random.default_rng(100 + L + 7 * S)
     b = np.sort(rng.uniform(1.0, 4.0, (S, L)), axis=1)
     d = rng.uniform(0.05, 0.6, (S, L))
     a, rho = _brocher(b)
