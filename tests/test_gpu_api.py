@@ -239,7 +239,8 @@ def test_dense_grid_extractor_converges_to_roots(api):
     assert np.max(np.abs(F) / (cmax - cmin).cpu().numpy()) < 1e-9
 
 
-@pytest.mark.parametrize("case", ["brocher_thick_damped", "constant_thick", "brocher_vs_raw"])
+@pytest.mark.parametrize("case", ["brocher_thick_damped", "constant_thick", "brocher_vs_raw", "usarray_vs_log",
+                                  "brocher_thick_LN_nonorm", "usarray_thick_hdamped"])
 def test_fused_optimiser_loop_matches_torch_loop(api, case, monkeypatch):
     """adsurf_ensemble_adam_step (velocity chain + Tikhonov + projection + Adam on the device) against the
     torch-autograd / torch.optim.Adam loop, same order of operations as the reference (_model.py:589-636)."""
@@ -259,17 +260,28 @@ def test_fused_optimiser_loop_matches_torch_loop(api, case, monkeypatch):
         b = np.tile(g["b"][0], (S, 1)) * (1 + rng.normal(0, 0.03, (S, 6)))
         a, rho = brocher_np(b)
         d = np.tile(g["d"][0], (S, 1))
-        clist, init_method = np.arange(2, 3.2, 0.01), "Brocher"
+        clist, init_method = np.arange(2, 3.2, 0.01), "USArray" if case.startswith("usarray") else "Brocher"
         lo, hi = np.full(6, 0.05), np.full(6, 4.0)
+        method, normalized = "exp", True
         if case == "brocher_thick_damped":
             inv_method, lm, dv, dh, compress, lr = "vs-and-thick", "LR", 0.002, 0.001, True, 0.005
+            lo, hi = np.cumsum(d[0]) * 0.8, np.cumsum(d[0]) * 1.2
+        elif case == "usarray_vs_log":
+            inv_method, lm, dv, dh, compress, lr, method = "vs", "None", 0.001, 0.0, True, 0.01, "log"
+        elif case == "brocher_thick_LN_nonorm":
+            inv_method, lm, dv, dh, compress, lr, normalized = "vs-and-thick", "LN", 0.0, 0.0, True, 0.005, False
+            lo, hi = d[0] * 0.7, d[0] * 1.4
+        elif case == "usarray_thick_hdamped":
+            inv_method, lm, dv, dh, compress, lr = "vs-and-thick", "LR", 0.0, 0.002, True, 0.005
             lo, hi = np.cumsum(d[0]) * 0.8, np.cumsum(d[0]) * 1.2
         else:
             inv_method, lm, dv, dh, compress, lr = "vs", "None", 0.0, 0.0, False, 0.03
     obs = np.stack([np.column_stack((g["t"][0], g["c"][0]))] * S)
     mp_ = types.SimpleNamespace(clist=clist, layering_method=lm, initialize_method=init_method, vp_vs_ratio=2.45, rho=2)
-    ip = types.SimpleNamespace(damp_vertical=dv, damp_horizontal=dh, compress=compress, normalized=True,
-                               compress_method="exp", inversion_method=inv_method, lr=lr, iteration=iters,
+    if case == "constant_thick":
+        method, normalized = "exp", True
+    ip = types.SimpleNamespace(damp_vertical=dv, damp_horizontal=dh, compress=compress, normalized=normalized,
+                               compress_method=method, inversion_method=inv_method, lr=lr, iteration=iters,
                                step_size=10, gamma=0.5, optimizer="Adam")
     init = types.SimpleNamespace(init_model={"vs": b, "vp": a, "rho": rho, "thick": d, "layer_mindepth": lo,
                                              "layer_maxdepth": hi})
