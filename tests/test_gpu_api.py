@@ -240,7 +240,7 @@ def test_dense_grid_extractor_converges_to_roots(api):
 
 
 @pytest.mark.parametrize("case", ["brocher_thick_damped", "constant_thick", "brocher_vs_raw", "usarray_vs_log",
-                                  "brocher_thick_LN_nonorm", "usarray_thick_hdamped"])
+                                  "brocher_thick_LN_nonorm", "usarray_thick_hdamped", "usarray_crossing_4p6"])
 def test_fused_optimiser_loop_matches_torch_loop(api, case, monkeypatch):
     """adsurf_ensemble_adam_step (velocity chain + Tikhonov + projection + Adam on the device) against the
     torch-autograd / torch.optim.Adam loop, same order of operations as the reference (_model.py:589-636)."""
@@ -274,6 +274,13 @@ def test_fused_optimiser_loop_matches_torch_loop(api, case, monkeypatch):
         elif case == "usarray_thick_hdamped":
             inv_method, lm, dv, dh, compress, lr = "vs-and-thick", "LR", 0.0, 0.002, True, 0.005
             lo, hi = np.cumsum(d[0]) * 0.8, np.cumsum(d[0]) * 1.2
+        elif case == "usarray_crossing_4p6":
+            # the two deepest layers start either side of 4.6 km/s and move across it: entries above keep the Vp / rho
+            # they last had
+            b[:, 4] = 4.6 + rng.uniform(-0.03, 0.03, S)
+            b[:, 5] = 4.62 + rng.uniform(-0.04, 0.04, S)
+            a, rho = brocher_np(b)
+            inv_method, lm, dv, dh, compress, lr = "vs", "None", 0.0, 0.0, True, 0.01
         else:
             inv_method, lm, dv, dh, compress, lr = "vs", "None", 0.0, 0.0, False, 0.03
     obs = np.stack([np.column_stack((g["t"][0], g["c"][0]))] * S)
@@ -288,7 +295,8 @@ def test_fused_optimiser_loop_matches_torch_loop(api, case, monkeypatch):
     runs = {}
     for flag in ("0", "1"):
         monkeypatch.setenv("ADSURF_FUSED_OPT", flag)
-        inv = multi_inversion(mp_, ip, init, obs, vsrange_sign="mul", vsrange=[0.7, 1.3], device="cuda")
+        ak135 = np.array([[0.0, 2.7, 5.8, 3.4], [35.0, 3.3, 8.0, 4.5], [120.0, 3.4, 8.1, 4.5]])  # depth, rho, vp, vs
+        inv = multi_inversion(mp_, ip, init, obs, vsrange_sign="mul", vsrange=[0.7, 1.3], AK135_data=ak135, device="cuda")
         runs[flag] = (np.asarray(inv.inv_process["loss"]), np.asarray(inv.inv_process["iter_vs"]),
                       np.asarray(inv.inv_process["iter_thick"]), np.asarray(inv.inv_model["vs"]))
     # both loops see bit-identical data gradients at identical models; their chain-rule / Adam arithmetic differs in
@@ -297,6 +305,10 @@ def test_fused_optimiser_loop_matches_torch_loop(api, case, monkeypatch):
     for x, y in zip(runs["1"], runs["0"]):
         np.testing.assert_allclose(x, y, rtol=1e-7, atol=1e-10)
     assert np.isfinite(runs["1"][0]).all()
+    if case == "usarray_crossing_4p6":
+        it = runs["1"][1]  # [iterations, S, L]
+        above = it[:, :, 4:] > 4.6
+        assert (above[0] != above[-1]).any(), "no entry crossed 4.6 km/s: the case does not test what it says"
 
 
 @pytest.mark.parametrize("inv_method", ["vs-and-thick", "vs"])
