@@ -56,11 +56,16 @@ class Model_param:
 
 
 class inv_param:
-    """Inversion parameters (reference _ADsurf.py:125-196)."""
+    """Inversion parameters (reference _ADsurf.py:125-196).
+
+    result_arrays (new keyword, default False = the reference's nested lists): return `inv_model` / `inv_process`
+    entries as float64 numpy arrays — for a 1024-model, 400-iteration run the list conversion costs several times
+    the optimisation loop itself."""
 
     def __init__(self, inversion_method="vs", wave="rayleigh", algorithm="dunkin", mode=0, compress=True,
                  compress_method="exp", normalized=True, lr=0, damp_vertical=0, damp_horizontal=0, iteration=200,
-                 step_size=100, gamma=0.85, optimizer="Adam"):
+                 step_size=100, gamma=0.85, optimizer="Adam", result_arrays=False):
+        self.result_arrays = result_arrays
         self.inversion_method = inversion_method
         self.wave = wave
         self.algorithm = algorithm

@@ -362,9 +362,9 @@ class iter_inversion:
         inv_thick = iter_thick[best] if vs_and_thick else tensor2numpy(list2numpy(im["thick"]))
         inv_vs = iter_vs[best]
         inv_vp, inv_vs, inv_rho = _final_model(mp, inv_thick, inv_vs, self.AK135_data)
-        self.inv_model = {"thick": np.asarray(inv_thick).tolist(), "vp": inv_vp.tolist(), "vs": inv_vs.tolist(),
-                          "rho": inv_rho.tolist()}
-        self.inv_process = {"iter_vs": iter_vs.tolist(), "iter_thick": iter_thick.tolist(), "loss": loss_np.tolist()}
+        out = _as_result(ip)
+        self.inv_model = {"thick": out(np.asarray(inv_thick)), "vp": out(inv_vp), "vs": out(inv_vs), "rho": out(inv_rho)}
+        self.inv_process = {"iter_vs": out(iter_vs), "iter_thick": out(iter_thick), "loss": out(loss_np)}
 
 
 def _halo_rows(b, row0, S_all):
@@ -425,8 +425,16 @@ def _fused_ensemble_loop(self, calculator, vlist, tlist, Clist, a_init, rho_init
         if vs_and_thick:
             calculator.d.data.copy_(state["d"])
     self.loop = loop
-    iter_thick = loop.iter_d_hist if vs_and_thick else torch.zeros_like(loop.iter_b_hist)
+    iter_thick = loop.iter_d_hist if vs_and_thick else loop.iter_b_hist[:0]  # Vs only: zeros, made by the caller
     return loop.loss_hist, loop.iter_b_hist, iter_thick
+
+
+def _as_result(inv_param):
+    """how result entries are returned: nested lists as in the reference (_model.py:691-701), or numpy arrays when
+    inv_param.result_arrays is set"""
+    if getattr(inv_param, "result_arrays", False):
+        return lambda x: np.asarray(x, dtype=np.float64)
+    return lambda x: np.asarray(x).tolist()
 
 
 def _final_model(model_param, thick, vs, AK135_data):
@@ -563,15 +571,14 @@ class multi_inversion:
             iter_vs = _dist.all_gather_rows(iter_vs, S_all, dim=1)
             if vs_and_thick:
                 iter_thick = _dist.all_gather_rows(iter_thick, S_all, dim=1)
-            else:
-                iter_thick = torch.zeros_like(iter_vs)
             S = S_all
             if dev.type == "cuda":
                 torch.cuda.synchronize(dev)
             self.timing["gather_s"] = time.perf_counter() - t_end
         loss_np = loss_list.cpu().numpy()
         iter_vs = iter_vs.cpu().numpy()
-        iter_thick = iter_thick.cpu().numpy()
+        # a Vs-only run records zeros as its thickness history (reference :609-621 never writes it): made on the host
+        iter_thick = iter_thick.cpu().numpy() if vs_and_thick else np.zeros(iter_vs.shape)
         best_num = np.argmin(loss_np, axis=0)
         inv_thick = np.array(tensor2numpy(list2numpy(im["thick"])), dtype=np.float64, copy=True)
         if vs_and_thick:
@@ -580,6 +587,9 @@ class multi_inversion:
         inv_vs, inv_vp, inv_rho = (np.zeros_like(inv_thick) for _ in range(3))
         for i in range(S):
             inv_vp[i], inv_vs[i], inv_rho[i] = _final_model(mp, inv_thick[i], iter_vs[best_num[i], i], self.AK135_data)
-        self.inv_model = {"thick": inv_thick.tolist(), "vp": inv_vp.tolist(), "vs": inv_vs.tolist(),
-                          "rho": inv_rho.tolist()}
-        self.inv_process = {"iter_vs": iter_vs.tolist(), "iter_thick": iter_thick.tolist(), "loss": loss_np.tolist()}
+        out = _as_result(ip)
+        self.inv_model = {"thick": out(inv_thick), "vp": out(inv_vp), "vs": out(inv_vs), "rho": out(inv_rho)}
+        self.inv_process = {"iter_vs": out(iter_vs), "iter_thick": out(iter_thick), "loss": out(loss_np)}
+        # host-side time after the loop (and the gather): device -> host copies of the histories, best-model pick,
+        # result conversion
+        self.timing["results_s"] = time.perf_counter() - t_end - self.timing["gather_s"]

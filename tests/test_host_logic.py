@@ -131,6 +131,30 @@ def test_config2_trajectory_head(ab):
     assert set(inv.inv_model) == {"thick", "vp", "vs", "rho"}
 
 
+def test_result_arrays_option(ab):
+    """inv_param.result_arrays: the same numbers as the reference-style nested lists, as float64 arrays"""
+    from adsurf_b200._model import iter_inversion, multi_inversion
+    from tests.test_dist_gloo import _problem
+    mp_, ip, init, obs = _problem()
+    runs = {}
+    for flag in (False, True):
+        ip.result_arrays = flag
+        inv = multi_inversion(mp_, ip, init, obs, vsrange_sign="add", vsrange=[-0.5, 0.5], device="cpu")
+        runs[flag] = inv
+    for key in ("iter_vs", "iter_thick", "loss"):
+        lst, arr = runs[False].inv_process[key], runs[True].inv_process[key]
+        assert isinstance(lst, list) and isinstance(arr, np.ndarray) and arr.dtype == np.float64
+        assert np.array_equal(np.asarray(lst), arr)
+    for key in ("thick", "vp", "vs", "rho"):
+        assert isinstance(runs[False].inv_model[key], list)
+        assert np.array_equal(np.asarray(runs[False].inv_model[key]), runs[True].inv_model[key])
+    one = types.SimpleNamespace(init_model={k: np.asarray(v)[0] if np.ndim(v) == 2 else v
+                                            for k, v in init.init_model.items()})
+    ip.damp_horizontal = 0.0
+    inv1 = iter_inversion(mp_, ip, one, obs[0], vsrange_sign="add", vsrange=[-0.5, 0.5], device="cpu")
+    assert isinstance(inv1.inv_process["loss"], np.ndarray) and isinstance(inv1.inv_model["vs"], np.ndarray)
+
+
 def test_gpu_dispersion_extraction_logic(ab):
     """dense-grid bracketing + batched regula falsi (adsurf_b200.dispersion) against the reference solver's
     roots; kernels served by the oracle here, the real kernels in tests/test_gpu_api.py."""
