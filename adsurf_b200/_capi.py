@@ -95,7 +95,7 @@ def lib():
         L.adsurf_math_probe.restype = ci
         L.adsurf_plan_describe.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(ci)]
         L.adsurf_plan_describe.restype = ci
-        L.adsurf_dispersion_curves.argtypes = [vp] * 5 + [ci] * 4 + [ctypes.c_double, vp, vp, vp, sz, vp]
+        L.adsurf_dispersion_curves.argtypes = [vp] * 5 + [ci] * 4 + [ctypes.c_double, ci, vp, vp, vp, sz, vp]
         L.adsurf_dispersion_curves.restype = ci
         L.adsurf_mc_generate.argtypes = ([vp] * 9 + [ci, ci, ci, ci, ctypes.c_double, ctypes.c_double, ctypes.c_double, ci,
                                           ctypes.c_ulonglong] + [vp] * 5)
@@ -308,8 +308,9 @@ def dmf_step(d, a, b, rho, t, c, C, compress, with_grad=True, want_F=False, want
     return (loss, F, norm) + grads
 
 
-def dispersion_curves(d, a, b, rho, t, nmodes, dc):
-    """(c [S,nmodes,NF], status int32 [S]): modal phase velocities by the reference's root search, one warp per model"""
+def dispersion_curves(d, a, b, rho, t, nmodes, dc, ifunc=2):
+    """(c [S,nmodes,NF], status int32 [S]): modal phase velocities by the reference's root search, one warp per model;
+    ifunc 2 = Rayleigh, 1 = Love"""
     global launch_count
     _req(d, a, b, rho, t)
     S, L = d.shape
@@ -320,7 +321,8 @@ def dispersion_curves(d, a, b, rho, t, nmodes, dc):
     ws, nbytes = _workspace(OP_DISPERSION, S, L, NF, 0, d)
     with torch.cuda.device(dev):
         _check(lib().adsurf_dispersion_curves(_ptr(d), _ptr(a), _ptr(b), _ptr(rho), _ptr(t), S, L, NF, int(nmodes),
-                                              float(dc), _ptr(c), _ptr(status), _ptr(ws), nbytes, _stream(d)))
+                                              float(dc), int(ifunc), _ptr(c), _ptr(status), _ptr(ws), nbytes,
+                                              _stream(d)))
     launch_count += 1
     return c, status
 

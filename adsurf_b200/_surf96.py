@@ -91,22 +91,45 @@ def rayleigh_secular(wvno, omega, d, a, b, rho):
     return e0
 
 
-def _delta(t, c, d, a, b, rho):
+def love_secular(wvno, omega, d, b, rho):
+    """Normalised Love secular function for one (k, omega) (reference dltar1, :168-215, llw=-1): the SH
+    stress-displacement pair carried up from the half-space, max-normalised after every layer."""
+    L = len(d)
+    xkb = omega / b[L - 1]
+    rb = np.sqrt((wvno + xkb) * abs(wvno - xkb))
+    e1, e2 = rho[L - 1] * rb, 1.0 / (b[L - 1] * b[L - 1])
+    for m in range(L - 2, -1, -1):
+        xmu = rho[m] * b[m] * b[m]
+        xkb = omega / b[m]
+        rb = np.sqrt((wvno + xkb) * abs(wvno - xkb))
+        cq, y, z, _ = _eig(wvno, xkb, rb, d[m])
+        n1 = e1 * cq + e2 * xmu * z
+        n2 = e1 * y / xmu + e2 * cq
+        big = max(abs(n1), abs(n2))
+        if big < 1.0e-40:
+            big = 1.0
+        e1, e2 = n1 / big, n2 / big
+    return e1
+
+
+def _delta(t, c, d, a, b, rho, ifunc=2):
     omega = TWOPI / t
+    if ifunc == 1:
+        return love_secular(omega / c, omega, d, b, rho)
     return rayleigh_secular(omega / c, omega, d, a, b, rho)
 
 
-def nevill(t, c1, c2, del1, del2, d, a, b, rho):
+def nevill(t, c1, c2, del1, del2, d, a, b, rho, ifunc=2):
     """Refine a bracketed root: Neville rational interpolation with bisection safeguards (:452-541)."""
     xs, ys = np.zeros(20), np.zeros(20)
     c3 = 0.5 * (c1 + c2)
-    del3 = _delta(t, c3, d, a, b, rho)
+    del3 = _delta(t, c3, d, a, b, rho, ifunc)
     nev, m = 1, 1
     for _ in range(98):
         if c3 < min(c1, c2) or c3 > max(c1, c2):  # estimate left the bracket: halve instead
             nev = 0
             c3 = 0.5 * (c1 + c2)
-            del3 = _delta(t, c3, d, a, b, rho)
+            del3 = _delta(t, c3, d, a, b, rho, ifunc)
         s13, s32 = del1 - del3, del3 - del2
         if np.sign(del3) * np.sign(del1) < 0.0:
             c2, del2 = c3, del3
@@ -119,7 +142,7 @@ def nevill(t, c1, c2, del1, del2, d, a, b, rho):
         ss1, ss2 = abs(del1), abs(del2)
         if 0.01 * ss1 > ss2 or 0.01 * ss2 > ss1 or nev == 0:  # values too unequal for a polynomial fit
             c3 = 0.5 * (c1 + c2)
-            del3 = _delta(t, c3, d, a, b, rho)
+            del3 = _delta(t, c3, d, a, b, rho, ifunc)
             nev, m = 1, 1
             continue
         if nev == 2:
@@ -137,19 +160,19 @@ def nevill(t, c1, c2, del1, del2, d, a, b, rho):
             xs[j - 1] = (-ys[j - 1] * xs[j] + ys[m] * xs[j - 1]) / denom
         if ok:
             c3 = xs[0]
-            del3 = _delta(t, c3, d, a, b, rho)
+            del3 = _delta(t, c3, d, a, b, rho, ifunc)
             nev = 2
             m = min(m + 1, 10)
         else:
             c3 = 0.5 * (c1 + c2)
-            del3 = _delta(t, c3, d, a, b, rho)
+            del3 = _delta(t, c3, d, a, b, rho, ifunc)
             nev, m = 1, 1
     return c3
 
 
-def getsol(t1, c1, clow, dc, cm, betmx, ifirst, del1st, d, a, b, rho):
+def getsol(t1, c1, clow, dc, cm, betmx, ifirst, del1st, d, a, b, rho, ifunc=2):
     """Walk the dc ladder until the secular function changes sign, then refine (:543-574)."""
-    del1 = _delta(t1, c1, d, a, b, rho)
+    del1 = _delta(t1, c1, d, a, b, rho, ifunc)
     if ifirst:
         del1st = del1
     idir = -1.0 if (not ifirst and np.sign(del1st) * np.sign(del1) < 0.0) else 1.0
@@ -159,9 +182,9 @@ def getsol(t1, c1, clow, dc, cm, betmx, ifirst, del1st, d, a, b, rho):
             idir = 1.0
             c1 = clow
             continue
-        del2 = _delta(t1, c2, d, a, b, rho)
+        del2 = _delta(t1, c2, d, a, b, rho, ifunc)
         if np.sign(del1) != np.sign(del2):
-            c1 = nevill(t1, c1, c2, del1, del2, d, a, b, rho)
+            c1 = nevill(t1, c1, c2, del1, del2, d, a, b, rho, ifunc)
             return c1, del1st, c1 > betmx
         c1, del1 = c2, del2
         if c1 < cm or c1 >= betmx + dc:
@@ -188,8 +211,8 @@ def gtsolh(a, b):
 
 def getc(t, d, a, b, rho, mode, ifunc, dc):
     """Phase velocities of mode `mode` at the periods t; 0 where the mode does not exist (:596-691)."""
-    if ifunc != 2:
-        raise NotImplementedError("adsurf_b200: Rayleigh / Dunkin (ifunc=2) only")
+    if ifunc not in (1, 2):  # 3 = fast delta matrix: the reference's own path fails on numpy >= 2 (np.complex_)
+        raise NotImplementedError("adsurf_b200: Love (ifunc=1) and Rayleigh / Dunkin (ifunc=2) only")
     if b[0] <= 0.0:
         raise NotImplementedError("adsurf_b200: water layer not supported")
     kmax = len(t)
@@ -215,7 +238,7 @@ def getc(t, d, a, b, rho, mode, ifunc, dc):
                 c1 = max(c[k - 1], clow)
             else:
                 clow, c1 = cm, c[k - 1] - onea * dc
-            c1, del1st, iret = getsol(t[k], c1, clow, dc, cm, betmx, ifirst, del1st, d, a, b, rho)
+            c1, del1st, iret = getsol(t[k], c1, clow, dc, cm, betmx, ifirst, del1st, d, a, b, rho, ifunc)
             if iret:
                 if iq == 0:
                     raise DispersionError("failed to find root for fundamental mode")

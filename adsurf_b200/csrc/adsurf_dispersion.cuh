@@ -24,6 +24,7 @@ namespace adsurf {
 struct DispModel {
   const double *d, *a, *b, *rho;
   int L;
+  int ifunc;  // 1: Love waves (dltar1), 2: Rayleigh waves, Dunkin's matrix (dltar4) — the reference's ifunc
 };
 
 // The normalised Rayleigh secular function (dltar4 with llw = -1, :217-297) in three pieces, so that the scalar
@@ -166,6 +167,37 @@ ADSURF_HD double disp_finish(double e0, double e1, double e2, double e3, double 
   return big > 0.0 ? e0 / big : e0;
 }
 
+// Love waves (dltar1, :168-215): the SH stress-displacement pair (e1, e2) carried up from the half-space,
+//   e1' = e1 cos + e2 mu z,  e2' = e1 y / mu + e2 cos,   mu = rho beta^2,
+// with the same eigenfunction terms (disp_eig on k_beta), the same max-normalisation per layer in the reference and
+// the same treatment here (power-of-two rescale, one normalisation at the top).
+enum { LT_CQ = 0, LT_Y, LT_Z, LT_MU, LT_IMU };
+ADSURF_HD void disp_love_terms(double* __restrict__ q, double xkb, double wvno, double dm, double xmu, double ixmu) {
+  double rb, irb, ex;
+  disp_root((wvno + xkb) * fabs(wvno - xkb), rb, irb);
+  disp_eig(wvno, xkb, rb, irb, dm, q[LT_CQ], q[LT_Y], q[LT_Z], ex);
+  q[LT_MU] = xmu;
+  q[LT_IMU] = ixmu;
+}
+ADSURF_HD void disp_love_half(double* __restrict__ q, double xkb, double wvno, double rho1, double beta1) {
+  double rb, irb;
+  disp_root((wvno + xkb) * fabs(wvno - xkb), rb, irb);
+  q[0] = rho1 * rb;
+  q[1] = 1.0 / (beta1 * beta1);
+}
+ADSURF_HD void disp_love_apply(double& e1, double& e2, const double* __restrict__ q) {
+  const double cq = q[LT_CQ], y = q[LT_Y], z = q[LT_Z];
+  const double n1 = e1 * cq + (e2 * q[LT_MU]) * z;
+  const double n2 = (e1 * y) * q[LT_IMU] + e2 * cq;
+  const double sc = disp_pow2_scale(n1, n2, 0.0, 0.0, 0.0);
+  e1 = n1 * sc;
+  e2 = n2 * sc;
+}
+ADSURF_HD double disp_love_finish(double e1, double e2) {
+  const double big = fmax(fabs(e1), fabs(e2));
+  return big > 0.0 ? e1 / big : e1;
+}
+
 // One thread evaluates everything (host check; any number of layers).
 struct DispScalarEval {
   DispModel M;
@@ -178,6 +210,16 @@ struct DispScalarEval {
     const double k2 = wvno * wvno, t2 = -2.0 * k2;
     const int L = M.L;
     alignas(16) double per[kDispPer], q[kDispTerms];
+    if (M.ifunc == 1) {
+      disp_love_half(q, omega / M.b[L - 1], wvno, M.rho[L - 1], M.b[L - 1]);
+      double e1 = q[0], e2 = q[1];
+      for (int m = L - 2; m >= 0; --m) {
+        const double xmu = M.rho[m] * M.b[m] * M.b[m];
+        disp_love_terms(q, omega / M.b[m], wvno, M.d[m], xmu, 1.0 / xmu);
+        disp_love_apply(e1, e2, q);
+      }
+      return L > 1 ? disp_love_finish(e1, e2) : e1;
+    }
     disp_period_consts(per, M.a[L - 1], M.b[L - 1], omega);
     disp_half_terms(q, per, wvno, k2, M.rho[L - 1]);
     double e0 = q[0], e1 = q[1], e2 = q[2], e3 = q[3], e4 = q[4];
@@ -210,10 +252,18 @@ struct DispWarpEval {
     __syncwarp();
     for (int m = lane; m < M.L; m += 32) {
       double* pm = per + m * kDispPer;
-      disp_period_consts(pm, M.a[m], M.b[m], omega);
+      if (M.ifunc == 1) {  // Love: beta, k_beta, mu, d, rho, 1/mu
+        const double bm = M.b[m], xmu = M.rho[m] * bm * bm;
+        pm[0] = bm;
+        pm[1] = omega / bm;
+        pm[2] = xmu;
+        pm[5] = 1.0 / xmu;
+      } else {
+        disp_period_consts(pm, M.a[m], M.b[m], omega);
+        pm[5] = 1.0 / M.rho[m];
+      }
       pm[3] = M.d[m];
       pm[4] = M.rho[m];
-      pm[5] = 1.0 / M.rho[m];
     }
     __syncwarp();
   }
@@ -223,6 +273,19 @@ struct DispWarpEval {
     const int L = M.L;
     const double* per = scratch();
     double* lay = scratch() + L * kDispPer;
+    if (M.ifunc == 1) {
+      for (int m = lane; m < L; m += 32) {
+        const double* pm = per + m * kDispPer;
+        if (m < L - 1) disp_love_terms(lay + m * kDispTerms, pm[1], wvno, pm[3], pm[2], pm[5]);
+        else disp_love_half(lay + m * kDispTerms, pm[1], wvno, pm[4], pm[0]);
+      }
+      __syncwarp();
+      const double* q = lay + (L - 1) * kDispTerms;
+      double e1 = q[0], e2 = q[1];
+      for (int m = L - 2; m >= 0; --m) disp_love_apply(e1, e2, lay + m * kDispTerms);
+      __syncwarp();
+      return L > 1 ? disp_love_finish(e1, e2) : e1;
+    }
     for (int m = lane; m < L; m += 32) {
       const double* pm = per + m * kDispPer;
       if (m < L - 1) disp_layer_terms(lay + m * kDispTerms, pm, wvno, k2, t2, pm[3], pm[4], pm[5]);

@@ -894,13 +894,13 @@ __host__ __device__ inline size_t disp_warp_doubles(int L) { return (size_t)L * 
 __global__ void __launch_bounds__(kDispThreads)
 k_dispersion(const double* __restrict__ d, const double* __restrict__ a, const double* __restrict__ b,
              const double* __restrict__ rho, const double* __restrict__ t, int S, int L, int NF, int nmodes, double dc,
-             double* __restrict__ cout, double* __restrict__ work, int* __restrict__ status) {
+             int ifunc, double* __restrict__ cout, double* __restrict__ work, int* __restrict__ status) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * (kDispThreads / kWarp) + warp;
   stage_exp_table();
   __syncthreads();
   if (s >= S) return;  // whole warps: the evaluator synchronises the warp only
-  const DispModel M{d + (size_t)s * L, a + (size_t)s * L, b + (size_t)s * L, rho + (size_t)s * L, L};
+  const DispModel M{d + (size_t)s * L, a + (size_t)s * L, b + (size_t)s * L, rho + (size_t)s * L, L, ifunc};
   DispWarpEval ev{M, kSmemHead + warp * (int)disp_warp_doubles(L), lane, 0.0};
   const int rc = disp_getc(ev, M, t + (size_t)s * NF, NF, nmodes, dc, cout + (size_t)s * nmodes * NF, work + (size_t)s * NF);
   if (lane == 0) status[s] = rc;
@@ -1667,11 +1667,11 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
 }
 
 int adsurf_dispersion_curves(const double* d, const double* alpha, const double* beta, const double* rho,
-                             const double* t, int S, int L, int NF, int nmodes, double dc, double* c, int* status,
-                             void* ws, size_t ws_bytes, void* stream) {
+                             const double* t, int S, int L, int NF, int nmodes, double dc, int ifunc, double* c,
+                             int* status, void* ws, size_t ws_bytes, void* stream) {
   if (!d || !alpha || !beta || !rho || !t || !c || !status) return ADSURF_E_NULL;
   if (S <= 0 || L <= 0 || NF <= 0 || nmodes <= 0) return ADSURF_E_SHAPE;
-  if (!(dc > 0.0)) return ADSURF_E_ARG;
+  if (!(dc > 0.0) || (ifunc != 1 && ifunc != 2)) return ADSURF_E_ARG;
   if (!ws || ws_bytes < (size_t)S * NF * sizeof(double)) return ADSURF_E_WORKSPACE;
   const int wpb = kDispThreads / kWarp;  // one model per warp
   const long long blocks = ((long long)S + wpb - 1) / wpb;
@@ -1680,7 +1680,7 @@ int adsurf_dispersion_curves(const double* d, const double* alpha, const double*
   if (smem > 227 * 1024) return ADSURF_E_SHAPE;  // more than 360 layers
   if (const int rc = set_smem(k_dispersion, smem)) return rc;
   k_dispersion<<<(unsigned)blocks, kDispThreads, smem, (cudaStream_t)stream>>>(d, alpha, beta, rho, t, S, L, NF, nmodes,
-                                                                              dc, c, (double*)ws, status);
+                                                                              dc, ifunc, c, (double*)ws, status);
   return check_launch();
 }
 

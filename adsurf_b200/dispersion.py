@@ -25,9 +25,9 @@ from ._surf96 import DispersionError, gtsolh
 
 
 @torch.no_grad()
-def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, device=None, itype=0, dt=0.025):
-    """Phase (itype=0) or group (itype=1) velocities of the requested Rayleigh modes by the reference's root search
-    on the GPU.
+def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, device=None, itype=0, dt=0.025, ifunc=2):
+    """Phase (itype=0) or group (itype=1) velocities of the requested Rayleigh (ifunc=2, Dunkin's matrix) or Love
+    (ifunc=1) modes by the reference's root search on the GPU (`surf96`'s ifunc, _surf96.py:693-760).
 
     t: periods [NF] (or [S,NF]); d, a, b, rho: thickness, Vp, Vs, density [L] (one model) or [S,L] (an ensemble).
     Returns c[len(modes), NF] (one model) or c[S, len(modes), NF]; 0 where a mode does not exist.
@@ -37,8 +37,8 @@ def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, device=None, itype=
     if itype == 1:
         t_np = np.asarray(t, dtype=np.float64)
         t1, t2 = t_np / (1.0 + dt), t_np / (1.0 - dt)
-        c1 = dispersion_curves(t1, d, a, b, rho, modes, dc, device)
-        c2 = dispersion_curves(t2, d, a, b, rho, modes, dc, device)
+        c1 = dispersion_curves(t1, d, a, b, rho, modes, dc, device, ifunc=ifunc)
+        c2 = dispersion_curves(t2, d, a, b, rho, modes, dc, device, ifunc=ifunc)
         f1 = np.broadcast_to((1.0 / t1) if t_np.ndim == 1 else (1.0 / t1)[:, None, :], c1.shape)
         f2 = np.broadcast_to((1.0 / t2) if t_np.ndim == 1 else (1.0 / t2)[:, None, :], c1.shape)
         out = np.zeros_like(c1)
@@ -56,8 +56,10 @@ def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, device=None, itype=
     if bool((B_[:, 0] <= 0).any()):
         raise NotImplementedError("adsurf_b200: water layer not supported")
     modes = [int(m) for m in modes]
+    if ifunc not in (1, 2):
+        raise NotImplementedError("adsurf_b200: Love (ifunc=1) and Rayleigh / Dunkin (ifunc=2) only")
     c, status = _capi.dispersion_curves(D.contiguous(), A_.contiguous(), B_.contiguous(), R.contiguous(),
-                                        T.contiguous(), max(modes) + 1, float(dc))
+                                        T.contiguous(), max(modes) + 1, float(dc), ifunc=ifunc)
     if bool(status.any()):
         raise DispersionError("failed to find root for fundamental mode")
     out = c[:, modes, :].cpu().numpy()

@@ -226,9 +226,12 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
  * Periods are searched in the order given (the reference passes them ascending).  status[s] = 1 when the fundamental
  * mode cannot be bracketed (the reference raises DispersionError), else 0.  ws >= S*NF doubles.
  * Replaces _surf96.surf96 / getc / getsol / nevill / gtsolh (_surf96.py:452-760) behind cal_dispersion_curve
- * (_ADsurf.py:232-310), phase velocity (itype = 0); group velocity is two calls at t/(1 +- dt) on the host. */
+ * (_ADsurf.py:232-310), phase velocity (itype = 0); group velocity is two calls at t/(1 +- dt) on the host.
+ * ifunc as in the reference (_utils.py:20-23): 2 = Rayleigh waves, Dunkin's matrix (dltar4; what cal_dispersion_curve
+ * uses), 1 = Love waves (dltar1, _surf96.py:168-215: the same search on the SH secular function; alpha only enters the
+ * starting velocity); 3 (fast delta matrix) is ADSURF_E_ARG. */
 int adsurf_dispersion_curves(const double* d, const double* alpha, const double* beta, const double* rho,
-                             const double* t, int S, int L, int NF, int nmodes, double dc,
+                             const double* t, int S, int L, int NF, int nmodes, double dc, int ifunc,
                              double* c, int* status, void* ws, size_t ws_bytes, void* stream);
 
 /* Monte-Carlo ensemble of initial models, generated on the device: row 0 = the base model

@@ -242,6 +242,8 @@ def case_surf96_roots(name):
         for mode in modes:
             c = ref_surf.surf96(t, d, vp, b, rho, mode, 0, 2, dc)
             out[f"{tag}_mode{mode}_c"] = np.asarray(c, dtype=np.float64)
+            c = ref_surf.surf96(t, d, vp, b, rho, mode, 0, 1, dc)  # Love waves (ifunc = 1)
+            out[f"{tag}_love_mode{mode}_c"] = np.asarray(c, dtype=np.float64)
         out[f"{tag}_t"], out[f"{tag}_d"], out[f"{tag}_a"], out[f"{tag}_b"], out[f"{tag}_rho"] = t, d, vp, b, rho
         out[f"{tag}_dc"] = np.asarray(dc)
     np.savez_compressed(os.path.join(OUT, name), **out)
@@ -284,4 +286,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "surf96_roots":  # only the root-search fixture
+        case_surf96_roots("surf96_roots")
+    else:
+        main()

@@ -24,10 +24,10 @@ extern "C" {
 
 // modal dispersion curves of S models by the kernel's root search (adsurf_dispersion.cuh), run on the host
 void host_dispersion(const double* d, const double* a, const double* b, const double* rho, const double* t, int S, int L,
-                     int NF, int nmodes, double dc, double* c, int* status) {
+                     int NF, int nmodes, double dc, int ifunc, double* c, int* status) {
   std::vector<double> work(NF);
   for (int s = 0; s < S; ++s) {
-    const DispModel M{d + (size_t)s * L, a + (size_t)s * L, b + (size_t)s * L, rho + (size_t)s * L, L};
+    const DispModel M{d + (size_t)s * L, a + (size_t)s * L, b + (size_t)s * L, rho + (size_t)s * L, L, ifunc};
     DispScalarEval ev{M, 0.0};
     status[s] = disp_getc(ev, M, t + (size_t)s * NF, NF, nmodes, dc, c + (size_t)s * nmodes * NF, work.data());
   }

@@ -149,6 +149,21 @@ def test_gpu_dispersion_curves_match_reference_solver(api, tag, modes):
         assert np.max(np.abs(c[i] - ref)) <= 1e-6          # km/s, 100 % of the points
 
 
+@pytest.mark.parametrize("tag,modes", [("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,))])
+def test_gpu_love_dispersion_curves_match_reference_solver(api, tag, modes):
+    """ifunc = 1: Love waves (the reference's dltar1 behind the same root search) on the GPU"""
+    from adsurf_b200.dispersion import dispersion_curves
+    g = load("surf96_roots")
+    t, d, a, b, rho = (g[f"{tag}_{k}"] for k in ("t", "d", "a", "b", "rho"))
+    c = dispersion_curves(t, d, a, b, rho, modes=modes, dc=float(g[f"{tag}_dc"]), ifunc=1)
+    for i, mode in enumerate(modes):
+        ref = g[f"{tag}_love_mode{mode}_c"]
+        assert np.array_equal(c[i] > 0, ref > 0)
+        assert np.max(np.abs(c[i] - ref)) <= 1e-6
+    with pytest.raises(NotImplementedError):
+        dispersion_curves(t, d, a, b, rho, modes=modes, dc=0.01, ifunc=3)
+
+
 def test_gpu_group_velocity_matches_host_solver(api):
     """itype=1 (group velocity from two phase curves, _surf96.py:735-758) on the GPU against the host solver"""
     from adsurf_b200._surf96 import surf96

@@ -193,11 +193,12 @@ def test_pointwise_period_beyond_omega_clamp(hm):
         assert_grad_close(new, ref.numpy(), what=key)
 
 
+@pytest.mark.parametrize("ifunc", [2, 1])
 @pytest.mark.parametrize("tag,nmodes", [("m6", 1), ("m3", 3), ("m20", 1)])
-def test_dispersion_search_matches_reference_solver(hm, tag, nmodes):
+def test_dispersion_search_matches_reference_solver(hm, tag, nmodes, ifunc):
     """adsurf_dispersion.cuh (what k_dispersion runs per thread) compiled for the host: the reference solver's roots
     (tests/golden/surf96_roots.npz) within 1e-6 km/s, identical zeros for absent modes — and the same numbers as the
-    Python host port `_surf96.surf96` to rounding (same control flow)."""
+    Python host port `_surf96.surf96` to rounding (same control flow).  ifunc 2: Rayleigh (dltar4), 1: Love (dltar1)."""
     from adsurf_b200._surf96 import surf96
     g = load("surf96_roots")
     t, d, a, b, rho = (C(g[f"{tag}_{k}"]) for k in ("t", "d", "a", "b", "rho"))
@@ -205,12 +206,14 @@ def test_dispersion_search_matches_reference_solver(hm, tag, nmodes):
     NF, L = len(t), len(d)
     c = np.empty((nmodes, NF))
     status = np.zeros(1, dtype=np.int32)
-    hm.host_dispersion.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 4 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
-    hm.host_dispersion(P(d), P(a), P(b), P(rho), P(t), 1, L, NF, nmodes, dc, P(c), status.ctypes.data_as(ctypes.c_void_p))
+    hm.host_dispersion.argtypes = ([ctypes.c_void_p] * 5 + [ctypes.c_int] * 4 +
+                                   [ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p])
+    hm.host_dispersion(P(d), P(a), P(b), P(rho), P(t), 1, L, NF, nmodes, dc, ifunc, P(c),
+                       status.ctypes.data_as(ctypes.c_void_p))
     assert status[0] == 0
     for mode in range(nmodes):
-        ref = g[f"{tag}_mode{mode}_c"]
+        ref = g[f"{tag}_mode{mode}_c" if ifunc == 2 else f"{tag}_love_mode{mode}_c"]
         assert np.array_equal(c[mode] > 0, ref > 0)
         assert np.max(np.abs(c[mode] - ref)) <= 1e-6
-        port = surf96(t, d, a, b, rho, mode, 0, 2, dc)
+        port = surf96(t, d, a, b, rho, mode, 0, ifunc, dc)
         assert np.max(np.abs(c[mode] - port)) <= 1e-9

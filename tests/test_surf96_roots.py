@@ -42,4 +42,15 @@ def test_group_velocity_and_errors():
     c = surf96(t[::6], d, a, b, rho, 0, 0, 2, 0.005)
     assert np.all(u > 0) and np.all(u <= c + 1e-9)  # normal dispersion: group <= phase velocity
     with pytest.raises(NotImplementedError):
-        surf96(t, d, a, b, rho, 0, 0, 1, 0.005)  # Love
+        surf96(t, d, a, b, rho, 0, 0, 3, 0.005)  # fast delta matrix: not provided
+
+
+def test_love_waves_match_reference_solver():
+    """ifunc = 1 (dltar1): the host twin against the reference's float64 roots, every fixture model and mode"""
+    g = load("surf96_roots")
+    for tag, modes in (("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,))):
+        t, d, a, b, rho = (g[f"{tag}_{k}"] for k in ("t", "d", "a", "b", "rho"))
+        for mode in modes:
+            ref = g[f"{tag}_love_mode{mode}_c"]
+            c = surf96(t, d, a, b, rho, mode, 0, 1, float(g[f"{tag}_dc"]))
+            assert np.array_equal(c > 0, ref > 0) and np.max(np.abs(c - ref)) <= 1e-12
