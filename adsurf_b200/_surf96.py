@@ -39,8 +39,9 @@ def _eig(k, kx, r, dm):
     return (1.0 + fac) * 0.5, s / r, r * s, p
 
 
-def rayleigh_secular(wvno, omega, d, a, b, rho):
-    """Normalised Rayleigh secular function for one (k, omega) (reference dltar4, :217-297, llw=-1)."""
+def rayleigh_secular(wvno, omega, d, a, b, rho, llw=-1):
+    """Normalised Rayleigh secular function for one (k, omega) (reference dltar4, :217-297).  llw = 0: layer 0 is
+    water (Vs = 0): the solid stack ends above it and the water column closes the equation (:284-295)."""
     omega = max(omega, 1.0e-4)
     k2 = wvno * wvno
     t2 = -2.0 * k2
@@ -58,7 +59,7 @@ def rayleigh_secular(wvno, omega, d, a, b, rho):
     e2 = r1 * (g1 - gk * ra * rb)
     e3 = r1 * rb
     e4 = k2 - ra * rb
-    for m in range(L - 2, -1, -1):
+    for m in range(L - 2, llw, -1):
         xka, xkb = omega / a[m], omega / b[m]
         tt = b[m] / omega
         gk = 2.0 * tt * tt
@@ -88,17 +89,22 @@ def rayleigh_secular(wvno, omega, d, a, b, rho):
         if big < 1.0e-40:
             big = 1.0
         e0, e1, e2, e3, e4 = n0 / big, n1 / big, n2 / big, n3 / big, n4 / big
+    if llw == 0:
+        xka = omega / a[0]
+        ra = np.sqrt((wvno + xka) * abs(wvno - xka))
+        cp, w, _, _ = _eig(wvno, xka, ra, d[0])
+        return cp * e0 - rho[0] * w * e1
     return e0
 
 
-def love_secular(wvno, omega, d, b, rho):
+def love_secular(wvno, omega, d, b, rho, llw=-1):
     """Normalised Love secular function for one (k, omega) (reference dltar1, :168-215, llw=-1): the SH
     stress-displacement pair carried up from the half-space, max-normalised after every layer."""
     L = len(d)
     xkb = omega / b[L - 1]
     rb = np.sqrt((wvno + xkb) * abs(wvno - xkb))
     e1, e2 = rho[L - 1] * rb, 1.0 / (b[L - 1] * b[L - 1])
-    for m in range(L - 2, -1, -1):
+    for m in range(L - 2, llw, -1):  # a water layer carries no SH motion
         xmu = rho[m] * b[m] * b[m]
         xkb = omega / b[m]
         rb = np.sqrt((wvno + xkb) * abs(wvno - xkb))
@@ -114,9 +120,10 @@ def love_secular(wvno, omega, d, b, rho):
 
 def _delta(t, c, d, a, b, rho, ifunc=2):
     omega = TWOPI / t
+    llw = 0 if b[0] <= 0.0 else -1
     if ifunc == 1:
-        return love_secular(omega / c, omega, d, b, rho)
-    return rayleigh_secular(omega / c, omega, d, a, b, rho)
+        return love_secular(omega / c, omega, d, b, rho, llw)
+    return rayleigh_secular(omega / c, omega, d, a, b, rho, llw)
 
 
 def nevill(t, c1, c2, del1, del2, d, a, b, rho, ifunc=2):
@@ -213,16 +220,19 @@ def getc(t, d, a, b, rho, mode, ifunc, dc):
     """Phase velocities of mode `mode` at the periods t; 0 where the mode does not exist (:596-691)."""
     if ifunc not in (1, 2):  # 3 = fast delta matrix: the reference's own path fails on numpy >= 2 (np.complex_)
         raise NotImplementedError("adsurf_b200: Love (ifunc=1) and Rayleigh / Dunkin (ifunc=2) only")
-    if b[0] <= 0.0:
-        raise NotImplementedError("adsurf_b200: water layer not supported")
+    if b[0] <= 0.0 and len(d) < 3:
+        raise NotImplementedError("adsurf_b200: a water layer needs a solid layer above the half-space")
     kmax = len(t)
     c, cg = np.zeros(kmax), np.zeros(kmax)
-    betmx, betmn, jmn = -1.0e20, 1.0e20, 0
+    betmx, betmn, jmn, jsol = -1.0e20, 1.0e20, 0, False
     for i in range(len(d)):
         if 0.01 < b[i] < betmn:
-            betmn, jmn = b[i], i
+            betmn, jmn, jsol = b[i], i, False
+        elif b[i] < 0.01 and a[i] < betmn:  # a fluid layer slower than every solid so far (:617-620)
+            betmn, jmn, jsol = a[i], i, True
         betmx = max(betmx, b[i])
-    cc = 0.9 * gtsolh(a[jmn], b[jmn])  # start a little below the slowest layer's Rayleigh velocity
+    # start a little below the slowest layer's Rayleigh velocity (the fluid's Vp if that is the slowest)
+    cc = 0.9 * (betmn if jsol else gtsolh(a[jmn], b[jmn]))
     c1, cm = cc, cc
     one, onea = 1.0e-2, 1.5
     for iq in range(mode + 1):

@@ -25,6 +25,8 @@ struct DispModel {
   const double *d, *a, *b, *rho;
   int L;
   int ifunc;  // 1: Love waves (dltar1), 2: Rayleigh waves, Dunkin's matrix (dltar4) — the reference's ifunc
+  // index of the topmost solid layer: 1 when layer 0 is water (Vs <= 0; the reference's llw = 0, :608), else 0
+  ADSURF_HD int top() const { return b[0] <= 0.0 ? 1 : 0; }
 };
 
 // The normalised Rayleigh secular function (dltar4 with llw = -1, :217-297) in three pieces, so that the scalar
@@ -166,6 +168,23 @@ ADSURF_HD double disp_finish(double e0, double e1, double e2, double e3, double 
   const double big = fmax(fmax(fmax(fabs(e0), fabs(e1)), fmax(fabs(e2), fabs(e3))), fabs(e4));
   return big > 0.0 ? e0 / big : e0;
 }
+// a water layer on top (:284-295): the normalised vector of the topmost solid layer closed by the water column,
+// cos-like(p) E[0] - rho_w sin-like(p)/r E[1] with the P terms of the water layer (q: DT_CP, DT_W of layer 0)
+ADSURF_HD double disp_finish_water(double e0, double e1, double e2, double e3, double e4, const double* __restrict__ q,
+                                   double rho_w) {
+  const double big = fmax(fmax(fmax(fabs(e0), fabs(e1)), fmax(fabs(e2), fabs(e3))), fabs(e4));
+  if (big > 0.0) {
+    e0 = e0 / big;
+    e1 = e1 / big;
+  }
+  return q[DT_CP] * e0 - rho_w * q[DT_W] * e1;
+}
+// P terms of the water layer
+ADSURF_HD void disp_water_terms(double* __restrict__ q, double xka, double wvno, double dm) {
+  double ra, ira, x, ex;
+  disp_root((wvno + xka) * fabs(wvno - xka), ra, ira);
+  disp_eig(wvno, xka, ra, ira, dm, q[DT_CP], q[DT_W], x, ex);
+}
 
 // Love waves (dltar1, :168-215): the SH stress-displacement pair (e1, e2) carried up from the half-space,
 //   e1' = e1 cos + e2 mu z,  e2' = e1 y / mu + e2 cos,   mu = rho beta^2,
@@ -208,25 +227,29 @@ struct DispScalarEval {
     const double wvno = omega / c;
     omega = fmax(omega, 1.0e-4);
     const double k2 = wvno * wvno, t2 = -2.0 * k2;
-    const int L = M.L;
+    const int L = M.L, top = M.top();
     alignas(16) double per[kDispPer], q[kDispTerms];
     if (M.ifunc == 1) {
       disp_love_half(q, omega / M.b[L - 1], wvno, M.rho[L - 1], M.b[L - 1]);
       double e1 = q[0], e2 = q[1];
-      for (int m = L - 2; m >= 0; --m) {
+      for (int m = L - 2; m >= top; --m) {  // a water layer carries no SH motion
         const double xmu = M.rho[m] * M.b[m] * M.b[m];
         disp_love_terms(q, omega / M.b[m], wvno, M.d[m], xmu, 1.0 / xmu);
         disp_love_apply(e1, e2, q);
       }
-      return L > 1 ? disp_love_finish(e1, e2) : e1;
+      return L - 1 > top ? disp_love_finish(e1, e2) : e1;
     }
     disp_period_consts(per, M.a[L - 1], M.b[L - 1], omega);
     disp_half_terms(q, per, wvno, k2, M.rho[L - 1]);
     double e0 = q[0], e1 = q[1], e2 = q[2], e3 = q[3], e4 = q[4];
-    for (int m = L - 2; m >= 0; --m) {
+    for (int m = L - 2; m >= top; --m) {
       disp_period_consts(per, M.a[m], M.b[m], omega);
       disp_layer_terms(q, per, wvno, k2, t2, M.d[m], M.rho[m], 1.0 / M.rho[m]);
       disp_layer_apply(e0, e1, e2, e3, e4, disp_load_terms(q));
+    }
+    if (top == 1) {
+      disp_water_terms(q, omega / M.a[0], wvno, M.d[0]);
+      return disp_finish_water(e0, e1, e2, e3, e4, q, M.rho[0]);
     }
     return L > 1 ? disp_finish(e0, e1, e2, e3, e4) : e0;
   }
@@ -270,11 +293,11 @@ struct DispWarpEval {
   __device__ __noinline__ double operator()(double c) const {
     const double wvno = omega0 / c;
     const double k2 = wvno * wvno, t2 = -2.0 * k2;
-    const int L = M.L;
+    const int L = M.L, top = M.top();
     const double* per = scratch();
     double* lay = scratch() + L * kDispPer;
     if (M.ifunc == 1) {
-      for (int m = lane; m < L; m += 32) {
+      for (int m = top + lane; m < L; m += 32) {
         const double* pm = per + m * kDispPer;
         if (m < L - 1) disp_love_terms(lay + m * kDispTerms, pm[1], wvno, pm[3], pm[2], pm[5]);
         else disp_love_half(lay + m * kDispTerms, pm[1], wvno, pm[4], pm[0]);
@@ -282,28 +305,29 @@ struct DispWarpEval {
       __syncwarp();
       const double* q = lay + (L - 1) * kDispTerms;
       double e1 = q[0], e2 = q[1];
-      for (int m = L - 2; m >= 0; --m) disp_love_apply(e1, e2, lay + m * kDispTerms);
+      for (int m = L - 2; m >= top; --m) disp_love_apply(e1, e2, lay + m * kDispTerms);
       __syncwarp();
-      return L > 1 ? disp_love_finish(e1, e2) : e1;
+      return L - 1 > top ? disp_love_finish(e1, e2) : e1;
     }
     for (int m = lane; m < L; m += 32) {
       const double* pm = per + m * kDispPer;
-      if (m < L - 1) disp_layer_terms(lay + m * kDispTerms, pm, wvno, k2, t2, pm[3], pm[4], pm[5]);
+      if (m < top) disp_water_terms(lay, pm[0], wvno, pm[3]);  // layer 0 is water
+      else if (m < L - 1) disp_layer_terms(lay + m * kDispTerms, pm, wvno, k2, t2, pm[3], pm[4], pm[5]);
       else disp_half_terms(lay + m * kDispTerms, pm, wvno, k2, pm[4]);
     }
     __syncwarp();
     const double* q = lay + (L - 1) * kDispTerms;
     double e0 = q[0], e1 = q[1], e2 = q[2], e3 = q[3], e4 = q[4];
-    if (L > 1) {
+    if (L - 1 > top) {
       q -= kDispTerms;
       DispTermRegs cur = disp_load_terms(q);
-      for (int m = L - 2; m >= 0; --m) {
-        if (m > 0) q -= kDispTerms;  // layer 0 re-reads its own terms: no predicated loads
+      for (int m = L - 2; m >= top; --m) {
+        if (m > top) q -= kDispTerms;  // the last layer re-reads its own terms: no predicated loads
         const DispTermRegs nxt = disp_load_terms(q);
         disp_layer_apply(e0, e1, e2, e3, e4, cur);
         cur = nxt;
       }
-      e0 = disp_finish(e0, e1, e2, e3, e4);
+      e0 = top ? disp_finish_water(e0, e1, e2, e3, e4, lay, per[4]) : disp_finish(e0, e1, e2, e3, e4);
     }
     __syncwarp();  // the next evaluation overwrites the staged terms
     return e0;
@@ -415,12 +439,15 @@ ADSURF_HD int disp_getc(Eval& ev, const DispModel& M, const double* ts, int NF, 
   const int L = M.L;
   double betmx = -1.0e20, betmn = 1.0e20;
   int jmn = 0;
+  bool jsol = false;
   for (int i = 0; i < L; ++i) {
     const double v = M.b[i];
-    if (v > 0.01 && v < betmn) { betmn = v; jmn = i; }
+    if (v > 0.01 && v < betmn) { betmn = v; jmn = i; jsol = false; }
+    else if (v < 0.01 && M.a[i] < betmn) { betmn = M.a[i]; jmn = i; jsol = true; }  // a fluid slower than the solids (:617-620)
     betmx = fmax(betmx, v);
   }
-  const double cc = 0.9 * disp_gtsolh(M.a[jmn], M.b[jmn]);  // start a little below the slowest layer's Rayleigh velocity
+  // start a little below the slowest layer's Rayleigh velocity (the fluid's Vp if that is the slowest)
+  const double cc = 0.9 * (jsol ? betmn : disp_gtsolh(M.a[jmn], M.b[jmn]));
   double c1 = cc;
   const double cm = cc, one = 1.0e-2, onea = 1.5;
   for (int i = 0; i < nmodes * NF; ++i) cout[i] = 0.0;

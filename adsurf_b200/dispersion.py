@@ -53,8 +53,8 @@ def dispersion_curves(t, d, a, b, rho, modes=(0,), dc=0.005, device=None, itype=
     S = D.shape[0]
     T = torch.as_tensor(np.asarray(t, dtype=np.float64), device=dev)
     T = T.reshape(1, -1).expand(S, -1) if T.dim() == 1 else T
-    if bool((B_[:, 0] <= 0).any()):
-        raise NotImplementedError("adsurf_b200: water layer not supported")
+    if bool((B_[:, 0] <= 0).any()) and D.shape[1] < 3:  # layer 0 water (Vs <= 0): as in _surf96.getc
+        raise NotImplementedError("adsurf_b200: a water layer needs a solid layer above the half-space")
     modes = [int(m) for m in modes]
     if ifunc not in (1, 2):
         raise NotImplementedError("adsurf_b200: Love (ifunc=1) and Rayleigh / Dunkin (ifunc=2) only")

@@ -229,7 +229,8 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
  * (_ADsurf.py:232-310), phase velocity (itype = 0); group velocity is two calls at t/(1 +- dt) on the host.
  * ifunc as in the reference (_utils.py:20-23): 2 = Rayleigh waves, Dunkin's matrix (dltar4; what cal_dispersion_curve
  * uses), 1 = Love waves (dltar1, _surf96.py:168-215: the same search on the SH secular function; alpha only enters the
- * starting velocity); 3 (fast delta matrix) is ADSURF_E_ARG. */
+ * starting velocity); 3 (fast delta matrix) is ADSURF_E_ARG.  beta[s,0] <= 0 marks layer 0 of model s as water (the
+ * reference's llw = 0, :608, :284-295): the solid stack ends above it and the water column closes the equation. */
 int adsurf_dispersion_curves(const double* d, const double* alpha, const double* beta, const double* rho,
                              const double* t, int S, int L, int NF, int nmodes, double dc, int ifunc,
                              double* c, int* status, void* ws, size_t ws_bytes, void* stream);

@@ -233,10 +233,18 @@ def case_shipped_fixtures(name):
 def case_surf96_roots(name):
     """Scalar root search (`_surf96.surf96`) with float64 numpy inputs: the N1 root oracle."""
     out = {}
+    # w5 / w5s: a water layer (Vs = 0) over four solid layers; in w5s the water is slower than every solid
+    water = {"thick": [0.3, 0.4, 0.5, 0.6, 0.0], "vs": [0.0, 1.0, 1.5, 2.0, 2.6]}
     for tag, model, tr, n, modes, dc in (("m6", MODEL6, (0.1, 5), 60, [0], 0.001),
                                          ("m3", MODEL3, (0.01, 0.2), 60, [0, 1, 2], 0.001),
-                                         ("m20", friul(20), (0.05, 5), 40, [0], 0.01)):
-        vp, rho = brocher(model["vs"])
+                                         ("m20", friul(20), (0.05, 5), 40, [0], 0.01),
+                                         ("w5", water, (0.1, 4), 30, [0, 1], 0.005),
+                                         ("w5s", water, (0.1, 4), 30, [0], 0.005)):
+        if tag.startswith("w5"):
+            vp, rho = brocher(np.maximum(model["vs"], 0.5))
+            vp[0], rho[0] = (1.5 if tag == "w5" else 0.6), 1.03
+        else:
+            vp, rho = brocher(model["vs"])
         t = log_wavelength_periods(tr[0], tr[1], n)
         d, b = np.asarray(model["thick"], float), np.asarray(model["vs"], float)
         for mode in modes:

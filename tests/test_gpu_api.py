@@ -134,7 +134,7 @@ def test_config4_friul_ensemble_step_and_sensitivity(api):
     assert np.max(np.abs(got - kern) / scale) < 1e-6   # roots are float32-accurate: dF/dc is well away from 0
 
 
-@pytest.mark.parametrize("tag,modes", [("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,))])
+@pytest.mark.parametrize("tag,modes", [("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,)), ("w5", (0, 1)), ("w5s", (0,))])
 def test_gpu_dispersion_curves_match_reference_solver(api, tag, modes):
     """k_dispersion (the reference's root search with its mode bookkeeping, one warp per model) against the
     reference's sequential solver in float64: every period, every mode, 1e-6 km/s; identical zeros for absent modes."""
@@ -149,7 +149,7 @@ def test_gpu_dispersion_curves_match_reference_solver(api, tag, modes):
         assert np.max(np.abs(c[i] - ref)) <= 1e-6          # km/s, 100 % of the points
 
 
-@pytest.mark.parametrize("tag,modes", [("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,))])
+@pytest.mark.parametrize("tag,modes", [("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,)), ("w5", (0, 1)), ("w5s", (0,))])
 def test_gpu_love_dispersion_curves_match_reference_solver(api, tag, modes):
     """ifunc = 1: Love waves (the reference's dltar1 behind the same root search) on the GPU"""
     from adsurf_b200.dispersion import dispersion_curves

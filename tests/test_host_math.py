@@ -194,11 +194,11 @@ def test_pointwise_period_beyond_omega_clamp(hm):
 
 
 @pytest.mark.parametrize("ifunc", [2, 1])
-@pytest.mark.parametrize("tag,nmodes", [("m6", 1), ("m3", 3), ("m20", 1)])
+@pytest.mark.parametrize("tag,nmodes", [("m6", 1), ("m3", 3), ("m20", 1), ("w5", 2), ("w5s", 1)])
 def test_dispersion_search_matches_reference_solver(hm, tag, nmodes, ifunc):
     """adsurf_dispersion.cuh (what k_dispersion runs per thread) compiled for the host: the reference solver's roots
     (tests/golden/surf96_roots.npz) within 1e-6 km/s, identical zeros for absent modes — and the same numbers as the
-    Python host port `_surf96.surf96` to rounding (same control flow).  ifunc 2: Rayleigh (dltar4), 1: Love (dltar1)."""
+    Python host port `_surf96.surf96` to rounding (same control flow).  ifunc 2: Rayleigh (dltar4), 1: Love (dltar1); w5 / w5s: a water layer on top."""
     from adsurf_b200._surf96 import surf96
     g = load("surf96_roots")
     t, d, a, b, rho = (C(g[f"{tag}_{k}"]) for k in ("t", "d", "a", "b", "rho"))

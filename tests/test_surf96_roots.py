@@ -48,9 +48,22 @@ def test_group_velocity_and_errors():
 def test_love_waves_match_reference_solver():
     """ifunc = 1 (dltar1): the host twin against the reference's float64 roots, every fixture model and mode"""
     g = load("surf96_roots")
-    for tag, modes in (("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,))):
+    for tag, modes in (("m6", (0,)), ("m3", (0, 1, 2)), ("m20", (0,)), ("w5", (0, 1)), ("w5s", (0,))):
         t, d, a, b, rho = (g[f"{tag}_{k}"] for k in ("t", "d", "a", "b", "rho"))
         for mode in modes:
             ref = g[f"{tag}_love_mode{mode}_c"]
             c = surf96(t, d, a, b, rho, mode, 0, 1, float(g[f"{tag}_dc"]))
+            assert np.array_equal(c > 0, ref > 0) and np.max(np.abs(c - ref)) <= 1e-12
+
+
+def test_water_layer_matches_reference_solver():
+    """layer 0 with Vs = 0 (the reference's llw = 0): Rayleigh roots of the host twin against the reference's, for a
+    water layer faster (w5) and slower (w5s: the search starts below the water's Vp) than the solid layers"""
+    g = load("surf96_roots")
+    for tag, modes in (("w5", (0, 1)), ("w5s", (0,))):
+        t, d, a, b, rho = (g[f"{tag}_{k}"] for k in ("t", "d", "a", "b", "rho"))
+        assert b[0] == 0.0
+        for mode in modes:
+            ref = g[f"{tag}_mode{mode}_c"]
+            c = surf96(t, d, a, b, rho, mode, 0, 2, float(g[f"{tag}_dc"]))
             assert np.array_equal(c > 0, ref > 0) and np.max(np.abs(c - ref)) <= 1e-12
