@@ -143,7 +143,7 @@ __constant__ double kRedCD[7] = ADSURF_RED_CONSTS;
 // 2^(j/32), j = 0..31 (correctly rounded).  On the device the table lives in the first kSmemHead
 // doubles of every kernel's dynamic shared memory (per-lane indices: a constant-memory table would
 // serialise); every kernel that evaluates exp_neg stages it with stage_exp_table().
-constexpr int kSmemHead = 32;
+constexpr int kSmemHead = 40;  // 32 table entries + the constants of ADSURF_HC
 #define ADSURF_EXP2_TABLE                                                                                     \
   { 1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,    \
     1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484,            \
@@ -155,15 +155,22 @@ constexpr int kSmemHead = 32;
 static const double kExp2TabH[32] = ADSURF_EXP2_TABLE;
 #if defined(__CUDACC__)
 __constant__ double kExp2TabD[32] = ADSURF_EXP2_TABLE;
+// constants that share an FMA with another constant: an FP64 instruction takes one immediate / constant-bank operand,
+// the second one would be rebuilt in a register pair (two moves) at every use; read from the shared-memory head it
+// costs one load, or nothing where the compiler keeps it in registers across the layer loop
+__constant__ double kHeadConstD[8] = {6755399441055744.0, 0.00138888880610466, -0.5, 0.0, 0.0, 0.0, 0.0, 0.0};
 extern __shared__ double adsurf_smem_head[];
 __device__ __forceinline__ void stage_exp_table() {
-  for (int j = threadIdx.x; j < kSmemHead; j += blockDim.x) adsurf_smem_head[j] = kExp2TabD[j];
+  for (int j = threadIdx.x; j < 32; j += blockDim.x) adsurf_smem_head[j] = kExp2TabD[j];
+  if (threadIdx.x < 8) adsurf_smem_head[32 + threadIdx.x] = kHeadConstD[threadIdx.x];
 }
 #endif
 #if defined(__CUDA_ARCH__)
 #define ADSURF_EXP2_TAB(j) adsurf_smem_head[j]
+#define ADSURF_HC(i, literal) adsurf_smem_head[32 + (i)]
 #else
 #define ADSURF_EXP2_TAB(j) kExp2TabH[j]
+#define ADSURF_HC(i, literal) (literal)
 #endif
 
 // exp(-p) for 0 <= p < ~700: n = rint(-p 32/ln2), r = -p - n ln2/32 (two-term, |r| <= ln2/64),
@@ -181,12 +188,12 @@ ADSURF_HD double exp_neg(double p_in) {
   // (e^-700 ~ 1e-304: its square and its products underflow to 0) in one ALU instruction; beyond ~708 the exponent arithmetic below would wrap.
   const double p = clamp_hi(p_in, 0x4085E000);
   const double x = -p;
-  const double t = fma(x, 46.166229248046875, kShifter);
+  const double t = fma(x, 46.166229248046875, ADSURF_HC(0, kShifter));
   const double fn = t - kShifter;
   double r = fma(fn, -0.021660849452018738, x);
   r = fma(fn, ADSURF_K(kExpC, 0), r);
   const int n = (int)dbl_bits(t);  // low 32 bits hold the (two's complement) integer
-  double q = fma(0.00138888880610466, r, 0.00833333283662796);
+  double q = fma(ADSURF_HC(1, 0.00138888880610466), r, 0.00833333283662796);
   q = fma(q, r, ADSURF_K(kExpC, 1));
   q = fma(q, r, ADSURF_K(kExpC, 2));
   q = fma(q, r, 0.5);
@@ -212,7 +219,7 @@ ADSURF_HD void sincos_fast(double q, double* sn, double* cs) {
 
 // branch-free core, valid for |q| < 1e5
 ADSURF_HD void sincos_core(double q, double* sn, double* cs) {
-  const double t = fma(q, ADSURF_K(kRedC, 3), kShifter);
+  const double t = fma(q, ADSURF_K(kRedC, 3), ADSURF_HC(0, kShifter));
   const double fn = t - kShifter;
   double r = fma(fn, ADSURF_K(kRedC, 4), q);
   r = fma(fn, ADSURF_K(kRedC, 5), r);
@@ -225,7 +232,7 @@ ADSURF_HD void sincos_core(double q, double* sn, double* cs) {
   double pc = ADSURF_K(kCosC, 0);
 #pragma unroll
   for (int i = 1; i < 6; ++i) pc = fma(pc, z, ADSURF_K(kCosC, i));
-  const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const double c = fma(z * z, pc, fma(ADSURF_HC(2, -0.5), z, 1.0));
   const int n = (int)dbl_bits(t);
   const double a = (n & 1) ? c : s;
   const double b = (n & 1) ? s : c;
