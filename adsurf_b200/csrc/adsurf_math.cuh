@@ -199,8 +199,13 @@ ADSURF_HD double exp_neg(double p_in) {
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   q = fma(q, r, 1.0);
-  const double tj = bits_dbl((long long)((unsigned long long)dbl_bits(ADSURF_EXP2_TAB(n & 31)) +
-                                         ((unsigned long long)(long long)(n >> 5) << 52)));
+  // 2^(n div 32) goes into the exponent field: an add on the high word only (the 64-bit form costs a second add)
+  const double tab = ADSURF_EXP2_TAB(n & 31);
+#if defined(__CUDA_ARCH__)
+  const double tj = __hiloint2double(__double2hiint(tab) + ((n >> 5) << 20), __double2loint(tab));
+#else
+  const double tj = bits_dbl((long long)((unsigned long long)dbl_bits(tab) + ((unsigned long long)(long long)(n >> 5) << 52)));
+#endif
   return tj * q;
 }
 
