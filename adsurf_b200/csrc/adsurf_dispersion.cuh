@@ -34,8 +34,8 @@ struct DispModel {
 //   per (period, layer):      k_alpha, k_beta, gammk                               (disp_period_consts)
 //   per (evaluation, layer):  the layer's eigenfunction terms and matrix constants (disp_layer_terms: every sqrt,
 //                             division, sincos and exp of the evaluation; no dependence between layers)
-//   bottom-up:                E <- E . CA_m / max|.|                                (disp_layer_apply: 33 FMAs, one
-//                             reciprocal; the only sequential part)
+//   bottom-up:                E <- E . CA_m, rescaled                              (disp_layer_apply: 33 FMAs and an
+//                             exact power-of-two rescale; the only sequential part), E[0] / max|E| at the top
 constexpr int kDispTerms = 16;  // doubles per layer handed from disp_layer_terms to disp_layer_apply
 constexpr int kDispPer = 6;     // doubles per layer kept per period: k_alpha, k_beta, gammk | warp evaluator: d, rho, 1/rho
 enum { DT_CP = 0, DT_W, DT_X, DT_CQ, DT_Y, DT_Z, DT_A0, DT_GK, DT_G1, DT_AR, DT_BR, DT_KR, DT_IR, DT_TGK, DT_TG1 };
