@@ -1083,13 +1083,35 @@ inline GridPlan plan_grid_search(int S, int L, int NF, int K, bool adjoint, int 
   const int nft = best.nft;
   const int wmax = adjoint ? kBwdWarps : 8;
   const int per = L > 1 ? L - 1 : 1;
+  // one sample of L layers in units of a 20-layer one (measured: 2 590 instructions at L = 20, 390 at L = 3)
+  const double unit = 0.05 + 0.95 * per / 19.0;
   int tcmax = 8;  // table fills of up to 8 velocities, fewer for very deep models (keeps the table under 26 KB)
   while (tcmax > 1 && table_bytes(L, tcmax, adjoint) > 26 * 1024) tcmax >>= 1;
+  // experiments: ADSURF_PLAN_GRID_FWD="warps per block,velocities per chunk,velocities per table fill" overrides the
+  // search for the forward-only kernel (ignored when it does not fit the kernel's limits)
+  if (!adjoint) {
+    int w = 0, chunk = 0, tc = 0;
+    const char* env = getenv("ADSURF_PLAN_GRID_FWD");
+    if (env && sscanf(env, "%d,%d,%d", &w, &chunk, &tc) == 3 && w >= 1 && w <= 4 && chunk >= 1 && tc >= 1 &&
+        table_bytes(L, tc < chunk ? tc : chunk, false) <= 26 * 1024) {
+      if (chunk > K) chunk = K;
+      best.wpb = w;
+      best.nfg = (nft + w - 1) / w;
+      best.chunk = chunk;
+      best.nchunk = (K + chunk - 1) / chunk;
+      best.tc = tc < chunk ? tc : chunk;
+      best.bpm = best.nchunk * best.nfg;
+      return best;
+    }
+  }
   for (int w = wmax < nft ? wmax : nft; w >= 1; w = (w > 4 ? 4 : w - 1)) {
     if (adjoint && w != (wmax < nft ? wmax : nft)) break;  // the adjoint kernel is compiled for 4-warp blocks
     const int nfg = (nft + w - 1) / w;
     int bps = adjoint ? kBwdBlocksPerSM : kFwdWarpsPerSM / w;
-    const size_t smem = adjoint ? grid_bwd_smem(L, tcmax, w) : grid_fwd_smem(L, tcmax, w);
+    // forward kernel, shallow models: as many velocities per fill as the table budget holds (one fill per block)
+    int tcw = tcmax;
+    while (!adjoint && tcw < 64 && table_bytes(L, 2 * tcw, adjoint) <= 26 * 1024) tcw <<= 1;
+    const size_t smem = adjoint ? grid_bwd_smem(L, tcw, w) : grid_fwd_smem(L, tcw, w);
     const int bsm = (int)(kSmemMax / (smem + 1024));
     if (bsm < bps) bps = bsm;
     if (bps < 1) bps = 1;
@@ -1102,7 +1124,7 @@ inline GridPlan plan_grid_search(int S, int L, int NF, int K, bool adjoint, int 
       if (chunk == prev_chunk) continue;
       prev_chunk = chunk;
       const int nch = (K + chunk - 1) / chunk;
-      const int tc = chunk < tcmax ? chunk : tcmax;
+      const int tc = chunk < tcw ? chunk : tcw;
       const double B = (double)S * nfg * nch;
       const double full = floor(B / R), rem = B - full * R;
       // a last wave that does not fill the machine: blocks are dealt round-robin to the SMs, so the busiest SM holds
@@ -1111,10 +1133,22 @@ inline GridPlan plan_grid_search(int S, int L, int NF, int K, bool adjoint, int 
       const double cap = adjoint ? (double)(kBwdBlocksPerSM * kBwdWarps) : (double)kFwdWarpsPerSM;
       const double waves = full + (rem > 0 ? fmin(1.0, fmax(0.55, ceil(rem / nsm) * w / cap)) : 0.0);
       const int fills = (chunk + tc - 1) / tc;
-      // costs in units of one sample: a table entry ~ 0.04, per-block staging ~ 0.3, a fill's two barriers ~ 0.05
-      const double fill_cost = 0.05 + 0.04 * ceil((double)tc * per / (w * kWarp));
-      double cost = waves * (chunk + fills * fill_cost + 0.3);
-      cost *= 1.0 + 0.02 * (1.0 - live);                        // dead warps only help with the fills
+      // Two views of the same launch, in units of one 20-layer sample per warp slot:
+      //  * latency (at most one wave of blocks: config 2's single model): a thread's own timeline, its chunk of
+      //    samples + per fill the entries it computes (~0.04 each round) and two barriers (~0.05) + staging (~0.3);
+      //  * throughput (several waves: ensembles): the instruction work of a block — its live warps' samples, per
+      //    fill a round of table entries per 32 entries (~0.1) and two barriers per warp, staging once — divided
+      //    over its warps.  The set-up is paid per block, not per warp: for shallow models it is a third of all
+      //    instructions with one-warp blocks (config 3, measured: 2 warps x 12-20 velocities with one fill run 7 %
+      //    faster than 1 x 20; larger chunks are slower, they leave the last wave emptier), and fewer resident
+      //    warps issue less (6-warp blocks: 12 of 16 warp slots, measured 9 % slower).
+      const double t_lat = chunk * unit + fills * (0.05 + 0.04 * ceil((double)tc * per / (w * kWarp))) + 0.3;
+      const double block_work = (double)w * live * chunk * unit + fills * (0.05 * w + 0.1 * ceil((double)tc * L / kWarp)) + 0.3;
+      const double occ = fmin(1.0, (double)bps * w * live / cap);  // warps that issue
+      const double t_thr = block_work / w / pow(occ, 0.6);
+      const double mix = fmin(1.0, fmax(0.0, B / R - 1.0));  // 0: one wave or less, 1: two waves or more
+      double cost = waves * ((1.0 - mix) * t_lat + mix * t_thr);
+      if (!(mix > 0.0)) cost *= 1.0 + 0.02 * (1.0 - live);  // dead warps only help with the fills
       cost *= 1.0 + 1e-3 * fabs(log2((B / R + 1e-9) / 16.0));  // tie-break: about 16 waves
       if (cost < best_cost) {
         best_cost = cost;

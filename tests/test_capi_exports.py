@@ -59,13 +59,18 @@ def test_grid_planner_covers_the_grid_and_fills_the_machine(lib):
             assert p["nft"] == (NF + 31) // 32 and 1 <= p["wpb"] <= (4 if adj else 8)
             assert p["wpb"] * p["nfg"] >= p["nft"] > p["wpb"] * (p["nfg"] - 1)
             assert p["nchunk"] * p["chunk"] >= K > (p["nchunk"] - 1) * p["chunk"]
-            assert 1 <= p["tc"] <= min(8, p["chunk"]) and p["bpm"] == p["nchunk"] * p["nfg"]
+            # table fills of up to 8 velocities (adjoint) / as many as the 26 KB table holds (forward, shallow models)
+            assert 1 <= p["tc"] <= min(8 if adj else 64, p["chunk"]) and p["bpm"] == p["nchunk"] * p["nfg"]
+            assert (p["tc"] * L + 1) * (20 if adj else 16) * 8 <= 26 * 1024 or p["tc"] == 1
     # config 2's dense pass (one model): about one wave of blocks instead of 24 serial velocities per thread
     p = _capi.plan_describe(_capi.OP_GRID_FWD, 1, 6, 500, 1201)
     assert p["chunk"] <= 12 and p["bpm"] * p["wpb"] <= 2 * p["sms"] * 16
     # the headline sweep keeps whole table fills and many waves
     p = _capi.plan_describe(_capi.OP_GRID_BWD, 4096, 20, 128, 1024)
     assert p["wpb"] == 4 and p["tc"] == 8 and p["chunk"] >= 64
+    # config 3's dense pass (100 shallow models, several waves): blocks of two warps share one table fill
+    p = _capi.plan_describe(_capi.OP_GRID_FWD, 100, 3, 174, 200)
+    assert p["wpb"] == 2 and p["tc"] == p["chunk"] and 10 <= p["chunk"] <= 25
 
 
 def test_argument_validation_without_gpu(lib):
