@@ -573,3 +573,16 @@ def test_device_side_monte_carlo_ensemble(api):
     pvs = np.ones((256, obs.shape[0], 2)) * obs[:, :2]
     inv = api.inversion(mp, ip, init, pvs, vsrange_sign="mul", vsrange=[0.1, 2.5], device="cuda")
     assert np.asarray(inv.inv_process["loss"]).shape == (3, 256) and np.isfinite(inv.inv_process["loss"]).all()
+
+
+
+def test_inversion_trajectories_match_the_reference(api):
+    """loss / iterate trajectories of BASELINE configs 2-4 against the reference's own
+    `inversion(...)` run in float64 on the CPU (tests/golden/make_golden_trajectories.py -> trajectories.npz):
+    eight iterations through the DMF, the velocity chain, the projections, Adam and StepLR."""
+    from tests.trajectories import trajectory_errors
+    errs = trajectory_errors(api, "cuda")
+    print("trajectory errors vs the reference (float64):", {k: f"{v:.2e}" for k, v in errs.items()})
+    tol = 1e-7   # Adam divides by sqrt(v): 1e-12 differences in the first gradients grow to ~1e-9 in the iterates
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f"trajectories differ from the reference's: {bad} (all: {errs})"

@@ -192,3 +192,13 @@ def test_bench_reference_arm_runs_on_the_cpu():
                             "--warmup", "0"], capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"),
                            timeout=600)
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+def test_inversion_trajectories_match_the_reference_on_the_oracle(ab):
+    """host logic + oracle against the reference's own float64 `inversion(...)` trajectories (configs 2-4 of
+    tests/golden/trajectories.npz; config 3 on its first 8 models): what the GPU test checks with the real kernels"""
+    import adsurf_b200._ADsurf as api
+    from tests.trajectories import trajectory_errors
+    errs = trajectory_errors(api, "cpu", c3_models=8)
+    bad = {k: v for k, v in errs.items() if not v <= 1e-10}
+    assert not bad, f"trajectories differ from the reference's: {bad} (all: {errs})"
