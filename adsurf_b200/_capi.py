@@ -545,3 +545,96 @@ class InversionLoop:
                     self._graph(n % k).replay()
                     launch_count += (n % k) * self.kernels_per_iteration
         self.done += n
+
+
+class InversionLoopGroup:
+    """Several `InversionLoop`s over disjoint, contiguous row ranges of ONE ensemble, each replaying its own CUDA
+    graph on its own stream (models are independent without horizontal damping, reference _model.py:589-636).
+
+    Why: an iteration of one loop is a dependent chain  sweep -> optimiser step -> sweep ...; the sweep's last wave
+    leaves SMs idle and the (tiny) optimiser launch leaves almost all of them idle.  With G independent chains the
+    hardware block scheduler fills one chain's tail and optimiser step with another chain's sweep: the work is the
+    same, the idle time is not.  Same interface as `InversionLoop` (histories are concatenated on first use)."""
+
+    def __init__(self, state, consts, t, c, C, *, groups, T, **kw):
+        b = state["b"]
+        S, dev = b.shape[0], b.device
+        G = max(1, min(int(groups), S))
+        if kw.get("halo_fn") is not None or kw.get("damp_horizontal", 0.0) > 0:
+            raise AdsurfError("InversionLoopGroup: horizontal damping couples the models (one loop only)")
+        for key in ("mb", "vb", "md", "vd"):
+            state.setdefault(key, torch.zeros_like(b))
+        self.state, self.consts, self.dev, self.S, self.T = state, consts, dev, S, int(T)
+        cuts = [(S * g) // G for g in range(G + 1)]
+        rows = lambda x, g: None if x is None else x[cuts[g]:cuts[g + 1]]
+        self.loops = [InversionLoop({k: rows(v, g) for k, v in state.items()}, {k: rows(v, g) for k, v in consts.items()},
+                                    rows(t, g), rows(c, g), rows(C, g), T=T, **kw) for g in range(G)]
+        self.streams = [torch.cuda.Stream(dev) for _ in range(G)] if b.is_cuda else [None] * G
+        self.kernels_per_iteration = sum(x.kernels_per_iteration for x in self.loops)
+        self.unroll = self.loops[0].unroll
+        self.done = 0
+        self._cat = {}
+
+    def prepare(self, n):
+        for loop in self.loops:
+            loop.prepare(n)
+
+    def run(self, n):
+        """advance every group `n` iterations; the caller's stream waits for all of them"""
+        n, k = int(n), self.unroll
+        self._cat.clear()
+        cur = torch.cuda.current_stream(self.dev) if self.streams[0] is not None else None
+        for st in self.streams:
+            if st is not None:
+                st.wait_stream(cur)
+        done = 0
+        while done < n:  # chunk by chunk, so that the groups advance side by side
+            step = min(k, n - done)
+            for loop, st in zip(self.loops, self.streams):
+                if st is None:
+                    loop.run(step)
+                else:
+                    with torch.cuda.stream(st):
+                        loop.run(step)
+            done += step
+        for st in self.streams:
+            if st is not None:
+                cur.wait_stream(st)
+        self.done += n
+
+    def _joined(self, name, dim):
+        if name not in self._cat:
+            parts = [getattr(x, name) for x in self.loops]
+            self._cat[name] = None if parts[0] is None else torch.cat(parts, dim=dim)
+        return self._cat[name]
+
+    loss = property(lambda self: self._joined("loss", 0))
+    loss_hist = property(lambda self: self._joined("loss_hist", 1))
+    iter_b_hist = property(lambda self: self._joined("iter_b_hist", 1))
+    iter_d_hist = property(lambda self: self._joined("iter_d_hist", 1))
+    counter = property(lambda self: self.loops[0].counter)
+
+
+def loop_groups(S, L, N, dev, damp_horizontal, dense_pass=False):
+    """how many concurrent row groups `_model` splits an ensemble's device-resident loop into (1 = one loop).
+    ADSURF_LOOP_GROUPS overrides; otherwise, from measurements on B200 (profiles/r2_loop_groups.txt):
+      * large ensembles (every group still takes the persistent L2-slab form of the pointwise kernel): 2 groups
+        (+7-8 % at 512 / 1024 / 4096 models x 300 picks x 20 layers, +20 % at 240-256; 3 and 4 groups the same or
+        lower); when halving would push the groups into the shared-memory-slab form: 1 (2 groups: -20 %);
+      * small ensembles (shared-memory-slab blocks): 2 groups when the blocks exceed one wave of resident blocks
+        (64-118 models x 300 picks x 20 layers: +20-45 %), else 1 (one wave is one latency-bound launch: 30 us);
+        with a dense pass in the iteration (normalised misfits, config 3: three short launches per iteration)
+        4 groups from 32 models (+25 %)."""
+    if damp_horizontal > 0 or dev.type != "cuda":
+        return 1
+    env = os.environ.get("ADSURF_LOOP_GROUPS", "")
+    if env:
+        return max(1, min(int(env), S))
+    plan = plan_describe(OP_DMF_STEP, S, L, N)
+    if plan["l2_slabs"]:
+        return 2 if plan_describe(OP_DMF_STEP, S // 2, L, N)["l2_slabs"] else 1
+    if dense_pass:
+        return 4 if S >= 32 else 1
+    block_smem = plan["wpb"] * ((L - 1) * 9 * 32 * 8 + 4 * L * 8) + 4096  # store slabs + accumulators + staged model
+    per_sm = max(1, min(227 * 1024 // block_smem, 8 // plan["wpb"]))    # shared memory / 232-register limit
+    return 2 if S * plan["bpm"] > per_sm * plan["sms"] else 1

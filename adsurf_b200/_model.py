@@ -407,13 +407,21 @@ def _fused_ensemble_loop(self, calculator, vlist, tlist, Clist, a_init, rho_init
         row0, _, S_all = shard
         if ip.damp_horizontal > 0:
             halo_fn = lambda bb: _halo_rows(bb, row0, S_all)
-    loop = _capi.InversionLoop(
-        state, consts, tlist.contiguous(), vlist.contiguous(), Clist.contiguous(), compress=mode,
-        vp_mode=_capi.VP_MODE[method], vp_vs_ratio=mp.vp_vs_ratio, invert_thick=vs_and_thick,
-        layering=_capi.LAYERING.get(mp.layering_method, 0),
-        proj_flags=_capi.PROJ_LAST_LAYER | (0 if vs_and_thick else _capi.PROJ_NAN_REPAIR),
-        damp_vertical=ip.damp_vertical, damp_horizontal=ip.damp_horizontal, lr=ip.lr, gamma=ip.gamma,
-        step_size=ip.step_size, T=ip.iteration, row0=row0, S_all=S_all, halo_fn=halo_fn)
+    kw = dict(compress=mode, vp_mode=_capi.VP_MODE[method], vp_vs_ratio=mp.vp_vs_ratio, invert_thick=vs_and_thick,
+              layering=_capi.LAYERING.get(mp.layering_method, 0),
+              proj_flags=_capi.PROJ_LAST_LAYER | (0 if vs_and_thick else _capi.PROJ_NAN_REPAIR),
+              damp_vertical=ip.damp_vertical, damp_horizontal=ip.damp_horizontal, lr=ip.lr, gamma=ip.gamma,
+              step_size=ip.step_size, T=ip.iteration)
+    # models are independent without horizontal damping: large ensembles run as concurrent groups of rows, so that
+    # one group's sweep fills the idle tail and the optimiser step of another (InversionLoopGroup)
+    groups = _capi.loop_groups(b.shape[0], b.shape[1], vlist.shape[1], b.device, ip.damp_horizontal,
+                                dense_pass=mode != ops.COMPRESS["none"])
+    if groups > 1:
+        loop = _capi.InversionLoopGroup(state, consts, tlist.contiguous(), vlist.contiguous(), Clist.contiguous(),
+                                        groups=groups, **kw)
+    else:
+        loop = _capi.InversionLoop(state, consts, tlist.contiguous(), vlist.contiguous(), Clist.contiguous(),
+                                   row0=row0, S_all=S_all, halo_fn=halo_fn, **kw)
     import time
     loop.prepare(ip.iteration)  # graph capture: set-up, not iterations
     if b.is_cuda:

@@ -426,6 +426,42 @@ def test_graph_replay_equals_direct_launches(api):
     assert torch.isfinite(out[True][0]).all() and (out[True][0] < 10.0).all()
 
 
+def test_concurrent_row_groups_equal_one_loop(api):
+    """InversionLoopGroup (3 row groups of a 41-model ensemble on 3 streams, CUDA-graph replay each) gives the state
+    and the histories of ONE InversionLoop over all rows: the models are independent without horizontal damping."""
+    from adsurf_b200 import _capi
+    from tests.golden_models import brocher_np
+    rng = np.random.default_rng(5)
+    g = load("dmf_exp_m6")
+    S, T = 41, 7
+    b = np.tile(g["b"][0], (S, 1)) * (1 + rng.normal(0, 0.03, (S, 6)))
+    a, rho = brocher_np(b)
+    d = np.tile(g["d"][0], (S, 1))
+    Gt = lambda x: torch.tensor(np.ascontiguousarray(x, dtype=np.float64), device="cuda")
+    t, c = Gt(np.tile(g["t"][0], (S, 1))), Gt(np.tile(g["c"][0], (S, 1)))
+    C = Gt(np.tile(np.arange(2, 3.2, 0.01), (S, 1)))
+    kw = dict(compress=_capi.COMPRESS_EXP, vp_mode=1, vp_vs_ratio=0.0, invert_thick=True, layering=1,
+              proj_flags=_capi.PROJ_LAST_LAYER, damp_vertical=0.002, damp_horizontal=0.0, lr=0.005, gamma=0.5,
+              step_size=3, T=T, unroll=3)
+    out = {}
+    for groups in (1, 3):
+        state = {"b": Gt(b), "d": Gt(d), "alpha": Gt(a), "rho": Gt(rho)}
+        consts = {"b0": Gt(b), "alpha0": Gt(a), "rho0": Gt(rho), "lower_b": Gt(0.7 * b), "upper_b": Gt(1.3 * b),
+                  "mindepth": Gt(np.cumsum(d, 1) * 0.8), "maxdepth": Gt(np.cumsum(d, 1) * 1.2)}
+        loop = (_capi.InversionLoop(state, consts, t, c, C, **kw) if groups == 1 else
+                _capi.InversionLoopGroup(state, consts, t, c, C, groups=groups, **kw))
+        loop.run(T)
+        torch.cuda.synchronize()
+        assert loop.counter.tolist() == [T, 0]
+        assert tuple(loop.loss_hist.shape) == (T, S) and tuple(loop.iter_b_hist.shape) == (T, S, 6)
+        out[groups] = (loop.loss_hist.clone(), loop.iter_b_hist.clone(), loop.iter_d_hist.clone(), state["b"].clone(),
+                       state["d"].clone(), state["alpha"].clone(), state["mb"].clone(), state["vd"].clone())
+    for x, y in zip(out[1], out[3]):
+        assert torch.equal(x, y)
+    with pytest.raises(_capi.AdsurfError):
+        _capi.InversionLoopGroup(state, consts, t, c, C, groups=2, **dict(kw, damp_horizontal=0.001))
+
+
 def test_config4_device_loop_matches_torch_loop_at_1024_models(api, monkeypatch):
     """1024-model FRIUL7W ensemble (N=300 picks, 20 layers, compress=False): every loss, iterate and final model of
     the device-resident loop against the torch-autograd loop over 4 iterations."""
@@ -583,6 +619,6 @@ def test_inversion_trajectories_match_the_reference(api):
     from tests.trajectories import trajectory_errors
     errs = trajectory_errors(api, "cuda")
     print("trajectory errors vs the reference (float64):", {k: f"{v:.2e}" for k, v in errs.items()})
-    tol = 1e-7   # Adam divides by sqrt(v): 1e-12 differences in the first gradients grow to ~1e-9 in the iterates
+    tol = 1e-9   # north-star tolerance; measured on B200: <= 4e-12 (losses), <= 4e-13 (iterates)
     bad = {k: v for k, v in errs.items() if not v <= tol}
     assert not bad, f"trajectories differ from the reference's: {bad} (all: {errs})"
