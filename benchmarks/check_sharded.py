@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Sharded vs unsharded `multi_inversion` on real GPUs (torchrun, NCCL): the device-resident loop with horizontal
-damping (four-row halo exchange per iteration) and without it (CUDA-graph replay), each compared with the same
+damping (four-row halo exchange per iteration) and without it (CUDA-graph replay, concurrent row groups), each compared with the same
 ensemble inverted whole on rank 0.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
@@ -50,7 +50,9 @@ def main():
     # uneven shards (padded list all-gather) and even ones (single all_gather_into_tensor), with / without damping
     for name, S, dh in (("131 models, damp_h=0 (graph replay)", 64 * world + 3, 0.0),
                         ("131 models, damp_h=0.003 (halo exchange)", 64 * world + 3, 0.003),
-                        ("128 models, damp_h=0.003 (halo exchange, even shards)", 64 * world, 0.003)):
+                        ("128 models, damp_h=0.003 (halo exchange, even shards)", 64 * world, 0.003),
+                        ("512 models, damp_h=0 (even shards, two concurrent row groups per rank)",
+                         256 * world, 0.0)):
         got = run(S, dh)
         assert got[3]["fused"]
         dist.barrier()

@@ -28,9 +28,8 @@ class _MP:  # minimal monkeypatch stand-in usable inside spawned workers
         setattr(obj, name, val)
 
 
-def _problem():
+def _problem(S=5, damp_horizontal=0.003, iteration=3):
     g = load("dmf_exp_m6")
-    S = 5
     rng = np.random.default_rng(3)
     b = np.tile(g["b"][0], (S, 1)) * (1 + rng.normal(0, 0.02, (S, 6)))
     d = np.tile(g["d"][0], (S, 1))
@@ -39,17 +38,17 @@ def _problem():
     obs = np.stack([np.column_stack((g["t"][0][:12], g["c"][0][:12]))] * S)
     mp_ = types.SimpleNamespace(clist=np.arange(2, 3.2, 0.05), layering_method="LN", initialize_method="Brocher",
                                 vp_vs_ratio=2.45, rho=2)
-    ip = types.SimpleNamespace(damp_vertical=0.002, damp_horizontal=0.003, compress=True, normalized=True,
-                               compress_method="exp", inversion_method="vs-and-thick", lr=0.01, iteration=3,
+    ip = types.SimpleNamespace(damp_vertical=0.002, damp_horizontal=damp_horizontal, compress=True, normalized=True,
+                               compress_method="exp", inversion_method="vs-and-thick", lr=0.01, iteration=iteration,
                                step_size=2, gamma=0.5, optimizer="Adam")
     init = types.SimpleNamespace(init_model={"vs": b, "vp": a, "rho": rho, "thick": d,
                                              "layer_mindepth": np.full(6, 0.05), "layer_maxdepth": np.full(6, 4.0)})
     return mp_, ip, init, obs
 
 
-def _run(fused=True):
+def _run(fused=True, **problem):
     from adsurf_b200._model import multi_inversion
-    mp_, ip, init, obs = _problem()
+    mp_, ip, init, obs = _problem(**problem)
     os.environ["ADSURF_FUSED_OPT"] = "1" if fused else "0"
     inv = multi_inversion(mp_, ip, init, obs, vsrange_sign="add", vsrange=[-0.5, 0.5], device="cpu")
     assert inv.timing["fused"] == fused
@@ -65,6 +64,8 @@ def _worker(rank, world, port, out_dir):
     ref_torch = _run(fused=False)  # torch-autograd loop
     for x, y in zip(ref, ref_torch):
         np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-12)
+    even = dict(S=4, damp_horizontal=0.0, iteration=5)
+    ref_even = _run(**even)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         from adsurf_b200 import _dist
@@ -74,6 +75,10 @@ def _worker(rank, world, port, out_dir):
             np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-14)
         got_torch = _run(fused=False)  # sharded torch-autograd loop (full all-gather of Vs per iteration)
         for x, y in zip(got_torch, ref_torch):
+            np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-14)
+        # equal shards without horizontal damping (graph-replay form of the loop, one collective per history array)
+        got_even = _run(**even)
+        for x, y in zip(got_even, ref_even):
             np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-14)
         # uneven all-gather helper
         lo, hi = _dist.shard_bounds(5)
