@@ -365,18 +365,29 @@ def main():
         loop_s = max_over_ranks(rec["loop_seconds"] + rec["gather_seconds"])
         total_s = max_over_ranks(rec["loop_seconds"] + rec["gather_seconds"] + rec["setup_seconds"])
         extras["inversion"] = {
-            "what": f"multi_inversion (device-resident loop, CUDA graph of whole iterations) of {S_all} models x 300 "
+            "what": f"multi_inversion (device-resident loop, CUDA graphs of whole iterations, one per row group) of {S_all} models x 300 "
                     f"picks x 20 layers, Vs only, sharded over {world} rank(s), + final all-gather of losses / iterates",
             "iterations": args.inversion_iters, "it_per_s": args.inversion_iters / loop_s,
             "it_per_s_incl_setup": args.inversion_iters / total_s, "loop_plus_gather_s": loop_s,
             "pointwise_samples_per_s": args.inversion_iters * S_all * 300 / loop_s,
             "median_first_loss": rec["median_first_loss"], "median_last_loss": rec["median_last_loss"],
-            "kernels_per_iteration": 2}
+            "kernels_per_iteration": rec["kernels_per_iteration"], "concurrent_row_groups": rec["row_groups"]}
         if world == 1:
             CE.config2(5), CE.config3(5)
             c2, c3, c4 = CE.config2(600), CE.config3(400), CE.config4(300, S=1024)
             keep = ("what", "iterations_run", "it_per_s", "best_loss", "reference")
             extras["configs"] = {f"config{r['config']}": {k: r[k] for k in keep if k in r} for r in (c2, c3, c4)}
+            # the reference's own inversion(...) timed in the build container (it cannot travel to the GPU box); the
+            # loss / iterate trajectories of those runs are the fixture of tests/test_gpu_api.py (1e-9)
+            try:
+                with open(os.path.join(ROOT, "profiles", "r2_reference_configs_cpu.json")) as f:
+                    rc = json.load(f)
+                for n in (2, 3, 4):
+                    extras["configs"][f"config{n}"]["reference_code_cpu_build_container"] = {
+                        "it_per_s_float32": rc[f"config{n}_float32"]["it_per_s"], "cores": rc["cores"],
+                        "models": rc[f"config{n}_float32"].get("models", 1)}
+            except (OSError, KeyError, ValueError):
+                pass
 
     if rank == 0:
         achieved_tf = (n_local / (kernel_ms * 1e-3)) * flop_per_sample(L) / 1e12

@@ -102,6 +102,8 @@ def config4(iters, S=1024):
             "gather_seconds": inv.timing["gather_s"], "setup_seconds": inv.timing["setup_s"],
             "total_seconds_incl_result_lists": dt, "best_loss": float(loss.min()),
             "median_first_loss": float(np.median(loss[0])), "median_last_loss": float(np.median(loss[-1])),
+            "kernels_per_iteration": int(getattr(getattr(inv, "loop", None), "kernels_per_iteration", 0)),
+            "row_groups": len(getattr(getattr(inv, "loop", None), "loops", [0])),
             "reference": {"it_per_s": 2.60, "models": 100, "device": "cuda:0 (author's)", "best_loss": 2.1835e-4,
                           "iterations": 4000}}
 
