@@ -507,9 +507,21 @@ class InversionLoop:
                 self._warm()
             global launch_count
             g, count = torch.cuda.CUDAGraph(), launch_count
-            with torch.cuda.device(self.dev), torch.cuda.graph(g, capture_error_mode="thread_local"):
-                for _ in range(n):
-                    self._step()
+            # capture_begin / capture_end on a side stream instead of the `torch.cuda.graph` context: that context
+            # starts with gc.collect() and torch.cuda.empty_cache(), which cost 0.2-0.6 s when the caller holds the
+            # reference-style nested-list results of an earlier run (millions of Python objects) and hand the cached
+            # blocks back to the driver; the captured launches allocate nothing
+            with torch.cuda.device(self.dev):
+                side, cur = torch.cuda.Stream(self.dev), torch.cuda.current_stream(self.dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    g.capture_begin(capture_error_mode="thread_local")
+                    try:
+                        for _ in range(n):
+                            self._step()
+                    finally:
+                        g.capture_end()
+                cur.wait_stream(side)
             launch_count = count  # a capture records launches, it does not run them
             self._graphs[n] = g
         return g

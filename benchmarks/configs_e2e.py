@@ -24,11 +24,19 @@ GOLD = os.path.join(ROOT, "tests", "golden", "shipped_fixtures.npz")
 
 
 def timed(fn):
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = fn()
-    torch.cuda.synchronize()
-    return out, time.perf_counter() - t0
+    # the reference-style results are nested lists of millions of floats: their collection (or a cyclic-GC pass over
+    # them) must not land inside the next call's timers
+    import gc
+    gc.collect()
+    gc.disable()
+    try:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        return out, time.perf_counter() - t0
+    finally:
+        gc.enable()
 
 
 def config2(iters):
