@@ -359,7 +359,8 @@ def main():
         if world == 1:
             extras["e2e_api"] = CE.api_dense_e2e(models=min(512, S_all), steps=3)
         # ---------------- north-star loop: sharded multi_inversion (config-4 shape at 4096 models)
-        CE.config4(5, S=S_all)  # warm-up: library load, allocator, NCCL buffers
+        CE.config4(args.inversion_iters, S=S_all)  # warm-up run of the same size: library load, allocator blocks,
+        # NCCL's channels for the history-sized all-gather (its first call costs ~4 ms, later ones 0.7 ms)
         barrier()
         rec = CE.config4(args.inversion_iters, S=S_all)
         loop_s = max_over_ranks(rec["loop_seconds"] + rec["gather_seconds"])
