@@ -859,6 +859,7 @@ ADSURF_HD double forward_sweep(const DirectSourceT<kIc>& src, const Sample& z, c
     const int ur = uniform_regime(y);
     if (ur == kEO) forward_layer<kEO, kStore, Store>(y, e, z.omega, q);
     else if (ur == kEE) forward_layer<kEE, kStore, Store>(y, e, z.omega, q);
+    else if (ur == kOO) forward_layer<kOO, kStore, Store>(y, e, z.omega, q);  // shallow layers under long-period picks
     else forward_layer<-1, kStore, Store>(y, e, z.omega, q);
   }
   return e[0];
@@ -995,6 +996,7 @@ ADSURF_HD double sample_adjoint(const DirectSourceT<kIc>& src, const Sample& z, 
     const int ur = uniform_regime(y);
     if (ur == kEO) body(std::integral_constant<int, kEO>{});
     else if (ur == kEE) body(std::integral_constant<int, kEE>{});
+    else if (ur == kOO) body(std::integral_constant<int, kOO>{});
     else body(std::integral_constant<int, -1>{});
   }
   if (L > 1) sink(last, pend.d, pend.a, pend.b, pend.rho);
