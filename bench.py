@@ -378,6 +378,23 @@ def main():
             c2, c3, c4 = CE.config2(600), CE.config3(400), CE.config4(300, S=1024)
             keep = ("what", "iterations_run", "it_per_s", "best_loss", "reference")
             extras["configs"] = {f"config{r['config']}": {k: r[k] for k in keep if k in r} for r in (c2, c3, c4)}
+            if not args.no_cpu_baseline:
+                # the same inversion(...) calls on this box's host cores with the C ABI served by the oracle port
+                # (subprocess without a GPU), >= 5 iterations, first losses compared with the GPU runs above
+                try:
+                    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+                    res = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "cpu_port_configs.py"),
+                                          "--iters", "5"], capture_output=True, text=True, timeout=600, env=env)
+                    port = json.loads(res.stdout.strip().splitlines()[-1])
+                    for r in (c2, c3, c4):
+                        name = f"config{r['config']}"
+                        a_, b_ = np.asarray(r["first_losses"], dtype=np.float64), np.asarray(port[name]["first_losses"])
+                        extras["configs"][name]["cpu_port_same_box"] = {
+                            "it_per_s": port[name]["it_per_s"], "iterations": port["iterations"], "cores": port["cores"],
+                            "kind": "port (oracle-served C ABI, the package's host loop)",
+                            "max_rel_diff_first_losses_gpu_vs_cpu": float(np.max(np.abs(a_ - b_) / np.maximum(np.abs(b_), 1e-3)))}
+                except Exception as exc:  # the headline line must not depend on this leg
+                    extras["configs"]["cpu_port_same_box_error"] = repr(exc)[:200]
             # the reference's own inversion(...) timed in the build container (it cannot travel to the GPU box); the
             # loss / iterate trajectories of those runs are the fixture of tests/test_gpu_api.py (1e-9)
             try:
