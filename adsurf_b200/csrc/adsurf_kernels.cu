@@ -60,6 +60,34 @@ namespace {
 using namespace adsurf;
 
 
+// Programmatic dependent launch (the kernels of one inversion iteration form a dependent chain in one stream /
+// CUDA graph): every kernel of the chain first waits for the grid before it (griddepcontrol.wait: completion and
+// memory visibility; a no-op for a plain launch) and then lets the grid after it start being scheduled
+// (griddepcontrol.launch_dependents: that grid's blocks become resident as slots free up and wait at their own
+// griddepcontrol.wait), so launch latency and the ramp of the next kernel overlap the tail of this one.
+__device__ __forceinline__ void chain_wait_then_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+// host side: launches issued while t_chain_pdl is set carry the programmatic-serialisation attribute
+thread_local bool t_chain_pdl = false;
+template <typename... KArgs, typename... Args>
+inline void launch_chain(void (*kern)(KArgs...), unsigned grid, unsigned threads, size_t smem, cudaStream_t st,
+                         Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = t_chain_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -224,6 +252,7 @@ __global__ void __maxnreg__(kMaxRegs) k_grid_fwd(const double* __restrict__ d, c
                                                   int NF, int K, GridPlan gp, double* __restrict__ det,
                                                   double* __restrict__ pmax, double* __restrict__ pmin, int keyed,
                                                   uint32_t* __restrict__ signbits) {
+  chain_wait_then_release();
   extern __shared__ double smem[];
   double* par = smem + kSmemHead;
   constexpr int kTab = kTabFwd;
@@ -515,6 +544,7 @@ __device__ __forceinline__ EnsCell ens_prepare_cell(const EnsArgs& A, int s, int
 }
 
 __global__ void k_ens_prepare(EnsArgs A) {
+  chain_wait_then_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < A.S * A.L) ens_prepare_cell(A, i / A.L, i % A.L);
 }
@@ -647,6 +677,7 @@ __device__ __forceinline__ void ens_advance(const EnsArgs& A, int j) {
 }
 
 __global__ void k_ens_adam(EnsArgs A) {
+  chain_wait_then_release();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const EnsStep T = ens_step_of(A);
   if (i < A.S * A.L) ens_adam_cell<false>(A, T, i / A.L, i % A.L, EnsCell{});
@@ -656,6 +687,7 @@ __global__ void k_ens_adam(EnsArgs A) {
 // both phases in one launch when no model needs another block's data (damp_horizontal == 0): a block owns
 // blockDim / L whole models, a barrier separates the phases
 __global__ void k_ens_fused(EnsArgs A) {
+  chain_wait_then_release();
   const int L = A.L, mpb = blockDim.x / L;
   const int local = threadIdx.x / L, l = threadIdx.x - local * L;
   const int s = blockIdx.x * mpb + local;
@@ -736,6 +768,7 @@ k_points_bwd(const double* __restrict__ d, const double* __restrict__ alpha, con
              double* __restrict__ norm, double* __restrict__ loss_part,
              // fused optimiser step (DMF kind, no horizontal damping): the block that completes a model's partials runs it
              int* __restrict__ model_done, EnsArgs E) {
+  chain_wait_then_release();
   // kGlobal: persistent blocks, store slabs in the L2-resident global slab, per-lane fold accumulators (large
   // ensembles); otherwise one block per (model, 32*wpb picks) with the slabs in shared memory (small problems).
   extern __shared__ double smem[];
@@ -1259,15 +1292,14 @@ inline int launch_points_bwd(const PointsPlan& pp, int S, int L, int N, const do
     if (occ > cap) occ = cap;
     long long grid = (long long)occ * nsm;
     if (grid > total_vb) grid = total_vb;
-    kern<<<(unsigned)grid, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F, gc, part,
-                                                estore, Jd, Ja, Jb, Jrho, pmax, pmin, nchunk, compress, with_grad,
-                                                norm, loss_part, model_done, E);
+    launch_chain(kern, (unsigned)grid, threads, smem, st, d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F, gc,
+                 part, estore, Jd, Ja, Jb, Jrho, pmax, pmin, nchunk, compress, with_grad, norm, loss_part, model_done, E);
   } else {
     auto kern = k_points_bwd<kKind, false>;
     if (set_smem(kern, smem)) return ADSURF_E_CUDA;
-    kern<<<(unsigned)total_vb, threads, smem, st>>>(d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F, gc,
-                                                    part, nullptr, Jd, Ja, Jb, Jrho, pmax, pmin, nchunk, compress,
-                                                    with_grad, norm, loss_part, model_done, E);
+    launch_chain(kern, (unsigned)total_vb, threads, smem, st, d, alpha, beta, rho, t, c, gF, L, N, pp, (int)total_vb, F,
+                 gc, part, (double*)nullptr, Jd, Ja, Jb, Jrho, pmax, pmin, nchunk, compress, with_grad, norm, loss_part,
+                 model_done, E);
   }
   return check_launch();
 }
@@ -1438,8 +1470,8 @@ static int grid_fwd_launch(const double* d, const double* alpha, const double* b
   const size_t smem = grid_fwd_smem(L, gp.tc, gp.wpb);
   if (smem > kSmemMax) return ADSURF_E_SHAPE;
   if (set_smem(k_grid_fwd<128>, smem)) return ADSURF_E_CUDA;
-  k_grid_fwd<128><<<(unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st>>>(d, alpha, beta, rho, t, c, L, NF, K,
-                                                                                 gp, det, pmax, pmin, keyed, signbits);
+  launch_chain(k_grid_fwd<128>, (unsigned)((size_t)S * gp.bpm), gp.wpb * kWarp, smem, st, d, alpha, beta, rho, t, c, L,
+               NF, K, gp, det, pmax, pmin, keyed, signbits);
   return check_launch();
 }
 
@@ -1604,13 +1636,13 @@ static int ens_launch(EnsArgs& A, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int threads = 128;
   if (!(A.dh > 0.0) && A.L <= threads) {
     const int mpb = threads / A.L;
-    k_ens_fused<<<(A.S + mpb - 1) / mpb, threads, 0, st>>>(A);
+    launch_chain(k_ens_fused, (unsigned)((A.S + mpb - 1) / mpb), threads, 0, st, A);
     return check_launch();
   }
   const int blocks = (int)((SL + threads - 1) / threads);
-  k_ens_prepare<<<blocks, threads, 0, st>>>(A);
+  launch_chain(k_ens_prepare, (unsigned)blocks, threads, 0, st, A);
   if (check_launch()) return ADSURF_E_CUDA;
-  k_ens_adam<<<blocks, threads, 0, st>>>(A);
+  launch_chain(k_ens_adam, (unsigned)blocks, threads, 0, st, A);
   return check_launch();
 }
 
@@ -1692,6 +1724,12 @@ int adsurf_inversion_step(const adsurf_inversion* p, void* ws, size_t ws_bytes, 
   const bool in_kernel = !(p->damp_horizontal > 0.0) && (long long)p->S * ppq.bpm <= sm_count();
   int* model_done = (int*)((char*)ws + dmf_bytes + ens_bytes);
   DmfLaunch dl;
+  // the launches of an iteration are a dependent chain: programmatic dependent launch when ADSURF_PDL=1
+  static const bool pdl = []() { const char* e = getenv("ADSURF_PDL"); return e && e[0] == '1'; }();
+  struct Scope {
+    explicit Scope(bool on) { t_chain_pdl = on; }
+    ~Scope() { t_chain_pdl = false; }
+  } scope(pdl);
   const int rc = dmf_launch(p->d, p->alpha, p->b, p->rho, p->t, p->c, p->C, p->S, p->L, p->N, p->K, p->compress, 1,
                             nullptr, nullptr, ws, dmf_bytes, false, st, dl, in_kernel ? model_done : nullptr,
                             in_kernel ? &A : nullptr);
