@@ -338,6 +338,7 @@ __device__ __forceinline__ unsigned long long l2_evict_last_policy() {
   return pol;
 }
 struct GlobalStore {
+  static constexpr bool kPairs = false;
   double* p;
   struct Slot {
     double* q;
@@ -354,6 +355,34 @@ struct GlobalStore {
   __device__ __forceinline__ static void st(Slot s, int j, double v) {
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(s.q + j * kWarp), "d"(v), "l"(s.pol) : "memory");
   }
+};
+
+// the same slab as 16-byte pairs (adsurf_math.cuh, kPairSlot): p = slab base + 2 * lane
+struct PairStore {
+  static constexpr bool kPairs = true;
+  double* p;
+  struct Slot {
+    double* q;
+    unsigned long long pol;
+  };
+  unsigned long long pol;
+  __device__ __forceinline__ Slot slot(int m) const { return Slot{p + (ptrdiff_t)m * (kPairSlot * kWarp), pol}; }
+  __device__ __forceinline__ static Slot step(Slot s, int n) { return Slot{s.q + n * (kPairSlot * kWarp), s.pol}; }
+  __device__ __forceinline__ static Dbl2 ld2(Slot s, int pr) {
+    Dbl2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(s.q + pr * (2 * kWarp)), "l"(s.pol));
+    return v;
+  }
+  __device__ __forceinline__ static void st2(Slot s, int pr, double a, double b) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(s.q + pr * (2 * kWarp)), "d"(a), "d"(b),
+                 "l"(s.pol)
+                 : "memory");
+  }
+  // scalar interface (unused by the pair paths; keeps the templates that name it well-formed)
+  __device__ __forceinline__ static double ld(Slot, int) { return 0.0; }
+  __device__ __forceinline__ static void st(Slot, int, double) {}
 };
 
 // Dense grid, fused forward + adjoint with per-model gradient reduction.  Persistent: each block
@@ -375,8 +404,8 @@ k_grid_bwd(const double* __restrict__ d, const double* __restrict__ alpha, const
   double* ics = tab + table_doubles(L, gp.tc, kTab);    // [tc]
   double* hks = ics + ((gp.tc + 1) & ~1);               // [wpb*32][2]: omega/alpha_hs, omega/beta_hs per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t slab = (size_t)(L - 1) * kSlot * kWarp;  // (the read-ahead of the last layer touches the next slab)
-  const GlobalStore st{estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + lane, l2_evict_last_policy()};
+  const size_t slab = (size_t)(L - 1) * kPairSlot * kWarp;  // (the read-ahead of the last layer touches the next slab)
+  const PairStore st{estore + ((size_t)blockIdx.x * gp.wpb + warp) * slab + 2 * lane, l2_evict_last_policy()};
   double* acc = accs + (size_t)warp * kAccRow * (L + 1);
   for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
     const BlockCoord bc = block_coord(vb, gp);
@@ -1062,6 +1091,7 @@ inline size_t par_bytes(int L) { return (size_t)(kSmemHead + par_doubles(L)) * s
 // touches the slot after it — the next warp's first slot (values unused) — so the whole store ends with one spare
 // slot (slab_bytes); a spare slot per warp would push the live slabs past the persisting-L2 capacity.
 inline size_t slot_bytes() { return (size_t)kSlot * kWarp * sizeof(double); }
+inline size_t pair_slot_bytes() { return (size_t)kPairSlot * kWarp * sizeof(double); }  // global slabs: the larger layout
 inline size_t est_bytes_per_warp(int L) { return (size_t)(L > 1 ? L - 1 : 0) * slot_bytes(); }
 
 // warps per block for the pointwise adjoint with the slabs in shared memory; 0 if even one warp does not fit
@@ -1086,7 +1116,7 @@ inline size_t adj_smem(int L, int wpb) {
 constexpr int kBwdWarps = 4, kBwdBlocksPerSM = 3, kFwdWarpsPerSM = 16;
 inline int max_resident_adj_warps(int nsm) { return nsm * kBwdBlocksPerSM * kBwdWarps; }
 inline size_t slab_bytes(int L, int nsm) {
-  return (size_t)max_resident_adj_warps(nsm) * est_bytes_per_warp(L) + slot_bytes();
+  return (size_t)max_resident_adj_warps(nsm) * (size_t)(L > 1 ? L - 1 : 0) * pair_slot_bytes() + pair_slot_bytes();
 }
 
 inline size_t table_bytes(int L, int tc, bool adjoint) {

@@ -776,9 +776,15 @@ ADSURF_HD void half_start(const double* __restrict__ par, int L, const Sample& z
 // (m, j) of this thread lives at p[(m*kSlot+j)*kStride] (kStride = 32: lane-interleaved, i.e.
 // conflict-free in shared memory and coalesced in global memory; kStride = 1 on the host).
 constexpr int kSlot = 9;
+// Pair stores (Store::kPairs, the dense adjoint kernel's global slab): the same values as 16-byte pairs, one vector
+// access per pair — (E0,E1) (E2,E3) (E4,cP0) (cS0,cS1) and, only under an oscillatory P term, (cP1,-) — in slots of
+// kPairSlot doubles: 4 accesses per layer and sweep instead of 7-8 (a slab access costs an LSU instruction besides
+// its bytes, profiles/r2_variants.txt).  st2 / ld2 address a pair by its index.
+constexpr int kPairSlot = 10;
 
 template <int kStride>
 struct PlainStore {
+  static constexpr bool kPairs = false;
   double* p;
   typedef double* Slot;
   ADSURF_HD Slot slot(int m) const { return p + (size_t)m * (kSlot * kStride); }
@@ -787,6 +793,7 @@ struct PlainStore {
   ADSURF_HD static void st(Slot q, int j, double v) { q[j * kStride] = v; }
 };
 struct NoStore {
+  static constexpr bool kPairs = false;
   typedef int Slot;
   ADSURF_HD Slot slot(int) const { return 0; }
   ADSURF_HD static Slot step(Slot q, int) { return q; }
@@ -830,7 +837,14 @@ ADSURF_HD void forward_layer(Layer& y, double (&e)[5], double omega, typename St
     eig_forward(y.S, wd);
   }
   y.a0 = layer_a0(y.P, y.S);
-  if (kStore) {
+  if constexpr (kStore && Store::kPairs) {
+    // e is still E_{m+1} here (row_apply below turns it into E_m): the whole slot in 4 (5) vector stores
+    Store::st2(q, 0, e[0], e[1]);
+    Store::st2(q, 1, e[2], e[3]);
+    Store::st2(q, 2, e[4], y.P.c0);
+    Store::st2(q, 3, y.S.c0, y.S.c1);
+    if (kFl >= 0 ? (kFl & F_LTP) != 0 : y.P.lt) Store::st2(q, 4, y.P.c1, y.P.c1);
+  } else if (kStore) {
     // the second value (cos) exists only for an oscillatory term; the adjoint sweep loads it on the same rule
     Store::st(q, 5, y.P.c0);
     if (kFl >= 0 ? (kFl & F_LTP) != 0 : y.P.lt) Store::st(q, 6, y.P.c1);
@@ -880,7 +894,7 @@ ADSURF_HD double forward_sweep(const TableSource<kN>& src, const Sample& z, cons
   typename Store::Slot sq = est.slot(L - 2);
   int fl = TableSource<kN>::flags(q);
   Dbl2 ph = ld2(q + T_PDA);
-  if (kStore && !(fl & F_END)) {
+  if (kStore && !Store::kPairs && !(fl & F_END)) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) Store::st(sq, i, e[i]);
   }
@@ -895,7 +909,7 @@ ADSURF_HD double forward_sweep(const TableSource<kN>& src, const Sample& z, cons
       forward_layer<kFl, kStore, Store>(y, e, z.omega, sq);
       q -= kN;
       sq = Store::step(sq, -1);
-      if (kStore && !(fln & F_END)) {  // E_m multiplies CA_{m-1}: stored right after it is formed, a whole layer
+      if (kStore && !Store::kPairs && !(fln & F_END)) {  // E_m multiplies CA_{m-1}: stored right after it is formed, a whole layer
 #pragma unroll                          // before its registers are overwritten (no store/overwrite hazard)
         for (int i = 0; i < 5; ++i) Store::st(sq, i, e[i]);
       }
@@ -1023,14 +1037,27 @@ ADSURF_HD void sample_adjoint(const TableSource<kN>& src, const Sample& z, doubl
   double tq = seed * det;  // T_0
   double e[5], cv[4] = {0.0, 0.0, 0.0, 0.0};
   auto fetch_c = [&](typename Store::Slot q, int flm) {  // flm: regime flags of the layer in slot q
-    cv[0] = Store::ld(q, 5);
-    if (flm & F_LTP) cv[1] = Store::ld(q, 6);
-    cv[2] = Store::ld(q, 7);
-    if (flm & F_LTS) cv[3] = Store::ld(q, 8);
+    if constexpr (!Store::kPairs) {
+      cv[0] = Store::ld(q, 5);
+      if (flm & F_LTP) cv[1] = Store::ld(q, 6);
+      cv[2] = Store::ld(q, 7);
+      if (flm & F_LTS) cv[3] = Store::ld(q, 8);
+    }
   };
   auto fetch_e = [&](typename Store::Slot q) {
+    if constexpr (!Store::kPairs) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) e[i] = Store::ld(q, i);
+      for (int i = 0; i < 5; ++i) e[i] = Store::ld(q, i);
+    }
+  };
+  // pair stores: the whole slot (row vector into en, transcendental values into cv) in 4 (5) vector loads
+  auto fetch_pairs = [&](typename Store::Slot q, int flm, double (&en)[5]) {
+    if constexpr (Store::kPairs) {
+      const Dbl2 p0 = Store::ld2(q, 0), p1 = Store::ld2(q, 1), p2 = Store::ld2(q, 2), p3 = Store::ld2(q, 3);
+      en[0] = p0.x; en[1] = p0.y; en[2] = p1.x; en[3] = p1.y; en[4] = p2.x;
+      cv[0] = p2.y; cv[2] = p3.x; cv[3] = p3.y;
+      if (flm & F_LTP) cv[1] = Store::ld2(q, 4).x;
+    }
   };
   LayerGrad pend;
   pend.d = pend.a = pend.b = pend.rho = 0.0;
@@ -1040,6 +1067,7 @@ ADSURF_HD void sample_adjoint(const TableSource<kN>& src, const Sample& z, doubl
   if (!(fl & F_END)) {
     fetch_c(sq, fl);
     fetch_e(sq);
+    fetch_pairs(sq, fl, e);
   }
   auto layer = [&](auto tag) {
     constexpr int kFl = decltype(tag)::value;
@@ -1056,8 +1084,12 @@ ADSURF_HD void sample_adjoint(const TableSource<kN>& src, const Sample& z, doubl
     // the last use of e it arrives late and the top of the next layer waits for L2 (long-scoreboard stalls;
     // measured 2.776 vs 2.711 G samples/s, profiles/r2_variants.txt)
     double en[5];
+    if constexpr (Store::kPairs) {
+      fetch_pairs(sq, fln, en);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) en[i] = Store::ld(sq, i);
+      for (int i = 0; i < 5; ++i) en[i] = Store::ld(sq, i);
+    }
     const LayerGrad g = layer_adjoint<false>(y, e, s, tq, z.omega, z.ic, z.ic2, z.t2);
 #pragma unroll
     for (int i = 0; i < 5; ++i) e[i] = en[i];
