@@ -131,6 +131,11 @@ class InversionLoop:
         self.iter_d_hist = torch.zeros((T, S, L), dtype=torch.float64) if invert_thick else None
         self.j = 0
         self.done = 0
+        self.kernels_per_iteration, self.unroll = 0, 8
+
+    @property
+    def counter(self):
+        return torch.tensor([self.j, 0], dtype=torch.int32)
 
     def prepare(self, n):
         pass

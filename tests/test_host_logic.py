@@ -202,3 +202,40 @@ def test_inversion_trajectories_match_the_reference_on_the_oracle(ab):
     errs = trajectory_errors(api, "cpu", c3_models=8)
     bad = {k: v for k, v in errs.items() if not v <= 1e-10}
     assert not bad, f"trajectories differ from the reference's: {bad} (all: {errs})"
+
+
+def test_row_groups_slice_and_join_the_ensemble(ab):
+    """_capi.InversionLoopGroup (host logic: contiguous row views of state / constants / picks per group, histories
+    joined along the model axis, state updated in place) over the oracle-served loop: 3 groups of a 7-model ensemble
+    give exactly the single loop's histories and final state; horizontal damping is refused."""
+    from adsurf_b200 import _capi
+    from tests.golden_models import brocher_np
+    g = load("dmf_exp_m6")
+    S, n_it = 7, 4
+    rng = np.random.default_rng(9)
+    b = np.tile(g["b"][0], (S, 1)) * (1 + rng.normal(0, 0.03, (S, 6)))
+    a, rho = brocher_np(b)
+    d = np.tile(g["d"][0], (S, 1))
+    t, c = T(np.tile(g["t"][0][:10], (S, 1))), T(np.tile(g["c"][0][:10], (S, 1)))
+    C = T(np.tile(np.arange(2, 3.2, 0.05), (S, 1)))
+    kw = dict(compress=_capi.COMPRESS_EXP, vp_mode=1, vp_vs_ratio=0.0, invert_thick=True, layering=1,
+              proj_flags=_capi.PROJ_LAST_LAYER, damp_vertical=0.002, damp_horizontal=0.0, lr=0.005, gamma=0.5,
+              step_size=2, T=n_it)
+    out = {}
+    for groups in (1, 3):
+        state = {"b": T(b), "d": T(d), "alpha": T(a), "rho": T(rho)}
+        consts = {"b0": T(b), "alpha0": T(a), "rho0": T(rho), "lower_b": T(0.7 * b), "upper_b": T(1.3 * b),
+                  "mindepth": T(np.cumsum(d, 1) * 0.8), "maxdepth": T(np.cumsum(d, 1) * 1.2)}
+        loop = (_capi.InversionLoop(state, consts, t, c, C, **kw) if groups == 1 else
+                _capi.InversionLoopGroup(state, consts, t, c, C, groups=groups, **kw))
+        loop.run(n_it)
+        assert loop.counter.tolist() == [n_it, 0]
+        out[groups] = (loop.loss_hist, loop.iter_b_hist, loop.iter_d_hist, state["b"], state["d"], state["alpha"],
+                       state["mb"], state["vd"])
+        if groups == 3:
+            assert [x.loss_hist.shape[1] for x in loop.loops] == [2, 2, 3] and tuple(loop.loss_hist.shape) == (n_it, S)
+    for x, y in zip(out[1], out[3]):  # (the oracle's batched torch kernels round differently for other batch sizes:
+        torch.testing.assert_close(x, y, rtol=1e-12, atol=1e-15)  # 1-ulp level; bit for bit on the GPU)
+    with pytest.raises(_capi.AdsurfError):
+        _capi.InversionLoopGroup(state, consts, t, c, C, groups=2, **dict(kw, damp_horizontal=0.001))
+    assert _capi.loop_groups(4096, 20, 300, torch.device("cpu"), 0.0) == 1  # grouping is a GPU scheduling matter
